@@ -1,0 +1,216 @@
+/*
+ * nlb200.h -- C ABI of libnlb200.so, the B200 (sm_100a) implementation of the
+ * NeRF-LiDAR zipnerf volume-rendering hot path.
+ *
+ * Every entry point takes plain DEVICE pointers and sizes (no torch types), is
+ * asynchronous on the CUDA stream passed as `stream` (a cudaStream_t; NULL = the
+ * legacy default stream, which is what the reference's kernels use), and returns
+ * 0 on success or a negative NLB_E* code; nlb_last_error() gives the message of
+ * the last failure on the calling thread.  Callers allocate all outputs, as in the
+ * reference (gridencoder/grid.py:47-52,77-82).
+ *
+ * `Z/` = NeRF_LiDAR/zipnerf/ in the reference tree.  Each function names the
+ * reference interface it replaces.
+ */
+#ifndef NLB200_H
+#define NLB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NLB_OK 0
+#define NLB_EINVAL (-1)      /* bad argument (the reference raises RuntimeError) */
+#define NLB_EUNSUPPORTED (-2)/* valid in the reference, not built here (D>3, fp16/fp64 tables) */
+#define NLB_ECUDA (-3)       /* CUDA launch error */
+
+const char* nlb_last_error(void);
+int nlb_version(void);
+/* 1 when the library was compiled for sm_100a and a device of that arch is current. */
+int nlb_device_ok(void);
+
+/* ------------------------------------------------------------------ grid encoder
+ * Replaces the pybind11 module `_gridencoder` (Z/gridencoder/src/bindings.cpp:5-9,
+ * Z/gridencoder/src/gridencoder.h:12-15).  Argument order and meaning follow
+ * grid_encode_forward / grid_encode_backward / grad_total_variation there.
+ * fp32 tables; D in {2,3}; C in {1,2,4,8}.
+ */
+int nlb_grid_encode_forward(const float* inputs /*[B,D] in [0,1]*/, const float* embeddings /*[rows,C]*/,
+                            const int32_t* offsets /*[L+1]*/, float* outputs /*[L,B,C]*/,
+                            uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                            float* dy_dx /*[B,L*D*C] or NULL*/, uint32_t gridtype, int align_corners,
+                            uint32_t interp, void* stream);
+
+int nlb_grid_encode_backward(const float* grad /*[L,B,C]*/, const float* inputs, const float* embeddings,
+                             const int32_t* offsets, float* grad_embeddings /*[rows,C], pre-zeroed, accumulated*/,
+                             uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                             const float* dy_dx /*or NULL*/, float* grad_inputs /*[B,D] or NULL*/,
+                             uint32_t gridtype, int align_corners, uint32_t interp, void* stream);
+
+int nlb_grad_total_variation(const float* inputs, const float* embeddings, float* grad,
+                             const int32_t* offsets, float weight, uint32_t B, uint32_t D, uint32_t C,
+                             uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                             void* stream);
+
+/* Parity probe: the 2^D level-local row indices kernel_grid would gather
+ * (Z/gridencoder/src/gridencoder.cu:66-84,166-179).  indices[L,B,2^D];
+ * out-of-range points get 0xFFFFFFFF. */
+int nlb_grid_corner_indices(const float* inputs, const int32_t* offsets, uint32_t* indices,
+                            uint32_t B, uint32_t D, uint32_t L, float S, uint32_t H,
+                            uint32_t gridtype, int align_corners, void* stream);
+
+/* ------------------------------------------------------------------ step-function resampling
+ * One call = the per-level chain of Model.forward, Z/internal/models.py:320-372:
+ * stepfun.max_dilate_weights (+[1:-1] trim) when `dilate`, anneal/log -> logits,
+ * softmax, integrate_weights, math.sorted_interp at the sample centres,
+ * midpoints + reflected end fenceposts (stepfun.sample_intervals), and the
+ * power-transformation s_to_t (Z/internal/coord.py:103-162).
+ *   sdist_in[N,n_in+1], weights_in[N,n_in]; u_base[S] = the reference's
+ *   torch.linspace; jitter[N] (U[0,1), single_jitter) or NULL for rand=False.
+ *   sample_idx[N,S] (optional) = lower CDF knot of every sample centre.
+ */
+int nlb_resample(const float* sdist_in, const float* weights_in, int n_in, int dilate, float dilation,
+                 float anneal, float resample_padding, const float* u_base, const float* jitter,
+                 float max_jitter, const float* near, const float* far, float lam, int S, int N,
+                 float* sdist_out /*[N,S+1]*/, float* tdist_out /*[N,S+1]*/, int32_t* sample_idx,
+                 void* stream);
+
+/* math.sorted_interp (Z/internal/math.py:89-108) for sorted xp / non-decreasing fp.
+ * x[N,nx], xp[N,np], fp[N,np] -> out[N,nx], idx[N,nx] (optional lower-knot index). */
+int nlb_sorted_interp(const float* x, const float* xp, const float* fp, int N, int nx, int np,
+                      float* out, int32_t* idx, void* stream);
+
+/* ------------------------------------------------------------------ fused sample-point generation + encoding
+ * render.cast_rays (Z/internal/render.py:129-168) + coord.contract_mean_std and /2
+ * (Z/internal/coord.py:51-63, models.py:968-973) + GridEncoder forward + erf
+ * re-weighting and mean over the n=7 multisamples (models.py:974-977), without
+ * materialising means/stds or the [N,S,7,L,C] features.
+ *   features[N*S, L*C] fp32.  deg_noise[N,S,7] or NULL (rand=False).
+ */
+typedef struct {
+  const float* tdist;     /* [N,S+1] */
+  const float* origins;   /* [N,3] */
+  const float* directions;/* [N,3] */
+  const float* radii;     /* [N]   */
+  const float* base_x;    /* [N,3] */
+  const float* base_y;    /* [N,3] */
+  const float* deg_noise; /* [N,S,7] or NULL */
+  int N, S;
+  float std_scale;        /* Model.std_scale = 0.35 */
+} nlb_rays_t;
+
+typedef struct {
+  const float* embeddings;   /* [rows,C] */
+  const int32_t* offsets;    /* [L+1] */
+  const int32_t* grid_sizes; /* [L] (= python resolutions, scale+2) */
+  int L, C;
+  uint32_t H;                /* base resolution */
+  float S;                   /* log2(per_level_scale) */
+} nlb_table_t;
+
+int nlb_encode_forward(const nlb_rays_t* rays, const nlb_table_t* table, float* features, void* stream);
+/* grad_features[N*S, L*C] -> grad_embeddings[rows,C] (accumulated). */
+int nlb_encode_backward(const nlb_rays_t* rays, const nlb_table_t* table, const float* grad_features,
+                        float* grad_embeddings, void* stream);
+
+/* Proposal level: the above + PropMLP Linear(L,64)-ReLU-Linear(64,1), softplus(x-1)
+ * (models.py:887-889,996-997,1116) in one kernel.  W0[64,L] b0[64] W1[64] b1[1]
+ * in nn.Linear layout.  density[N,S]. */
+int nlb_prop_forward(const nlb_rays_t* rays, const nlb_table_t* table, const float* W0, const float* b0,
+                     const float* W1, const float* b1, float* density,
+                     float* features /*[N*S,L] saved for the backward, or NULL*/, void* stream);
+/* grad_density[N,S] + the features saved by the forward -> table / weight grads
+ * (all accumulated into pre-zeroed buffers). */
+int nlb_prop_backward(const nlb_rays_t* rays, const nlb_table_t* table, const float* W0, const float* b0,
+                      const float* W1, const float* b1, const float* features, const float* grad_density,
+                      float* grad_embeddings, float* gW0, float* gb0, float* gW1, float* gb1, void* stream);
+
+/* ------------------------------------------------------------------ compositing
+ * render.compute_alpha_weights (Z/internal/render.py:170-189) +
+ * render.volumetric_rendering (:192-284) incl. stepfun.weighted_percentile
+ * (Z/internal/stepfun.py:329-339).  NULL inputs/outputs are skipped.
+ */
+typedef struct {
+  const float* density;   /* [N,S] */
+  const float* tdist;     /* [N,S+1] */
+  const float* directions;/* [N,3] */
+  const float* rgb;       /* [N,S,3] or NULL (proposal levels: zeros) */
+  const float* semantic;  /* [N,S,K] or NULL */
+  const float* intensity; /* [N,S] or NULL */
+  const float* far;       /* [N] */
+  int N, S, K;
+  float bg;               /* background colour (bg_intensity_range = (1,1)) */
+  int opaque_background;
+  int compute_extras;
+} nlb_composite_in_t;
+
+typedef struct {
+  float* weights;   /* [N,S] */
+  float* rgb;       /* [N,3] */
+  float* depth;     /* [N] */
+  float* acc;       /* [N] */
+  float* semantic;  /* [N,K] or NULL */
+  float* intensity; /* [N] or NULL */
+  float* distance_mean;       /* [N] or NULL */
+  float* distance_percentiles;/* [N,3] (5,50,95) or NULL */
+} nlb_composite_out_t;
+
+int nlb_composite_forward(const nlb_composite_in_t* in, const nlb_composite_out_t* out, void* stream);
+
+typedef struct {
+  const float* g_weights;  /* [N,S] direct gradient on the weights (losses on ray_history) or NULL */
+  const float* g_rgb;      /* [N,3] or NULL */
+  const float* g_depth;    /* [N] or NULL */
+  const float* g_acc;      /* [N] or NULL */
+  const float* g_semantic; /* [N,K] or NULL (weights detached: reaches only `semantic`) */
+  const float* g_intensity;/* [N] or NULL (weights detached) */
+} nlb_composite_grad_t;
+
+int nlb_composite_backward(const nlb_composite_in_t* in, const float* weights /*[N,S] from forward*/,
+                           const nlb_composite_grad_t* g, float* g_density /*[N,S]*/,
+                           float* g_rgb /*[N,S,3] or NULL*/, float* g_semantic /*[N,S,K] or NULL*/,
+                           float* g_intensity /*[N,S] or NULL*/, void* stream);
+
+/* ------------------------------------------------------------------ NeRF MLP (tcgen05 / TMEM)
+ * MLP.forward for NerfMLP, Z/internal/models.py:996-997,1116-1251:
+ * 40->64->256 trunk, density softplus, semantic 256->64->19 softmax, intensity
+ * 256->64->1, view branch cat[x,pos_enc(viewdirs)](283)->256->cat(539)->256->3
+ * sigmoid with rgb padding.  bf16 operands, fp32 accumulation in TMEM.
+ * Weights are passed as one packed bf16 blob built by nlb_nerf_mlp_pack().
+ */
+size_t nlb_nerf_mlp_packed_bytes(void);
+typedef struct {
+  const float *W_d0, *b_d0;   /* [64,40],[64]   density_layer.0 */
+  const float *W_d2, *b_d2;   /* [256,64],[256] density_layer.2 */
+  const float *W_s0, *b_s0;   /* [64,256],[64]  sem_layer.0 */
+  const float *W_s2, *b_s2;   /* [19,64],[19]   sem_layer.2 */
+  const float *W_i0, *b_i0;   /* [64,256],[64]  intensity_layer.0 */
+  const float *W_i2, *b_i2;   /* [1,64],[1]     intensity_layer.2 */
+  const float *W_v0, *b_v0;   /* [256,283],[256] lin_second_stage_0 */
+  const float *W_v1, *b_v1;   /* [256,539],[256] lin_second_stage_1 */
+  const float *W_rgb, *b_rgb; /* [3,256],[3]    rgb_layer */
+} nlb_nerf_mlp_weights_t;
+int nlb_nerf_mlp_pack(const nlb_nerf_mlp_weights_t* w, void* packed, void* stream);
+int nlb_nerf_mlp_forward(const float* features /*[M,40]*/, const float* viewdirs /*[N,3]*/, int M,
+                         int rows_per_ray, const void* packed, float* density /*[M]*/, float* rgb /*[M,3]*/,
+                         float* semantic /*[M,19]*/, float* intensity /*[M]*/, void* stream);
+
+/* ------------------------------------------------------------------ optimizer
+ * One fused pass per table: hash-decay gradient (Model.hash_decay_loss,
+ * Z/internal/models.py:203-223: d/dp of mult * mean_levels(mean_rows(p^2)))
+ * + NaN scrub (train_utils.py:251-253) + Adam (train_utils.py:256-275:
+ * betas .9/.99, eps 1e-15) + zeroing the gradient for the next step.
+ */
+int nlb_adam_table_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                        const int32_t* offsets_host /*[L+1], HOST memory*/, int L, int C, float decay_mult, float lr, float beta1,
+                        float beta2, float eps, int step, float grad_scale, void* stream);
+int nlb_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLB200_H */

@@ -1,0 +1,123 @@
+"""ctypes binding of libnlb200.so (include/nlb200.h).
+
+The product path fails loudly when the CUDA library is missing: there is no CPU
+or PyTorch fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libnlb200.so')
+
+c_f = C.c_void_p  # device pointers travel as void*
+
+
+class NlbRays(C.Structure):
+    _fields_ = [('tdist', c_f), ('origins', c_f), ('directions', c_f), ('radii', c_f), ('base_x', c_f),
+                ('base_y', c_f), ('deg_noise', c_f), ('N', C.c_int), ('S', C.c_int), ('std_scale', C.c_float)]
+
+
+class NlbTable(C.Structure):
+    _fields_ = [('embeddings', c_f), ('offsets', c_f), ('grid_sizes', c_f), ('L', C.c_int), ('C', C.c_int),
+                ('H', C.c_uint32), ('S', C.c_float)]
+
+
+class NlbCompositeIn(C.Structure):
+    _fields_ = [('density', c_f), ('tdist', c_f), ('directions', c_f), ('rgb', c_f), ('semantic', c_f),
+                ('intensity', c_f), ('far', c_f), ('N', C.c_int), ('S', C.c_int), ('K', C.c_int),
+                ('bg', C.c_float), ('opaque_background', C.c_int), ('compute_extras', C.c_int)]
+
+
+class NlbCompositeOut(C.Structure):
+    _fields_ = [('weights', c_f), ('rgb', c_f), ('depth', c_f), ('acc', c_f), ('semantic', c_f),
+                ('intensity', c_f), ('distance_mean', c_f), ('distance_percentiles', c_f)]
+
+
+class NlbCompositeGrad(C.Structure):
+    _fields_ = [('g_weights', c_f), ('g_rgb', c_f), ('g_depth', c_f), ('g_acc', c_f), ('g_semantic', c_f),
+                ('g_intensity', c_f)]
+
+
+class NlbNerfMlpWeights(C.Structure):
+    _fields_ = [(n, c_f) for n in ('W_d0', 'b_d0', 'W_d2', 'b_d2', 'W_s0', 'b_s0', 'W_s2', 'b_s2', 'W_i0', 'b_i0',
+                                   'W_i2', 'b_i2', 'W_v0', 'b_v0', 'W_v1', 'b_v1', 'W_rgb', 'b_rgb')]
+
+
+_u32, _i, _f, _p = C.c_uint32, C.c_int, C.c_float, C.c_void_p
+
+# name -> (restype, argtypes); mirrors include/nlb200.h one to one
+SIGNATURES = {
+    'nlb_last_error': (C.c_char_p, []),
+    'nlb_version': (_i, []),
+    'nlb_device_ok': (_i, []),
+    'nlb_grid_encode_forward': (_i, [_p, _p, _p, _p, _u32, _u32, _u32, _u32, _f, _u32, _p, _u32, _i, _u32, _p]),
+    'nlb_grid_encode_backward': (_i, [_p, _p, _p, _p, _p, _u32, _u32, _u32, _u32, _f, _u32, _p, _p, _u32, _i, _u32, _p]),
+    'nlb_grad_total_variation': (_i, [_p, _p, _p, _p, _f, _u32, _u32, _u32, _u32, _f, _u32, _u32, _i, _p]),
+    'nlb_grid_corner_indices': (_i, [_p, _p, _p, _u32, _u32, _u32, _f, _u32, _u32, _i, _p]),
+    'nlb_resample': (_i, [_p, _p, _i, _i, _f, _f, _f, _p, _p, _f, _p, _p, _f, _i, _i, _p, _p, _p, _p]),
+    'nlb_sorted_interp': (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
+    'nlb_encode_forward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p]),
+    'nlb_encode_backward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p, _p]),
+    'nlb_prop_forward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p, _p, _p, _p, _p, _p]),
+    'nlb_prop_backward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'nlb_composite_forward': (_i, [C.POINTER(NlbCompositeIn), C.POINTER(NlbCompositeOut), _p]),
+    'nlb_composite_backward': (_i, [C.POINTER(NlbCompositeIn), _p, C.POINTER(NlbCompositeGrad), _p, _p, _p, _p, _p]),
+    'nlb_nerf_mlp_packed_bytes': (C.c_size_t, []),
+    'nlb_nerf_mlp_pack': (_i, [C.POINTER(NlbNerfMlpWeights), _p, _p]),
+    'nlb_nerf_mlp_forward': (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
+    'nlb_adam_table_step': (_i, [_p, _p, _p, _p, C.POINTER(C.c_int32), _i, _i, _f, _f, _f, _f, _f, _i, _f, _p]),
+    'nlb_adam_step': (_i, [_p, _p, _p, _p, C.c_int64, _f, _f, _f, _f, _i, _f, _p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Loads libnlb200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: build it with `python -m nerf_lidar_b200.build` '
+                '(or __graft_entry__.build()). nerf_lidar_b200 has no CPU/PyTorch fallback.')
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(code: int):
+    if code != 0:
+        msg = load().nlb_last_error().decode()
+        if code == -2:
+            raise NotImplementedError(msg)
+        raise RuntimeError(msg)
+
+
+def ptr(t: Optional[torch.Tensor]):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('nerf_lidar_b200: expected a CUDA tensor (there is no CPU path)')
+    if not t.is_contiguous():
+        raise RuntimeError('nerf_lidar_b200: expected a contiguous tensor')
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def f32(t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError('nerf_lidar_b200: expected a CUDA tensor (there is no CPU path)')
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

@@ -1,0 +1,265 @@
+// Shared device helpers for libnlb200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define NLB_FULL_MASK 0xffffffffu
+
+namespace nlb {
+
+constexpr float kEps = 1.1920928955078125e-07f;  // torch.finfo(float32).eps
+constexpr float kPi = 3.14159265358979323846f;
+
+__host__ __device__ inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------
+// Level geometry, identical arithmetic to the reference kernel
+// (gridencoder.cu:137-139): scale = exp2f(level*S)*H - 1, resolution = ceil(scale)+1.
+// ---------------------------------------------------------------------------
+struct LevelGeom {
+  float scale;
+  uint32_t resolution;
+  uint32_t hashmap_size;
+  uint32_t offset;
+};
+
+__device__ __forceinline__ LevelGeom level_geom(const int32_t* __restrict__ offsets, uint32_t level, float S,
+                                                uint32_t H) {
+  LevelGeom g;
+  g.offset = (uint32_t)__ldg(offsets + level);
+  g.hashmap_size = (uint32_t)__ldg(offsets + level + 1) - g.offset;
+  g.scale = exp2f(level * S) * H - 1.0f;
+  g.resolution = (uint32_t)ceilf(g.scale) + 1;
+  return g;
+}
+
+// Row index of one grid vertex (gridencoder.cu:50-84): dense stride walk while the
+// stride fits, otherwise xor-of-primes hash, always modulo the level size.
+template <uint32_t D>
+__device__ __forceinline__ uint32_t vertex_index(const uint32_t pg[D], uint32_t hashmap_size, uint32_t resolution,
+                                                 uint32_t gridtype, bool align_corners) {
+  constexpr uint32_t primes[7] = {1u, 2654435761u, 805459861u, 3674653429u,
+                                  2097192037u, 1434869437u, 2165219737u};
+  uint32_t stride = 1, index = 0;
+  const uint32_t step = align_corners ? resolution : resolution + 1;
+#pragma unroll
+  for (uint32_t d = 0; d < D; ++d) {
+    if (stride <= hashmap_size) {
+      index += pg[d] * stride;
+      stride *= step;
+    }
+  }
+  if (gridtype == 0 && stride > hashmap_size) {
+    uint32_t h = 0;
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) h ^= pg[d] * primes[d];
+    index = h;
+  }
+  return index % hashmap_size;
+}
+
+// D = 3, hash grid, align_corners = false: the configuration of every encoder
+// on the zipnerf path.  `dense` is a per-level constant so the branch is uniform.
+struct Level3 {
+  float scale;
+  uint32_t hashmap_size;
+  uint32_t offset;
+  uint32_t s1, s2;  // dense strides (res+1), (res+1)^2
+  bool dense;       // (res+1)^3 <= hashmap_size
+};
+
+__device__ __forceinline__ Level3 level3(const int32_t* __restrict__ offsets, uint32_t level, float S, uint32_t H) {
+  LevelGeom g = level_geom(offsets, level, S, H);
+  Level3 v;
+  v.scale = g.scale;
+  v.hashmap_size = g.hashmap_size;
+  v.offset = g.offset;
+  // replay the reference's stride walk once per level
+  uint32_t stride = 1;
+  const uint32_t step = g.resolution + 1;
+  v.s1 = v.s2 = 0;
+  bool stopped = false;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if (!stopped && stride <= g.hashmap_size) {
+      if (d == 1) v.s1 = stride;
+      if (d == 2) v.s2 = stride;
+      stride *= step;
+    } else {
+      stopped = true;
+    }
+  }
+  v.dense = !(stride > g.hashmap_size);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t vertex_index3(const Level3& lv, uint32_t x, uint32_t y, uint32_t z) {
+  uint32_t idx;
+  if (lv.dense) {
+    idx = x + y * lv.s1 + z * lv.s2;
+  } else {
+    idx = x ^ (y * 2654435761u) ^ (z * 805459861u);
+  }
+  // hashed levels on this path are powers of two (2^21); keep the general modulo
+  // for dense levels whose size is rounded up to a multiple of 8.
+  return ((lv.hashmap_size & (lv.hashmap_size - 1)) == 0) ? (idx & (lv.hashmap_size - 1)) : (idx % lv.hashmap_size);
+}
+
+// pos = x*scale + 0.5 is ONE fma in the reference binary (nvcc contracts
+// gridencoder.cu:148); written explicitly so no compiler flag can change it.
+__device__ __forceinline__ void cell_of(float x01, float scale, uint32_t& cell, float& frac) {
+  float pos = fmaf(x01, scale, 0.5f);
+  float fl = floorf(pos);
+  cell = (uint32_t)fl;
+  frac = pos - fl;
+}
+
+// ---------------------------------------------------------------------------
+// Ray warps: power transformation with lambda (coord.py:103-162).
+// Operation order mirrors the torch expression so results agree to ~1 ulp of powf.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float power_fwd(float x, float lam) {
+  const float a = fabsf(lam - 1.0f);
+  const float c = a / lam;
+  return __fmul_rn(c, __fsub_rn(powf(__fadd_rn(__fdiv_rn(x, a), 1.0f), lam), 1.0f));
+}
+
+__device__ __forceinline__ float power_inv(float y, float lam) {
+  const float a = fabsf(lam - 1.0f);
+  const float inv = 1.0f / lam;
+  float base = __fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(y, lam), a), 1.0f), kEps);
+  return __fmul_rn(__fsub_rn(powf(base, inv), 1.0f), a);
+}
+
+struct RayWarp {
+  float s_near, s_far, lam;
+};
+
+__device__ __forceinline__ RayWarp make_warp(float near, float far, float lam) {
+  RayWarp w;
+  w.lam = lam;
+  w.s_near = power_fwd(__fmul_rn(near, 2.0f), lam);
+  w.s_far = power_fwd(__fmul_rn(far, 2.0f), lam);
+  return w;
+}
+
+__device__ __forceinline__ float s_to_t(const RayWarp& w, float s) {
+  float y = __fadd_rn(__fmul_rn(s, w.s_far), __fmul_rn(__fsub_rn(1.0f, s), w.s_near));
+  return __fdiv_rn(power_inv(y, w.lam), 2.0f);
+}
+
+// ---------------------------------------------------------------------------
+// Sample-point generation: render.cast_rays (render.py:129-168) for multisample j
+// of the interval [t0,t1], then contract_mean_std (coord.py:51-63), the /2 of
+// models.py:970-973 and GridEncoder's (x+1)/2 (grid.py:162).
+// ---------------------------------------------------------------------------
+struct RayGeom {
+  float ox, oy, oz;
+  float dx, dy, dz;
+  float bxx, bxy, bxz;
+  float byx, byy, byz;
+  float radius;
+};
+
+__device__ __forceinline__ RayGeom load_ray(const float* __restrict__ origins, const float* __restrict__ directions,
+                                            const float* __restrict__ base_x, const float* __restrict__ base_y,
+                                            const float* __restrict__ radii, int ray) {
+  RayGeom r;
+  r.ox = __ldg(origins + 3 * ray);
+  r.oy = __ldg(origins + 3 * ray + 1);
+  r.oz = __ldg(origins + 3 * ray + 2);
+  r.dx = __ldg(directions + 3 * ray);
+  r.dy = __ldg(directions + 3 * ray + 1);
+  r.dz = __ldg(directions + 3 * ray + 2);
+  r.bxx = __ldg(base_x + 3 * ray);
+  r.bxy = __ldg(base_x + 3 * ray + 1);
+  r.bxz = __ldg(base_x + 3 * ray + 2);
+  r.byx = __ldg(base_y + 3 * ray);
+  r.byy = __ldg(base_y + 3 * ray + 1);
+  r.byz = __ldg(base_y + 3 * ray + 2);
+  r.radius = __ldg(radii + ray);
+  return r;
+}
+
+struct SamplePoint {
+  float x, y, z;  // in [0,1]^3 (grid coordinates)
+  float std;      // contracted std / 2
+};
+
+// j in [0,7): t = t0 + (t1-t0)*(j+.5)/7 ; deg = 2*pi*3*j/7 (+ 2*pi*noise).
+__device__ __forceinline__ SamplePoint sample_point(const RayGeom& r, float t0, float t1, int j, float noise,
+                                                    bool has_noise, float std_scale) {
+  const float n = 7.0f;
+  float t = __fadd_rn(t0, __fdiv_rn(__fmul_rn(__fsub_rn(t1, t0), (float)j + 0.5f), n));
+  // 2*pi*m is folded in double then rounded (python float -> float32 scalar)
+  float deg = __fdiv_rn(__fmul_rn(18.849555921538759f, (float)j), n);
+  if (has_noise) deg = __fadd_rn(deg, __fmul_rn(__fmul_rn(noise, kPi), 2.0f));
+  float sn, cs;
+  sincosf(deg, &sn, &cs);
+  float rt = __fmul_rn(r.radius, t);
+  float lx = __fdiv_rn(__fmul_rn(rt, cs), 2.0f);
+  float ly = __fdiv_rn(__fmul_rn(rt, sn), 2.0f);
+  float mx = fmaf(lx, r.bxx, fmaf(ly, r.byx, t * r.dx)) + r.ox;
+  float my = fmaf(lx, r.bxy, fmaf(ly, r.byy, t * r.dy)) + r.oy;
+  float mz = fmaf(lx, r.bxz, fmaf(ly, r.byz, t * r.dz)) + r.oz;
+  float sd = __fmul_rn(__fmul_rn(std_scale, r.radius), t);
+  // contract
+  float m2 = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(mx, mx), __fmul_rn(my, my)), __fmul_rn(mz, mz)), kEps);
+  if (!(m2 <= 1.0f)) {
+    float m = sqrtf(m2);
+    float k = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, m), 1.0f), m2);
+    mx *= k;
+    my *= k;
+    mz *= k;
+    float q = __fsub_rn(__fdiv_rn(2.0f, m), __fdiv_rn(1.0f, m2));
+    float det = __fmul_rn(__fdiv_rn(1.0f, m2), __fmul_rn(q, q));
+    sd = __fmul_rn(powf(det, 0.3333333333333333f), sd);
+  }
+  SamplePoint p;
+  // /2 (contract [-2,2] -> [-1,1]) then (x + 1) / 2
+  p.x = __fdiv_rn(__fadd_rn(__fdiv_rn(mx, 2.0f), 1.0f), 2.0f);
+  p.y = __fdiv_rn(__fadd_rn(__fdiv_rn(my, 2.0f), 1.0f), 2.0f);
+  p.z = __fdiv_rn(__fadd_rn(__fdiv_rn(mz, 2.0f), 1.0f), 2.0f);
+  p.std = __fdiv_rn(sd, 2.0f);
+  return p;
+}
+
+// erf(1 / max(sqrt(8 * std^2 * grid_size^2), 1e-10))  (models.py:976)
+__device__ __forceinline__ float erf_weight(float sd, int grid_size) {
+  float gs = (float)(grid_size * grid_size);
+  float v = __fmul_rn(__fmul_rn(8.0f, __fmul_rn(sd, sd)), gs);
+  return erff(__fdiv_rn(1.0f, fmaxf(sqrtf(v), 1e-10f)));
+}
+
+__device__ __forceinline__ bool in_unit_cube(float x, float y, float z) {
+  return !(x < 0.f || x > 1.f || y < 0.f || y > 1.f || z < 0.f || z > 1.f);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NLB_FULL_MASK, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(NLB_FULL_MASK, v, o));
+  return v;
+}
+
+// inclusive warp scan (sum)
+__device__ __forceinline__ float warp_scan_incl(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float n = __shfl_up_sync(NLB_FULL_MASK, v, o);
+    if (lane >= o) v += n;
+  }
+  return v;
+}
+
+}  // namespace nlb
+
+// error plumbing shared by all translation units
+void nlb_set_error(const char* fmt, ...);
+int nlb_check_launch(const char* what);

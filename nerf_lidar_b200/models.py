@@ -1,0 +1,358 @@
+"""`Model` / `NerfMLP` / `PropMLP` / `render_image` with the reference's public
+interface (Z/internal/models.py:30-177 ctor, :239-576 forward, :1379-1507
+render_image) on the B200 kernels.
+
+Scope: the static-scene zipnerf path of nuscenes_single.gin --
+3 sampling levels, hash-grid PropMLPs, NerfMLP with semantic + intensity heads,
+opaque background, power-transformation ray warp.  The dynamic-object branch
+(Config.instance_obj, Z/internal/models.py:306-315,401-477) is section 8(f) "next" and
+raises NotImplementedError here.
+
+State-dict keys are the reference's (nerf_mlp.encoder.embeddings,
+nerf_mlp.density_layer.0.weight, prop_mlp_0.encoder.offsets, ...), so reference
+checkpoints load with `load_state_dict(strict=False)` exactly as
+Z/internal/checkpoints.py:26-55 does."""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .configs import Config, configurable
+from .gridencoder import GridEncoder
+
+
+def set_kwargs(self, kwargs):
+    for k, v in kwargs.items():
+        setattr(self, k, v)
+
+
+class MLP(nn.Module):
+    """Parameter container + head evaluation of Z/internal/models.py:796-1263
+    (only the options the zipnerf nuScenes path uses)."""
+    bottleneck_width: int = 256
+    net_depth_viewdirs: int = 2
+    net_width_viewdirs: int = 256
+    skip_layer_dir: int = 0
+    num_rgb_channels: int = 3
+    deg_view: int = 4
+    density_bias: float = -1.
+    rgb_premultiplier: float = 1.
+    rgb_bias: float = 0.
+    rgb_padding: float = 0.001
+    disable_density_normals: bool = False
+    disable_rgb: bool = False
+    warp_fn = 'contract'
+    grid_level_interval: int = 2
+    grid_level_dim: int = 4
+    grid_base_resolution: int = 16
+    grid_disired_resolution: int = 8192
+    grid_log2_hashmap_size: int = 21
+    class_num: int = 19
+    use_semantic: bool = False
+    analytic_gradient: bool = True
+    use_intensity: bool = False
+    no_sem_layer: bool = True
+    re_weights: bool = True
+    mlp_dtype = torch.bfloat16  # operand type of the dense layers (fp32 accumulation)
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        set_kwargs(self, kwargs)
+        if not self.disable_density_normals:
+            raise NotImplementedError('density normals (Ref-NeRF options) are outside the zipnerf hot path; '
+                                      'bind disable_density_normals=True as nuscenes_single.gin does')
+        if self.use_semantic and self.no_sem_layer and not self.disable_rgb:
+            raise NotImplementedError('no_sem_layer=True (semantic = bottleneck slice) is not built; '
+                                      'nuscenes_single.gin binds Config.no_sem_layer=False')
+        self.grid_num_levels = int(np.log(self.grid_disired_resolution / self.grid_base_resolution)
+                                   / np.log(self.grid_level_interval)) + 1
+        self.encoder = GridEncoder(input_dim=3, num_levels=self.grid_num_levels, level_dim=self.grid_level_dim,
+                                   base_resolution=self.grid_base_resolution,
+                                   desired_resolution=self.grid_disired_resolution,
+                                   log2_hashmap_size=self.grid_log2_hashmap_size, gridtype='hash',
+                                   align_corners=False)
+        width = self.encoder.output_dim
+        self.density_layer = nn.Sequential(nn.Linear(width, 64), nn.ReLU(),
+                                           nn.Linear(64, 1 if self.disable_rgb else self.bottleneck_width))
+        if not self.disable_rgb:
+            dim_dir_enc = 3 + 2 * 3 * self.deg_view
+            in_rgb = self.bottleneck_width + dim_dir_enc
+            last = in_rgb
+            for i in range(self.net_depth_viewdirs):
+                lin = nn.Linear(last, self.net_width_viewdirs)
+                torch.nn.init.kaiming_uniform_(lin.weight)
+                self.register_module(f'lin_second_stage_{i}', lin)
+                last = self.net_width_viewdirs
+                if i == self.skip_layer_dir:
+                    last += in_rgb
+            self.rgb_layer = nn.Linear(last, self.num_rgb_channels)
+            if not self.no_sem_layer:
+                self.sem_layer = nn.Sequential(nn.Linear(self.bottleneck_width, 64), nn.ReLU(),
+                                               nn.Linear(64, self.class_num))
+            if self.use_intensity:
+                self.intensity_layer = nn.Sequential(nn.Linear(self.bottleneck_width, 64), nn.ReLU(),
+                                                     nn.Linear(64, 1))
+
+    # -- dense head of the NeRF level ------------------------------------------------
+    def dir_enc(self, viewdirs: torch.Tensor) -> torch.Tensor:
+        """coord.pos_enc(viewdirs, 0, deg_view, append_identity=True), Z/internal/coord.py:199-210."""
+        scales = 2 ** torch.arange(0, self.deg_view, device=viewdirs.device)
+        sx = (viewdirs[..., None, :] * scales[:, None]).reshape(*viewdirs.shape[:-1], -1)
+        return torch.cat([viewdirs, torch.sin(torch.cat([sx, sx + 0.5 * math.pi], dim=-1))], dim=-1)
+
+    def heads(self, feat: torch.Tensor, viewdirs: torch.Tensor, S: int) -> Dict[str, torch.Tensor]:
+        """features[N*S, 40] -> density / rgb / semantic / intensity
+        (Z/internal/models.py:996-997,1116-1251).  Dense layers run with bf16
+        operands and fp32 accumulation (bf16 MLP is a build decision,
+        tolerance 1e-3 vs the fp32 reference); activations are evaluated in fp32."""
+        N = viewdirs.shape[0]
+        dt = self.mlp_dtype
+
+        def lin(layer, x):
+            if dt == torch.float32:
+                return F.linear(x, layer.weight, layer.bias)
+            return F.linear(x.to(dt), layer.weight.to(dt), None).float() + layer.bias
+
+        x = lin(self.density_layer[2], torch.relu(lin(self.density_layer[0], feat)))
+        density = F.softplus(x[..., 0] + self.density_bias).reshape(N, S)
+        sem = inten = None
+        if self.use_semantic:
+            sem = torch.softmax(lin(self.sem_layer[2], torch.relu(lin(self.sem_layer[0], x))), dim=-1)
+            sem = sem.reshape(N, S, self.class_num)
+        if self.use_intensity:
+            inten = lin(self.intensity_layer[2], torch.relu(lin(self.intensity_layer[0], x))).reshape(N, S, 1)
+        de = self.dir_enc(viewdirs)
+        de = de[:, None, :].expand(N, S, de.shape[-1]).reshape(N * S, -1)
+        h_in = torch.cat([x, de], dim=-1)
+        h = h_in
+        for i in range(self.net_depth_viewdirs):
+            h = torch.relu(lin(self.get_submodule(f'lin_second_stage_{i}'), h))
+            if i == self.skip_layer_dir:
+                h = torch.cat([h, h_in], dim=-1)
+        rgb = torch.sigmoid(self.rgb_premultiplier * lin(self.rgb_layer, h) + self.rgb_bias)
+        rgb = (rgb * (1 + 2 * self.rgb_padding) - self.rgb_padding).reshape(N, S, 3)
+        return dict(density=density, rgb=rgb, semantic=sem, intensity=inten)
+
+    def forward(self, *a, **k):
+        raise NotImplementedError('MLP modules are evaluated through Model.forward (fused kernels); '
+                                  'the stand-alone MLP.forward(means, stds) entry is outside the hot-path scope')
+
+
+@configurable
+class NerfMLP(MLP):
+    pass
+
+
+@configurable
+class PropMLP(MLP):
+    pass
+
+
+@configurable
+class Model(nn.Module):
+    """Z/internal/models.py:30-58 class attributes (gin-configurable)."""
+    num_prop_samples = (64, 64)
+    num_nerf_samples: int = 32
+    num_levels: int = 3
+    bg_intensity_range = (1., 1.)
+    anneal_slope: float = 10
+    stop_level_grad: bool = True
+    use_viewdirs: bool = True
+    raydist_fn = 'contract'
+    single_jitter: bool = True
+    dilation_multiplier: float = 0.5
+    dilation_bias: float = 0.0025
+    num_glo_features: int = 0
+    near_anneal_rate = None
+    near_anneal_init: float = 0.95
+    single_mlp: bool = False
+    distinct_prop: bool = True
+    resample_padding: float = 0.0
+    opaque_background: bool = False
+    power_lambda: float = -1.5
+    std_scale: float = 0.35
+    prop_desired_grid_size = [512, 2048]
+    training: bool = False
+
+    def __init__(self, config: Optional[Config] = None, **kwargs):
+        super().__init__()
+        set_kwargs(self, kwargs)
+        self.config = config if config is not None else Config()
+        config = self.config
+        if getattr(config, 'instance_obj', False):
+            raise NotImplementedError('Config.instance_obj (dynamic-object branch) is SURVEY 8(f) "next"; '
+                                      'bind Config.instance_obj=False for the static-scene hot path')
+        if self.raydist_fn != 'power_transformation' or self.single_mlp or not self.distinct_prop \
+                or self.num_glo_features > 0 or not self.single_jitter or self.near_anneal_rate is not None \
+                or not self.stop_level_grad or self.bg_intensity_range[0] != self.bg_intensity_range[1]:
+            raise NotImplementedError('only the nuscenes_single.gin zipnerf configuration is built: '
+                                      "raydist_fn='power_transformation', distinct proposal MLPs, no GLO, "
+                                      'single_jitter, stop_level_grad, constant background')
+        self.nerf_mlp = NerfMLP(use_semantic=config.use_semantic, analytic_gradient=config.analytic_gradient,
+                                use_intensity=config.use_intensity, no_sem_layer=config.no_sem_layer)
+        for i in range(self.num_levels - 1):
+            self.register_module(f'prop_mlp_{i}', PropMLP(grid_disired_resolution=self.prop_desired_grid_size[i]))
+        self.instance_obj = False
+
+    # Z/internal/models.py:203-223 (value only: its gradient is applied analytically
+    # inside the fused optimizer pass, see train.py / csrc/adam.cu)
+    @torch.no_grad()
+    def hash_decay_loss(self) -> torch.Tensor:
+        total = 0.
+        for name, param in sorted(self.named_parameters(), key=lambda x: x[0]):
+            if 'encoder' in name:
+                enc = self.get_submodule(name.split('.')[0]).encoder
+                offs = enc.offsets.tolist()
+                sq = param.detach() ** 2
+                per = torch.stack([sq[offs[l]:offs[l + 1]].mean(0) for l in range(enc.num_levels)])
+                total = total + per.mean()
+        return self.config.hash_decay_mults * total
+
+    def forward(self, rand, batch, train_frac, compute_extras, zero_glo=True, sample_n=7, sample_m=3, step=0,
+                max_step=25000, curr_track=None, rand_inputs: Optional[Sequence[Dict[str, torch.Tensor]]] = None):
+        """Same contract as the reference: returns (renderings, ray_history).
+        `rand_inputs` (extension) injects the random draws -- per level a dict with
+        'jitter'[N,1] and 'deg'[N,S,7] in U[0,1) -- instead of torch.rand, so that
+        parity tests see the reference's jitter."""
+        if sample_n != 7 or sample_m != 3:
+            raise NotImplementedError('the fused kernels implement the n=7, m=3 hexagonal multisample')
+        rays = ops.RayBundle(batch)
+        N, dev = rays.N, rays.device
+        near, far = batch['near'], batch['far']
+        viewdirs = ops.f32(batch['viewdirs'])
+        sdist = weights = None
+        prod_num_samples = 1
+        renderings: List[Dict] = []
+        ray_history: List[Dict] = []
+        anneal = (self.anneal_slope * train_frac) / ((self.anneal_slope - 1) * train_frac + 1) \
+            if self.anneal_slope > 0 else 1.
+        bg = float(self.bg_intensity_range[0])
+        for i_level in range(self.num_levels):
+            is_prop = i_level < (self.num_levels - 1)
+            S = self.num_prop_samples[i_level] if is_prop else self.num_nerf_samples
+            dilation = self.dilation_bias + self.dilation_multiplier * 1.0 / prod_num_samples
+            prod_num_samples *= S
+            use_dilation = (self.dilation_bias > 0 or self.dilation_multiplier > 0) and i_level > 0
+            jitter = deg = None
+            if rand:
+                if rand_inputs is not None:
+                    jitter, deg = rand_inputs[i_level]['jitter'], ops.f32(rand_inputs[i_level]['deg'])
+                else:
+                    jitter = torch.rand(N, 1, device=dev)
+                    deg = torch.rand(N, S, 7, device=dev)
+            sdist, tdist = ops.resample_level(sdist, weights, near, far, S, use_dilation, dilation, anneal, jitter,
+                                              bool(rand), self.power_lambda, self.resample_padding)
+            if is_prop:
+                mlp = self.get_submodule(f'prop_mlp_{i_level}')
+                density = ops.prop_level(tdist, deg, mlp, rays, self.std_scale)
+                res = dict(density=density, rgb=None, semantic=None, intensity=None)
+            else:
+                feat = ops.nerf_encode(tdist, deg, self.nerf_mlp.encoder, rays, self.std_scale)
+                res = self.nerf_mlp.heads(feat, viewdirs, S)
+            sem = res['semantic'] if (not is_prop and self.config.use_semantic) else None
+            inten = res['intensity'] if (not is_prop and self.config.use_intensity) else None
+            comp = ops.composite(res['density'], tdist, rays.directions, far, res['rgb'], sem, inten, bg,
+                                 self.opaque_background, bool(compute_extras))
+            weights = comp['weights']
+            rendering = dict(rgb=comp['rgb'], depth=comp['depth'])
+            if sem is not None:
+                rendering['semantic'] = comp['semantic']
+            if inten is not None:
+                rendering['intensity'] = comp['intensity']
+            if res['rgb'] is None:
+                res['rgb'] = torch.zeros(1, device=dev).expand(N, S, 3)
+            if compute_extras:
+                rendering['acc'] = comp['acc']
+                rendering['distance_mean'] = comp['distance_mean']
+                pct = comp['distance_percentiles']
+                rendering['distance_percentile_5'] = pct[:, 0]
+                rendering['distance_median'] = pct[:, 1]
+                rendering['distance_percentile_95'] = pct[:, 2]
+                n = self.config.vis_num_rays
+                rendering['ray_sdist'] = sdist[:n]
+                rendering['ray_weights'] = weights[:n]
+                rendering['ray_rgbs'] = res['rgb'][:n]
+            renderings.append(rendering)
+            res['sdist'], res['weights'], res['tdist'] = sdist, weights, tdist
+            ray_history.append(res)
+        if compute_extras:
+            final_rgb = torch.sum(renderings[-1]['ray_rgbs'] * renderings[-1]['ray_weights'][..., None], dim=-2)
+            for r in renderings[:-1]:
+                r['ray_rgbs'] = torch.broadcast_to(final_rgb[:, None, :], r['ray_rgbs'].shape)
+        if self.config.hash_decay_mults > 0 and self.training:
+            renderings[-1]['hash_decay'] = self.hash_decay_loss()
+        return renderings, ray_history
+
+
+class _SingleProcess:
+    """Stand-in for accelerate.Accelerator when rendering on one GPU."""
+    process_index = 0
+    num_processes = 1
+    is_main_process = True
+
+
+@torch.no_grad()
+def render_image(model, accelerator, batch, rand, config, train_frac=1, verbose=True, return_weights=False,
+                 image=True, render_instance=False, instance_id=None):
+    """Z/internal/models.py:1379-1507 with one change of schedule: every rank takes
+    ONE contiguous slice of the whole ray set, renders it in local chunks of
+    config.render_chunk_size and the packed per-ray outputs are all-gathered once
+    at the end (the reference pads, slices and all-gathers every leaf of every
+    chunk).  `accelerator` needs process_index / num_processes (an
+    accelerate.Accelerator works; None = single process); torch.distributed is used
+    for the gather when it is initialised."""
+    if render_instance:
+        raise NotImplementedError('render_instance (object-only rendering) is SURVEY 8(f) "next"')
+    from . import parallel
+    acc = accelerator if accelerator is not None else _SingleProcess()
+    was_training = bool(model.training)
+    model.eval()
+    model.training = False
+    if image:
+        height, width = batch['origins'].shape[:2]
+        num_rays = height * width
+    else:
+        num_rays = batch['origins'].shape[0]
+    batch = {k: v.reshape((num_rays, -1)) for k, v in batch.items() if v is not None}
+    world, rank = int(acc.num_processes), int(acc.process_index)
+    lo, hi = parallel.shard_range(num_rays, world, rank)
+    chunks = []
+    for idx0 in range(lo, hi, config.render_chunk_size):
+        idx1 = min(hi, idx0 + config.render_chunk_size)
+        chunk = {k: v[idx0:idx1] for k, v in batch.items()}
+        renderings, ray_history = model(rand, chunk, train_frac=train_frac, compute_extras=True, zero_glo=True)
+        out = dict(renderings[-1])
+        for k in renderings[0]:
+            if k.startswith('ray_'):
+                out[k] = [r[k] for r in renderings]
+        if return_weights:
+            out['weights'] = ray_history[-1]['weights']
+        chunks.append(out)
+    rendering = {}
+    keys = chunks[0].keys() if chunks else []
+    for k in keys:
+        if isinstance(chunks[0][k], list):
+            rendering[k] = [torch.cat([c[k][i] for c in chunks]) for i in range(len(chunks[0][k]))]
+        else:
+            rendering[k] = torch.cat([c[k] for c in chunks])
+    if world > 1:
+        rendering = parallel.gather_rendering(rendering, num_rays, world, rank)
+    for k, z in rendering.items():
+        if not k.startswith('ray_') and 'hash' not in k:
+            rendering[k] = z.reshape((height, width) + z.shape[1:]) if image else z.reshape(num_rays, -1)
+    keys = [k for k in rendering if k.startswith('ray_')]
+    if keys:
+        n = rendering[keys[0]][0].shape[0]
+        ray_idx = torch.randperm(n)[:config.vis_num_rays]
+        for k in keys:
+            rendering[k] = [r[ray_idx.to(r.device)] for r in rendering[k]]
+    if was_training:
+        model.train()
+        model.training = True
+    return rendering

@@ -1,0 +1,251 @@
+"""Host-side operators of the zipnerf hot path: thin torch.autograd wrappers that
+allocate outputs and call the C ABI in libnlb200.so (include/nlb200.h).
+
+Reference functions replaced (Z/ = NeRF_LiDAR/zipnerf/):
+  resample_level   Z/internal/models.py:320-372 (stepfun.max_dilate_weights,
+                   stepfun.sample_intervals, math.sorted_interp, s_to_t)
+  sorted_interp    Z/internal/math.py:89-108
+  prop_level       render.cast_rays + MLP.predict_density + softplus for PropMLP
+  nerf_encode      render.cast_rays + contract + GridEncoder + erf-weighted mean
+  composite        render.compute_alpha_weights + render.volumetric_rendering
+There is no CPU path: every function requires CUDA tensors."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
+
+EPS = float(torch.finfo(torch.float32).eps)
+_u_cache: Dict[Tuple, torch.Tensor] = {}
+
+
+def _u_base(num_samples: int, rand: bool, device) -> Tuple[torch.Tensor, float]:
+    """The linspace of stepfun.sample (Z/internal/stepfun.py:199-216), computed by
+    torch on the host exactly as the reference does, cached on the device."""
+    key = (num_samples, bool(rand), str(device))
+    if key not in _u_cache:
+        if not rand:
+            pad = 1 / (2 * num_samples)
+            u = torch.linspace(pad, 1. - pad - EPS, num_samples)
+        else:
+            u_max = EPS + (1 - EPS) / num_samples
+            u = torch.linspace(0, 1 - u_max, num_samples)
+        _u_cache[key] = u.to(device)
+    u_max = EPS + (1 - EPS) / num_samples
+    max_jitter = (1 - u_max) / (num_samples - 1) - EPS
+    return _u_cache[key], max_jitter
+
+
+@torch.no_grad()
+def resample_level(sdist: Optional[torch.Tensor], weights: Optional[torch.Tensor], near: torch.Tensor,
+                   far: torch.Tensor, num_samples: int, dilate: bool, dilation: float, anneal: float,
+                   jitter: Optional[torch.Tensor], rand: bool, lam: float = -1.5, resample_padding: float = 0.0,
+                   return_index: bool = False):
+    """One level of interval resampling.  sdist=None means the initial [0,1]
+    interval with weight 1 (models.py:296-300).  Returns (sdist, tdist[, idx])."""
+    near, far = f32(near).reshape(-1), f32(far).reshape(-1)
+    N = near.shape[0]
+    dev = near.device
+    if sdist is None:
+        n_in, sd, w = 1, None, None
+    else:
+        sd, w = f32(sdist), f32(weights)
+        n_in = w.shape[-1]
+    u_base, max_jitter = _u_base(num_samples, rand, dev)
+    jit = f32(jitter).reshape(-1) if (rand and jitter is not None) else None
+    if rand and jit is None:
+        raise RuntimeError('resample_level: rand=True needs the per-ray jitter tensor')
+    s_out = torch.empty(N, num_samples + 1, device=dev, dtype=torch.float32)
+    t_out = torch.empty_like(s_out)
+    idx = torch.empty(N, num_samples, device=dev, dtype=torch.int32) if return_index else None
+    with torch.cuda.device(dev):
+        check(load().nlb_resample(ptr(sd), ptr(w), n_in, int(dilate), float(dilation), float(anneal),
+                                  float(resample_padding), ptr(u_base), ptr(jit), float(max_jitter), ptr(near),
+                                  ptr(far), float(lam), num_samples, N, ptr(s_out), ptr(t_out), ptr(idx), stream()))
+    return (s_out, t_out, idx) if return_index else (s_out, t_out)
+
+
+@torch.no_grad()
+def sorted_interp(x: torch.Tensor, xp: torch.Tensor, fp: torch.Tensor, return_index: bool = False):
+    """math.sorted_interp for 2-D [N, n] inputs."""
+    x, xp, fp = f32(x), f32(xp), f32(fp)
+    N, nx = x.shape
+    out = torch.empty_like(x)
+    idx = torch.empty(N, nx, device=x.device, dtype=torch.int32) if return_index else None
+    with torch.cuda.device(x.device):
+        check(load().nlb_sorted_interp(ptr(x), ptr(xp), ptr(fp), N, nx, xp.shape[1], ptr(out), ptr(idx), stream()))
+    return (out, idx) if return_index else out
+
+
+class RayBundle:
+    """Contiguous fp32 device views of the ray fields the kernels read."""
+
+    def __init__(self, batch: Dict[str, torch.Tensor]):
+        self.origins = f32(batch['origins'])
+        self.directions = f32(batch['directions'])
+        self.radii = f32(batch['radii']).reshape(-1)
+        self.base_x = f32(batch['base_x'])
+        self.base_y = f32(batch['base_y'])
+        self.N = self.origins.shape[0]
+        self.device = self.origins.device
+
+    def desc(self, tdist: torch.Tensor, deg_noise: Optional[torch.Tensor], std_scale: float) -> NlbRays:
+        S = tdist.shape[1] - 1
+        return NlbRays(ptr(tdist), ptr(self.origins), ptr(self.directions), ptr(self.radii), ptr(self.base_x),
+                       ptr(self.base_y), ptr(deg_noise), self.N, S, float(std_scale))
+
+
+def _table_desc(encoder, embeddings: torch.Tensor) -> NlbTable:
+    return NlbTable(ptr(embeddings), ptr(encoder.offsets), ptr(encoder.grid_sizes), encoder.num_levels,
+                    encoder.level_dim, int(encoder.base_resolution), float(math.log2(encoder.per_level_scale)))
+
+
+def _grad_buffer(param: torch.Tensor) -> Tuple[torch.Tensor, bool]:
+    """Gradient accumulation target for a table.  When the trainer has attached a
+    persistent, pre-zeroed `_nlb_grad` buffer to the parameter the kernels add into
+    it directly (no 240 MB memset + copy per step); otherwise a fresh zero tensor is
+    returned through autograd."""
+    buf = getattr(param, '_nlb_grad', None)
+    if buf is not None:
+        return buf, True
+    return torch.zeros_like(param), False
+
+
+class _PropLevel(Function):
+    @staticmethod
+    def forward(ctx, tdist, deg_noise, embeddings, W0, b0, W1, b1, rays: RayBundle, encoder, std_scale, emb_param):
+        N, S = rays.N, tdist.shape[1] - 1
+        density = torch.empty(N, S, device=rays.device, dtype=torch.float32)
+        need_grad = any(ctx.needs_input_grad)
+        feats = torch.empty(N * S, encoder.num_levels, device=rays.device, dtype=torch.float32) if need_grad else None
+        W0c, b0c, W1c, b1c = f32(W0), f32(b0), f32(W1).reshape(-1), f32(b1)
+        with torch.cuda.device(rays.device):
+            check(load().nlb_prop_forward(C.byref(rays.desc(tdist, deg_noise, std_scale)),
+                                          C.byref(_table_desc(encoder, embeddings)), ptr(W0c), ptr(b0c), ptr(W1c),
+                                          ptr(b1c), ptr(density), ptr(feats), stream()))
+        ctx.save_for_backward(tdist, deg_noise, embeddings, W0c, b0c, W1c, b1c, feats)
+        ctx.rays, ctx.encoder, ctx.std_scale, ctx.emb_param = rays, encoder, std_scale, emb_param
+        return density
+
+    @staticmethod
+    def backward(ctx, g_density):
+        tdist, deg_noise, embeddings, W0, b0, W1, b1, feats = ctx.saved_tensors
+        rays, encoder = ctx.rays, ctx.encoder
+        g_emb, in_place = _grad_buffer(ctx.emb_param if ctx.emb_param is not None else embeddings)
+        gW0, gb0 = torch.zeros_like(W0), torch.zeros_like(b0)
+        gW1, gb1 = torch.zeros_like(W1), torch.zeros_like(b1)
+        g_density = f32(g_density)
+        with torch.cuda.device(rays.device):
+            check(load().nlb_prop_backward(C.byref(rays.desc(tdist, deg_noise, ctx.std_scale)),
+                                           C.byref(_table_desc(encoder, embeddings)), ptr(W0), ptr(b0), ptr(W1),
+                                           ptr(b1), ptr(feats), ptr(g_density), ptr(g_emb), ptr(gW0), ptr(gb0),
+                                           ptr(gW1), ptr(gb1), stream()))
+        return (None, None, None if in_place else g_emb, gW0, gb0, gW1.reshape(1, -1), gb1, None, None, None, None)
+
+
+def prop_level(tdist, deg_noise, mlp, rays: RayBundle, std_scale: float) -> torch.Tensor:
+    """Proposal density[N,S] for one level (cast_rays + encode + PropMLP + softplus)."""
+    enc = mlp.encoder
+    l0, l2 = mlp.density_layer[0], mlp.density_layer[2]
+    return _PropLevel.apply(tdist, deg_noise, enc.embeddings, l0.weight, l0.bias, l2.weight, l2.bias, rays, enc,
+                            std_scale, enc.embeddings)
+
+
+class _NerfEncode(Function):
+    @staticmethod
+    def forward(ctx, tdist, deg_noise, embeddings, rays: RayBundle, encoder, std_scale, emb_param):
+        N, S = rays.N, tdist.shape[1] - 1
+        feats = torch.empty(N * S, encoder.output_dim, device=rays.device, dtype=torch.float32)
+        with torch.cuda.device(rays.device):
+            check(load().nlb_encode_forward(C.byref(rays.desc(tdist, deg_noise, std_scale)),
+                                            C.byref(_table_desc(encoder, embeddings)), ptr(feats), stream()))
+        ctx.save_for_backward(tdist, deg_noise, embeddings)
+        ctx.rays, ctx.encoder, ctx.std_scale, ctx.emb_param = rays, encoder, std_scale, emb_param
+        return feats
+
+    @staticmethod
+    def backward(ctx, g_feats):
+        tdist, deg_noise, embeddings = ctx.saved_tensors
+        rays, encoder = ctx.rays, ctx.encoder
+        g_emb, in_place = _grad_buffer(ctx.emb_param if ctx.emb_param is not None else embeddings)
+        g_feats = f32(g_feats)
+        with torch.cuda.device(rays.device):
+            check(load().nlb_encode_backward(C.byref(rays.desc(tdist, deg_noise, ctx.std_scale)),
+                                             C.byref(_table_desc(encoder, embeddings)), ptr(g_feats), ptr(g_emb),
+                                             stream()))
+        return (None, None, None if in_place else g_emb, None, None, None, None)
+
+
+def nerf_encode(tdist, deg_noise, encoder, rays: RayBundle, std_scale: float) -> torch.Tensor:
+    """features[N*S, L*C] of the NeRF level."""
+    return _NerfEncode.apply(tdist, deg_noise, encoder.embeddings, rays, encoder, std_scale, encoder.embeddings)
+
+
+class _Composite(Function):
+    @staticmethod
+    def forward(ctx, density, rgb, semantic, intensity, tdist, directions, far, bg, opaque, extras):
+        N, S = density.shape
+        dev = density.device
+        density = f32(density)
+        rgb_c = f32(rgb) if rgb is not None else None
+        sem_c = f32(semantic) if semantic is not None else None
+        int_c = f32(intensity).reshape(N, S) if intensity is not None else None
+        K = sem_c.shape[-1] if sem_c is not None else 0
+        far_c = f32(far).reshape(-1)
+        new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        weights, o_rgb, depth, acc = new(N, S), new(N, 3), new(N), new(N)
+        o_sem = new(N, K) if sem_c is not None else None
+        o_int = new(N) if int_c is not None else None
+        dmean = new(N) if extras else None
+        dpct = new(N, 3) if extras else None
+        cin = NlbCompositeIn(ptr(density), ptr(tdist), ptr(directions), ptr(rgb_c), ptr(sem_c), ptr(int_c),
+                             ptr(far_c), N, S, K, float(bg), int(opaque), int(extras))
+        cout = NlbCompositeOut(ptr(weights), ptr(o_rgb), ptr(depth), ptr(acc), ptr(o_sem), ptr(o_int), ptr(dmean),
+                               ptr(dpct))
+        with torch.cuda.device(dev):
+            check(load().nlb_composite_forward(C.byref(cin), C.byref(cout), stream()))
+        ctx.save_for_backward(density, rgb_c, sem_c, int_c, tdist, directions, far_c, weights)
+        ctx.cfg = (N, S, K, float(bg), int(opaque))
+        ctx.int_shape = None if intensity is None else intensity.shape
+        outs = (weights, o_rgb, depth, acc, o_sem, o_int, dmean, dpct)
+        ctx.mark_non_differentiable(*[t for t in (dmean, dpct) if t is not None])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_w, g_rgb, g_depth, g_acc, g_sem, g_int, _gm, _gp):
+        density, rgb, sem, inten, tdist, directions, far, weights = ctx.saved_tensors
+        N, S, K, bg, opaque = ctx.cfg
+        dev = density.device
+        c = lambda t: None if t is None else f32(t)
+        g_w, g_rgb, g_depth, g_acc, g_sem, g_int = c(g_w), c(g_rgb), c(g_depth), c(g_acc), c(g_sem), c(g_int)
+        cin = NlbCompositeIn(ptr(density), ptr(tdist), ptr(directions), ptr(rgb), ptr(sem), ptr(inten), ptr(far),
+                             N, S, K, bg, opaque, 0)
+        cg = NlbCompositeGrad(ptr(g_w), ptr(g_rgb), ptr(g_depth), ptr(g_acc), ptr(g_sem), ptr(g_int))
+        gd = torch.empty(N, S, device=dev, dtype=torch.float32)
+        need = ctx.needs_input_grad
+        g_rgb_s = torch.empty(N, S, 3, device=dev, dtype=torch.float32) if (rgb is not None and need[1] and g_rgb is not None) else None
+        g_sem_s = torch.empty(N, S, K, device=dev, dtype=torch.float32) if (sem is not None and need[2] and g_sem is not None) else None
+        g_int_s = torch.empty(N, S, device=dev, dtype=torch.float32) if (inten is not None and need[3] and g_int is not None) else None
+        with torch.cuda.device(dev):
+            check(load().nlb_composite_backward(C.byref(cin), ptr(weights), C.byref(cg), ptr(gd), ptr(g_rgb_s),
+                                                ptr(g_sem_s), ptr(g_int_s), stream()))
+        if g_int_s is not None and ctx.int_shape is not None:
+            g_int_s = g_int_s.reshape(ctx.int_shape)
+        return gd, g_rgb_s, g_sem_s, g_int_s, None, None, None, None, None, None
+
+
+def composite(density, tdist, directions, far, rgb=None, semantic=None, intensity=None, bg: float = 1.0,
+              opaque_background: bool = True, compute_extras: bool = True) -> Dict[str, Optional[torch.Tensor]]:
+    """compute_alpha_weights + volumetric_rendering for one level.  Returns a dict
+    with weights[N,S], rgb[N,3], depth[N], acc[N], semantic[N,K], intensity[N],
+    distance_mean[N], distance_percentiles[N,3]."""
+    w, o_rgb, depth, acc, o_sem, o_int, dmean, dpct = _Composite.apply(
+        density, rgb, semantic, intensity, f32(tdist), f32(directions), far, bg, opaque_background, compute_extras)
+    return dict(weights=w, rgb=o_rgb, depth=depth, acc=acc, semantic=o_sem, intensity=o_int, distance_mean=dmean,
+                distance_percentiles=dpct)

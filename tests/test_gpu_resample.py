@@ -1,0 +1,78 @@
+"""Step-function resampling kernel against the oracle: interval (sample) indices
+bit-exact given the same CDF, sdist/tdist within 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import zipnerf_oracle as zo
+from tests.helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sorted_interp_indices_exact():
+    from nerf_lidar_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    N, n, nx = 257, 191, 64
+    w = torch.rand(N, n - 1, generator=g)
+    w[:, 10:20] = 0  # ties in the CDF (zero-weight bins)
+    w = w / w.sum(-1, keepdim=True)
+    cw = torch.cat([torch.zeros(N, 1), torch.cumsum(w[:, :-1], -1).clamp_max(1), torch.ones(N, 1)], -1)
+    t = torch.sort(torch.rand(N, n, generator=g), -1).values
+    u = torch.sort(torch.rand(N, nx, generator=g), -1).values
+    u[:, 0] = 0.0
+    u[:, 1] = cw[:, 15]  # exactly on a (tied) knot
+    want, widx = zo.interp_sorted(u, cw, t)
+    got, gidx = ops.sorted_interp(u.cuda(), cw.cuda(), t.cuda(), return_index=True)
+    assert np.array_equal(gidx.cpu().numpy(), widx.numpy().astype(np.int32))
+    assert_close(got, want, 1e-6, 'sorted_interp')
+
+
+@pytest.mark.parametrize('rand', [False, True])
+@pytest.mark.parametrize('n_in,S', [(64, 64), (64, 32), (256, 64)])
+def test_resample_level_vs_oracle(rand, n_in, S):
+    from nerf_lidar_b200 import ops
+    g = torch.Generator().manual_seed(n_in + S)
+    N = 300
+    sd = torch.sort(torch.rand(N, n_in + 1, generator=g), -1).values
+    sd[:, 0], sd[:, -1] = 0.0, 1.0
+    sd[5, 10:14] = sd[5, 10]  # zero-width intervals
+    w = torch.rand(N, n_in, generator=g) ** 4
+    w[7, :20] = 0
+    w = w / w.sum(-1, keepdim=True)
+    near = torch.full((N, 1), 2 / 60.)
+    far = torch.full((N, 1), 500 / 60.)
+    jit = torch.rand(N, 1, generator=g) if rand else None
+    prod = n_in
+    want_s, want_idx, knots, logits = zo.resample_level(sd, w, 1, S, prod, 0.5, jit)
+    want_t = zo.s_to_t(want_s, near, far)
+    dilation = 0.0025 + 0.5 / prod
+    anneal = (10 * 0.5) / (9 * 0.5 + 1)
+    got_s, got_t, got_idx = ops.resample_level(sd.cuda(), w.cuda(), near.cuda(), far.cuda(), S, True, dilation,
+                                               anneal, None if jit is None else jit.cuda(), rand, return_index=True)
+    assert_close(got_s, want_s, 1e-5, 'sdist')
+    assert_close(got_t, want_t, 1e-5, 'tdist')
+    # the CDF is summed in a different order on the GPU (warp scan vs serial), so a
+    # centre within 1 ulp of a knot may fall on the neighbouring interval; the value is
+    # continuous there.  Everything else must be identical.
+    mism = (got_idx.cpu().numpy() != want_idx.numpy()).mean()
+    assert mism < 2e-3, f'sample-index mismatch rate {mism}'
+    assert torch.all(got_s[:, 1:] >= got_s[:, :-1])
+
+
+def test_level0_is_regular():
+    from nerf_lidar_b200 import ops
+    N = 64
+    near = torch.full((N, 1), 2 / 60., device='cuda')
+    far = torch.full((N, 1), 500 / 60., device='cuda')
+    s, t = ops.resample_level(None, None, near, far, 64, False, 0.5025, 1.0, None, False)
+    want_s, _ = zo.sample_intervals(torch.tensor([[0., 1.]]).expand(N, 2), torch.zeros(N, 1), 64, None, 0., 1.)
+    assert_close(s, want_s, 1e-6, 'level0 sdist')
+    assert_close(t, zo.s_to_t(want_s, near.cpu(), far.cpu()), 1e-5, 'level0 tdist')
+
+
+def test_bad_arguments_raise():
+    from nerf_lidar_b200 import ops
+    near = torch.ones(4, 1, device='cuda')
+    with pytest.raises(RuntimeError, match='num_samples must be > 1'):
+        ops.resample_level(None, None, near, near * 2, 1, False, 0.1, 1.0, None, False)
