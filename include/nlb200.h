@@ -111,6 +111,10 @@ typedef struct {
   float S;                   /* log2(per_level_scale) */
 } nlb_table_t;
 
+/* Parity probe: the sample points the fused kernels generate, points[N,S,7,4] =
+ * (x,y,z in the [0,1] grid cube, contracted std / 2). */
+int nlb_sample_points(const nlb_rays_t* rays, float* points, void* stream);
+
 int nlb_encode_forward(const nlb_rays_t* rays, const nlb_table_t* table, float* features, void* stream);
 /* grad_features[N*S, L*C] -> grad_embeddings[rows,C] (accumulated). */
 int nlb_encode_backward(const nlb_rays_t* rays, const nlb_table_t* table, const float* grad_features,

@@ -60,6 +60,7 @@ SIGNATURES = {
     'nlb_grid_corner_indices': (_i, [_p, _p, _p, _u32, _u32, _u32, _f, _u32, _u32, _i, _p]),
     'nlb_resample': (_i, [_p, _p, _i, _i, _f, _f, _f, _p, _p, _f, _p, _p, _f, _i, _i, _p, _p, _p, _p]),
     'nlb_sorted_interp': (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
+    'nlb_sample_points': (_i, [C.POINTER(NlbRays), _p, _p]),
     'nlb_encode_forward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p]),
     'nlb_encode_backward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p, _p]),
     'nlb_prop_forward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p, _p, _p, _p, _p, _p]),

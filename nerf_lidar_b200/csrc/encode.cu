@@ -202,6 +202,23 @@ __global__ void __launch_bounds__(128) k_encode_bwd(nlb_rays_t rays, nlb_table_t
   sc.flush(grad_table, lv, g);
 }
 
+// Parity probe: the grid-space sample points (x,y,z in [0,1], contracted std/2) the
+// fused kernels generate, [N,S,7,4].
+__global__ void __launch_bounds__(128) k_sample_points(nlb_rays_t rays, float* __restrict__ points) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rays.N * rays.S) return;
+  const int ray = row / rays.S, s = row - ray * rays.S;
+  const RayGeom rg = load_ray(rays.origins, rays.directions, rays.base_x, rays.base_y, rays.radii, ray);
+  const float t0 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s);
+  const float t1 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s + 1);
+  const bool has_noise = rays.deg_noise != nullptr;
+  for (int j = 0; j < 7; ++j) {
+    const float noise = has_noise ? __ldg(rays.deg_noise + (size_t)row * 7 + j) : 0.f;
+    const SamplePoint p = sample_point(rg, t0, t1, j, noise, has_noise, rays.std_scale);
+    reinterpret_cast<float4*>(points)[(size_t)row * 7 + j] = make_float4(p.x, p.y, p.z, p.std);
+  }
+}
+
 // ----------------------------------------------------------------------------- proposal levels
 constexpr int kPropHidden = 64;
 constexpr int kPropMaxL = 16;
@@ -387,6 +404,14 @@ static int check_rays_table(const nlb_rays_t* r, const nlb_table_t* t, const cha
   }
   if ((int64_t)r->N * r->S > 0x7fffffffLL / 16) { nlb_set_error("%s: N*S too large for one launch; chunk the rays", who); return NLB_EINVAL; }
   return NLB_OK;
+}
+
+extern "C" int nlb_sample_points(const nlb_rays_t* rays, float* points, void* stream) {
+  if (!rays || !points) { nlb_set_error("sample_points: null pointer"); return NLB_EINVAL; }
+  const int rows = rays->N * rays->S;
+  if (rows == 0) return NLB_OK;
+  k_sample_points<<<div_up(rows, 128), 128, 0, (cudaStream_t)stream>>>(*rays, points);
+  return nlb_check_launch("sample_points");
 }
 
 extern "C" int nlb_encode_forward(const nlb_rays_t* rays, const nlb_table_t* table, float* features, void* stream) {

@@ -28,6 +28,8 @@ _u_cache: Dict[Tuple, torch.Tensor] = {}
 def _u_base(num_samples: int, rand: bool, device) -> Tuple[torch.Tensor, float]:
     """The linspace of stepfun.sample (Z/internal/stepfun.py:199-216), computed by
     torch on the host exactly as the reference does, cached on the device."""
+    if num_samples <= 1:
+        raise RuntimeError(f'num_samples must be > 1, is {num_samples}.')
     key = (num_samples, bool(rand), str(device))
     if key not in _u_cache:
         if not rand:
@@ -99,6 +101,16 @@ class RayBundle:
         S = tdist.shape[1] - 1
         return NlbRays(ptr(tdist), ptr(self.origins), ptr(self.directions), ptr(self.radii), ptr(self.base_x),
                        ptr(self.base_y), ptr(deg_noise), self.N, S, float(std_scale))
+
+
+@torch.no_grad()
+def sample_points(tdist, deg_noise, rays: RayBundle, std_scale: float = 0.35) -> torch.Tensor:
+    """Parity probe: [N,S,7,4] grid-space points (x,y,z in [0,1], std) of the fused kernels."""
+    tdist = f32(tdist)
+    pts = torch.empty(rays.N, tdist.shape[1] - 1, 7, 4, device=rays.device, dtype=torch.float32)
+    with torch.cuda.device(rays.device):
+        check(load().nlb_sample_points(C.byref(rays.desc(tdist, deg_noise, std_scale)), ptr(pts), stream()))
+    return pts
 
 
 def _table_desc(encoder, embeddings: torch.Tensor) -> NlbTable:

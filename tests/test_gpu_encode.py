@@ -1,9 +1,17 @@
 """Fused cast_rays + contract + hash-grid + erf-mean kernels (NeRF level and
-proposal levels) against the oracle chain."""
+proposal levels) against the oracle chain.
+
+At the finest level (resolution 8192) one float32 ulp of a coordinate is 5e-4 of
+a cell, so features of a RANDOM table move by ~1e-4 relative when the sample
+point is computed with a different (equally valid) fp32 operation order.  The
+tests therefore split the chain: (1) the generated points against the oracle's
+cast_rays + contract to a few ulp, (2) the encode + erf-mean against the oracle
+evaluated ON THE KERNEL'S POINTS to 1e-5, (3) the whole chain loosely."""
 import numpy as np
 import pytest
 import torch
 
+from oracle import grid_oracle as go
 from oracle import zipnerf_oracle as zo
 from nerf_lidar_b200 import synthetic
 from tests.helpers import assert_close
@@ -21,77 +29,119 @@ def _setup(seed, S, rand):
     return batch, t, deg
 
 
+def _model(sd):
+    from nerf_lidar_b200 import configs, models
+    model = models.Model(configs.nuscenes_single()).cuda()
+    model.load_state_dict(sd, strict=False)
+    return model
+
+
+def _oracle_features_from_points(pts, emb, offsets, grid_sizes, C):
+    """encode + erf re-weighting + mean (models.py:974-977) on given grid-space points."""
+    N, S, n, _ = pts.shape
+    L = offsets.shape[0] - 1
+    out, _ = go.grid_encode_forward(pts[..., :3].reshape(-1, 3), emb, offsets, 1.0, 16)
+    feat = out.permute(1, 0, 2).reshape(N, S, n, L, C)
+    sd = pts[..., 3]
+    w = torch.erf(1 / torch.clamp(torch.sqrt(8 * sd[..., None] ** 2 * grid_sizes ** 2), min=1e-10))
+    return (feat * w[..., None]).mean(-3).flatten(-2, -1)
+
+
 @pytest.mark.parametrize('rand', [False, True])
-def test_nerf_encode_forward_backward(rand, full_state_dict_visible):
-    from nerf_lidar_b200 import models, configs, ops
-    sd = full_state_dict_visible
+def test_sample_points_vs_oracle(rand):
+    from nerf_lidar_b200 import ops
     batch, t, deg = _setup(5, 32, rand)
     means, stds = zo.cast_rays(t, batch['origins'], batch['directions'], batch['radii'], batch['base_x'],
                                batch['base_y'], deg)
-    emb = sd['nerf_mlp.encoder.embeddings']
-    want = zo.encode_features(means, stds, emb, sd['nerf_mlp.encoder.offsets'], sd['nerf_mlp.encoder.grid_sizes'], 4)
-    cfg = configs.nuscenes_single()
-    model = models.Model(cfg).cuda()
-    model.load_state_dict(sd, strict=False)
+    z, sd = zo.contract_mean_std(means.reshape(-1, 3), stds.reshape(-1))
+    want_x = ((z / 2 + 1) / 2).reshape(*means.shape)
+    want_s = (sd / 2).reshape(*stds.shape)
     rays = ops.RayBundle({k: v.cuda() for k, v in batch.items()})
-    feat = ops.nerf_encode(t.cuda(), None if deg is None else deg.cuda(), model.nerf_mlp.encoder, rays, 0.35)
+    pts = ops.sample_points(t.cuda(), None if deg is None else deg.cuda(), rays).cpu()
+    # coordinates live in [0,1]: 4 ulp of 1.0
+    assert float((pts[..., :3] - want_x).abs().max()) <= 4 * 1.2e-7
+    assert_close(pts[..., 3], want_s, 1e-5, 'std')
+
+
+@pytest.mark.parametrize('rand', [False, True])
+def test_nerf_encode_forward_backward(rand, full_state_dict_visible):
+    from nerf_lidar_b200 import ops
+    sd = full_state_dict_visible
+    batch, t, deg = _setup(5, 32, rand)
+    model = _model(sd)
+    enc = model.nerf_mlp.encoder
+    rays = ops.RayBundle({k: v.cuda() for k, v in batch.items()})
+    degc = None if deg is None else deg.cuda()
+    feat = ops.nerf_encode(t.cuda(), degc, enc, rays, 0.35)
     N, S = t.shape[0], 32
-    # points within 1 ulp of a cell boundary may land in the neighbouring cell (the
-    # interpolant is continuous), so compare values, not cells
-    assert_close(feat.reshape(N, S, 40), want, 2e-5, 'nerf features')
-    # backward: linear in the table -> <g, F(e)> = <dF^T g, e>
-    g = torch.randn(N * S, 40, generator=torch.Generator().manual_seed(1)).cuda()
-    feat.backward(g)
-    ge = model.nerf_mlp.encoder.embeddings.grad
-    lhs = float((g.double() * feat.detach().double()).sum())
-    rhs = float((ge.double() * model.nerf_mlp.encoder.embeddings.detach().double()).sum())
-    assert abs(lhs - rhs) <= 1e-4 * float((g.double() * feat.detach().double()).abs().sum())
+    pts = ops.sample_points(t.cuda(), degc, rays).cpu()
+    emb = sd['nerf_mlp.encoder.embeddings']
+    want = _oracle_features_from_points(pts, emb, sd['nerf_mlp.encoder.offsets'], sd['nerf_mlp.encoder.grid_sizes'], 4)
+    assert_close(feat.reshape(N, S, 40), want, 1e-5, 'nerf features on the kernel points')
+    # whole chain against the oracle's own points (ulp-sensitive at level 9, see module doc)
+    means, stds = zo.cast_rays(t, batch['origins'], batch['directions'], batch['radii'], batch['base_x'],
+                               batch['base_y'], deg)
+    chain = zo.encode_features(means, stds, emb, sd['nerf_mlp.encoder.offsets'], sd['nerf_mlp.encoder.grid_sizes'], 4)
+    assert_close(feat.reshape(N, S, 40), chain, 1e-3, 'nerf features, whole chain')
+    # coarse levels (0-5, resolution <= 512) are insensitive: tight on the whole chain
+    assert_close(feat.reshape(N, S, 10, 4)[:, :, :6], chain.reshape(N, S, 10, 4)[:, :, :6], 3e-5, 'coarse levels')
+    # backward: the op is linear in the table -> <g, F(e)> = <F^T g, e>, and F^T g must
+    # equal the oracle's scatter on the same points
+    g = torch.randn(N * S, 40, generator=torch.Generator().manual_seed(1))
+    feat.backward(g.cuda())
+    ge = enc.embeddings.grad.cpu()
+    lhs = float((g.double() * feat.detach().cpu().double()).sum())
+    rhs = float((ge.double() * emb.double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * float((g.double() * feat.detach().cpu().double()).abs().sum())
+    # explicit scatter oracle: d feat / d table = erf_w/7 * trilinear weights
+    g_pts = g.reshape(N, S, 1, 10, 4).expand(N, S, 7, 10, 4)
+    sdv = pts[..., 3]
+    wj = torch.erf(1 / torch.clamp(torch.sqrt(8 * sdv[..., None] ** 2 * sd['nerf_mlp.encoder.grid_sizes'] ** 2), min=1e-10))
+    g_lbc = (g_pts * wj[..., None] / 7).reshape(-1, 10, 4).permute(1, 0, 2).contiguous()
+    want_ge, _ = go.grid_encode_backward(g_lbc, pts[..., :3].reshape(-1, 3), emb, sd['nerf_mlp.encoder.offsets'], 1.0, 16)
+    assert_close(ge, want_ge, 2e-5, 'table gradient')
 
 
 @pytest.mark.parametrize('lvl,L', [(0, 6), (1, 8)])
 def test_prop_level_forward_backward(lvl, L, full_state_dict_visible):
-    from nerf_lidar_b200 import models, configs, ops
-    sd = {k: v.clone() for k, v in full_state_dict_visible.items()}
+    from nerf_lidar_b200 import _lib, ops
+    import ctypes as C
+    sd = full_state_dict_visible
     pre = f'prop_mlp_{lvl}.'
     batch, t, deg = _setup(6 + lvl, 64, True)
     N, S = t.shape[0], 64
-    emb = sd[pre + 'encoder.embeddings'].clone().requires_grad_(True)
-    p = dict(sd)
-    p[pre + 'encoder.embeddings'] = emb
-    for k in list(p):
-        if k.startswith(pre + 'density_layer'):
-            p[k] = p[k].clone().requires_grad_(True)
-    means, stds = zo.cast_rays(t, batch['origins'], batch['directions'], batch['radii'], batch['base_x'],
-                               batch['base_y'], deg)
-
-    # differentiable oracle features: gather with autograd through the table
-    from oracle import grid_oracle as go
-    z, s2 = zo.contract_mean_std(means.reshape(-1, 3), stds.reshape(-1))
-    x01 = (z / 2 + 1) / 2
-    offs = sd[pre + 'encoder.offsets'].numpy().astype(np.int64)
-    feats = []
-    for l in range(L):
-        idx, w, valid, *_ = go.corner_setup(x01, l, 1.0, 16, offs)
-        f = (emb[idx + int(offs[l]), 0] * w).sum(-1)
-        feats.append(torch.where(valid, f, torch.zeros_like(f)))
-    feat = torch.stack(feats, -1).reshape(N, S, 7, L, 1)
-    sdv = (s2 / 2).reshape(N, S, 7)
-    wj = torch.erf(1 / torch.clamp(torch.sqrt(8 * sdv[..., None] ** 2 * sd[pre + 'encoder.grid_sizes'] ** 2), min=1e-10))
-    feat = (feat * wj[..., None]).mean(-3).flatten(-2, -1)
-    dens_want = zo.prop_mlp(p, pre, feat)
-    gd = torch.randn(N, S, generator=torch.Generator().manual_seed(2))
-    dens_want.backward(gd)
-
-    cfg = configs.nuscenes_single()
-    model = models.Model(cfg).cuda()
-    model.load_state_dict(sd, strict=False)
+    model = _model(sd)
     mlp = model.get_submodule(f'prop_mlp_{lvl}')
     rays = ops.RayBundle({k: v.cuda() for k, v in batch.items()})
-    dens = ops.prop_level(t.cuda(), deg.cuda(), mlp, rays, 0.35)
-    assert_close(dens, dens_want, 2e-5, 'prop density')
+    tc, degc = t.cuda(), deg.cuda()
+    dens = ops.prop_level(tc, degc, mlp, rays, 0.35)
+    pts = ops.sample_points(tc, degc, rays).cpu()
+    emb = sd[pre + 'encoder.embeddings']
+    feat = _oracle_features_from_points(pts, emb, sd[pre + 'encoder.offsets'], sd[pre + 'encoder.grid_sizes'], 1)
+    feat = feat.clone().requires_grad_(True)
+    p = {k: (v.clone().requires_grad_(True) if 'density_layer' in k and k.startswith(pre) else v) for k, v in sd.items()}
+    want = zo.prop_mlp(p, pre, feat)
+    assert_close(dens, want, 1e-5, 'prop density on the kernel points')
+    # whole chain
+    means, stds = zo.cast_rays(t, batch['origins'], batch['directions'], batch['radii'], batch['base_x'],
+                               batch['base_y'], deg)
+    chain = zo.prop_mlp(sd, pre, zo.encode_features(means, stds, emb, sd[pre + 'encoder.offsets'],
+                                                    sd[pre + 'encoder.grid_sizes'], 1))
+    assert_close(dens, chain, 2e-4, 'prop density, whole chain')
+    gd = torch.randn(N, S, generator=torch.Generator().manual_seed(2))
+    want.backward(gd)
     dens.backward(gd.cuda())
-    assert_close(mlp.density_layer[0].weight.grad, p[pre + 'density_layer.0.weight'].grad, 2e-4, 'gW0')
-    assert_close(mlp.density_layer[0].bias.grad, p[pre + 'density_layer.0.bias'].grad, 2e-4, 'gb0')
-    assert_close(mlp.density_layer[2].weight.grad, p[pre + 'density_layer.2.weight'].grad, 2e-4, 'gW1')
-    assert_close(mlp.density_layer[2].bias.grad, p[pre + 'density_layer.2.bias'].grad, 2e-4, 'gb1')
-    assert_close(mlp.encoder.embeddings.grad, emb.grad, 2e-4, 'grad table')
+    l0, l2 = mlp.density_layer[0], mlp.density_layer[2]
+    # ReLU units within rounding of zero may flip between the two evaluations; the
+    # gradients are compared relative to the sum of absolute contributions
+    assert_close(l0.weight.grad, p[pre + 'density_layer.0.weight'].grad, 2e-4, 'gW0')
+    assert_close(l0.bias.grad, p[pre + 'density_layer.0.bias'].grad, 2e-4, 'gb0')
+    assert_close(l2.weight.grad, p[pre + 'density_layer.2.weight'].grad, 2e-4, 'gW1')
+    assert_close(l2.bias.grad, p[pre + 'density_layer.2.bias'].grad, 2e-4, 'gb1')
+    # table gradient = scatter of d loss / d features on the kernel points
+    gf = feat.grad.reshape(N, S, 1, L, 1).expand(N, S, 7, L, 1)
+    sdv = pts[..., 3]
+    wj = torch.erf(1 / torch.clamp(torch.sqrt(8 * sdv[..., None] ** 2 * sd[pre + 'encoder.grid_sizes'] ** 2), min=1e-10))
+    g_lbc = (gf * wj[..., None] / 7).reshape(-1, L, 1).permute(1, 0, 2).contiguous()
+    want_ge, _ = go.grid_encode_backward(g_lbc, pts[..., :3].reshape(-1, 3), emb, sd[pre + 'encoder.offsets'], 1.0, 16)
+    assert_close(mlp.encoder.embeddings.grad, want_ge, 2e-4, 'table gradient')
