@@ -130,7 +130,9 @@ int nlb_prop_forward(const nlb_rays_t* rays, const nlb_table_t* table, const flo
  * (all accumulated into pre-zeroed buffers). */
 int nlb_prop_backward(const nlb_rays_t* rays, const nlb_table_t* table, const float* W0, const float* b0,
                       const float* W1, const float* b1, const float* features, const float* grad_density,
-                      float* grad_embeddings, float* gW0, float* gb0, float* gW1, float* gb1, void* stream);
+                      float* grad_embeddings, float* gW0, float* gb0, float* gW1, float* gb1,
+                      float* workspace /*nlb_prop_backward_workspace_bytes()*/, void* stream);
+size_t nlb_prop_backward_workspace_bytes(int N, int S, int L);
 
 /* ------------------------------------------------------------------ compositing
  * render.compute_alpha_weights (Z/internal/render.py:170-189) +

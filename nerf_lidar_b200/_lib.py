@@ -64,7 +64,8 @@ SIGNATURES = {
     'nlb_encode_forward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p]),
     'nlb_encode_backward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p, _p]),
     'nlb_prop_forward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p, _p, _p, _p, _p, _p]),
-    'nlb_prop_backward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'nlb_prop_backward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'nlb_prop_backward_workspace_bytes': (C.c_size_t, [_i, _i, _i]),
     'nlb_composite_forward': (_i, [C.POINTER(NlbCompositeIn), C.POINTER(NlbCompositeOut), _p]),
     'nlb_composite_backward': (_i, [C.POINTER(NlbCompositeIn), _p, C.POINTER(NlbCompositeGrad), _p, _p, _p, _p, _p]),
     'nlb_nerf_mlp_packed_bytes': (C.c_size_t, []),
@@ -93,7 +94,51 @@ def load() -> C.CDLL:
     return _lib
 
 
+LAUNCHES = 0  # kernels launched through the ABI since import (bench.py reads deltas)
+
+
+class KernelTimer:
+    """CUDA-event timing of named ABI calls on the launching stream (bench.py's
+    roofline line).  Enabled by assigning an instance to `_lib.TIMER`."""
+
+    def __init__(self):
+        self.events = {}
+
+    def start(self, name):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        self.events.setdefault(name, []).append((e0, e1))
+        e0.record(torch.cuda.current_stream())
+        return e1
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.events.items()}
+
+
+TIMER: Optional[KernelTimer] = None
+
+
+class timed:
+    """with timed('name'): <one ABI call>"""
+
+    def __init__(self, name):
+        self.name = name
+        self.end = None
+
+    def __enter__(self):
+        if TIMER is not None:
+            self.end = TIMER.start(self.name)
+
+    def __exit__(self, *a):
+        if self.end is not None:
+            self.end.record(torch.cuda.current_stream())
+        return False
+
+
 def check(code: int):
+    global LAUNCHES
+    LAUNCHES += 1
     if code != 0:
         msg = load().nlb_last_error().decode()
         if code == -2:

@@ -89,43 +89,50 @@ __device__ __forceinline__ void lookup(const float* __restrict__ table, const Le
     for (int c = 0; c < C; ++c) out[c] = fmaf(w[i], rows[i][c], out[c]);
 }
 
-// ----------------------------------------------------------------------------- NeRF level
-template <int C>
-__global__ void __launch_bounds__(128) k_encode_fwd(nlb_rays_t rays, nlb_table_t tab, float* __restrict__ features) {
-  const int rows_total = rays.N * rays.S;
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= rows_total) return;
-  const int level = blockIdx.y;
+// ----------------------------------------------------------------------------- shared structure
+// Every kernel below has one thread per interval.  Phase A computes the interval's 7
+// multisample points ONCE into shared memory ([7][128] float4, 14 KB per block);
+// phase B walks the levels with compact, non-unrolled (level, sample) loops.  A first
+// version recomputed the points per level with everything unrolled: ncu showed it
+// issue-bound at 743 instructions per point-level with `no_instruction` (I-cache
+// miss) the top stall.  Blocks of one wave sweep the levels together, so the L2
+// working set is still about one level of the table at a time.
+constexpr int kEncThreads = 128;
+
+__device__ __forceinline__ void stage_points(const nlb_rays_t& rays, int row, float4 (*s_pts)[kEncThreads]) {
   const int ray = row / rays.S, s = row - ray * rays.S;
   const RayGeom rg = load_ray(rays.origins, rays.directions, rays.base_x, rays.base_y, rays.radii, ray);
   const float t0 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s);
   const float t1 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s + 1);
-  const Level3 lv = level3(tab.offsets, level, tab.S, tab.H);
-  const int gs = __ldg(tab.grid_sizes + level);
   const bool has_noise = rays.deg_noise != nullptr;
-  float acc[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) acc[c] = 0.f;
-#pragma unroll
+#pragma unroll 1
   for (int j = 0; j < 7; ++j) {
     const float noise = has_noise ? __ldg(rays.deg_noise + (size_t)row * 7 + j) : 0.f;
     const SamplePoint p = sample_point(rg, t0, t1, j, noise, has_noise, rays.std_scale);
-    if (!in_unit_cube(p.x, p.y, p.z)) continue;  // kernel_grid writes zeros for such points
-    const float wj = erf_weight(p.std, gs);
+    // points outside the unit cube contribute zero features (kernel_grid writes zeros):
+    // flag them with a negative std
+    s_pts[j][threadIdx.x] = make_float4(p.x, p.y, p.z, in_unit_cube(p.x, p.y, p.z) ? p.std : -1.0f);
+  }
+}
+
+// erf-weighted sum over the 7 samples of the interpolated feature at one level
+template <int C>
+__device__ __forceinline__ void level_feature(const float* __restrict__ table, const Level3& lv, int gs,
+                                              const float4 (*s_pts)[kEncThreads], float (&acc)[C]) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+#pragma unroll 1
+  for (int j = 0; j < 7; ++j) {
+    const float4 p = s_pts[j][threadIdx.x];
+    if (p.w < 0.f) continue;
+    const float wj = erf_weight(p.w, gs);
     float f[C];
-    lookup<C>(tab.embeddings, lv, p.x, p.y, p.z, f);
+    lookup<C>(table, lv, p.x, p.y, p.z, f);
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(f[c], wj));
   }
-  float* out = features + (size_t)row * (tab.L * C) + level * C;
-  if constexpr (C == 4) {
-    *reinterpret_cast<float4*>(out) = make_float4(acc[0] / 7.0f, acc[1] / 7.0f, acc[2] / 7.0f, acc[3] / 7.0f);
-  } else if constexpr (C == 2) {
-    *reinterpret_cast<float2*>(out) = make_float2(acc[0] / 7.0f, acc[1] / 7.0f);
-  } else {
 #pragma unroll
-    for (int c = 0; c < C; ++c) out[c] = acc[c] / 7.0f;
-  }
+  for (int c = 0; c < C; ++c) acc[c] = acc[c] / 7.0f;
 }
 
 // Scatter helper: accumulates corner coefficients of consecutive multisamples that
@@ -170,36 +177,65 @@ struct CellScatter {
   }
 };
 
+// scatter of one level's feature gradient g (already divided by 7) over the 7 samples
 template <int C>
-__global__ void __launch_bounds__(128) k_encode_bwd(nlb_rays_t rays, nlb_table_t tab,
-                                                    const float* __restrict__ grad_features,
-                                                    float* __restrict__ grad_table) {
-  const int rows_total = rays.N * rays.S;
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= rows_total) return;
-  const int level = blockIdx.y;
-  const int ray = row / rays.S, s = row - ray * rays.S;
-  float g[C];
-  gather_row<C>(grad_features + (size_t)row * (tab.L * C) + level * C, g);
-  bool any = false;
-#pragma unroll
-  for (int c = 0; c < C; ++c) { g[c] = g[c] / 7.0f; any |= (g[c] != 0.f); }
-  if (!any) return;
-  const RayGeom rg = load_ray(rays.origins, rays.directions, rays.base_x, rays.base_y, rays.radii, ray);
-  const float t0 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s);
-  const float t1 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s + 1);
-  const Level3 lv = level3(tab.offsets, level, tab.S, tab.H);
-  const int gs = __ldg(tab.grid_sizes + level);
-  const bool has_noise = rays.deg_noise != nullptr;
+__device__ __forceinline__ void level_scatter(float* __restrict__ grad_table, const Level3& lv, int gs,
+                                              const float4 (*s_pts)[kEncThreads], const float (&g)[C]) {
   CellScatter<C> sc;
-#pragma unroll
+#pragma unroll 1
   for (int j = 0; j < 7; ++j) {
-    const float noise = has_noise ? __ldg(rays.deg_noise + (size_t)row * 7 + j) : 0.f;
-    const SamplePoint p = sample_point(rg, t0, t1, j, noise, has_noise, rays.std_scale);
-    if (!in_unit_cube(p.x, p.y, p.z)) continue;
-    sc.add(grad_table, lv, g, p.x, p.y, p.z, erf_weight(p.std, gs));
+    const float4 p = s_pts[j][threadIdx.x];
+    if (p.w < 0.f) continue;
+    sc.add(grad_table, lv, g, p.x, p.y, p.z, erf_weight(p.w, gs));
   }
   sc.flush(grad_table, lv, g);
+}
+
+// ----------------------------------------------------------------------------- NeRF level
+template <int C>
+__global__ void __launch_bounds__(kEncThreads) k_encode_fwd(nlb_rays_t rays, nlb_table_t tab,
+                                                            float* __restrict__ features) {
+  __shared__ float4 s_pts[7][kEncThreads];
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rays.N * rays.S) return;
+  stage_points(rays, row, s_pts);
+  float* out = features + (size_t)row * (tab.L * C);
+#pragma unroll 1
+  for (int level = 0; level < tab.L; ++level) {
+    const Level3 lv = level3(tab.offsets, level, tab.S, tab.H);
+    float acc[C];
+    level_feature<C>(tab.embeddings, lv, __ldg(tab.grid_sizes + level), s_pts, acc);
+    if constexpr (C == 4) {
+      *reinterpret_cast<float4*>(out + level * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else if constexpr (C == 2) {
+      *reinterpret_cast<float2*>(out + level * 2) = make_float2(acc[0], acc[1]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) out[level * C + c] = acc[c];
+    }
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kEncThreads) k_encode_bwd(nlb_rays_t rays, nlb_table_t tab,
+                                                            const float* __restrict__ grad_features,
+                                                            float* __restrict__ grad_table) {
+  __shared__ float4 s_pts[7][kEncThreads];
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rays.N * rays.S) return;
+  stage_points(rays, row, s_pts);
+  const float* gin = grad_features + (size_t)row * (tab.L * C);
+#pragma unroll 1
+  for (int level = 0; level < tab.L; ++level) {
+    float g[C];
+    gather_row<C>(gin + level * C, g);
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { g[c] = g[c] / 7.0f; any |= (g[c] != 0.f); }
+    if (!any) continue;
+    const Level3 lv = level3(tab.offsets, level, tab.S, tab.H);
+    level_scatter<C>(grad_table, lv, __ldg(tab.grid_sizes + level), s_pts, g);
+  }
 }
 
 // Parity probe: the grid-space sample points (x,y,z in [0,1], contracted std/2) the
@@ -212,6 +248,7 @@ __global__ void __launch_bounds__(128) k_sample_points(nlb_rays_t rays, float* _
   const float t0 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s);
   const float t1 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s + 1);
   const bool has_noise = rays.deg_noise != nullptr;
+#pragma unroll 1
   for (int j = 0; j < 7; ++j) {
     const float noise = has_noise ? __ldg(rays.deg_noise + (size_t)row * 7 + j) : 0.f;
     const SamplePoint p = sample_point(rg, t0, t1, j, noise, has_noise, rays.std_scale);
@@ -237,50 +274,33 @@ __device__ __forceinline__ void load_prop_weights(PropSmem& sm, int L, const flo
   if (threadIdx.x == 0) sm.b1 = __ldg(b1);
 }
 
-// features of one interval at all L levels (C = 1)
 template <int L>
-__device__ __forceinline__ void prop_features(const nlb_rays_t& rays, const nlb_table_t& tab, int row, float (&f)[L]) {
-  const int ray = row / rays.S, s = row - ray * rays.S;
-  const RayGeom rg = load_ray(rays.origins, rays.directions, rays.base_x, rays.base_y, rays.radii, ray);
-  const float t0 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s);
-  const float t1 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s + 1);
-  const bool has_noise = rays.deg_noise != nullptr;
-#pragma unroll
-  for (int l = 0; l < L; ++l) f[l] = 0.f;
-  for (int j = 0; j < 7; ++j) {
-    const float noise = has_noise ? __ldg(rays.deg_noise + (size_t)row * 7 + j) : 0.f;
-    const SamplePoint p = sample_point(rg, t0, t1, j, noise, has_noise, rays.std_scale);
-    if (!in_unit_cube(p.x, p.y, p.z)) continue;
-#pragma unroll
-    for (int l = 0; l < L; ++l) {
-      const Level3 lv = level3(tab.offsets, l, tab.S, tab.H);
-      float v[1];
-      lookup<1>(tab.embeddings, lv, p.x, p.y, p.z, v);
-      f[l] = __fadd_rn(f[l], __fmul_rn(v[0], erf_weight(p.std, __ldg(tab.grid_sizes + l))));
-    }
-  }
-#pragma unroll
-  for (int l = 0; l < L; ++l) f[l] = f[l] / 7.0f;
-}
-
-template <int L>
-__global__ void __launch_bounds__(128) k_prop_fwd(nlb_rays_t rays, nlb_table_t tab, const float* __restrict__ W0,
-                                                  const float* __restrict__ b0, const float* __restrict__ W1,
-                                                  const float* __restrict__ b1, float* __restrict__ density,
-                                                  float* __restrict__ features) {
+__global__ void __launch_bounds__(kEncThreads) k_prop_fwd(nlb_rays_t rays, nlb_table_t tab,
+                                                          const float* __restrict__ W0, const float* __restrict__ b0,
+                                                          const float* __restrict__ W1, const float* __restrict__ b1,
+                                                          float* __restrict__ density, float* __restrict__ features) {
   __shared__ PropSmem sm;
+  __shared__ float4 s_pts[7][kEncThreads];
+  __shared__ float s_f[L][kEncThreads];
   load_prop_weights(sm, L, W0, b0, W1, b1);
   __syncthreads();
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tid = threadIdx.x;
+  const int row = blockIdx.x * blockDim.x + tid;
   if (row >= rays.N * rays.S) return;
-  float f[L];
-  prop_features<L>(rays, tab, row, f);
-  if (features) {
-#pragma unroll
-    for (int l = 0; l < L; ++l) features[(size_t)row * L + l] = f[l];
+  stage_points(rays, row, s_pts);
+#pragma unroll 1
+  for (int l = 0; l < L; ++l) {
+    const Level3 lv = level3(tab.offsets, l, tab.S, tab.H);
+    float acc[1];
+    level_feature<1>(tab.embeddings, lv, __ldg(tab.grid_sizes + l), s_pts, acc);
+    s_f[l][tid] = acc[0];
+    if (features) features[(size_t)row * L + l] = acc[0];
   }
+  float f[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) f[l] = s_f[l][tid];
   float raw = sm.b1;
-#pragma unroll 8
+#pragma unroll 4
   for (int k = 0; k < kPropHidden; ++k) {
     float h = sm.b0[k];
 #pragma unroll
@@ -292,31 +312,38 @@ __global__ void __launch_bounds__(128) k_prop_fwd(nlb_rays_t rays, nlb_table_t t
   density[row] = xin > 20.f ? xin : log1pf(expf(xin));
 }
 
-// Backward of the proposal level.  Phase 1: per-interval MLP backward from the saved
-// features; weight gradients are reduced over the 128 rows of the block in shared
-// memory (a [128 x 64]^T [128 x L] product) and leave with one atomic per entry.
+// Backward of the proposal level, one 128-row tile per block.  Phase 1: per-interval
+// MLP backward from the saved features; the tile's weight gradients are a
+// [128 x 64]^T [128 x L] product reduced through shared memory and written to a
+// per-block partial buffer (no atomics; k_prop_wgrad_reduce sums the partials).
 // Phase 2: feature gradients are scattered into the table.
 template <int L>
-__global__ void __launch_bounds__(128) k_prop_bwd(nlb_rays_t rays, nlb_table_t tab, const float* __restrict__ W0,
-                                                  const float* __restrict__ b0, const float* __restrict__ W1,
-                                                  const float* __restrict__ b1, const float* __restrict__ features,
-                                                  const float* __restrict__ grad_density,
-                                                  float* __restrict__ grad_table, float* __restrict__ gW0,
-                                                  float* __restrict__ gb0, float* __restrict__ gW1,
-                                                  float* __restrict__ gb1) {
+__global__ void __launch_bounds__(kEncThreads) k_prop_bwd(nlb_rays_t rays, nlb_table_t tab,
+                                                          const float* __restrict__ W0, const float* __restrict__ b0,
+                                                          const float* __restrict__ W1, const float* __restrict__ b1,
+                                                          const float* __restrict__ features,
+                                                          const float* __restrict__ grad_density,
+                                                          float* __restrict__ grad_table,
+                                                          float* __restrict__ partial /*[blocks][64*L+129]*/) {
   __shared__ PropSmem sm;
-  __shared__ float s_h[128][kPropHidden + 1];   // relu output per row (gW1, and the relu mask)
-  __shared__ float s_f[128][L + 1];
-  __shared__ float s_graw[128];
+  // phase 1 view: relu output per row (gW1 and the relu mask); phase 2 view: the points
+  // and the per-level feature gradients (phase-1 data is dead by then)
+  __shared__ __align__(16) float s_raw[kEncThreads * (kPropHidden + 1)];
+  float (*s_h)[kPropHidden + 1] = reinterpret_cast<float (*)[kPropHidden + 1]>(s_raw);
+  __shared__ float s_f[kEncThreads][L + 1];
+  __shared__ float s_graw[kEncThreads];
+  static_assert(sizeof(float4) * 7 * kEncThreads + sizeof(float) * L * kEncThreads <= sizeof(s_raw), "smem views");
   load_prop_weights(sm, L, W0, b0, W1, b1);
   __syncthreads();
   const int tid = threadIdx.x;
-  const int row = blockIdx.x * blockDim.x + tid;
-  const bool valid = row < rays.N * rays.S;
+  const int rows_total = rays.N * rays.S;
+  const int row = blockIdx.x * kEncThreads + tid;
+  const bool valid = row < rows_total;
   float f[L], gf[L];
 #pragma unroll
   for (int l = 0; l < L; ++l) { f[l] = valid ? __ldg(features + (size_t)row * L + l) : 0.f; gf[l] = 0.f; }
   float raw = sm.b1;
+#pragma unroll 4
   for (int k = 0; k < kPropHidden; ++k) {
     float h = sm.b0[k];
 #pragma unroll
@@ -328,6 +355,7 @@ __global__ void __launch_bounds__(128) k_prop_bwd(nlb_rays_t rays, nlb_table_t t
   const float sig = xin > 20.f ? 1.0f : 1.0f / (1.0f + expf(-xin));  // d softplus
   const float graw = valid ? __ldg(grad_density + row) * sig : 0.f;
   s_graw[tid] = graw;
+#pragma unroll 4
   for (int k = 0; k < kPropHidden; ++k) {
     const float gh = (s_h[tid][k] > 0.f) ? graw * sm.W1[k] : 0.f;
 #pragma unroll
@@ -336,58 +364,65 @@ __global__ void __launch_bounds__(128) k_prop_bwd(nlb_rays_t rays, nlb_table_t t
 #pragma unroll
   for (int l = 0; l < L; ++l) s_f[tid][l] = f[l];
   __syncthreads();
-  // block-level weight gradients
-  for (int e = tid; e < kPropHidden * L; e += blockDim.x) {
+  constexpr int kEntries = kPropHidden * L + 2 * kPropHidden + 1;
+  float* my = partial + (size_t)blockIdx.x * kEntries;
+  for (int e = tid; e < kPropHidden * L; e += kEncThreads) {
     const int k = e / L, l = e - k * L;
-    float a = 0.f;
     const float w1k = sm.W1[k];
-    for (int r = 0; r < 128; ++r) a = fmaf((s_h[r][k] > 0.f) ? s_graw[r] * w1k : 0.f, s_f[r][l], a);
-    atomicAdd(gW0 + e, a);
+    float a = 0.f;
+#pragma unroll 4
+    for (int r = 0; r < kEncThreads; ++r) a = fmaf((s_h[r][k] > 0.f) ? s_graw[r] * w1k : 0.f, s_f[r][l], a);
+    my[e] = a;
   }
   if (tid < kPropHidden) {
-    float a0 = 0.f, a1 = 0.f;
     const float w1k = sm.W1[tid];
-    for (int r = 0; r < 128; ++r) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+    for (int r = 0; r < kEncThreads; ++r) {
       a0 += (s_h[r][tid] > 0.f) ? s_graw[r] * w1k : 0.f;
       a1 = fmaf(s_graw[r], s_h[r][tid], a1);
     }
-    atomicAdd(gb0 + tid, a0);
-    atomicAdd(gW1 + tid, a1);
+    my[kPropHidden * L + tid] = a0;                // gb0
+    my[kPropHidden * L + kPropHidden + tid] = a1;  // gW1
   } else if (tid == kPropHidden) {
     float a = 0.f;
-    for (int r = 0; r < 128; ++r) a += s_graw[r];
-    atomicAdd(gb1, a);
+    for (int r = 0; r < kEncThreads; ++r) a += s_graw[r];
+    my[kPropHidden * L + 2 * kPropHidden] = a;     // gb1
   }
+  __syncthreads();  // every thread is done reading s_h / s_f / s_graw
   if (!valid) return;
   bool any = false;
 #pragma unroll
   for (int l = 0; l < L; ++l) { gf[l] = gf[l] / 7.0f; any |= (gf[l] != 0.f); }
   if (!any) return;
   // phase 2: scatter
-  const int ray = row / rays.S, s = row - ray * rays.S;
-  const RayGeom rg = load_ray(rays.origins, rays.directions, rays.base_x, rays.base_y, rays.radii, ray);
-  const float t0 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s);
-  const float t1 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s + 1);
-  const bool has_noise = rays.deg_noise != nullptr;
-  SamplePoint pts[7];
+  float4 (*s_pts)[kEncThreads] = reinterpret_cast<float4 (*)[kEncThreads]>(s_raw);
+  float (*s_gf)[kEncThreads] = reinterpret_cast<float (*)[kEncThreads]>(s_raw + 4 * 7 * kEncThreads);
 #pragma unroll
-  for (int j = 0; j < 7; ++j) {
-    const float noise = has_noise ? __ldg(rays.deg_noise + (size_t)row * 7 + j) : 0.f;
-    pts[j] = sample_point(rg, t0, t1, j, noise, has_noise, rays.std_scale);
-  }
-#pragma unroll
+  for (int l = 0; l < L; ++l) s_gf[l][tid] = gf[l];
+  stage_points(rays, row, s_pts);
+#pragma unroll 1
   for (int l = 0; l < L; ++l) {
     const Level3 lv = level3(tab.offsets, l, tab.S, tab.H);
-    const int gs = __ldg(tab.grid_sizes + l);
-    CellScatter<1> sc;
-    float g1[1] = {gf[l]};
-#pragma unroll
-    for (int j = 0; j < 7; ++j) {
-      if (!in_unit_cube(pts[j].x, pts[j].y, pts[j].z)) continue;
-      sc.add(grad_table, lv, g1, pts[j].x, pts[j].y, pts[j].z, erf_weight(pts[j].std, gs));
-    }
-    sc.flush(grad_table, lv, g1);
+    float g1[1] = {s_gf[l][tid]};
+    if (g1[0] == 0.f) continue;
+    level_scatter<1>(grad_table, lv, __ldg(tab.grid_sizes + l), s_pts, g1);
   }
+}
+
+// sums the per-block partial weight gradients: one thread per entry, coalesced reads
+__global__ void __launch_bounds__(256) k_prop_wgrad_reduce(const float* __restrict__ partial, int blocks, int entries,
+                                                           int L, float* __restrict__ gW0, float* __restrict__ gb0,
+                                                           float* __restrict__ gW1, float* __restrict__ gb1) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= entries) return;
+  float a = 0.f;
+  for (int b = 0; b < blocks; ++b) a += __ldg(partial + (size_t)b * entries + e);
+  const int n0 = kPropHidden * L;
+  if (e < n0) gW0[e] += a;
+  else if (e < n0 + kPropHidden) gb0[e - n0] += a;
+  else if (e < n0 + 2 * kPropHidden) gW1[e - n0 - kPropHidden] += a;
+  else gb1[0] += a;
 }
 
 }  // namespace nlb
@@ -418,7 +453,7 @@ extern "C" int nlb_encode_forward(const nlb_rays_t* rays, const nlb_table_t* tab
   if (int e = check_rays_table(rays, table, "encode_forward")) return e;
   const int rows = rays->N * rays->S;
   if (rows == 0) return NLB_OK;
-  dim3 grid(div_up(rows, 128), table->L);
+  dim3 grid(div_up(rows, kEncThreads));
   cudaStream_t st = (cudaStream_t)stream;
   switch (table->C) {
     case 1: k_encode_fwd<1><<<grid, 128, 0, st>>>(*rays, *table, features); break;
@@ -435,7 +470,7 @@ extern "C" int nlb_encode_backward(const nlb_rays_t* rays, const nlb_table_t* ta
   if (int e = check_rays_table(rays, table, "encode_backward")) return e;
   const int rows = rays->N * rays->S;
   if (rows == 0) return NLB_OK;
-  dim3 grid(div_up(rows, 128), table->L);
+  dim3 grid(div_up(rows, kEncThreads));
   cudaStream_t st = (cudaStream_t)stream;
   switch (table->C) {
     case 1: k_encode_bwd<1><<<grid, 128, 0, st>>>(*rays, *table, grad_features, grad_embeddings); break;
@@ -470,17 +505,27 @@ extern "C" int nlb_prop_forward(const nlb_rays_t* rays, const nlb_table_t* table
   return nlb_check_launch("prop_forward");
 }
 
+extern "C" size_t nlb_prop_backward_workspace_bytes(int N, int S, int L) {
+  const size_t blocks = ((size_t)N * S + kEncThreads - 1) / kEncThreads;
+  return blocks * (size_t)(kPropHidden * L + 2 * kPropHidden + 1) * sizeof(float);
+}
+
 extern "C" int nlb_prop_backward(const nlb_rays_t* rays, const nlb_table_t* table, const float* W0, const float* b0,
                                  const float* W1, const float* b1, const float* features, const float* grad_density,
                                  float* grad_embeddings, float* gW0, float* gb0, float* gW1, float* gb1,
-                                 void* stream) {
+                                 float* workspace, void* stream) {
   if (int e = check_rays_table(rays, table, "prop_backward")) return e;
   if (table->C != 1) { nlb_set_error("prop_backward: PropMLP tables have level_dim 1"); return NLB_EINVAL; }
   if (!features || !grad_density) { nlb_set_error("prop_backward: features saved by the forward are required"); return NLB_EINVAL; }
+  if (!workspace) { nlb_set_error("prop_backward: workspace of nlb_prop_backward_workspace_bytes() is required"); return NLB_EINVAL; }
   const int rows = rays->N * rays->S;
   if (rows == 0) return NLB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  NLB_PROP_DISPATCH(table->L, (k_prop_bwd<L_><<<div_up(rows, 128), 128, 0, st>>>(
-      *rays, *table, W0, b0, W1, b1, features, grad_density, grad_embeddings, gW0, gb0, gW1, gb1)));
-  return nlb_check_launch("prop_backward");
+  const int blocks = (int)div_up(rows, kEncThreads);
+  NLB_PROP_DISPATCH(table->L, (k_prop_bwd<L_><<<blocks, kEncThreads, 0, st>>>(
+      *rays, *table, W0, b0, W1, b1, features, grad_density, grad_embeddings, workspace)));
+  if (int e = nlb_check_launch("prop_backward")) return e;
+  const int entries = kPropHidden * table->L + 2 * kPropHidden + 1;
+  k_prop_wgrad_reduce<<<div_up(entries, 256), 256, 0, st>>>(workspace, blocks, entries, table->L, gW0, gb0, gW1, gb1);
+  return nlb_check_launch("prop_wgrad_reduce");
 }

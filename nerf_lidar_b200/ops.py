@@ -19,7 +19,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
+from ._lib import timed, NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
 
 EPS = float(torch.finfo(torch.float32).eps)
 _u_cache: Dict[Tuple, torch.Tensor] = {}
@@ -67,9 +67,10 @@ def resample_level(sdist: Optional[torch.Tensor], weights: Optional[torch.Tensor
     t_out = torch.empty_like(s_out)
     idx = torch.empty(N, num_samples, device=dev, dtype=torch.int32) if return_index else None
     with torch.cuda.device(dev):
-        check(load().nlb_resample(ptr(sd), ptr(w), n_in, int(dilate), float(dilation), float(anneal),
-                                  float(resample_padding), ptr(u_base), ptr(jit), float(max_jitter), ptr(near),
-                                  ptr(far), float(lam), num_samples, N, ptr(s_out), ptr(t_out), ptr(idx), stream()))
+        with timed('resample'):
+            check(load().nlb_resample(ptr(sd), ptr(w), n_in, int(dilate), float(dilation), float(anneal),
+                                      float(resample_padding), ptr(u_base), ptr(jit), float(max_jitter), ptr(near),
+                                      ptr(far), float(lam), num_samples, N, ptr(s_out), ptr(t_out), ptr(idx), stream()))
     return (s_out, t_out, idx) if return_index else (s_out, t_out)
 
 
@@ -138,9 +139,10 @@ class _PropLevel(Function):
         feats = torch.empty(N * S, encoder.num_levels, device=rays.device, dtype=torch.float32) if need_grad else None
         W0c, b0c, W1c, b1c = f32(W0), f32(b0), f32(W1).reshape(-1), f32(b1)
         with torch.cuda.device(rays.device):
-            check(load().nlb_prop_forward(C.byref(rays.desc(tdist, deg_noise, std_scale)),
-                                          C.byref(_table_desc(encoder, embeddings)), ptr(W0c), ptr(b0c), ptr(W1c),
-                                          ptr(b1c), ptr(density), ptr(feats), stream()))
+            with timed(f'prop{encoder.num_levels}_fwd'):
+                check(load().nlb_prop_forward(C.byref(rays.desc(tdist, deg_noise, std_scale)),
+                                              C.byref(_table_desc(encoder, embeddings)), ptr(W0c), ptr(b0c), ptr(W1c),
+                                              ptr(b1c), ptr(density), ptr(feats), stream()))
         ctx.save_for_backward(tdist, deg_noise, embeddings, W0c, b0c, W1c, b1c, feats)
         ctx.rays, ctx.encoder, ctx.std_scale, ctx.emb_param = rays, encoder, std_scale, emb_param
         return density
@@ -153,11 +155,14 @@ class _PropLevel(Function):
         gW0, gb0 = torch.zeros_like(W0), torch.zeros_like(b0)
         gW1, gb1 = torch.zeros_like(W1), torch.zeros_like(b1)
         g_density = f32(g_density)
+        ws_bytes = load().nlb_prop_backward_workspace_bytes(rays.N, tdist.shape[1] - 1, encoder.num_levels)
+        ws = torch.empty(ws_bytes // 4, device=rays.device, dtype=torch.float32)
         with torch.cuda.device(rays.device):
-            check(load().nlb_prop_backward(C.byref(rays.desc(tdist, deg_noise, ctx.std_scale)),
-                                           C.byref(_table_desc(encoder, embeddings)), ptr(W0), ptr(b0), ptr(W1),
-                                           ptr(b1), ptr(feats), ptr(g_density), ptr(g_emb), ptr(gW0), ptr(gb0),
-                                           ptr(gW1), ptr(gb1), stream()))
+            with timed(f'prop{encoder.num_levels}_bwd'):
+                check(load().nlb_prop_backward(C.byref(rays.desc(tdist, deg_noise, ctx.std_scale)),
+                                               C.byref(_table_desc(encoder, embeddings)), ptr(W0), ptr(b0), ptr(W1),
+                                               ptr(b1), ptr(feats), ptr(g_density), ptr(g_emb), ptr(gW0), ptr(gb0),
+                                               ptr(gW1), ptr(gb1), ptr(ws), stream()))
         return (None, None, None if in_place else g_emb, gW0, gb0, gW1.reshape(1, -1), gb1, None, None, None, None)
 
 
@@ -175,8 +180,9 @@ class _NerfEncode(Function):
         N, S = rays.N, tdist.shape[1] - 1
         feats = torch.empty(N * S, encoder.output_dim, device=rays.device, dtype=torch.float32)
         with torch.cuda.device(rays.device):
-            check(load().nlb_encode_forward(C.byref(rays.desc(tdist, deg_noise, std_scale)),
-                                            C.byref(_table_desc(encoder, embeddings)), ptr(feats), stream()))
+            with timed('nerf_encode_fwd'):
+                check(load().nlb_encode_forward(C.byref(rays.desc(tdist, deg_noise, std_scale)),
+                                                C.byref(_table_desc(encoder, embeddings)), ptr(feats), stream()))
         ctx.save_for_backward(tdist, deg_noise, embeddings)
         ctx.rays, ctx.encoder, ctx.std_scale, ctx.emb_param = rays, encoder, std_scale, emb_param
         return feats
@@ -188,9 +194,10 @@ class _NerfEncode(Function):
         g_emb, in_place = _grad_buffer(ctx.emb_param if ctx.emb_param is not None else embeddings)
         g_feats = f32(g_feats)
         with torch.cuda.device(rays.device):
-            check(load().nlb_encode_backward(C.byref(rays.desc(tdist, deg_noise, ctx.std_scale)),
-                                             C.byref(_table_desc(encoder, embeddings)), ptr(g_feats), ptr(g_emb),
-                                             stream()))
+            with timed('nerf_encode_bwd'):
+                check(load().nlb_encode_backward(C.byref(rays.desc(tdist, deg_noise, ctx.std_scale)),
+                                                 C.byref(_table_desc(encoder, embeddings)), ptr(g_feats), ptr(g_emb),
+                                                 stream()))
         return (None, None, None if in_place else g_emb, None, None, None, None)
 
 
@@ -221,7 +228,8 @@ class _Composite(Function):
         cout = NlbCompositeOut(ptr(weights), ptr(o_rgb), ptr(depth), ptr(acc), ptr(o_sem), ptr(o_int), ptr(dmean),
                                ptr(dpct))
         with torch.cuda.device(dev):
-            check(load().nlb_composite_forward(C.byref(cin), C.byref(cout), stream()))
+            with timed(f'composite{S}_fwd'):
+                check(load().nlb_composite_forward(C.byref(cin), C.byref(cout), stream()))
         ctx.save_for_backward(density, rgb_c, sem_c, int_c, tdist, directions, far_c, weights)
         ctx.cfg = (N, S, K, float(bg), int(opaque))
         ctx.int_shape = None if intensity is None else intensity.shape
@@ -245,8 +253,9 @@ class _Composite(Function):
         g_sem_s = torch.empty(N, S, K, device=dev, dtype=torch.float32) if (sem is not None and need[2] and g_sem is not None) else None
         g_int_s = torch.empty(N, S, device=dev, dtype=torch.float32) if (inten is not None and need[3] and g_int is not None) else None
         with torch.cuda.device(dev):
-            check(load().nlb_composite_backward(C.byref(cin), ptr(weights), C.byref(cg), ptr(gd), ptr(g_rgb_s),
-                                                ptr(g_sem_s), ptr(g_int_s), stream()))
+            with timed(f'composite{S}_bwd'):
+                check(load().nlb_composite_backward(C.byref(cin), ptr(weights), C.byref(cg), ptr(gd), ptr(g_rgb_s),
+                                                    ptr(g_sem_s), ptr(g_int_s), stream()))
         if g_int_s is not None and ctx.int_shape is not None:
             g_int_s = g_int_s.reshape(ctx.int_shape)
         return gd, g_rgb_s, g_sem_s, g_int_s, None, None, None, None, None, None

@@ -280,7 +280,8 @@ class Trainer:
         for t in self.tables:
             enc = t['enc']
             decay = 0. if (c.obj_nodecay and 'obj' in t['name']) else self.decay
-            _lib.check(lib.nlb_adam_table_step(t['param'].data_ptr(), t['grad'].data_ptr(), t['m'].data_ptr(),
+            with _lib.timed('adam_table'):
+              _lib.check(lib.nlb_adam_table_step(t['param'].data_ptr(), t['grad'].data_ptr(), t['m'].data_ptr(),
                                                t['v'].data_ptr(), t['offsets'], enc.num_levels, enc.level_dim,
                                                float(decay), float(lr), c.adam_beta1, c.adam_beta2, c.adam_eps,
                                                int(step), scale, st))

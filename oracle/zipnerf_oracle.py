@@ -161,8 +161,9 @@ def encode_features(means, stds, table, offsets, grid_sizes, C, base_resolution=
     z, sd = z / 2, sd / 2
     x01 = (z + 1) / 2
     L = offsets.shape[0] - 1
-    out, _ = grid_oracle.grid_encode_forward(x01, table, offsets, 1.0, base_resolution)
-    feat = out.permute(1, 0, 2).reshape(N, S, n, L, C)
+    # autograd-capable wrapper (gradient w.r.t. the table) around grid_encode_forward
+    flat = grid_oracle._GridEncodeFn.apply(x01, table, offsets, 1.0, base_resolution, False, 0, False, 0)
+    feat = flat.reshape(N, S, n, L, C)
     sd = sd.reshape(N, S, n)
     w = torch.erf(1 / torch.clamp(torch.sqrt(8 * sd[..., None] ** 2 * grid_sizes ** 2), min=1e-10))
     return (feat * w[..., None]).mean(-3).flatten(-2, -1)
