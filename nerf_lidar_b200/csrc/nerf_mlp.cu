@@ -1,18 +1,451 @@
-// NerfMLP forward on the 5th-generation tensor cores (tcgen05 + TMEM).
-// Placeholder translation unit: the entry points exist so the ABI is complete; the
-// kernel lands in the next commit.
+// NerfMLP forward as ONE persistent tcgen05 kernel (Z/internal/models.py:996-997,
+// 1116-1251): 40->64->256 trunk, density softplus, semantic 256->64->19 softmax,
+// intensity 256->64->1, view branch cat[x, pos_enc(viewdirs)] (283) -> 256 ->
+// cat (539) -> 256 -> 3 sigmoid.  bf16 operands, fp32 accumulation in TMEM.
+//
+// Per CTA (one per SM, 192 threads): a 128-row tile of samples stays on chip for the
+// whole chain.  Activations live in shared memory as UMMA operand blocks
+// ([128 rows][64 k] bf16, K-major, SWIZZLE_128B, 16 KB each): X0-3 (bottleneck),
+// H0-3 (layer outputs, reused), D (view-direction encoding).  Weights are pre-packed
+// (nlb_nerf_mlp_pack) into the same block format and streamed from L2 through a
+// 4 x 16 KB ring with 1-D bulk async copies (UBLKCP) by a producer warp; one MMA
+// thread issues tcgen05.mma (M=128, N<=128 per instruction) into two 256-column
+// TMEM accumulators; four epilogue warps read TMEM (LDTM), apply bias/activation
+// and write the next layer's A operand back to shared memory.  The concatenations
+// of the reference are just extra K blocks (X, D) of the next GEMM.
+// Layer order on the tensor pipe: L0, L1, HS0 (sem|int hidden), V0, HS1 (sem|int
+// out), V1, RGB; the HS0/HS1 epilogues overlap the V0 MMAs.
 #include "common.cuh"
+#include "umma.cuh"
 #include "../../include/nlb200.h"
+#include <cuda_bf16.h>
 
-extern "C" size_t nlb_nerf_mlp_packed_bytes(void) { return 0; }
+namespace nlb {
+namespace mlp {
 
-extern "C" int nlb_nerf_mlp_pack(const nlb_nerf_mlp_weights_t*, void*, void*) {
-  nlb_set_error("nerf_mlp_pack: tcgen05 kernel not built in this revision");
-  return NLB_EUNSUPPORTED;
+using namespace nlb::umma;
+
+constexpr int kFeat = 40, kDir = 27, kSem = 19;
+constexpr int kBlockBytes = 16384;            // [128][64] bf16
+// shared-memory A blocks
+constexpr int BX = 0, BH = 4, BD = 8, kNumABlocks = 9;
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+
+struct LayerDef {
+  int N, nkb;
+  int a_blk[9];
+  int ksteps[9];
+  int tmem_col;
+};
+enum { L0 = 0, L1, HS0, V0, HS1, V1, RGB, kNumLayers };
+__host__ __device__ constexpr LayerDef layer_def(int l) {
+  switch (l) {
+    case L0:  return {64, 1, {BH + 0}, {3}, 0};
+    case L1:  return {256, 1, {BH + 1}, {4}, 256};
+    case HS0: return {128, 4, {BX, BX + 1, BX + 2, BX + 3}, {4, 4, 4, 4}, 0};
+    case V0:  return {256, 5, {BX, BX + 1, BX + 2, BX + 3, BD}, {4, 4, 4, 4, 2}, 256};
+    case HS1: return {32, 2, {BH + 2, BH + 3}, {4, 4}, 128};
+    case V1:  return {256, 9, {BH, BH + 1, BH + 2, BH + 3, BX, BX + 1, BX + 2, BX + 3, BD}, {4, 4, 4, 4, 4, 4, 4, 4, 2}, 0};
+    default:  return {16, 4, {BH, BH + 1, BH + 2, BH + 3}, {4, 4, 4, 4}, 256};
+  }
+}
+__host__ __device__ constexpr int layer_nrows(int l) { return layer_def(l).N > 128 ? 128 : layer_def(l).N; }
+__host__ __device__ constexpr int layer_nhalves(int l) { return layer_def(l).N > 128 ? 2 : 1; }
+__host__ __device__ constexpr int layer_chunks(int l) { return layer_def(l).nkb * layer_nhalves(l); }
+__host__ __device__ constexpr int layer_chunk_bytes(int l) { return layer_nrows(l) * 128; }
+__host__ __device__ constexpr int layer_offset(int l) {  // byte offset of the layer's first chunk in the blob
+  int o = 0;
+  for (int i = 0; i < l; ++i) o += layer_chunks(i) * layer_chunk_bytes(i);
+  return o;
+}
+__host__ __device__ constexpr int bias_offset(int l) {  // float index in the bias section
+  int o = 0;
+  for (int i = 0; i < l; ++i) o += layer_def(i).N;
+  return o;
+}
+constexpr int kWeightBytes = layer_offset(kNumLayers);
+constexpr int kBiasFloats = bias_offset(kNumLayers);
+constexpr int kPackedBytes = kWeightBytes + kBiasFloats * 4;
+
+// ----------------------------------------------------------------------------- packing
+// value of the (padded) weight matrix of layer l at output row n, input column k
+__device__ float packed_weight(const nlb_nerf_mlp_weights_t& w, int l, int n, int k) {
+  switch (l) {
+    case L0:  return (n < 64 && k < kFeat) ? w.W_d0[n * kFeat + k] : 0.f;
+    case L1:  return w.W_d2[n * 64 + k];
+    case HS0: return n < 64 ? w.W_s0[n * 256 + k] : w.W_i0[(n - 64) * 256 + k];
+    case V0:  return k < 256 ? w.W_v0[n * 283 + k] : (k - 256 < kDir ? w.W_v0[n * 283 + k] : 0.f);
+    case HS1:
+      if (n < kSem) return k < 64 ? w.W_s2[n * 64 + k] : 0.f;
+      if (n == kSem) return k >= 64 ? w.W_i2[k - 64] : 0.f;
+      return 0.f;
+    case V1:  return k < 512 ? w.W_v1[n * 539 + k] : (k - 512 < kDir ? w.W_v1[n * 539 + k] : 0.f);
+    default:  return n < 3 ? w.W_rgb[n * 256 + k] : 0.f;
+  }
+}
+__device__ float packed_bias(const nlb_nerf_mlp_weights_t& w, int l, int n) {
+  switch (l) {
+    case L0:  return w.b_d0[n];
+    case L1:  return w.b_d2[n];
+    case HS0: return n < 64 ? w.b_s0[n] : w.b_i0[n - 64];
+    case V0:  return w.b_v0[n];
+    case HS1: return n < kSem ? w.b_s2[n] : (n == kSem ? w.b_i2[0] : 0.f);
+    case V1:  return w.b_v1[n];
+    default:  return n < 3 ? w.b_rgb[n] : 0.f;
+  }
 }
 
-extern "C" int nlb_nerf_mlp_forward(const float*, const float*, int, int, const void*, float*, float*, float*, float*,
-                                    void*) {
-  nlb_set_error("nerf_mlp_forward: tcgen05 kernel not built in this revision");
-  return NLB_EUNSUPPORTED;
+__global__ void k_pack(nlb_nerf_mlp_weights_t w, uint8_t* __restrict__ blob) {
+  for (int l = 0; l < kNumLayers; ++l) {
+    const LayerDef d = layer_def(l);
+    const int nrows = layer_nrows(l), nh_count = layer_nhalves(l);
+    const int total = d.nkb * nh_count * nrows * 64;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+      const int c = e & 63;
+      const int r = (e >> 6) % nrows;
+      const int chunk = (e >> 6) / nrows;       // kb-major, n-half minor
+      const int kb = chunk / nh_count, nh = chunk % nh_count;
+      const float v = packed_weight(w, l, nh * 128 + r, kb * 64 + c);
+      uint8_t* dst = blob + layer_offset(l) + (size_t)chunk * layer_chunk_bytes(l) + sw128_offset(r, c);
+      *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16(v);
+    }
+    float* bias = reinterpret_cast<float*>(blob + kWeightBytes) + bias_offset(l);
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < d.N; n += gridDim.x * blockDim.x) bias[n] = packed_bias(w, l, n);
+  }
+}
+
+// ----------------------------------------------------------------------------- kernel
+struct Smem {
+  uint64_t w_full[kStages], w_empty[kStages];
+  uint64_t acc_ready[kNumLayers];
+  uint64_t a_ready[6];
+  uint32_t tmem_base;
+  float bias[kBiasFloats];
+};
+enum { E_F = 0, E_H0, E_X, E_G, E_H1, E_H2 };
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// 32 accumulator columns [c0, c0+32) of this thread's row -> bias (+relu) -> bf16 -> A block
+template <bool kRelu>
+__device__ __forceinline__ void epi_cols_to_block(uint32_t taddr, const float* __restrict__ bias, uint8_t* block,
+                                                  int row, int col_in_block, float* keep0 = nullptr) {
+  float v[32];
+  tmem_ld32(taddr, v);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    v[i] += bias[i];
+    if (kRelu) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (keep0) *keep0 = v[0];
+  uint8_t* rowp = block + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int chunk = ((col_in_block >> 3) + q) ^ (row & 7);
+    uint4 u;
+    u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+    u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+    u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+    u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(rowp + chunk * 16) = u;
+  }
+}
+
+__device__ __forceinline__ void signal_a_ready(uint64_t* bar) {
+  tcgen05_fence_before();
+  fence_proxy_async();
+  mbar_arrive(bar);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __restrict__ features,
+                                                              const float* __restrict__ viewdirs, int M,
+                                                              int rows_per_ray, const uint8_t* __restrict__ blob,
+                                                              float* __restrict__ o_density, float* __restrict__ o_rgb,
+                                                              float* __restrict__ o_sem, float* __restrict__ o_int) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_blocks = base;                                  // 9 x 16 KB
+  uint8_t* w_ring = base + kNumABlocks * kBlockBytes;        // 4 x 16 KB
+  Smem& sm = *reinterpret_cast<Smem*>(w_ring + kStages * kBlockBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (M + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
+    for (int i = 0; i < kNumLayers; ++i) mbar_init(&sm.acc_ready[i], 1);
+    for (int i = 0; i < 6; ++i) mbar_init(&sm.a_ready[i], 128);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < kBiasFloats; i += kThreads)
+    sm.bias[i] = reinterpret_cast<const float*>(blob + kWeightBytes)[i];
+  if (warp == 5) tmem_alloc(&sm.tmem_base, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 4) {
+    // ===== weight producer: streams the packed chunks of every tile through the ring
+    if (lane == 0) {
+      uint32_t c = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+#pragma unroll 1
+        for (int l = 0; l < kNumLayers; ++l) {
+          const int n = layer_chunks(l), bytes = layer_chunk_bytes(l);
+          const uint8_t* src = blob + layer_offset(l);
+#pragma unroll 1
+          for (int i = 0; i < n; ++i, ++c) {
+            const int st = c % kStages;
+            mbar_wait(&sm.w_empty[st], ((c / kStages) & 1) ^ 1);
+            mbar_expect_tx(&sm.w_full[st], bytes);
+            bulk_g2s(w_ring + st * kBlockBytes, src + (size_t)i * bytes, bytes, &sm.w_full[st]);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer (one thread)
+    if (lane == 0) {
+      uint32_t c = 0, it = 0;
+      auto run_layer = [&](int l) {
+        const LayerDef d = layer_def(l);
+        const int nrows = layer_nrows(l), nh_count = layer_nhalves(l);
+        const uint32_t idesc = make_idesc_bf16(128, nrows);
+#pragma unroll 1
+        for (int kb = 0; kb < d.nkb; ++kb) {
+          const uint64_t adesc = make_desc_sw128(a_blocks + d.a_blk[kb] * kBlockBytes);
+#pragma unroll 1
+          for (int nh = 0; nh < nh_count; ++nh, ++c) {
+            const int st = c % kStages;
+            mbar_wait(&sm.w_full[st], (c / kStages) & 1);
+            tcgen05_fence_after();
+            const uint64_t bdesc = make_desc_sw128(w_ring + st * kBlockBytes);
+            const uint32_t dcol = tmem + d.tmem_col + nh * 128;
+#pragma unroll 1
+            for (int kk = 0; kk < d.ksteps[kb]; ++kk)
+              mma_bf16_ss(dcol, adesc + kk * 2, bdesc + kk * 2, idesc, (kb | kk) != 0);
+            mma_commit(&sm.w_empty[st]);
+          }
+        }
+        mma_commit(&sm.acc_ready[l]);
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t ph = it & 1;
+        mbar_wait(&sm.a_ready[E_F], ph);  tcgen05_fence_after(); run_layer(L0);
+        mbar_wait(&sm.a_ready[E_H0], ph); tcgen05_fence_after(); run_layer(L1);
+        mbar_wait(&sm.a_ready[E_X], ph);  tcgen05_fence_after(); run_layer(HS0); run_layer(V0);
+        mbar_wait(&sm.a_ready[E_G], ph);  tcgen05_fence_after(); run_layer(HS1);
+        mbar_wait(&sm.a_ready[E_H1], ph); tcgen05_fence_after(); run_layer(V1);
+        mbar_wait(&sm.a_ready[E_H2], ph); tcgen05_fence_after(); run_layer(RGB);
+      }
+    }
+  } else {
+    // ===== epilogue warps 0..3: thread r owns row r of the tile (TMEM lane r)
+    const int r = threadIdx.x;
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    uint8_t* HB = a_blocks + BH * kBlockBytes;
+    uint8_t* XB = a_blocks + BX * kBlockBytes;
+    uint8_t* DB = a_blocks + BD * kBlockBytes;
+    uint8_t* myrow_off = nullptr;
+    (void)myrow_off;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const int row = tile * 128 + r;
+      const bool valid = row < M;
+      // ---- stage features (H0) and the view-direction encoding (D)
+      {
+        float f[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) f[i] = 0.f;
+        if (valid) {
+          const float4* src = reinterpret_cast<const float4*>(features + (size_t)row * kFeat);
+#pragma unroll
+          for (int q = 0; q < kFeat / 4; ++q) {
+            const float4 t = __ldg(src + q);
+            f[q * 4] = t.x; f[q * 4 + 1] = t.y; f[q * 4 + 2] = t.z; f[q * 4 + 3] = t.w;
+          }
+        }
+        uint8_t* rowp = HB + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint4 u;
+          u.x = pack_bf16(f[q * 8], f[q * 8 + 1]); u.y = pack_bf16(f[q * 8 + 2], f[q * 8 + 3]);
+          u.z = pack_bf16(f[q * 8 + 4], f[q * 8 + 5]); u.w = pack_bf16(f[q * 8 + 6], f[q * 8 + 7]);
+          *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) * 16)) = u;
+        }
+        float d[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) d[i] = 0.f;
+        if (valid) {
+          const int ray = row / rows_per_ray;
+          const float vx = __ldg(viewdirs + 3 * ray), vy = __ldg(viewdirs + 3 * ray + 1), vz = __ldg(viewdirs + 3 * ray + 2);
+          d[0] = vx; d[1] = vy; d[2] = vz;
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            const float sc = (float)(1 << s);
+            const float ax = vx * sc, ay = vy * sc, az = vz * sc;
+            d[3 + s * 3] = sinf(ax); d[4 + s * 3] = sinf(ay); d[5 + s * 3] = sinf(az);
+            d[15 + s * 3] = sinf(ax + 1.5707963267948966f);
+            d[16 + s * 3] = sinf(ay + 1.5707963267948966f);
+            d[17 + s * 3] = sinf(az + 1.5707963267948966f);
+          }
+        }
+        uint8_t* drow = DB + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint4 u = make_uint4(0, 0, 0, 0);
+          if (q < 4) {
+            u.x = pack_bf16(d[q * 8], d[q * 8 + 1]); u.y = pack_bf16(d[q * 8 + 2], d[q * 8 + 3]);
+            u.z = pack_bf16(d[q * 8 + 4], d[q * 8 + 5]); u.w = pack_bf16(d[q * 8 + 6], d[q * 8 + 7]);
+          }
+          *reinterpret_cast<uint4*>(drow + ((q ^ (r & 7)) * 16)) = u;
+        }
+      }
+      signal_a_ready(&sm.a_ready[E_F]);
+
+      // ---- L0: h0 = relu(acc + b) -> H1
+      mbar_wait(&sm.acc_ready[L0], ph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32)
+        epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(L0) + c0, HB + 1 * kBlockBytes, r, c0);
+      signal_a_ready(&sm.a_ready[E_H0]);
+
+      // ---- L1: x = acc + b -> X0..3 ; density = softplus(x[0] - 1)
+      mbar_wait(&sm.acc_ready[L1], ph);
+      tcgen05_fence_after();
+      float x0 = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32)
+        epi_cols_to_block<false>(tlane + 256 + c0, sm.bias + bias_offset(L1) + c0, XB + (c0 >> 6) * kBlockBytes, r,
+                                 c0 & 63, c0 == 0 ? &x0 : nullptr);
+      signal_a_ready(&sm.a_ready[E_X]);
+      if (valid) {
+        const float xin = x0 - 1.0f;
+        o_density[row] = xin > 20.f ? xin : log1pf(expf(xin));
+      }
+
+      // ---- HS0: hidden = relu(acc + b) -> H2, H3
+      mbar_wait(&sm.acc_ready[HS0], ph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32)
+        epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(HS0) + c0, HB + (2 + (c0 >> 6)) * kBlockBytes, r,
+                                c0 & 63);
+      signal_a_ready(&sm.a_ready[E_G]);
+
+      // ---- HS1: semantic softmax (19) + intensity
+      mbar_wait(&sm.acc_ready[HS1], ph);
+      tcgen05_fence_after();
+      {
+        float v[32];
+        tmem_ld32(tlane + 128, v);
+        const float* b = sm.bias + bias_offset(HS1);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < kSem; ++i) { v[i] += b[i]; mx = fmaxf(mx, v[i]); }
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < kSem; ++i) { v[i] = expf(v[i] - mx); sum += v[i]; }
+        const float inv = 1.0f / sum;
+        if (valid) {
+          if (o_sem) {
+#pragma unroll
+            for (int i = 0; i < kSem; ++i) o_sem[(size_t)row * kSem + i] = v[i] * inv;
+          }
+          if (o_int) o_int[row] = v[kSem] + b[kSem];
+        }
+      }
+
+      // ---- V0: h1 = relu(acc + b) -> H0..3
+      mbar_wait(&sm.acc_ready[V0], ph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32)
+        epi_cols_to_block<true>(tlane + 256 + c0, sm.bias + bias_offset(V0) + c0, HB + (c0 >> 6) * kBlockBytes, r,
+                                c0 & 63);
+      signal_a_ready(&sm.a_ready[E_H1]);
+
+      // ---- V1: h2 = relu(acc + b) -> H0..3
+      mbar_wait(&sm.acc_ready[V1], ph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32)
+        epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(V1) + c0, HB + (c0 >> 6) * kBlockBytes, r, c0 & 63);
+      signal_a_ready(&sm.a_ready[E_H2]);
+
+      // ---- RGB: sigmoid(acc + b) * (1 + 2 pad) - pad
+      mbar_wait(&sm.acc_ready[RGB], ph);
+      tcgen05_fence_after();
+      {
+        float v[16];
+        tmem_ld16(tlane + 256, v);
+        const float* b = sm.bias + bias_offset(RGB);
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float s = 1.0f / (1.0f + expf(-(v[i] + b[i])));
+            o_rgb[(size_t)row * 3 + i] = s * (1.0f + 2.0f * 0.001f) - 0.001f;
+          }
+        }
+      }
+      tcgen05_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 512);
+}
+
+constexpr size_t kSmemBytes = 1024 + (kNumABlocks + kStages) * (size_t)kBlockBytes + sizeof(Smem);
+
+}  // namespace mlp
+}  // namespace nlb
+
+using namespace nlb;
+
+extern "C" size_t nlb_nerf_mlp_packed_bytes(void) { return mlp::kPackedBytes; }
+
+extern "C" int nlb_nerf_mlp_pack(const nlb_nerf_mlp_weights_t* w, void* packed, void* stream) {
+  if (!w || !packed) { nlb_set_error("nerf_mlp_pack: null pointer"); return NLB_EINVAL; }
+  const void* const* p = reinterpret_cast<const void* const*>(w);
+  for (size_t i = 0; i < sizeof(*w) / sizeof(void*); ++i) {
+    // the intensity head is optional in the reference (Config.use_intensity)
+    if (!p[i] && !(i >= 8 && i < 12)) { nlb_set_error("nerf_mlp_pack: null weight pointer %zu", i); return NLB_EINVAL; }
+  }
+  if (!w->W_i0 || !w->b_i0 || !w->W_i2 || !w->b_i2) {
+    nlb_set_error("nerf_mlp_pack: the intensity head is required (Config.use_intensity=True)");
+    return NLB_EUNSUPPORTED;
+  }
+  mlp::k_pack<<<148, 256, 0, (cudaStream_t)stream>>>(*w, reinterpret_cast<uint8_t*>(packed));
+  return nlb_check_launch("nerf_mlp_pack");
+}
+
+extern "C" int nlb_nerf_mlp_forward(const float* features, const float* viewdirs, int M, int rows_per_ray,
+                                    const void* packed, float* density, float* rgb, float* semantic, float* intensity,
+                                    void* stream) {
+  if (M == 0) return NLB_OK;
+  if (!features || !viewdirs || !packed || !density || !rgb) { nlb_set_error("nerf_mlp_forward: null pointer"); return NLB_EINVAL; }
+  if (rows_per_ray < 1) { nlb_set_error("nerf_mlp_forward: rows_per_ray must be >= 1"); return NLB_EINVAL; }
+  if (reinterpret_cast<uintptr_t>(features) & 15 || reinterpret_cast<uintptr_t>(packed) & 15) {
+    nlb_set_error("nerf_mlp_forward: features / packed weights must be 16-byte aligned");
+    return NLB_EINVAL;
+  }
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(mlp::k_nerf_mlp_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp::kSmemBytes);
+  }
+  const int tiles = (M + 127) / 128;
+  const int grid = tiles < sms ? tiles : sms;
+  mlp::k_nerf_mlp_fwd<<<grid, mlp::kThreads, mlp::kSmemBytes, (cudaStream_t)stream>>>(
+      features, viewdirs, M, rows_per_ray, reinterpret_cast<const uint8_t*>(packed), density, rgb, semantic, intensity);
+  return nlb_check_launch("nerf_mlp_forward");
 }

@@ -19,7 +19,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import timed, NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
+from ._lib import timed, NlbNerfMlpWeights, NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
 
 EPS = float(torch.finfo(torch.float32).eps)
 _u_cache: Dict[Tuple, torch.Tensor] = {}
@@ -270,3 +270,53 @@ def composite(density, tdist, directions, far, rgb=None, semantic=None, intensit
         density, rgb, semantic, intensity, f32(tdist), f32(directions), far, bg, opaque_background, compute_extras)
     return dict(weights=w, rgb=o_rgb, depth=depth, acc=acc, semantic=o_sem, intensity=o_int, distance_mean=dmean,
                 distance_percentiles=dpct)
+
+
+# ----------------------------------------------------------------------------- NeRF MLP (tcgen05)
+_NERF_WEIGHT_FIELDS = (('W_d0', 'density_layer.0.weight'), ('b_d0', 'density_layer.0.bias'),
+                       ('W_d2', 'density_layer.2.weight'), ('b_d2', 'density_layer.2.bias'),
+                       ('W_s0', 'sem_layer.0.weight'), ('b_s0', 'sem_layer.0.bias'),
+                       ('W_s2', 'sem_layer.2.weight'), ('b_s2', 'sem_layer.2.bias'),
+                       ('W_i0', 'intensity_layer.0.weight'), ('b_i0', 'intensity_layer.0.bias'),
+                       ('W_i2', 'intensity_layer.2.weight'), ('b_i2', 'intensity_layer.2.bias'),
+                       ('W_v0', 'lin_second_stage_0.weight'), ('b_v0', 'lin_second_stage_0.bias'),
+                       ('W_v1', 'lin_second_stage_1.weight'), ('b_v1', 'lin_second_stage_1.bias'),
+                       ('W_rgb', 'rgb_layer.weight'), ('b_rgb', 'rgb_layer.bias'))
+
+
+@torch.no_grad()
+def nerf_mlp_pack(mlp) -> torch.Tensor:
+    """Packs the NerfMLP dense layers into the bf16 operand-block blob the fused
+    kernel streams (nlb_nerf_mlp_pack).  Cached on the module and refreshed when any
+    parameter has been modified in place (optimizer step, load_state_dict)."""
+    params = dict(mlp.named_parameters())
+    tensors = [params[name] for _, name in _NERF_WEIGHT_FIELDS]
+    version = tuple((t.data_ptr(), t._version) for t in tensors)
+    cache = getattr(mlp, '_nlb_packed', None)
+    if cache is not None and cache[0] == version:
+        return cache[1]
+    dev = tensors[0].device
+    blob = torch.empty(load().nlb_nerf_mlp_packed_bytes(), dtype=torch.uint8, device=dev)
+    keep = [f32(t.detach()) for t in tensors]
+    w = NlbNerfMlpWeights(*[ptr(t) for t in keep])
+    with torch.cuda.device(dev):
+        check(load().nlb_nerf_mlp_pack(C.byref(w), ptr(blob), stream()))
+    mlp._nlb_packed = (version, blob)
+    return blob
+
+
+@torch.no_grad()
+def nerf_mlp_forward(mlp, features: torch.Tensor, viewdirs: torch.Tensor, S: int) -> Dict[str, torch.Tensor]:
+    """Fused tcgen05 NerfMLP forward: features[N*S,40] -> density[N,S], rgb[N,S,3],
+    semantic[N,S,19], intensity[N,S,1]."""
+    features, viewdirs = f32(features), f32(viewdirs)
+    M, N = features.shape[0], viewdirs.shape[0]
+    dev = features.device
+    blob = nerf_mlp_pack(mlp)
+    new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    density, rgb, sem, inten = new(N, S), new(N, S, 3), new(N, S, 19), new(N, S, 1)
+    with torch.cuda.device(dev):
+        with timed('nerf_mlp_fwd'):
+            check(load().nlb_nerf_mlp_forward(ptr(features), ptr(viewdirs), M, S, ptr(blob), ptr(density), ptr(rgb),
+                                              ptr(sem), ptr(inten), stream()))
+    return dict(density=density, rgb=rgb, semantic=sem, intensity=inten)

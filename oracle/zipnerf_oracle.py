@@ -177,8 +177,13 @@ def pos_enc_dirs(v, deg=4):
 
 
 # ---------------------------------------------------------------- MLPs
-def _lin(p, name, x):
-    return F.linear(x, p[name + '.weight'], p[name + '.bias'])
+def _lin(p, name, x, q=None):
+    """nn.Linear; `q` (optional) rounds the OPERANDS (activations and weights), e.g. to
+    bfloat16, while the accumulation and the bias add stay fp32 -- the arithmetic of
+    the tensor-core kernel."""
+    if q is None:
+        return F.linear(x, p[name + '.weight'], p[name + '.bias'])
+    return F.linear(q(x), q(p[name + '.weight'])) + p[name + '.bias']
 
 
 def prop_mlp(p, prefix, feat):
@@ -192,21 +197,21 @@ def nerf_mlp(p, feat, viewdirs, use_intensity=True, cast=None):
     """NerfMLP, Z/internal/models.py:996-997,1116-1251.  `cast` (e.g. bfloat16
     round-trip) lets tests model the bf16 operand rounding of the tensor-core
     kernel; None = the reference's fp32."""
-    q = (lambda t: t) if cast is None else cast
+    q = cast
     pre = 'nerf_mlp.'
-    x = _lin(p, pre + 'density_layer.2', torch.relu(_lin(p, pre + 'density_layer.0', feat)))
+    x = _lin(p, pre + 'density_layer.2', torch.relu(_lin(p, pre + 'density_layer.0', feat, q)), q)
     density = F.softplus(x[..., 0] - 1.0)
-    sem = torch.softmax(_lin(p, pre + 'sem_layer.2', torch.relu(_lin(p, pre + 'sem_layer.0', x))), -1)
+    sem = torch.softmax(_lin(p, pre + 'sem_layer.2', torch.relu(_lin(p, pre + 'sem_layer.0', x, q)), q), -1)
     inten = None
     if use_intensity:
-        inten = _lin(p, pre + 'intensity_layer.2', torch.relu(_lin(p, pre + 'intensity_layer.0', x)))
+        inten = _lin(p, pre + 'intensity_layer.2', torch.relu(_lin(p, pre + 'intensity_layer.0', x, q)), q)
     de = pos_enc_dirs(viewdirs)
     de = de[:, None, :].expand(x.shape[0], x.shape[1], de.shape[-1])
     h_in = torch.cat([x, de], -1)
-    h = torch.relu(_lin(p, pre + 'lin_second_stage_0', h_in))
+    h = torch.relu(_lin(p, pre + 'lin_second_stage_0', h_in, q))
     h = torch.cat([h, h_in], -1)
-    h = torch.relu(_lin(p, pre + 'lin_second_stage_1', h))
-    rgb = torch.sigmoid(_lin(p, pre + 'rgb_layer', h)) * (1 + 2 * 0.001) - 0.001
+    h = torch.relu(_lin(p, pre + 'lin_second_stage_1', h, q))
+    rgb = torch.sigmoid(_lin(p, pre + 'rgb_layer', h, q)) * (1 + 2 * 0.001) - 0.001
     return dict(density=density, rgb=rgb, semantic=sem, intensity=inten, bottleneck=x)
 
 
