@@ -200,9 +200,48 @@ typedef struct {
   const float *W_rgb, *b_rgb; /* [3,256],[3]    rgb_layer */
 } nlb_nerf_mlp_weights_t;
 int nlb_nerf_mlp_pack(const nlb_nerf_mlp_weights_t* w, void* packed, void* stream);
+/* Row-major bf16 activations the forward can save for the backward pass
+ * (post-ReLU hidden states; x = bottleneck before the heads).  All-NULL = inference. */
+typedef struct {
+  void* h0; /* [M,64]  relu(density_layer.0) */
+  void* x;  /* [M,256] density_layer.2 output */
+  void* g;  /* [M,128] relu(sem_layer.0) | relu(intensity_layer.0) */
+  void* h1; /* [M,256] relu(lin_second_stage_0) */
+  void* h2; /* [M,256] relu(lin_second_stage_1) */
+} nlb_nerf_mlp_saved_t;
 int nlb_nerf_mlp_forward(const float* features /*[M,40]*/, const float* viewdirs /*[N,3]*/, int M,
                          int rows_per_ray, const void* packed, float* density /*[M]*/, float* rgb /*[M,3]*/,
-                         float* semantic /*[M,19]*/, float* intensity /*[M]*/, void* stream);
+                         float* semantic /*[M,19]*/, float* intensity /*[M]*/,
+                         const nlb_nerf_mlp_saved_t* saved /*or NULL*/, void* stream);
+
+/* Data-gradient chain of the NerfMLP on tcgen05 (transposed packed weights from
+ * nlb_nerf_mlp_pack_transposed): from the output gradients and the activations saved
+ * by the forward it produces grad_features[M,40] (fp32) and the pre-activation
+ * gradients of every layer as row-major bf16 (inputs of the weight-gradient GEMMs
+ * dW = dZ^T A, which are plain GEMMs left to the caller). */
+size_t nlb_nerf_mlp_packed_transposed_bytes(void);
+int nlb_nerf_mlp_pack_transposed(const nlb_nerf_mlp_weights_t* w, void* packed_t, void* stream);
+typedef struct {
+  const float* g_density;   /* [M] or NULL */
+  const float* g_rgb;       /* [M,3] or NULL */
+  const float* g_semantic;  /* [M,19] or NULL */
+  const float* g_intensity; /* [M] or NULL */
+  const float* density;     /* [M]    forward outputs */
+  const float* rgb;         /* [M,3]  */
+  const float* semantic;    /* [M,19] */
+} nlb_nerf_mlp_grad_in_t;
+typedef struct {
+  void* d_rgb; /* [M,16]  bf16: d(rgb pre-sigmoid) in cols 0..2 */
+  void* d_v1;  /* [M,256] bf16: d(lin_second_stage_1 pre-relu) */
+  void* d_v0;  /* [M,256] bf16: d(lin_second_stage_0 pre-relu) */
+  void* d_hs1; /* [M,32]  bf16: d(sem logits) cols 0..18, d(intensity) col 19 */
+  void* d_g;   /* [M,128] bf16: d(sem_layer.0 | intensity_layer.0 pre-relu) */
+  void* d_x;   /* [M,256] bf16: d(bottleneck) */
+  void* d_h0;  /* [M,64]  bf16: d(density_layer.0 pre-relu) */
+} nlb_nerf_mlp_grad_out_t;
+int nlb_nerf_mlp_backward(const nlb_nerf_mlp_grad_in_t* gin, const nlb_nerf_mlp_saved_t* saved, int M,
+                          const void* packed_t, float* grad_features /*[M,40]*/,
+                          const nlb_nerf_mlp_grad_out_t* gout, void* stream);
 
 /* ------------------------------------------------------------------ optimizer
  * One fused pass per table: hash-decay gradient (Model.hash_decay_loss,

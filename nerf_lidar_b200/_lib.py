@@ -47,6 +47,18 @@ class NlbNerfMlpWeights(C.Structure):
                                    'W_i2', 'b_i2', 'W_v0', 'b_v0', 'W_v1', 'b_v1', 'W_rgb', 'b_rgb')]
 
 
+class NlbNerfMlpSaved(C.Structure):
+    _fields_ = [(n, c_f) for n in ('h0', 'x', 'g', 'h1', 'h2')]
+
+
+class NlbNerfMlpGradIn(C.Structure):
+    _fields_ = [(n, c_f) for n in ('g_density', 'g_rgb', 'g_semantic', 'g_intensity', 'density', 'rgb', 'semantic')]
+
+
+class NlbNerfMlpGradOut(C.Structure):
+    _fields_ = [(n, c_f) for n in ('d_rgb', 'd_v1', 'd_v0', 'd_hs1', 'd_g', 'd_x', 'd_h0')]
+
+
 _u32, _i, _f, _p = C.c_uint32, C.c_int, C.c_float, C.c_void_p
 
 # name -> (restype, argtypes); mirrors include/nlb200.h one to one
@@ -70,7 +82,11 @@ SIGNATURES = {
     'nlb_composite_backward': (_i, [C.POINTER(NlbCompositeIn), _p, C.POINTER(NlbCompositeGrad), _p, _p, _p, _p, _p]),
     'nlb_nerf_mlp_packed_bytes': (C.c_size_t, []),
     'nlb_nerf_mlp_pack': (_i, [C.POINTER(NlbNerfMlpWeights), _p, _p]),
-    'nlb_nerf_mlp_forward': (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
+    'nlb_nerf_mlp_forward': (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p, C.POINTER(NlbNerfMlpSaved), _p]),
+    'nlb_nerf_mlp_packed_transposed_bytes': (C.c_size_t, []),
+    'nlb_nerf_mlp_pack_transposed': (_i, [C.POINTER(NlbNerfMlpWeights), _p, _p]),
+    'nlb_nerf_mlp_backward': (_i, [C.POINTER(NlbNerfMlpGradIn), C.POINTER(NlbNerfMlpSaved), _i, _p, _p,
+                                   C.POINTER(NlbNerfMlpGradOut), _p]),
     'nlb_adam_table_step': (_i, [_p, _p, _p, _p, C.POINTER(C.c_int32), _i, _i, _f, _f, _f, _f, _f, _i, _f, _p]),
     'nlb_adam_step': (_i, [_p, _p, _p, _p, C.c_int64, _f, _f, _f, _f, _i, _f, _p]),
 }

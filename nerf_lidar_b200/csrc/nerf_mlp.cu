@@ -130,18 +130,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// 32 accumulator columns [c0, c0+32) of this thread's row -> bias (+relu) -> bf16 -> A block
-template <bool kRelu>
-__device__ __forceinline__ void epi_cols_to_block(uint32_t taddr, const float* __restrict__ bias, uint8_t* block,
-                                                  int row, int col_in_block, float* keep0 = nullptr) {
-  float v[32];
-  tmem_ld32(taddr, v);
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    v[i] += bias[i];
-    if (kRelu) v[i] = fmaxf(v[i], 0.f);
-  }
-  if (keep0) *keep0 = v[0];
+// 32 values of this thread's row -> bf16 -> A block (swizzled) and, optionally, a
+// row-major bf16 copy in global memory (saved for the backward pass / wgrad GEMMs)
+__device__ __forceinline__ void store_cols(const float (&v)[32], uint8_t* block, int row, int col_in_block,
+                                           __nv_bfloat16* gdst /*this row, first of the 32 columns, or null*/) {
   uint8_t* rowp = block + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -152,7 +144,24 @@ __device__ __forceinline__ void epi_cols_to_block(uint32_t taddr, const float* _
     u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
     u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
     *reinterpret_cast<uint4*>(rowp + chunk * 16) = u;
+    if (gdst) reinterpret_cast<uint4*>(gdst)[q] = u;
   }
+}
+
+// 32 accumulator columns [c0, c0+32) of this thread's row -> bias (+relu) -> bf16 -> A block
+template <bool kRelu>
+__device__ __forceinline__ void epi_cols_to_block(uint32_t taddr, const float* __restrict__ bias, uint8_t* block,
+                                                  int row, int col_in_block, float* keep0 = nullptr,
+                                                  __nv_bfloat16* gdst = nullptr) {
+  float v[32];
+  tmem_ld32(taddr, v);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    v[i] += bias[i];
+    if (kRelu) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (keep0) *keep0 = v[0];
+  store_cols(v, block, row, col_in_block, gdst);
 }
 
 __device__ __forceinline__ void signal_a_ready(uint64_t* bar) {
@@ -165,7 +174,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
                                                               const float* __restrict__ viewdirs, int M,
                                                               int rows_per_ray, const uint8_t* __restrict__ blob,
                                                               float* __restrict__ o_density, float* __restrict__ o_rgb,
-                                                              float* __restrict__ o_sem, float* __restrict__ o_int) {
+                                                              float* __restrict__ o_sem, float* __restrict__ o_int,
+                                                              nlb_nerf_mlp_saved_t sv) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_blocks = base;                                  // 9 x 16 KB
@@ -314,7 +324,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
       tcgen05_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32)
-        epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(L0) + c0, HB + 1 * kBlockBytes, r, c0);
+        epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(L0) + c0, HB + 1 * kBlockBytes, r, c0, nullptr,
+                                (sv.h0 && valid) ? reinterpret_cast<__nv_bfloat16*>(sv.h0) + (size_t)row * 64 + c0 : nullptr);
       signal_a_ready(&sm.a_ready[E_H0]);
 
       // ---- L1: x = acc + b -> X0..3 ; density = softplus(x[0] - 1)
@@ -324,7 +335,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
 #pragma unroll 1
       for (int c0 = 0; c0 < 256; c0 += 32)
         epi_cols_to_block<false>(tlane + 256 + c0, sm.bias + bias_offset(L1) + c0, XB + (c0 >> 6) * kBlockBytes, r,
-                                 c0 & 63, c0 == 0 ? &x0 : nullptr);
+                                 c0 & 63, c0 == 0 ? &x0 : nullptr,
+                                 (sv.x && valid) ? reinterpret_cast<__nv_bfloat16*>(sv.x) + (size_t)row * 256 + c0 : nullptr);
       signal_a_ready(&sm.a_ready[E_X]);
       if (valid) {
         const float xin = x0 - 1.0f;
@@ -337,7 +349,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32)
         epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(HS0) + c0, HB + (2 + (c0 >> 6)) * kBlockBytes, r,
-                                c0 & 63);
+                                c0 & 63, nullptr,
+                                (sv.g && valid) ? reinterpret_cast<__nv_bfloat16*>(sv.g) + (size_t)row * 128 + c0 : nullptr);
       signal_a_ready(&sm.a_ready[E_G]);
 
       // ---- HS1: semantic softmax (19) + intensity
@@ -369,7 +382,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
 #pragma unroll 1
       for (int c0 = 0; c0 < 256; c0 += 32)
         epi_cols_to_block<true>(tlane + 256 + c0, sm.bias + bias_offset(V0) + c0, HB + (c0 >> 6) * kBlockBytes, r,
-                                c0 & 63);
+                                c0 & 63, nullptr,
+                                (sv.h1 && valid) ? reinterpret_cast<__nv_bfloat16*>(sv.h1) + (size_t)row * 256 + c0 : nullptr);
       signal_a_ready(&sm.a_ready[E_H1]);
 
       // ---- V1: h2 = relu(acc + b) -> H0..3
@@ -377,7 +391,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
       tcgen05_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < 256; c0 += 32)
-        epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(V1) + c0, HB + (c0 >> 6) * kBlockBytes, r, c0 & 63);
+        epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(V1) + c0, HB + (c0 >> 6) * kBlockBytes, r, c0 & 63,
+                                nullptr,
+                                (sv.h2 && valid) ? reinterpret_cast<__nv_bfloat16*>(sv.h2) + (size_t)row * 256 + c0 : nullptr);
       signal_a_ready(&sm.a_ready[E_H2]);
 
       // ---- RGB: sigmoid(acc + b) * (1 + 2 pad) - pad
@@ -401,6 +417,345 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
   __syncthreads();
   if (warp == 5) tmem_dealloc(tmem, 512);
 }
+
+// =============================================================================
+// Backward data-gradient chain (same machinery, transposed weights).
+//   dc   = g_rgb * 1.002 * s(1-s)                       [16]   (S block)
+//   dzv1 = (dc  . Wrgb)        * [h2 > 0]               [256]  (P blocks)
+//   dh1 | dxa = dzv1 . Wv1[:, h1 | x]                   [512]
+//   dzv0 = dh1 * [h1 > 0]                               [256]  (Q blocks)
+//   dx  += dzv0 . Wv0[:, x]
+//   dhs1 = softmax' (g_sem) | g_int                     [32]   (S block)
+//   dzg  = (dhs1 . Whs1) * [g > 0]                      [128]  (Q0,Q1)
+//   dx  += dzg . Whs0 ;  dx[0] += g_density * sigmoid(x0 - 1)  (P blocks)
+//   dz0  = (dx . W1) * [h0 > 0]                         [64]   (Q2)
+//   df   = dz0 . W0                                     [40]   -> grad_features
+// Every dZ is also written row-major bf16 for the weight-gradient GEMMs.
+namespace bwd {
+
+constexpr int BP = 0, BQ = 4, BS = 8;
+enum { B_RGB = 0, B_V1, B_V0, B_HS1, B_HS0, B_L1, B_L0, kNumBLayers };
+struct BLayerDef {
+  int N, nkb;
+  int a_blk[4];
+  int ksteps[4];
+  int tmem_col[4];  // per 128-column part of N
+  bool accumulate;  // add onto the existing accumulator (dx gathers three terms)
+};
+__host__ __device__ constexpr BLayerDef blayer_def(int l) {
+  switch (l) {
+    case B_RGB: return {256, 1, {BS}, {1}, {256, 384, 0, 0}, false};
+    case B_V1:  return {512, 4, {BP, BP + 1, BP + 2, BP + 3}, {4, 4, 4, 4}, {256, 384, 0, 128}, false};
+    case B_V0:  return {256, 4, {BQ, BQ + 1, BQ + 2, BQ + 3}, {4, 4, 4, 4}, {0, 128, 0, 0}, true};
+    case B_HS1: return {128, 1, {BS}, {2}, {256, 0, 0, 0}, false};
+    case B_HS0: return {256, 2, {BQ, BQ + 1}, {4, 4}, {0, 128, 0, 0}, true};
+    case B_L1:  return {64, 4, {BP, BP + 1, BP + 2, BP + 3}, {4, 4, 4, 4}, {256, 0, 0, 0}, false};
+    default:    return {48, 1, {BQ + 2}, {4}, {320, 0, 0, 0}, false};
+  }
+}
+__host__ __device__ constexpr int bl_nrows(int l) { return blayer_def(l).N > 128 ? 128 : blayer_def(l).N; }
+__host__ __device__ constexpr int bl_nparts(int l) { return (blayer_def(l).N + 127) / 128; }
+__host__ __device__ constexpr int bl_chunks(int l) { return blayer_def(l).nkb * bl_nparts(l); }
+__host__ __device__ constexpr int bl_chunk_bytes(int l) { return bl_nrows(l) * 128; }
+__host__ __device__ constexpr int bl_offset(int l) {
+  int o = 0;
+  for (int i = 0; i < l; ++i) o += bl_chunks(i) * bl_chunk_bytes(i);
+  return o;
+}
+constexpr int kPackedTBytes = bl_offset(kNumBLayers);
+
+// B operand of backward layer l: row n = index of the layer INPUT being differentiated,
+// column k = index of the pre-activation gradient being contracted
+__device__ float packed_weight_t(const nlb_nerf_mlp_weights_t& w, int l, int n, int k) {
+  switch (l) {
+    case B_RGB: return k < 3 ? w.W_rgb[k * 256 + n] : 0.f;                       // n: h2 unit
+    case B_V1:  return w.W_v1[k * 539 + n];                                       // n < 512: h1 | x
+    case B_V0:  return w.W_v0[k * 283 + n];                                       // n < 256: x
+    case B_HS1:                                                                   // n: hidden unit (128)
+      if (n < 64) return k < kSem ? w.W_s2[k * 64 + n] : 0.f;
+      return k == kSem ? w.W_i2[n - 64] : 0.f;
+    case B_HS0: return k < 64 ? w.W_s0[k * 256 + n] : w.W_i0[(k - 64) * 256 + n]; // n: x col
+    case B_L1:  return w.W_d2[k * 64 + n];                                        // n: h0 unit
+    default:    return n < kFeat ? w.W_d0[k * kFeat + n] : 0.f;                   // n: feature
+  }
+}
+
+__global__ void k_pack_t(nlb_nerf_mlp_weights_t w, uint8_t* __restrict__ blob) {
+  for (int l = 0; l < kNumBLayers; ++l) {
+    const BLayerDef d = blayer_def(l);
+    const int nrows = bl_nrows(l), np_count = bl_nparts(l);
+    const int total = d.nkb * np_count * nrows * 64;
+    const int kvalid = (l == B_RGB) ? 16 : (l == B_HS1 ? 32 : 64 * d.nkb);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+      const int c = e & 63;
+      const int r = (e >> 6) % nrows;
+      const int chunk = (e >> 6) / nrows;  // kb-major, n-part minor
+      const int kb = chunk / np_count, np = chunk % np_count;
+      const int k = kb * 64 + c;
+      const float v = k < kvalid ? packed_weight_t(w, l, np * 128 + r, k) : 0.f;
+      uint8_t* dst = blob + bl_offset(l) + (size_t)chunk * bl_chunk_bytes(l) + sw128_offset(r, c);
+      *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16(v);
+    }
+  }
+}
+
+struct BSmem {
+  uint64_t w_full[kStages], w_empty[kStages];
+  uint64_t acc_ready[kNumBLayers];
+  uint64_t a_ready[kNumBLayers];
+  uint32_t tmem_base;
+};
+
+// 32 accumulator columns -> (optional) ReLU mask from a saved bf16 activation -> block + global.
+// `act_row` / `gdst` always point at dereferenceable memory (the caller clamps the row
+// index); `write_g` predicates the global store.
+template <bool kMask>
+__device__ __forceinline__ void epi_masked(uint32_t taddr, const __nv_bfloat16* __restrict__ act_row, uint8_t* block,
+                                           int row, int col_in_block, __nv_bfloat16* gdst, bool write_g,
+                                           float add0 = 0.f) {
+  uint4 m[4];
+  if (kMask) {
+    const uint4* a4 = reinterpret_cast<const uint4*>(act_row);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) m[q] = __ldg(a4 + q);
+  }
+  float v[32];
+  tmem_ld32(taddr, v);
+  v[0] += add0;
+  if (kMask) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      // post-ReLU activations are >= 0: a unit was active iff its bf16 bits are non-zero (ignoring -0)
+      if ((m[q].x & 0x7FFFu) == 0) v[q * 8 + 0] = 0.f;
+      if ((m[q].x & 0x7FFF0000u) == 0) v[q * 8 + 1] = 0.f;
+      if ((m[q].y & 0x7FFFu) == 0) v[q * 8 + 2] = 0.f;
+      if ((m[q].y & 0x7FFF0000u) == 0) v[q * 8 + 3] = 0.f;
+      if ((m[q].z & 0x7FFFu) == 0) v[q * 8 + 4] = 0.f;
+      if ((m[q].z & 0x7FFF0000u) == 0) v[q * 8 + 5] = 0.f;
+      if ((m[q].w & 0x7FFFu) == 0) v[q * 8 + 6] = 0.f;
+      if ((m[q].w & 0x7FFF0000u) == 0) v[q * 8 + 7] = 0.f;
+    }
+  }
+  uint8_t* rowp = block + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int chunk = ((col_in_block >> 3) + q) ^ (row & 7);
+    uint4 u;
+    u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+    u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+    u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+    u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(rowp + chunk * 16) = u;
+    if (write_g) reinterpret_cast<uint4*>(gdst)[q] = u;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_in_t gi, nlb_nerf_mlp_saved_t sv, int M,
+                                                              const uint8_t* __restrict__ blob,
+                                                              float* __restrict__ grad_features,
+                                                              nlb_nerf_mlp_grad_out_t go) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_blocks = base;
+  uint8_t* w_ring = base + kNumABlocks * kBlockBytes;
+  BSmem& sm = *reinterpret_cast<BSmem*>(w_ring + kStages * kBlockBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (M + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
+    for (int i = 0; i < kNumBLayers; ++i) { mbar_init(&sm.acc_ready[i], 1); mbar_init(&sm.a_ready[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(&sm.tmem_base, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t c = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+#pragma unroll 1
+        for (int l = 0; l < kNumBLayers; ++l) {
+          const int n = bl_chunks(l), bytes = bl_chunk_bytes(l);
+          const uint8_t* src = blob + bl_offset(l);
+#pragma unroll 1
+          for (int i = 0; i < n; ++i, ++c) {
+            const int st = c % kStages;
+            mbar_wait(&sm.w_empty[st], ((c / kStages) & 1) ^ 1);
+            mbar_expect_tx(&sm.w_full[st], bytes);
+            bulk_g2s(w_ring + st * kBlockBytes, src + (size_t)i * bytes, bytes, &sm.w_full[st]);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      uint32_t c = 0, it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t ph = it & 1;
+#pragma unroll 1
+        for (int l = 0; l < kNumBLayers; ++l) {
+          mbar_wait(&sm.a_ready[l], ph);
+          tcgen05_fence_after();
+          const BLayerDef d = blayer_def(l);
+          const int nrows = bl_nrows(l), np_count = bl_nparts(l);
+          const uint32_t idesc = make_idesc_bf16(128, nrows);
+#pragma unroll 1
+          for (int kb = 0; kb < d.nkb; ++kb) {
+            const uint64_t adesc = make_desc_sw128(a_blocks + d.a_blk[kb] * kBlockBytes);
+#pragma unroll 1
+            for (int np = 0; np < np_count; ++np, ++c) {
+              const int st = c % kStages;
+              mbar_wait(&sm.w_full[st], (c / kStages) & 1);
+              tcgen05_fence_after();
+              const uint64_t bdesc = make_desc_sw128(w_ring + st * kBlockBytes);
+              const uint32_t dcol = tmem + d.tmem_col[np];
+#pragma unroll 1
+              for (int kk = 0; kk < d.ksteps[kb]; ++kk)
+                mma_bf16_ss(dcol, adesc + kk * 2, bdesc + kk * 2, idesc, d.accumulate || (kb | kk) != 0);
+              mma_commit(&sm.w_empty[st]);
+            }
+          }
+          mma_commit(&sm.acc_ready[l]);
+        }
+      }
+    }
+  } else {
+    const int r = threadIdx.x;
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    uint8_t* PB = a_blocks + BP * kBlockBytes;
+    uint8_t* QB = a_blocks + BQ * kBlockBytes;
+    uint8_t* SB = a_blocks + BS * kBlockBytes;
+    auto bf = [](void* p) { return reinterpret_cast<__nv_bfloat16*>(p); };
+    auto cbf = [](const void* p) { return reinterpret_cast<const __nv_bfloat16*>(p); };
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const int row = tile * 128 + r;
+      const bool valid = row < M;
+      const int crow = valid ? row : M - 1;  // clamped row: always dereferenceable
+      uint8_t* srow = SB + (r >> 3) * 1024 + (r & 7) * 128;
+      // ---- dc -> S (cols 0..2)
+      {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        if (valid && gi.g_rgb) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float s = (__ldg(gi.rgb + (size_t)row * 3 + i) + 0.001f) / (1.0f + 2.0f * 0.001f);
+            v[i] = __ldg(gi.g_rgb + (size_t)row * 3 + i) * (1.0f + 2.0f * 0.001f) * s * (1.0f - s);
+          }
+        }
+        store_cols(v, SB, r, 0, nullptr);
+        if (valid && go.d_rgb) {
+          uint4* dst = reinterpret_cast<uint4*>(bf(go.d_rgb) + (size_t)row * 16);
+          dst[0] = *reinterpret_cast<uint4*>(srow + ((0 ^ (r & 7)) * 16));
+          dst[1] = make_uint4(0, 0, 0, 0);
+        }
+      }
+      signal_a_ready(&sm.a_ready[B_RGB]);
+
+      // ---- dzv1 = dh2 * [h2 > 0] -> P0..3
+      mbar_wait(&sm.acc_ready[B_RGB], ph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32)
+        epi_masked<true>(tlane + 256 + c0, cbf(sv.h2) + (size_t)crow * 256 + c0, PB + (c0 >> 6) * kBlockBytes, r,
+                         c0 & 63, bf(go.d_v1) + (size_t)crow * 256 + c0, valid);
+      signal_a_ready(&sm.a_ready[B_V1]);
+
+      // ---- dzv0 = dh1 * [h1 > 0] -> Q0..3   (dh1 in accB, dx partial stays in accA)
+      mbar_wait(&sm.acc_ready[B_V1], ph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32)
+        epi_masked<true>(tlane + 256 + c0, cbf(sv.h1) + (size_t)crow * 256 + c0, QB + (c0 >> 6) * kBlockBytes, r,
+                         c0 & 63, bf(go.d_v0) + (size_t)crow * 256 + c0, valid);
+      signal_a_ready(&sm.a_ready[B_V0]);
+
+      // ---- d(sem logits) | d(intensity) -> S (cols 0..19); S is free: B_RGB completed above
+      {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        if (valid) {
+          if (gi.g_semantic) {
+            float p[kSem], g[kSem], dot = 0.f;
+#pragma unroll
+            for (int i = 0; i < kSem; ++i) {
+              p[i] = __ldg(gi.semantic + (size_t)row * kSem + i);
+              g[i] = __ldg(gi.g_semantic + (size_t)row * kSem + i);
+              dot = fmaf(p[i], g[i], dot);
+            }
+#pragma unroll
+            for (int i = 0; i < kSem; ++i) v[i] = p[i] * (g[i] - dot);
+          }
+          if (gi.g_intensity) v[kSem] = __ldg(gi.g_intensity + row);
+        }
+        store_cols(v, SB, r, 0, (valid && go.d_hs1) ? bf(go.d_hs1) + (size_t)row * 32 : nullptr);
+      }
+      signal_a_ready(&sm.a_ready[B_HS1]);
+
+      // ---- dzg = dg * [g > 0] -> Q0,Q1  (B_V0 has finished reading Q: it precedes B_HS1 on the pipe)
+      mbar_wait(&sm.acc_ready[B_HS1], ph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32)
+        epi_masked<true>(tlane + 256 + c0, cbf(sv.g) + (size_t)crow * 128 + c0, QB + (c0 >> 6) * kBlockBytes, r,
+                         c0 & 63, bf(go.d_g) + (size_t)crow * 128 + c0, valid);
+      signal_a_ready(&sm.a_ready[B_HS0]);
+
+      // ---- dx = accA (+ density term on column 0) -> P0..3
+      mbar_wait(&sm.acc_ready[B_HS0], ph);
+      tcgen05_fence_after();
+      {
+        float dterm = 0.f;
+        if (valid && gi.g_density) dterm = __ldg(gi.g_density + row) * (1.0f - expf(-__ldg(gi.density + row)));
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32)
+          epi_masked<false>(tlane + c0, nullptr, PB + (c0 >> 6) * kBlockBytes, r, c0 & 63,
+                            bf(go.d_x) + (size_t)crow * 256 + c0, valid, c0 == 0 ? dterm : 0.f);
+      }
+      signal_a_ready(&sm.a_ready[B_L1]);
+
+      // ---- dz0 = dh0 * [h0 > 0] -> Q2
+      mbar_wait(&sm.acc_ready[B_L1], ph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32)
+        epi_masked<true>(tlane + 256 + c0, cbf(sv.h0) + (size_t)crow * 64 + c0, QB + 2 * kBlockBytes, r, c0,
+                         bf(go.d_h0) + (size_t)crow * 64 + c0, valid);
+      signal_a_ready(&sm.a_ready[B_L0]);
+
+      // ---- grad_features = accB[64:112) (40 valid columns)
+      mbar_wait(&sm.acc_ready[B_L0], ph);
+      tcgen05_fence_after();
+      {
+        float v[32], t[16];
+        tmem_ld32(tlane + 320, v);
+        tmem_ld16(tlane + 352, t);
+        if (valid) {
+          float4* dst = reinterpret_cast<float4*>(grad_features + (size_t)row * kFeat);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          dst[8] = make_float4(t[0], t[1], t[2], t[3]);
+          dst[9] = make_float4(t[4], t[5], t[6], t[7]);
+        }
+      }
+      tcgen05_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 512);
+}
+
+constexpr size_t kBSmemBytes = 1024 + (kNumABlocks + kStages) * (size_t)kBlockBytes + sizeof(BSmem);
+
+}  // namespace bwd
 
 constexpr size_t kSmemBytes = 1024 + (kNumABlocks + kStages) * (size_t)kBlockBytes + sizeof(Smem);
 
@@ -428,7 +783,7 @@ extern "C" int nlb_nerf_mlp_pack(const nlb_nerf_mlp_weights_t* w, void* packed, 
 
 extern "C" int nlb_nerf_mlp_forward(const float* features, const float* viewdirs, int M, int rows_per_ray,
                                     const void* packed, float* density, float* rgb, float* semantic, float* intensity,
-                                    void* stream) {
+                                    const nlb_nerf_mlp_saved_t* saved, void* stream) {
   if (M == 0) return NLB_OK;
   if (!features || !viewdirs || !packed || !density || !rgb) { nlb_set_error("nerf_mlp_forward: null pointer"); return NLB_EINVAL; }
   if (rows_per_ray < 1) { nlb_set_error("nerf_mlp_forward: rows_per_ray must be >= 1"); return NLB_EINVAL; }
@@ -445,7 +800,44 @@ extern "C" int nlb_nerf_mlp_forward(const float* features, const float* viewdirs
   }
   const int tiles = (M + 127) / 128;
   const int grid = tiles < sms ? tiles : sms;
+  nlb_nerf_mlp_saved_t sv = {};
+  if (saved) sv = *saved;
   mlp::k_nerf_mlp_fwd<<<grid, mlp::kThreads, mlp::kSmemBytes, (cudaStream_t)stream>>>(
-      features, viewdirs, M, rows_per_ray, reinterpret_cast<const uint8_t*>(packed), density, rgb, semantic, intensity);
+      features, viewdirs, M, rows_per_ray, reinterpret_cast<const uint8_t*>(packed), density, rgb, semantic, intensity, sv);
   return nlb_check_launch("nerf_mlp_forward");
+}
+
+extern "C" size_t nlb_nerf_mlp_packed_transposed_bytes(void) { return mlp::bwd::kPackedTBytes; }
+
+extern "C" int nlb_nerf_mlp_pack_transposed(const nlb_nerf_mlp_weights_t* w, void* packed_t, void* stream) {
+  if (!w || !packed_t) { nlb_set_error("nerf_mlp_pack_transposed: null pointer"); return NLB_EINVAL; }
+  const void* const* p = reinterpret_cast<const void* const*>(w);
+  for (size_t i = 0; i < sizeof(*w) / sizeof(void*); ++i)
+    if (!p[i]) { nlb_set_error("nerf_mlp_pack_transposed: null weight pointer %zu", i); return NLB_EINVAL; }
+  mlp::bwd::k_pack_t<<<148, 256, 0, (cudaStream_t)stream>>>(*w, reinterpret_cast<uint8_t*>(packed_t));
+  return nlb_check_launch("nerf_mlp_pack_transposed");
+}
+
+extern "C" int nlb_nerf_mlp_backward(const nlb_nerf_mlp_grad_in_t* gin, const nlb_nerf_mlp_saved_t* saved, int M,
+                                     const void* packed_t, float* grad_features, const nlb_nerf_mlp_grad_out_t* gout,
+                                     void* stream) {
+  if (M == 0) return NLB_OK;
+  if (!gin || !saved || !packed_t || !grad_features || !gout) { nlb_set_error("nerf_mlp_backward: null pointer"); return NLB_EINVAL; }
+  if (!saved->h0 || !saved->g || !saved->h1 || !saved->h2) { nlb_set_error("nerf_mlp_backward: the activations saved by the forward are required"); return NLB_EINVAL; }
+  if ((gin->g_rgb && !gin->rgb) || (gin->g_semantic && !gin->semantic) || (gin->g_density && !gin->density)) {
+    nlb_set_error("nerf_mlp_backward: forward outputs are required next to their gradients");
+    return NLB_EINVAL;
+  }
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(mlp::bwd::k_nerf_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp::bwd::kBSmemBytes);
+  }
+  const int tiles = (M + 127) / 128;
+  const int grid = tiles < sms ? tiles : sms;
+  mlp::bwd::k_nerf_mlp_bwd<<<grid, mlp::kThreads, mlp::bwd::kBSmemBytes, (cudaStream_t)stream>>>(
+      *gin, *saved, M, reinterpret_cast<const uint8_t*>(packed_t), grad_features, *gout);
+  return nlb_check_launch("nerf_mlp_backward");
 }

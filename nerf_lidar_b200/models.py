@@ -60,7 +60,7 @@ class MLP(nn.Module):
     no_sem_layer: bool = True
     re_weights: bool = True
     mlp_dtype = torch.bfloat16  # operand type of the dense layers (fp32 accumulation)
-    fused_mlp: bool = True      # NerfMLP forward on the fused tcgen05 kernel when no autograd graph is needed
+    fused_mlp: bool = True      # NerfMLP on the fused tcgen05 kernels (False: plain torch GEMMs, dev/debug only)
 
     def __init__(self, **kwargs):
         super().__init__()
@@ -114,9 +114,11 @@ class MLP(nn.Module):
         tolerance 1e-3 vs the fp32 reference); activations are evaluated in fp32."""
         N = viewdirs.shape[0]
         dt = self.mlp_dtype
-        if (dt == torch.bfloat16 and not torch.is_grad_enabled() and self.use_semantic and self.use_intensity
-                and self.fused_mlp):
-            return ops.nerf_mlp_forward(self, feat, viewdirs, S)  # tcgen05 / TMEM kernel
+        if dt == torch.bfloat16 and self.use_semantic and self.use_intensity and self.fused_mlp:
+            # tcgen05 / TMEM kernels (forward; in training also the data-gradient chain)
+            if torch.is_grad_enabled():
+                return ops.nerf_mlp_train(self, feat, viewdirs, S)
+            return ops.nerf_mlp_forward(self, feat, viewdirs, S)
 
         def lin(layer, x):
             if dt == torch.float32:

@@ -19,7 +19,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import timed, NlbNerfMlpWeights, NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
+from ._lib import timed, NlbNerfMlpWeights, NlbNerfMlpSaved, NlbNerfMlpGradIn, NlbNerfMlpGradOut, NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
 
 EPS = float(torch.finfo(torch.float32).eps)
 _u_cache: Dict[Tuple, torch.Tensor] = {}
@@ -284,39 +284,123 @@ _NERF_WEIGHT_FIELDS = (('W_d0', 'density_layer.0.weight'), ('b_d0', 'density_lay
                        ('W_rgb', 'rgb_layer.weight'), ('b_rgb', 'rgb_layer.bias'))
 
 
-@torch.no_grad()
-def nerf_mlp_pack(mlp) -> torch.Tensor:
-    """Packs the NerfMLP dense layers into the bf16 operand-block blob the fused
-    kernel streams (nlb_nerf_mlp_pack).  Cached on the module and refreshed when any
-    parameter has been modified in place (optimizer step, load_state_dict)."""
+def _mlp_tensors(mlp):
     params = dict(mlp.named_parameters())
-    tensors = [params[name] for _, name in _NERF_WEIGHT_FIELDS]
+    return [params[name] for _, name in _NERF_WEIGHT_FIELDS]
+
+
+@torch.no_grad()
+def nerf_mlp_pack(mlp, transposed: bool = False) -> torch.Tensor:
+    """Packs the NerfMLP dense layers into the bf16 operand-block blob the fused
+    kernels stream (nlb_nerf_mlp_pack / _pack_transposed).  Cached on the module and
+    refreshed when any parameter has been modified in place (optimizer step,
+    load_state_dict)."""
+    tensors = _mlp_tensors(mlp)
     version = tuple((t.data_ptr(), t._version) for t in tensors)
-    cache = getattr(mlp, '_nlb_packed', None)
+    key = '_nlb_packed_t' if transposed else '_nlb_packed'
+    cache = getattr(mlp, key, None)
     if cache is not None and cache[0] == version:
         return cache[1]
     dev = tensors[0].device
-    blob = torch.empty(load().nlb_nerf_mlp_packed_bytes(), dtype=torch.uint8, device=dev)
+    lib = load()
+    nbytes = lib.nlb_nerf_mlp_packed_transposed_bytes() if transposed else lib.nlb_nerf_mlp_packed_bytes()
+    blob = cache[1] if cache is not None else torch.empty(nbytes, dtype=torch.uint8, device=dev)
     keep = [f32(t.detach()) for t in tensors]
     w = NlbNerfMlpWeights(*[ptr(t) for t in keep])
     with torch.cuda.device(dev):
-        check(load().nlb_nerf_mlp_pack(C.byref(w), ptr(blob), stream()))
-    mlp._nlb_packed = (version, blob)
+        fn = lib.nlb_nerf_mlp_pack_transposed if transposed else lib.nlb_nerf_mlp_pack
+        check(fn(C.byref(w), ptr(blob), stream()))
+    setattr(mlp, key, (version, blob))
     return blob
 
 
-@torch.no_grad()
-def nerf_mlp_forward(mlp, features: torch.Tensor, viewdirs: torch.Tensor, S: int) -> Dict[str, torch.Tensor]:
-    """Fused tcgen05 NerfMLP forward: features[N*S,40] -> density[N,S], rgb[N,S,3],
-    semantic[N,S,19], intensity[N,S,1]."""
-    features, viewdirs = f32(features), f32(viewdirs)
+def _mlp_forward_raw(mlp, features, viewdirs, S, save: bool):
     M, N = features.shape[0], viewdirs.shape[0]
     dev = features.device
     blob = nerf_mlp_pack(mlp)
     new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
     density, rgb, sem, inten = new(N, S), new(N, S, 3), new(N, S, 19), new(N, S, 1)
+    saved = None
+    sv = None
+    if save:
+        bf = lambda c: torch.empty(M, c, device=dev, dtype=torch.bfloat16)
+        saved = dict(h0=bf(64), x=bf(256), g=bf(128), h1=bf(256), h2=bf(256))
+        sv = NlbNerfMlpSaved(*[ptr(saved[k]) for k in ('h0', 'x', 'g', 'h1', 'h2')])
     with torch.cuda.device(dev):
         with timed('nerf_mlp_fwd'):
             check(load().nlb_nerf_mlp_forward(ptr(features), ptr(viewdirs), M, S, ptr(blob), ptr(density), ptr(rgb),
-                                              ptr(sem), ptr(inten), stream()))
+                                              ptr(sem), ptr(inten), C.byref(sv) if sv is not None else None, stream()))
+    return density, rgb, sem, inten, saved
+
+
+@torch.no_grad()
+def nerf_mlp_forward(mlp, features: torch.Tensor, viewdirs: torch.Tensor, S: int) -> Dict[str, torch.Tensor]:
+    """Fused tcgen05 NerfMLP forward (inference): features[N*S,40] -> density[N,S],
+    rgb[N,S,3], semantic[N,S,19], intensity[N,S,1]."""
+    density, rgb, sem, inten, _ = _mlp_forward_raw(mlp, f32(features), f32(viewdirs), S, False)
+    return dict(density=density, rgb=rgb, semantic=sem, intensity=inten)
+
+
+def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """bf16 x bf16 -> fp32 plain GEMM (cuBLAS): the weight-gradient products dZ^T A."""
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except TypeError:
+        return torch.mm(a, b).float()
+
+
+class _NerfMLP(Function):
+    """Training path of the NerfMLP: fused tcgen05 forward that saves bf16
+    activations, fused tcgen05 data-gradient chain, weight gradients as plain GEMMs."""
+
+    @staticmethod
+    def forward(ctx, features, viewdirs, mlp, S, *weights):
+        features, viewdirs = f32(features), f32(viewdirs)
+        density, rgb, sem, inten, saved = _mlp_forward_raw(mlp, features, viewdirs, S, True)
+        ctx.mlp, ctx.S = mlp, S
+        ctx.save_for_backward(features, viewdirs, density, rgb, sem, *[saved[k] for k in ('h0', 'x', 'g', 'h1', 'h2')])
+        return density, rgb, sem, inten
+
+    @staticmethod
+    def backward(ctx, g_density, g_rgb, g_sem, g_int):
+        features, viewdirs, density, rgb, sem, h0, x, g, h1, h2 = ctx.saved_tensors
+        mlp, S = ctx.mlp, ctx.S
+        M, N = features.shape[0], viewdirs.shape[0]
+        dev = features.device
+        c = lambda t: None if t is None else f32(t)
+        g_density, g_rgb, g_sem, g_int = c(g_density), c(g_rgb), c(g_sem), c(g_int)
+        blob_t = nerf_mlp_pack(mlp, transposed=True)
+        bf = lambda cols: torch.empty(M, cols, device=dev, dtype=torch.bfloat16)
+        d_rgb, d_v1, d_v0, d_hs1, d_g, d_x, d_h0 = bf(16), bf(256), bf(256), bf(32), bf(128), bf(256), bf(64)
+        g_feat = torch.empty(M, 40, device=dev, dtype=torch.float32)
+        gin = NlbNerfMlpGradIn(ptr(g_density), ptr(g_rgb), ptr(g_sem), ptr(g_int), ptr(density), ptr(rgb), ptr(sem))
+        sv = NlbNerfMlpSaved(ptr(h0), ptr(x), ptr(g), ptr(h1), ptr(h2))
+        gout = NlbNerfMlpGradOut(ptr(d_rgb), ptr(d_v1), ptr(d_v0), ptr(d_hs1), ptr(d_g), ptr(d_x), ptr(d_h0))
+        with torch.cuda.device(dev):
+            with timed('nerf_mlp_bwd'):
+                check(load().nlb_nerf_mlp_backward(C.byref(gin), C.byref(sv), M, ptr(blob_t), ptr(g_feat),
+                                                   C.byref(gout), stream()))
+        # weight gradients: plain GEMMs dW = dZ^T A (bf16 operands, fp32 result)
+        colsum = lambda t: t.sum(0, dtype=torch.float32)
+        de = mlp.dir_enc(viewdirs)                                   # [N,27] per-ray constant
+        ray_sum = lambda t: t.view(N, S, -1).sum(1, dtype=torch.float32)
+        f0 = features.to(torch.bfloat16)
+        gW = {
+            'W_d0': _mm_f32(d_h0.t(), f0), 'b_d0': colsum(d_h0),
+            'W_d2': _mm_f32(d_x.t(), h0), 'b_d2': colsum(d_x),
+            'W_s0': _mm_f32(d_g[:, :64].t(), x), 'b_s0': colsum(d_g[:, :64]),
+            'W_s2': _mm_f32(d_hs1[:, :19].t(), g[:, :64]), 'b_s2': colsum(d_hs1[:, :19]),
+            'W_i0': _mm_f32(d_g[:, 64:].t(), x), 'b_i0': colsum(d_g[:, 64:]),
+            'W_i2': _mm_f32(d_hs1[:, 19:20].t(), g[:, 64:]), 'b_i2': colsum(d_hs1[:, 19:20]),
+            'W_v0': torch.cat([_mm_f32(d_v0.t(), x), ray_sum(d_v0).t() @ de], dim=1), 'b_v0': colsum(d_v0),
+            'W_v1': torch.cat([_mm_f32(d_v1.t(), h1), _mm_f32(d_v1.t(), x), ray_sum(d_v1).t() @ de], dim=1),
+            'b_v1': colsum(d_v1),
+            'W_rgb': _mm_f32(d_rgb[:, :3].t(), h2), 'b_rgb': colsum(d_rgb[:, :3]),
+        }
+        grads = [gW[name] for name, _ in _NERF_WEIGHT_FIELDS]
+        return (g_feat, None, None, None, *grads)
+
+
+def nerf_mlp_train(mlp, features: torch.Tensor, viewdirs: torch.Tensor, S: int) -> Dict[str, torch.Tensor]:
+    density, rgb, sem, inten = _NerfMLP.apply(features, viewdirs, mlp, S, *_mlp_tensors(mlp))
     return dict(density=density, rgb=rgb, semantic=sem, intensity=inten)

@@ -51,3 +51,53 @@ def test_repack_after_weight_update():
         mlp.rgb_layer.bias.add_(1.0)
     b = ops.nerf_mlp_forward(mlp, feat, vd, 32)['rgb']
     assert float((a - b).abs().max()) > 1e-2
+
+
+def test_fused_mlp_backward_vs_autograd():
+    """Gradients of the fused training path against autograd through the oracle MLP
+    evaluated with the same bf16 operand rounding."""
+    from nerf_lidar_b200 import configs, models, ops
+    sd = synthetic.init_state_dict(seed=33, table_std=0.3, small_tables=True)
+    n_rays, S = 150, 32
+    g = torch.Generator().manual_seed(5)
+    feat = torch.randn(n_rays, S, 40, generator=g) * 0.5
+    vd = torch.nn.functional.normalize(torch.randn(n_rays, 3, generator=g), dim=-1)
+    cd, cr, cs, ci = (torch.randn(n_rays, S, generator=g), torch.randn(n_rays, S, 3, generator=g),
+                      torch.randn(n_rays, S, 19, generator=g), torch.randn(n_rays, S, 1, generator=g))
+
+    def loss(o, dev):
+        return ((o['density'] * cd.to(dev)).sum() + (o['rgb'] * cr.to(dev)).sum()
+                + (o['semantic'] * cs.to(dev)).sum() + (o['intensity'] * ci.to(dev)).sum())
+
+    # straight-through bf16 rounding so autograd sees the same forward values
+    class Q(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, t):
+            return t.to(torch.bfloat16).to(torch.float32)
+
+        @staticmethod
+        def backward(ctx, gr):
+            return gr
+
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'encoder' not in k else v) for k, v in sd.items()}
+    fr = feat.clone().requires_grad_(True)
+    loss(zo.nerf_mlp(p, fr, vd, cast=Q.apply), 'cpu').backward()
+
+    model = models.Model(configs.nuscenes_single())
+    mlp = model.nerf_mlp.cuda()
+    mlp.load_state_dict({k[len('nerf_mlp.'):]: v for k, v in sd.items()
+                         if k.startswith('nerf_mlp.') and 'encoder' not in k}, strict=False)
+    fc = feat.reshape(-1, 40).cuda().requires_grad_(True)
+    out = ops.nerf_mlp_train(mlp, fc, vd.cuda(), S)
+    loss(out, 'cuda').backward()
+
+    def rel_l2(a, b):
+        return float((a.cpu().float() - b).norm() / (b.norm() + 1e-20))
+
+    assert rel_l2(fc.grad.reshape(n_rays, S, 40), fr.grad) < 2e-2
+    for name, prm in mlp.named_parameters():
+        if 'encoder' in name:
+            continue
+        want = p['nerf_mlp.' + name].grad
+        assert prm.grad is not None, name
+        assert rel_l2(prm.grad, want) < 3e-2, (name, rel_l2(prm.grad, want))
