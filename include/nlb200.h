@@ -243,6 +243,25 @@ int nlb_nerf_mlp_backward(const nlb_nerf_mlp_grad_in_t* gin, const nlb_nerf_mlp_
                           const void* packed_t, float* grad_features /*[M,40]*/,
                           const nlb_nerf_mlp_grad_out_t* gout, void* stream);
 
+/* Dev probe: clock64() stamps of block 0's MMA thread / epilogue thread for the first two
+ * tiles of nlb_nerf_mlp_forward are written to buf[128] (int64); NULL switches it off. */
+int nlb_debug_set_timeline(void* buf);
+
+/* ------------------------------------------------------------------ per-ray regularisers
+ * Value and gradient (w.r.t. the weights only; distances are detached in the
+ * reference) in one pass.
+ * distortion: stepfun.lossfun_distortion (Z/internal/stepfun.py:297-307);
+ *   loss_ray[N], grad_w[N,S] = d loss_ray / d weights.
+ * interlevel: train_utils.anti_interlevel_loss for ONE proposal level
+ *   (Z/internal/train_utils.py:134-172, stepfun.blur_stepfun, math.sorted_interp_quad);
+ *   (c[N,Sc+1], w[N,Sc]) = final level, (cp[N,Sp+1], wp[N,Sp]) = proposal level;
+ *   loss_ray[N] = sum over the Sp intervals, grad_wp[N,Sp] = d loss_ray / d wp.
+ */
+int nlb_distortion_loss(const float* sdist, const float* weights, int N, int S, float* loss_ray, float* grad_w,
+                        void* stream);
+int nlb_interlevel_loss(const float* c, const float* w, int Sc, const float* cp, const float* wp, int Sp,
+                        float pulse_width, int N, float* loss_ray, float* grad_wp, void* stream);
+
 /* ------------------------------------------------------------------ optimizer
  * One fused pass per table: hash-decay gradient (Model.hash_decay_loss,
  * Z/internal/models.py:203-223: d/dp of mult * mean_levels(mean_rows(p^2)))
@@ -251,7 +270,9 @@ int nlb_nerf_mlp_backward(const nlb_nerf_mlp_grad_in_t* gin, const nlb_nerf_mlp_
  */
 int nlb_adam_table_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
                         const int32_t* offsets_host /*[L+1], HOST memory*/, int L, int C, float decay_mult, float lr, float beta1,
-                        float beta2, float eps, int step, float grad_scale, void* stream);
+                        float beta2, float eps, int step, float grad_scale,
+                        float* level_sumsq /*[L] += per-level sum of squares of the UPDATED table, or NULL*/,
+                        void* stream);
 int nlb_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
 

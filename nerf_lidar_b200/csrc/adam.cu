@@ -36,10 +36,20 @@ template <bool kDecay>
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ param, float* __restrict__ grad,
                                               float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int64_t n,
                                               DecayTable dt, float lr_c, float rsqrt_bc2, float beta1, float beta2,
-                                              float eps, float grad_scale) {
+                                              float eps, float grad_scale, float* __restrict__ level_sumsq) {
+  __shared__ float s_sum[kMaxLevels];
+  if (kDecay && level_sumsq) {
+    if (threadIdx.x < kMaxLevels) s_sum[threadIdx.x] = 0.f;
+    __syncthreads();
+  }
   const int64_t n4 = n >> 2;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+  // blocked partition: a block owns one contiguous range, so it sees one (rarely two) levels
+  const int64_t per_block = (n4 + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * per_block;
+  const int64_t hi = lo + per_block < n4 ? lo + per_block : n4;
+  int cur_l = -1;
+  float sq = 0.f;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     float4 p = reinterpret_cast<float4*>(param)[i];
     float4 g = reinterpret_cast<float4*>(grad)[i];
     float4 m = reinterpret_cast<float4*>(exp_avg)[i];
@@ -47,9 +57,14 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ param, float* 
     float coef = 0.f;
     if (kDecay) {
       const int64_t e = i << 2;  // level sizes are multiples of 8 rows, so a float4 never straddles levels
-      int l = 0;
+      int l = cur_l < 0 ? 0 : cur_l;
       while (l < dt.L - 1 && e >= dt.end[l]) ++l;
       coef = dt.coef[l];
+      if (level_sumsq && l != cur_l) {
+        if (cur_l >= 0) atomicAdd(&s_sum[cur_l], sq);
+        sq = 0.f;
+        cur_l = l;
+      }
     }
     float gx = scrub(fmaf(p.x, coef, g.x * grad_scale));
     float gy = scrub(fmaf(p.y, coef, g.y * grad_scale));
@@ -63,6 +78,12 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ param, float* 
     reinterpret_cast<float4*>(exp_avg)[i] = m;
     reinterpret_cast<float4*>(exp_avg_sq)[i] = v;
     reinterpret_cast<float4*>(grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kDecay && level_sumsq) sq += p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;  // UPDATED parameters
+  }
+  if (kDecay && level_sumsq) {
+    if (cur_l >= 0) atomicAdd(&s_sum[cur_l], sq);
+    __syncthreads();
+    if (threadIdx.x < dt.L && s_sum[threadIdx.x] != 0.f) atomicAdd(level_sumsq + threadIdx.x, s_sum[threadIdx.x]);
   }
   // tail (n not a multiple of 4): dense-layer tensors only
   if (!kDecay && blockIdx.x == 0) {
@@ -88,7 +109,8 @@ static void bias_terms(float lr, float beta1, float beta2, int step, float& lr_c
 
 extern "C" int nlb_adam_table_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
                                    const int32_t* offsets_host, int L, int C, float decay_mult, float lr, float beta1,
-                                   float beta2, float eps, int step, float grad_scale, void* stream) {
+                                   float beta2, float eps, int step, float grad_scale, float* level_sumsq,
+                                   void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || !offsets_host) { nlb_set_error("adam_table_step: null pointer"); return NLB_EINVAL; }
   if (L < 1 || L > kMaxLevels) { nlb_set_error("adam_table_step: L=%d outside [1,%d]", L, kMaxLevels); return NLB_EINVAL; }
   if (step < 1) { nlb_set_error("adam_table_step: step counts from 1"); return NLB_EINVAL; }
@@ -105,9 +127,9 @@ extern "C" int nlb_adam_table_step(float* param, float* grad, float* exp_avg, fl
   bias_terms(lr, beta1, beta2, step, lr_c, rs);
   const int blocks = 148 * 8;
   if (decay_mult != 0.f)
-    k_adam<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale);
+    k_adam<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale, level_sumsq);
   else
-    k_adam<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale);
+    k_adam<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale, nullptr);
   return nlb_check_launch("adam_table_step");
 }
 
@@ -126,6 +148,6 @@ extern "C" int nlb_adam_step(float* param, float* grad, float* exp_avg, float* e
   bias_terms(lr, beta1, beta2, step, lr_c, rs);
   int64_t want = (n / 4 + 255) / 256;
   const int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
-  k_adam<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale);
+  k_adam<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale, nullptr);
   return nlb_check_launch("adam_step");
 }

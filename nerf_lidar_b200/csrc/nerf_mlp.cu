@@ -30,7 +30,7 @@ constexpr int kBlockBytes = 16384;            // [128][64] bf16
 // shared-memory A blocks
 constexpr int BX = 0, BH = 4, BD = 8, kNumABlocks = 9;
 constexpr int kStages = 4;
-constexpr int kThreads = 192;
+constexpr int kThreads = 288;  // warps 0-3 epilogue, 4 MMA issuer, 5-8 weight producers (one per ring stage)
 
 struct LayerDef {
   int N, nkb;
@@ -115,6 +115,12 @@ __global__ void k_pack(nlb_nerf_mlp_weights_t w, uint8_t* __restrict__ blob) {
   }
 }
 
+// optional timeline of block 0 / first two tiles (dev tool: nlb_debug_set_timeline)
+__device__ long long* g_timeline = nullptr;
+__device__ __forceinline__ void stamp(int slot) {
+  if (g_timeline && blockIdx.x == 0) g_timeline[slot] = clock64();
+}
+
 // ----------------------------------------------------------------------------- kernel
 struct Smem {
   uint64_t w_full[kStages], w_empty[kStages];
@@ -193,15 +199,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
   }
   for (int i = threadIdx.x; i < kBiasFloats; i += kThreads)
     sm.bias[i] = reinterpret_cast<const float*>(blob + kWeightBytes)[i];
-  if (warp == 5) tmem_alloc(&sm.tmem_base, 512);
+  if (warp == 4) tmem_alloc(&sm.tmem_base, 512);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp == 4) {
-    // ===== weight producer: streams the packed chunks of every tile through the ring
+  if (warp >= 5) {
+    // ===== weight producers: a 1-D bulk copy costs its issuing thread ~800 cycles whatever its
+    // size and consecutive copies of one thread do not overlap (tools/bulk_probe.cu), but
+    // different warps issue concurrently -> one producer warp per ring stage.
     if (lane == 0) {
+      const int my_stage = warp - 5;
       uint32_t c = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
 #pragma unroll 1
@@ -211,6 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
 #pragma unroll 1
           for (int i = 0; i < n; ++i, ++c) {
             const int st = c % kStages;
+            if (st != my_stage) continue;
             mbar_wait(&sm.w_empty[st], ((c / kStages) & 1) ^ 1);
             mbar_expect_tx(&sm.w_full[st], bytes);
             bulk_g2s(w_ring + st * kBlockBytes, src + (size_t)i * bytes, bytes, &sm.w_full[st]);
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 4) {
     // ===== MMA issuer (one thread)
     if (lane == 0) {
       uint32_t c = 0, it = 0;
@@ -232,26 +242,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
 #pragma unroll 1
           for (int nh = 0; nh < nh_count; ++nh, ++c) {
             const int st = c % kStages;
+            const bool trace = (l == V1 && it == 0);
+            if (trace) stamp(32 + (kb * 2 + nh) * 3 + 0 > 95 ? 95 : 32 + (kb * 2 + nh) * 3 + 0);
             mbar_wait(&sm.w_full[st], (c / kStages) & 1);
             tcgen05_fence_after();
+            if (trace && kb * 2 + nh < 10) stamp(32 + (kb * 2 + nh) * 3 + 1);
             const uint64_t bdesc = make_desc_sw128(w_ring + st * kBlockBytes);
             const uint32_t dcol = tmem + d.tmem_col + nh * 128;
 #pragma unroll 1
             for (int kk = 0; kk < d.ksteps[kb]; ++kk)
               mma_bf16_ss(dcol, adesc + kk * 2, bdesc + kk * 2, idesc, (kb | kk) != 0);
             mma_commit(&sm.w_empty[st]);
+            if (trace && kb * 2 + nh < 10) stamp(32 + (kb * 2 + nh) * 3 + 2);
           }
         }
         mma_commit(&sm.acc_ready[l]);
       };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const uint32_t ph = it & 1;
-        mbar_wait(&sm.a_ready[E_F], ph);  tcgen05_fence_after(); run_layer(L0);
-        mbar_wait(&sm.a_ready[E_H0], ph); tcgen05_fence_after(); run_layer(L1);
-        mbar_wait(&sm.a_ready[E_X], ph);  tcgen05_fence_after(); run_layer(HS0); run_layer(V0);
-        mbar_wait(&sm.a_ready[E_G], ph);  tcgen05_fence_after(); run_layer(HS1);
-        mbar_wait(&sm.a_ready[E_H1], ph); tcgen05_fence_after(); run_layer(V1);
-        mbar_wait(&sm.a_ready[E_H2], ph); tcgen05_fence_after(); run_layer(RGB);
+        const int tb = it < 2 ? (int)it * 16 : -1000;
+        if (tb >= 0) stamp(tb + 0);
+        mbar_wait(&sm.a_ready[E_F], ph);  tcgen05_fence_after(); if (tb >= 0) stamp(tb + 1); run_layer(L0); if (tb >= 0) stamp(tb + 2);
+        mbar_wait(&sm.a_ready[E_H0], ph); tcgen05_fence_after(); if (tb >= 0) stamp(tb + 3); run_layer(L1); if (tb >= 0) stamp(tb + 4);
+        mbar_wait(&sm.a_ready[E_X], ph);  tcgen05_fence_after(); if (tb >= 0) stamp(tb + 5); run_layer(HS0); if (tb >= 0) stamp(tb + 6); run_layer(V0); if (tb >= 0) stamp(tb + 7);
+        mbar_wait(&sm.a_ready[E_G], ph);  tcgen05_fence_after(); if (tb >= 0) stamp(tb + 8); run_layer(HS1); if (tb >= 0) stamp(tb + 9);
+        mbar_wait(&sm.a_ready[E_H1], ph); tcgen05_fence_after(); if (tb >= 0) stamp(tb + 10); run_layer(V1); if (tb >= 0) stamp(tb + 11);
+        mbar_wait(&sm.a_ready[E_H2], ph); tcgen05_fence_after(); if (tb >= 0) stamp(tb + 12); run_layer(RGB); if (tb >= 0) stamp(tb + 13);
       }
     }
   } else {
@@ -318,10 +334,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
         }
       }
       signal_a_ready(&sm.a_ready[E_F]);
+      if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 14);
 
       // ---- L0: h0 = relu(acc + b) -> H1
+      if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 0);
       mbar_wait(&sm.acc_ready[L0], ph);
       tcgen05_fence_after();
+      if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 1);
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32)
         epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(L0) + c0, HB + 1 * kBlockBytes, r, c0, nullptr,
@@ -329,8 +348,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
       signal_a_ready(&sm.a_ready[E_H0]);
 
       // ---- L1: x = acc + b -> X0..3 ; density = softplus(x[0] - 1)
+      if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 2);
       mbar_wait(&sm.acc_ready[L1], ph);
       tcgen05_fence_after();
+      if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 3);
       float x0 = 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < 256; c0 += 32)
@@ -344,8 +365,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
       }
 
       // ---- HS0: hidden = relu(acc + b) -> H2, H3
+      if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 4);
       mbar_wait(&sm.acc_ready[HS0], ph);
       tcgen05_fence_after();
+      if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 5);
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32)
         epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(HS0) + c0, HB + (2 + (c0 >> 6)) * kBlockBytes, r,
@@ -354,8 +377,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
       signal_a_ready(&sm.a_ready[E_G]);
 
       // ---- HS1: semantic softmax (19) + intensity
+      if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 6);
       mbar_wait(&sm.acc_ready[HS1], ph);
       tcgen05_fence_after();
+      if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 7);
       {
         float v[32];
         tmem_ld32(tlane + 128, v);
@@ -377,8 +402,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
       }
 
       // ---- V0: h1 = relu(acc + b) -> H0..3
+      if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 8);
       mbar_wait(&sm.acc_ready[V0], ph);
       tcgen05_fence_after();
+      if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 9);
 #pragma unroll 1
       for (int c0 = 0; c0 < 256; c0 += 32)
         epi_cols_to_block<true>(tlane + 256 + c0, sm.bias + bias_offset(V0) + c0, HB + (c0 >> 6) * kBlockBytes, r,
@@ -387,8 +414,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
       signal_a_ready(&sm.a_ready[E_H1]);
 
       // ---- V1: h2 = relu(acc + b) -> H0..3
+      if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 10);
       mbar_wait(&sm.acc_ready[V1], ph);
       tcgen05_fence_after();
+      if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 11);
 #pragma unroll 1
       for (int c0 = 0; c0 < 256; c0 += 32)
         epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(V1) + c0, HB + (c0 >> 6) * kBlockBytes, r, c0 & 63,
@@ -397,8 +426,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
       signal_a_ready(&sm.a_ready[E_H2]);
 
       // ---- RGB: sigmoid(acc + b) * (1 + 2 pad) - pad
+      if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 12);
       mbar_wait(&sm.acc_ready[RGB], ph);
       tcgen05_fence_after();
+      if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 13);
       {
         float v[16];
         tmem_ld16(tlane + 256, v);
@@ -567,14 +598,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
     for (int i = 0; i < kNumBLayers; ++i) { mbar_init(&sm.acc_ready[i], 1); mbar_init(&sm.a_ready[i], 128); }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(&sm.tmem_base, 512);
+  if (warp == 4) tmem_alloc(&sm.tmem_base, 512);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp == 4) {
+  if (warp >= 5) {
     if (lane == 0) {
+      const int my_stage = warp - 5;
       uint32_t c = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
 #pragma unroll 1
@@ -584,6 +616,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
 #pragma unroll 1
           for (int i = 0; i < n; ++i, ++c) {
             const int st = c % kStages;
+            if (st != my_stage) continue;
             mbar_wait(&sm.w_empty[st], ((c / kStages) & 1) ^ 1);
             mbar_expect_tx(&sm.w_full[st], bytes);
             bulk_g2s(w_ring + st * kBlockBytes, src + (size_t)i * bytes, bytes, &sm.w_full[st]);
@@ -591,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 4) {
     if (lane == 0) {
       uint32_t c = 0, it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -750,7 +783,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
     }
   }
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 512);
+  if (warp == 4) tmem_dealloc(tmem, 512);
 }
 
 constexpr size_t kBSmemBytes = 1024 + (kNumABlocks + kStages) * (size_t)kBlockBytes + sizeof(BSmem);
@@ -840,4 +873,10 @@ extern "C" int nlb_nerf_mlp_backward(const nlb_nerf_mlp_grad_in_t* gin, const nl
   mlp::bwd::k_nerf_mlp_bwd<<<grid, mlp::kThreads, mlp::bwd::kBSmemBytes, (cudaStream_t)stream>>>(
       *gin, *saved, M, reinterpret_cast<const uint8_t*>(packed_t), grad_features, *gout);
   return nlb_check_launch("nerf_mlp_backward");
+}
+
+extern "C" int nlb_debug_set_timeline(void* buf) {
+  long long* p = reinterpret_cast<long long*>(buf);
+  cudaError_t e = cudaMemcpyToSymbol(nlb::mlp::g_timeline, &p, sizeof(p));
+  return e == cudaSuccess ? 0 : NLB_ECUDA;
 }

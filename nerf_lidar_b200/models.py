@@ -292,7 +292,8 @@ class Model(nn.Module):
             for r in renderings[:-1]:
                 r['ray_rgbs'] = torch.broadcast_to(final_rgb[:, None, :], r['ray_rgbs'].shape)
         if self.config.hash_decay_mults > 0 and self.training:
-            renderings[-1]['hash_decay'] = self.hash_decay_loss()
+            cached = getattr(self, '_hash_decay_value', None)  # produced by the fused optimizer pass
+            renderings[-1]['hash_decay'] = cached if cached is not None else self.hash_decay_loss()
         return renderings, ray_history
 
 

@@ -404,3 +404,55 @@ class _NerfMLP(Function):
 def nerf_mlp_train(mlp, features: torch.Tensor, viewdirs: torch.Tensor, S: int) -> Dict[str, torch.Tensor]:
     density, rgb, sem, inten = _NerfMLP.apply(features, viewdirs, mlp, S, *_mlp_tensors(mlp))
     return dict(density=density, rgb=rgb, semantic=sem, intensity=inten)
+
+
+# ----------------------------------------------------------------------------- per-ray regularisers
+class _Distortion(Function):
+    @staticmethod
+    def forward(ctx, sdist, weights):
+        sdist, weights = f32(sdist), f32(weights)
+        N, S = weights.shape
+        loss = torch.empty(N, device=weights.device, dtype=torch.float32)
+        grad = torch.empty_like(weights)
+        with torch.cuda.device(weights.device):
+            with timed('distortion'):
+                check(load().nlb_distortion_loss(ptr(sdist), ptr(weights), N, S, ptr(loss), ptr(grad), stream()))
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return None, grad * g[:, None]
+
+
+def distortion_per_ray(sdist: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+    """stepfun.lossfun_distortion(sdist, weights) -> [N]."""
+    return _Distortion.apply(sdist, weights)
+
+
+class _Interlevel(Function):
+    @staticmethod
+    def forward(ctx, c, w, cp, wp, pulse_width):
+        c, w, cp, wp = f32(c), f32(w), f32(cp), f32(wp)
+        N, Sc = w.shape
+        Sp = wp.shape[1]
+        loss = torch.empty(N, device=wp.device, dtype=torch.float32)
+        grad = torch.empty_like(wp)
+        with torch.cuda.device(wp.device):
+            with timed('interlevel'):
+                check(load().nlb_interlevel_loss(ptr(c), ptr(w), Sc, ptr(cp), ptr(wp), Sp, float(pulse_width), N,
+                                                 ptr(loss), ptr(grad), stream()))
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return None, None, None, grad * g[:, None], None
+
+
+def interlevel_per_ray(c, w, cp, wp, pulse_width: float) -> torch.Tensor:
+    """Sum over the proposal intervals of max(w_s - wp, 0)^2 / (wp + 1e-5) -> [N];
+    (c, w) are the detached final-level histogram."""
+    return _Interlevel.apply(c.detach(), w.detach(), cp.detach(), wp, pulse_width)

@@ -134,7 +134,19 @@ def interp_quad(x, xp, fpdf, fcdf):
 
 
 def anti_interlevel_loss(ray_history, config: Config):
-    """train_utils.py:134-172."""
+    """train_utils.py:134-172 on the fused kernel (csrc/losses.cu)."""
+    from . import ops
+    last = ray_history[-1]
+    total = 0.
+    for i, rr in enumerate(ray_history[:-1]):
+        per_ray = ops.interlevel_per_ray(last['sdist'], last['weights'], rr['sdist'], rr['weights'],
+                                         config.pulse_width[i])
+        total = total + per_ray.sum() / (rr['weights'].shape[0] * rr['weights'].shape[1])
+    return config.anti_interlevel_loss_mult * total
+
+
+def anti_interlevel_loss_torch(ray_history, config: Config):
+    """The same loss with plain torch ops (kept for cross-checking the kernel)."""
     last = ray_history[-1]
     c = last['sdist'].detach()
     w = last['weights'].detach()
@@ -151,7 +163,15 @@ def anti_interlevel_loss(ray_history, config: Config):
 
 
 def distortion_loss(ray_history, config: Config):
-    """stepfun.lossfun_distortion (Z/internal/stepfun.py:297-307) on the final level."""
+    """stepfun.lossfun_distortion (Z/internal/stepfun.py:297-307) on the final level,
+    fused kernel (csrc/losses.cu)."""
+    from . import ops
+    t, w = ray_history[-1]['sdist'], ray_history[-1]['weights']
+    return config.distortion_loss_mult * ops.distortion_per_ray(t, w).mean()
+
+
+def distortion_loss_torch(ray_history, config: Config):
+    """The same loss with plain torch ops (kept for cross-checking the kernel)."""
     t, w = ray_history[-1]['sdist'], ray_history[-1]['weights']
     ut = (t[..., 1:] + t[..., :-1]) / 2
     dut = (ut[..., :, None] - ut[..., None, :]).abs()
@@ -222,9 +242,13 @@ class Trainer:
             if name.endswith('encoder.embeddings'):
                 enc = model.get_submodule(name.rsplit('.', 2)[0]).encoder
                 p._nlb_grad = torch.zeros_like(p)
+                offs = enc.offsets.tolist()
+                counts = torch.tensor([(offs[i + 1] - offs[i]) * enc.level_dim for i in range(enc.num_levels)],
+                                      dtype=torch.float32, device=p.device)
                 self.tables.append(dict(name=name, param=p, enc=enc, grad=p._nlb_grad,
                                         m=torch.zeros_like(p), v=torch.zeros_like(p),
-                                        offsets=(C.c_int32 * (enc.num_levels + 1))(*enc.offsets.tolist())))
+                                        sumsq=torch.zeros(enc.num_levels, device=p.device), counts=counts,
+                                        offsets=(C.c_int32 * (enc.num_levels + 1))(*offs)))
             else:
                 dense.append(p)
         # largest table first: it is the first gradient to be final in the backward pass
@@ -277,14 +301,23 @@ class Trainer:
         scale = 1.0 / self.world
         lib = _lib.load()
         st = _lib.stream()
+        decay_value = None
         for t in self.tables:
             enc = t['enc']
             decay = 0. if (c.obj_nodecay and 'obj' in t['name']) else self.decay
+            t['sumsq'].zero_()
             with _lib.timed('adam_table'):
-              _lib.check(lib.nlb_adam_table_step(t['param'].data_ptr(), t['grad'].data_ptr(), t['m'].data_ptr(),
-                                               t['v'].data_ptr(), t['offsets'], enc.num_levels, enc.level_dim,
-                                               float(decay), float(lr), c.adam_beta1, c.adam_beta2, c.adam_eps,
-                                               int(step), scale, st))
+                _lib.check(lib.nlb_adam_table_step(t['param'].data_ptr(), t['grad'].data_ptr(), t['m'].data_ptr(),
+                                                   t['v'].data_ptr(), t['offsets'], enc.num_levels, enc.level_dim,
+                                                   float(decay), float(lr), c.adam_beta1, c.adam_beta2, c.adam_eps,
+                                                   int(step), scale, t['sumsq'].data_ptr(), st))
+            if decay > 0:
+                # Model.hash_decay_loss of the UPDATED table: mean over levels of the per-level mean square
+                v = (t['sumsq'] / t['counts']).mean()
+                decay_value = v if decay_value is None else decay_value + v
+        if decay_value is not None:
+            # the next forward reports this as renderings[-1]['hash_decay'] without re-reading 310 MB of tables
+            self.model._hash_decay_value = self.decay * decay_value
         _lib.check(lib.nlb_adam_step(self.flat.data_ptr(), self.flat_grad.data_ptr(), self.flat_m.data_ptr(),
                                      self.flat_v.data_ptr(), self.flat.numel(), float(lr), c.adam_beta1,
                                      c.adam_beta2, c.adam_eps, int(step), scale, st))

@@ -84,9 +84,12 @@ def test_fused_decay_adam_vs_torch():
         pr.grad.nan_to_num_()
         opt.step()
         gd.copy_(grad.cuda() * 2.0)  # grad_scale 0.5 below (data-parallel mean)
+        sumsq = torch.zeros(L, device='cuda')
         _lib.check(lib.nlb_adam_table_step(pd.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), offs_c, L, Cc,
-                                           mult, lr, 0.9, 0.99, 1e-15, step, 0.5, _lib.stream()))
+                                           mult, lr, 0.9, 0.99, 1e-15, step, 0.5, sumsq.data_ptr(), _lib.stream()))
         assert float(gd.abs().sum()) == 0.0  # gradient buffer cleared for the next step
+        want_sq = torch.stack([(pd[offs[l]:offs[l + 1]].double() ** 2).sum() for l in range(L)]).float()
+        assert_close(sumsq, want_sq, 1e-4, 'per-level sum of squares of the updated table')
         ok = torch.isfinite(grad)
         assert_close(pd.cpu()[ok], pr.detach()[ok], 1e-5, f'params after step {step}')
 
@@ -105,6 +108,8 @@ def test_trainer_runs_and_learns():
         out = tr.train_step(batch, 6000 + i, (B // 4) // 1024)
         if first is None:
             first = float(out['data'])
+        # the hash-decay value handed over by the fused optimizer pass equals the direct evaluation
+        assert abs(float(model._hash_decay_value) - float(model.hash_decay_loss())) <= 1e-4 * float(model.hash_decay_loss())
     assert float(out['data']) < first
     for p in model.parameters():
         assert torch.isfinite(p).all()
