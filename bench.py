@@ -177,16 +177,21 @@ def run_cuda_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(n_steps, first_step, e2e):
+    step_fn = trainer.train_step if args.eager else trainer.train_step_graphed
+
+    def timed_loop(n_steps, first_step, e2e, fn=None):
+        fn = fn or step_fn
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(n_steps):
-            if e2e:
+            if e2e and fn == trainer.train_step:
                 b = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_pool].items()}
+            elif e2e:
+                b = host[i % n_pool]       # pinned host tensors: the graphed step copies them into its static buffers
             else:
                 b = resident[i % n_pool]
-            out = trainer.train_step(b, first_step + i, num_patch)
+            out = fn(b, first_step + i, num_patch)
             if e2e:
                 loss_pin.copy_(out['loss'].reshape(1), non_blocking=True)
                 torch.cuda.current_stream().synchronize()  # the user reads the loss every step
@@ -203,15 +208,20 @@ def run_cuda_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    _lib.TIMER = _lib.KernelTimer() if rank == 0 else None
-    launches0 = _lib.LAUNCHES
     ms = timed_loop(args.steps, step0 + 100, False)
-    launches = _lib.LAUNCHES - launches0
-    kt = _lib.TIMER.summary() if _lib.TIMER is not None else {}
-    _lib.TIMER = None
     clocks = sampler.stop() if rank == 0 else None
     timed_loop(2, step0 + 200, True)
     ms_e2e = timed_loop(args.steps, step0 + 300, True)
+    # per-kernel device times (roofline): the same steps issued eagerly with CUDA events around every
+    # ABI call on the launching stream (events cannot be read back from inside a replayed graph)
+    timed_loop(2, step0 + 400, False, trainer.train_step)
+    _lib.TIMER = _lib.KernelTimer() if rank == 0 else None
+    launches0 = _lib.LAUNCHES
+    n_prof = min(args.steps, 5)
+    ms_eager = timed_loop(n_prof, step0 + 500, False, trainer.train_step)
+    launches = (_lib.LAUNCHES - launches0) // n_prof * args.steps   # ABI calls per step x timed steps
+    kt = _lib.TIMER.summary() if _lib.TIMER is not None else {}
+    _lib.TIMER = None
 
     if rank != 0:
         if world > 1:
@@ -236,7 +246,7 @@ def run_cuda_arm(args):
             alg = ADAM_BYTES_PER_PARAM * 77346760 / 3.0  # three tables per step, averaged per launch
         else:
             alg = None
-        per_kernel[name] = {'launches': count, 'avg_ms': avg, 'share_of_step': total_ms / ms,
+        per_kernel[name] = {'launches': count, 'avg_ms': avg, 'share_of_step': total_ms / n_prof / (ms / args.steps),
                             'alg_gbs': (alg / (avg * 1e-3) / 1e9) if alg else None}
     dom = max((k for k in per_kernel if per_kernel[k]['alg_gbs']), key=lambda k: per_kernel[k]['share_of_step'],
               default=None)
@@ -262,6 +272,8 @@ def run_cuda_arm(args):
                    'rays_per_step_nominal_per_gpu': BATCH, 'rays_through_model_per_gpu': rays_model,
                    'global_batch': BATCH * world, 'samples': list(SAMPLES), 'multisamples': 7,
                    'params': 77656777, 'parallelism': f'dp{world}',
+                   'launch': 'eager' if args.eager else 'whole training step replayed as one CUDA graph',
+                   'eager_ms_per_step': ms_eager / n_prof,
                    'l2_policy': 'inputs larger than L2: 1.24 GB of table + optimizer state streamed every step, '
                                 'batches rotate over a pool of 4'},
         'clocks': clocks,
@@ -284,6 +296,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eager', action='store_true', help='issue the step eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

@@ -109,6 +109,8 @@ typedef struct {
   int L, C;
   uint32_t H;                /* base resolution */
   float S;                   /* log2(per_level_scale) */
+  const int32_t* offsets_host; /* [L+1] HOST copy of `offsets` (launch shapes, validation: hashed levels
+                                  must be powers of two, as GridEncoder builds them) */
 } nlb_table_t;
 
 /* Parity probe: the sample points the fused kernels generate, points[N,S,7,4] =
@@ -273,6 +275,16 @@ int nlb_adam_table_step(float* param, float* grad, float* exp_avg, float* exp_av
                         float beta2, float eps, int step, float grad_scale,
                         float* level_sumsq /*[L] += per-level sum of squares of the UPDATED table, or NULL*/,
                         void* stream);
+/* CUDA-graph support.  The scalars that change every training step -- the resampling
+ * anneal (Z/internal/models.py:343-349) and Adam's learning rate / bias corrections --
+ * are by-value arguments above, which a captured graph would freeze.  When a device buffer
+ * dyn[3] = {anneal, lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t)} is registered here,
+ * nlb_resample, nlb_adam_table_step and nlb_adam_step read these three from it at kernel
+ * execution time instead (NULL restores the by-value behaviour).  nlb_adam_bias_terms
+ * computes dyn[1], dyn[2] exactly as the by-value path does (host, double precision). */
+int nlb_set_dynamic_scalars(const float* dev);
+int nlb_adam_bias_terms(float lr, float beta1, float beta2, int step, float* out2 /*host [2]*/);
+
 int nlb_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
 

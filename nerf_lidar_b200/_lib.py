@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libnlb200.so')
+LIB_PATH = os.environ.get('NLB_LIB') or os.path.join(_HERE, 'libnlb200.so')  # NLB_LIB: dev A/B builds only
 
 c_f = C.c_void_p  # device pointers travel as void*
 
@@ -23,7 +23,7 @@ class NlbRays(C.Structure):
 
 class NlbTable(C.Structure):
     _fields_ = [('embeddings', c_f), ('offsets', c_f), ('grid_sizes', c_f), ('L', C.c_int), ('C', C.c_int),
-                ('H', C.c_uint32), ('S', C.c_float)]
+                ('H', C.c_uint32), ('S', C.c_float), ('offsets_host', C.POINTER(C.c_int32))]
 
 
 class NlbCompositeIn(C.Structure):
@@ -91,6 +91,8 @@ SIGNATURES = {
     'nlb_distortion_loss': (_i, [_p, _p, _i, _i, _p, _p, _p]),
     'nlb_interlevel_loss': (_i, [_p, _p, _i, _p, _p, _i, _f, _i, _p, _p, _p]),
     'nlb_adam_table_step': (_i, [_p, _p, _p, _p, C.POINTER(C.c_int32), _i, _i, _f, _f, _f, _f, _f, _i, _f, _p, _p]),
+    'nlb_set_dynamic_scalars': (_i, [_p]),
+    'nlb_adam_bias_terms': (_i, [_f, _f, _f, _i, C.POINTER(C.c_float)]),
     'nlb_adam_step': (_i, [_p, _p, _p, _p, C.c_int64, _f, _f, _f, _f, _i, _f, _p]),
 }
 

@@ -36,8 +36,13 @@ template <bool kDecay>
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ param, float* __restrict__ grad,
                                               float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int64_t n,
                                               DecayTable dt, float lr_c, float rsqrt_bc2, float beta1, float beta2,
-                                              float eps, float grad_scale, float* __restrict__ level_sumsq) {
+                                              float eps, float grad_scale, float* __restrict__ level_sumsq,
+                                              const float* __restrict__ dyn) {
   __shared__ float s_sum[kMaxLevels];
+  if (dyn) {  // CUDA-graph replay: this step's learning rate and bias corrections
+    lr_c = __ldg(dyn + NLB_DYN_LR_C);
+    rsqrt_bc2 = __ldg(dyn + NLB_DYN_RSQRT_BC2);
+  }
   if (kDecay && level_sumsq) {
     if (threadIdx.x < kMaxLevels) s_sum[threadIdx.x] = 0.f;
     __syncthreads();
@@ -127,9 +132,9 @@ extern "C" int nlb_adam_table_step(float* param, float* grad, float* exp_avg, fl
   bias_terms(lr, beta1, beta2, step, lr_c, rs);
   const int blocks = 148 * 8;
   if (decay_mult != 0.f)
-    k_adam<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale, level_sumsq);
+    k_adam<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale, level_sumsq, nlb_dynamic_scalars());
   else
-    k_adam<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale, nullptr);
+    k_adam<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale, nullptr, nlb_dynamic_scalars());
   return nlb_check_launch("adam_table_step");
 }
 
@@ -148,6 +153,6 @@ extern "C" int nlb_adam_step(float* param, float* grad, float* exp_avg, float* e
   bias_terms(lr, beta1, beta2, step, lr_c, rs);
   int64_t want = (n / 4 + 255) / 256;
   const int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
-  k_adam<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale, nullptr);
+  k_adam<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale, nullptr, nlb_dynamic_scalars());
   return nlb_check_launch("adam_step");
 }

@@ -1,6 +1,7 @@
 // Error plumbing and library-level entry points of libnlb200.
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cuda_runtime.h>
 #include "common.cuh"
 #include "../../include/nlb200.h"
@@ -33,4 +34,25 @@ extern "C" int nlb_device_ok(void) {
   cudaDeviceProp p;
   if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
   return p.major == 10 ? 1 : 0;
+}
+
+// ---------------------------------------------------------------- CUDA-graph support
+// Scalars that change every training step (see include/nlb200.h).  The pointer is
+// process-global host state; kernels receive it as an argument at launch/capture time
+// and read the values at execution time.
+static const float* g_dyn = nullptr;
+const float* nlb_dynamic_scalars() { return g_dyn; }
+
+extern "C" int nlb_set_dynamic_scalars(const float* dev) {
+  g_dyn = dev;
+  return NLB_OK;
+}
+
+extern "C" int nlb_adam_bias_terms(float lr, float beta1, float beta2, int step, float* out2) {
+  if (!out2 || step < 1) { nlb_set_error("adam_bias_terms: bad arguments"); return NLB_EINVAL; }
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  out2[0] = (float)((double)lr / bc1);
+  out2[1] = (float)(1.0 / sqrt(bc2));
+  return NLB_OK;
 }

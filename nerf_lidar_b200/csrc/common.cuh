@@ -60,14 +60,34 @@ __device__ __forceinline__ uint32_t vertex_index(const uint32_t pg[D], uint32_t 
 }
 
 // D = 3, hash grid, align_corners = false: the configuration of every encoder
-// on the zipnerf path.  `dense` is a per-level constant so the branch is uniform.
+// on the zipnerf path.  `dense` is a per-level constant.
 struct Level3 {
   float scale;
   uint32_t hashmap_size;
   uint32_t offset;
   uint32_t s1, s2;  // dense strides (res+1), (res+1)^2
+  uint32_t mask;    // hashmap_size - 1 (hashed levels are powers of two, validated on the host)
   bool dense;       // (res+1)^3 <= hashmap_size
 };
+
+// Host/device replay of the reference's stride walk (gridencoder.cu:66-84): a level is
+// dense when (res+1)^3 fits the level, hashed otherwise.
+__host__ __device__ inline bool level_is_dense(uint32_t resolution, uint32_t hashmap_size, uint32_t& s1, uint32_t& s2) {
+  uint32_t stride = 1;
+  const uint32_t step = resolution + 1;
+  s1 = s2 = 0;
+  bool stopped = false;
+  for (int d = 0; d < 3; ++d) {
+    if (!stopped && stride <= hashmap_size) {
+      if (d == 1) s1 = stride;
+      if (d == 2) s2 = stride;
+      stride *= step;
+    } else {
+      stopped = true;
+    }
+  }
+  return !(stride > hashmap_size);
+}
 
 __device__ __forceinline__ Level3 level3(const int32_t* __restrict__ offsets, uint32_t level, float S, uint32_t H) {
   LevelGeom g = level_geom(offsets, level, S, H);
@@ -75,34 +95,31 @@ __device__ __forceinline__ Level3 level3(const int32_t* __restrict__ offsets, ui
   v.scale = g.scale;
   v.hashmap_size = g.hashmap_size;
   v.offset = g.offset;
-  // replay the reference's stride walk once per level
-  uint32_t stride = 1;
-  const uint32_t step = g.resolution + 1;
-  v.s1 = v.s2 = 0;
-  bool stopped = false;
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    if (!stopped && stride <= g.hashmap_size) {
-      if (d == 1) v.s1 = stride;
-      if (d == 2) v.s2 = stride;
-      stride *= step;
-    } else {
-      stopped = true;
-    }
-  }
-  v.dense = !(stride > g.hashmap_size);
+  v.mask = g.hashmap_size - 1;
+  v.dense = level_is_dense(g.resolution, g.hashmap_size, v.s1, v.s2);
   return v;
 }
 
+// Row index of a vertex of a cell inside the unit cube, branch-free.  Dense levels need no
+// modulo there (corner <= res on every axis, so idx <= (res+1)^3 - 1 < hashmap_size);
+// hashed levels are powers of two (GridEncoder sizes them 2^log2_hashmap_size; the C API
+// rejects anything else), so the reference's `% hashmap_size` is a mask.
 __device__ __forceinline__ uint32_t vertex_index3(const Level3& lv, uint32_t x, uint32_t y, uint32_t z) {
-  uint32_t idx;
-  if (lv.dense) {
-    idx = x + y * lv.s1 + z * lv.s2;
-  } else {
-    idx = x ^ (y * 2654435761u) ^ (z * 805459861u);
-  }
-  // hashed levels on this path are powers of two (2^21); keep the general modulo
-  // for dense levels whose size is rounded up to a multiple of 8.
+  const uint32_t lin = x + y * lv.s1 + z * lv.s2;
+  const uint32_t h = (x ^ (y * 2654435761u) ^ (z * 805459861u)) & lv.mask;
+  return lv.dense ? lin : h;
+}
+
+// Same index with a (warp-uniform) branch on the level type and the reference's general
+// modulo kept for non-power-of-two levels.  Which form ptxas schedules better was measured
+// on B200 (tools/kernel_times.py): with this form it keeps all eight 16-byte corner loads
+// of a C=4 lookup in flight (64 registers, 0.555 ms for the NeRF level forward) where the
+// select form splits them in two groups (47 registers, 0.72 ms); for the 4-byte C=1
+// lookups the select form wins (prop levels 0.38 / 0.67 ms against 0.55 / 1.01 ms, L1
+// sector hit rate 51 % against 16 %).
+__device__ __forceinline__ uint32_t vertex_index3_branchy(const Level3& lv, uint32_t x, uint32_t y, uint32_t z) {
+  if (lv.dense) return x + y * lv.s1 + z * lv.s2;
+  const uint32_t idx = x ^ (y * 2654435761u) ^ (z * 805459861u);
   return ((lv.hashmap_size & (lv.hashmap_size - 1)) == 0) ? (idx & (lv.hashmap_size - 1)) : (idx % lv.hashmap_size);
 }
 
@@ -263,3 +280,6 @@ __device__ __forceinline__ float warp_scan_incl(float v, int lane) {
 // error plumbing shared by all translation units
 void nlb_set_error(const char* fmt, ...);
 int nlb_check_launch(const char* what);
+// device buffer of step-varying scalars {anneal, lr_c, rsqrt_bc2} or nullptr (nlb_set_dynamic_scalars)
+const float* nlb_dynamic_scalars();
+enum { NLB_DYN_ANNEAL = 0, NLB_DYN_LR_C = 1, NLB_DYN_RSQRT_BC2 = 2 };

@@ -13,10 +13,13 @@
 // Launch order is level-major (blockIdx.y = level) for the NeRF table so one 33.5 MB
 // level is L2-resident at a time; lanes of a warp are consecutive intervals of the
 // same ray, so coarse-level gathers coalesce in L1.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/nlb200.h"
 
 namespace nlb {
+
+constexpr int kMaxLevelsEnc = 16;
 
 template <int C>
 __device__ __forceinline__ void gather_row(const float* __restrict__ p, float (&v)[C]) {
@@ -63,6 +66,19 @@ __device__ __forceinline__ void corner_weights(float fx, float fy, float fz, flo
   }
 }
 
+// Per-level constants, computed once per block into shared memory.
+struct LevelCache {
+  Level3 lv[kMaxLevelsEnc];
+  int gs[kMaxLevelsEnc];
+};
+
+__device__ __forceinline__ void fill_level_cache(LevelCache& lc, const nlb_table_t& tab) {
+  if (threadIdx.x < tab.L) {
+    lc.lv[threadIdx.x] = level3(tab.offsets, threadIdx.x, tab.S, tab.H);
+    lc.gs[threadIdx.x] = __ldg(tab.grid_sizes + threadIdx.x);
+  }
+}
+
 // Interpolated feature of one point at one level (same accumulation order as
 // kernel_grid, gridencoder.cu:166-191).
 template <int C>
@@ -78,7 +94,8 @@ __device__ __forceinline__ void lookup(const float* __restrict__ table, const Le
   float rows[8][C];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    uint32_t idx = vertex_index3(lv, cx + (i & 1), cy + ((i >> 1) & 1), cz + ((i >> 2) & 1));
+    const uint32_t vx = cx + (i & 1), vy = cy + ((i >> 1) & 1), vz = cz + ((i >> 2) & 1);
+    const uint32_t idx = (C == 1) ? vertex_index3(lv, vx, vy, vz) : vertex_index3_branchy(lv, vx, vy, vz);
     gather_row<C>(table + ((size_t)lv.offset + idx) * C, rows[i]);
   }
 #pragma unroll
@@ -135,60 +152,102 @@ __device__ __forceinline__ void level_feature(const float* __restrict__ table, c
   for (int c = 0; c < C; ++c) acc[c] = acc[c] / 7.0f;
 }
 
-// Scatter helper: accumulates corner coefficients of consecutive multisamples that
-// fall in the same cell and issues one vector reduction per corner when the cell
-// changes (coarse levels: 8 instead of 56 reductions per interval).
-template <int C>
-struct CellScatter {
-  uint32_t cx, cy, cz;
-  float w[8];
-  bool live;
-  __device__ __forceinline__ CellScatter() : cx(0), cy(0), cz(0), live(false) {
+// ----------------------------------------------------------------------------- scatter (backward)
+// Adds v[C] into row `idx` of level `lv`: shared-memory accumulator (kStaged) or one
+// vector reduction to the global gradient table.
+template <int C, bool kStaged>
+__device__ __forceinline__ void add_row(float* __restrict__ acc, const Level3& lv, uint32_t idx, const float (&v)[C]) {
+  float* dst = acc + ((size_t)lv.offset + idx) * C;
+  if constexpr (kStaged) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = 0.f;
+    for (int c = 0; c < C; ++c) atomicAdd(dst + c, v[c]);
+  } else {
+    red_add_row<C>(dst, v);
   }
-  __device__ __forceinline__ void flush(float* __restrict__ grad_table, const Level3& lv, const float (&g)[C]) {
-    if (!live) return;
+}
+
+// Scatter of one level's feature gradient g (already divided by 7) over the 7 samples of
+// one interval.  Consecutive samples that fall in the same cell are merged before the 8
+// corner reductions are issued (coarse levels: 8 instead of 56 per interval); the loop
+// runs one sentinel iteration so there is a single flush site.
+//   kStaged: the level lives in the block's shared-memory accumulator `acc` (indexed like
+//            the table, offset included); otherwise reductions go to the global table.
+//   kWarpAgg (dense levels; the whole warp must call, `has_g` masks idle lanes): lanes are
+//            consecutive intervals of one ray, so neighbouring lanes end in the same cell;
+//            each lane's last cell group is summed over runs of equal cells with a
+//            segmented shuffle reduction and only the run head issues the 8 reductions.
+//            Every ray of a scene starts in the same few coarse cells -- without this,
+//            L2 serialises millions of same-address atomics (measured: 0.4 ms per level).
+template <int C, bool kStaged, bool kWarpAgg>
+__device__ __forceinline__ void level_scatter(float* __restrict__ acc, const Level3& lv, int gs,
+                                              const float4 (*s_pts)[kEncThreads], const float (&g)[C], bool has_g) {
+  uint32_t cx = 0, cy = 0, cz = 0;
+  float w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = 0.f;
+  bool live = false;
+  constexpr int kLast = kWarpAgg ? 6 : 7;  // the sentinel iteration flushes the last group
+#pragma unroll 1
+  for (int j = 0; j <= kLast; ++j) {
+    float4 p = make_float4(0.f, 0.f, 0.f, -1.f);
+    if (j < 7) p = s_pts[j][threadIdx.x];
+    const bool valid = has_g && p.w >= 0.f;
+    uint32_t nx = 0, ny = 0, nz = 0;
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    if (valid) {
+      cell_of(p.x, lv.scale, nx, fx);
+      cell_of(p.y, lv.scale, ny, fy);
+      cell_of(p.z, lv.scale, nz, fz);
+    }
+    if (live && (j == 7 || (valid && (nx != cx || ny != cy || nz != cz)))) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t idx = vertex_index3(lv, cx + (i & 1), cy + ((i >> 1) & 1), cz + ((i >> 2) & 1));
+        float v[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c] = g[c] * w[i];
+        add_row<C, kStaged>(acc, lv, idx, v);
+        w[i] = 0.f;
+      }
+      live = false;
+    }
+    if (valid) {
+      cx = nx; cy = ny; cz = nz;
+      live = true;
+      const float coef = erf_weight(p.w, gs);
+      float cw[8];
+      corner_weights(fx, fy, fz, cw);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = fmaf(coef, cw[i], w[i]);
+    }
+  }
+  if constexpr (kWarpAgg) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t key = live ? (cx + cy * lv.s1 + cz * lv.s2) : 0xffffffffu;  // dense level: unique per cell
+    const uint32_t prev = __shfl_up_sync(NLB_FULL_MASK, key, 1);
+    const bool head = lane == 0 || key != prev || !live;
+    const uint32_t heads = __ballot_sync(NLB_FULL_MASK, head);
+    const uint32_t later = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+    const int run_end = later ? __ffs(later) - 1 : 32;  // exclusive end of this lane's run
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      uint32_t idx = vertex_index3(lv, cx + (i & 1), cy + ((i >> 1) & 1), cz + ((i >> 2) & 1));
       float v[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) v[c] = g[c] * w[i];
-      red_add_row<C>(grad_table + ((size_t)lv.offset + idx) * C, v);
-      w[i] = 0.f;
-    }
-    live = false;
-  }
-  __device__ __forceinline__ void add(float* __restrict__ grad_table, const Level3& lv, const float (&g)[C],
-                                      float x, float y, float z, float coef) {
-    uint32_t nx, ny, nz;
-    float fx, fy, fz;
-    cell_of(x, lv.scale, nx, fx);
-    cell_of(y, lv.scale, ny, fy);
-    cell_of(z, lv.scale, nz, fz);
-    if (live && (nx != cx || ny != cy || nz != cz)) flush(grad_table, lv, g);
-    cx = nx; cy = ny; cz = nz;
-    live = true;
-    float cw[8];
-    corner_weights(fx, fy, fz, cw);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = fmaf(coef, cw[i], w[i]);
+      for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float t = __shfl_down_sync(NLB_FULL_MASK, v[c], o);
+          if (lane + o < run_end) v[c] += t;
+        }
+      }
+      if (head && live) {
+        const uint32_t idx = vertex_index3(lv, cx + (i & 1), cy + ((i >> 1) & 1), cz + ((i >> 2) & 1));
+        add_row<C, kStaged>(acc, lv, idx, v);
+      }
+    }
   }
-};
-
-// scatter of one level's feature gradient g (already divided by 7) over the 7 samples
-template <int C>
-__device__ __forceinline__ void level_scatter(float* __restrict__ grad_table, const Level3& lv, int gs,
-                                              const float4 (*s_pts)[kEncThreads], const float (&g)[C]) {
-  CellScatter<C> sc;
-#pragma unroll 1
-  for (int j = 0; j < 7; ++j) {
-    const float4 p = s_pts[j][threadIdx.x];
-    if (p.w < 0.f) continue;
-    sc.add(grad_table, lv, g, p.x, p.y, p.z, erf_weight(p.w, gs));
-  }
-  sc.flush(grad_table, lv, g);
 }
 
 // ----------------------------------------------------------------------------- NeRF level
@@ -196,15 +255,18 @@ template <int C>
 __global__ void __launch_bounds__(kEncThreads) k_encode_fwd(nlb_rays_t rays, nlb_table_t tab,
                                                             float* __restrict__ features) {
   __shared__ float4 s_pts[7][kEncThreads];
+  __shared__ LevelCache lc;
+  fill_level_cache(lc, tab);
+  __syncthreads();
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rays.N * rays.S) return;
   stage_points(rays, row, s_pts);
   float* out = features + (size_t)row * (tab.L * C);
 #pragma unroll 1
   for (int level = 0; level < tab.L; ++level) {
-    const Level3 lv = level3(tab.offsets, level, tab.S, tab.H);
+    const Level3 lv = lc.lv[level];
     float acc[C];
-    level_feature<C>(tab.embeddings, lv, __ldg(tab.grid_sizes + level), s_pts, acc);
+    level_feature<C>(tab.embeddings, lv, lc.gs[level], s_pts, acc);
     if constexpr (C == 4) {
       *reinterpret_cast<float4*>(out + level * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     } else if constexpr (C == 2) {
@@ -216,25 +278,59 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_fwd(nlb_rays_t rays, nlb
   }
 }
 
+// Backward of the fused encode for the levels [level_begin, level_end): persistent blocks
+// (a multiple of the SM count) walk the 128-interval tiles.  Dense (coarse) levels use the
+// warp-aggregated scatter; the coarsest ones that fit the shared-memory budget
+// (`staged_rows` table rows, chosen by the host) are additionally accumulated in a
+// per-block shared-memory copy of those rows and flushed once per block; hashed levels go
+// to L2 as one vector reduction per corner.  The host launches the fine levels in groups
+// whose gradient rows fit L2 together (level-major order), so a 33.5 MB level stays
+// resident while it is being updated.
 template <int C>
 __global__ void __launch_bounds__(kEncThreads) k_encode_bwd(nlb_rays_t rays, nlb_table_t tab,
                                                             const float* __restrict__ grad_features,
-                                                            float* __restrict__ grad_table) {
+                                                            float* __restrict__ grad_table, int staged_rows,
+                                                            int num_tiles, int level_begin, int level_end) {
+  extern __shared__ __align__(16) float s_acc[];  // [staged_rows * C]
   __shared__ float4 s_pts[7][kEncThreads];
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= rays.N * rays.S) return;
-  stage_points(rays, row, s_pts);
-  const float* gin = grad_features + (size_t)row * (tab.L * C);
+  __shared__ LevelCache lc;
+  fill_level_cache(lc, tab);
+  for (int i = threadIdx.x; i < staged_rows * C; i += kEncThreads) s_acc[i] = 0.f;
+  __syncthreads();
+  const int rows_total = rays.N * rays.S;
+  const int LC = tab.L * C;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int row = tile * kEncThreads + threadIdx.x;
+    const bool row_ok = row < rows_total;
+    if (row_ok) stage_points(rays, row, s_pts);  // column threadIdx.x is private to this thread: no barrier
+    const float* gin = grad_features + (size_t)row * LC;
 #pragma unroll 1
-  for (int level = 0; level < tab.L; ++level) {
-    float g[C];
-    gather_row<C>(gin + level * C, g);
-    bool any = false;
+    for (int level = level_begin; level < level_end; ++level) {
+      float g[C];
+      bool any = false;
+      if (row_ok) {
+        gather_row<C>(gin + level * C, g);
 #pragma unroll
-    for (int c = 0; c < C; ++c) { g[c] = g[c] / 7.0f; any |= (g[c] != 0.f); }
-    if (!any) continue;
-    const Level3 lv = level3(tab.offsets, level, tab.S, tab.H);
-    level_scatter<C>(grad_table, lv, __ldg(tab.grid_sizes + level), s_pts, g);
+        for (int c = 0; c < C; ++c) { g[c] = g[c] / 7.0f; any |= (g[c] != 0.f); }
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) g[c] = 0.f;
+      }
+      const Level3 lv = lc.lv[level];
+      if (lv.dense) {  // uniform per level: the whole warp takes the same branch
+        if ((int)(lv.offset + lv.hashmap_size) <= staged_rows)
+          level_scatter<C, true, true>(s_acc, lv, lc.gs[level], s_pts, g, any);
+        else
+          level_scatter<C, false, true>(grad_table, lv, lc.gs[level], s_pts, g, any);
+      } else if (any) {
+        level_scatter<C, false, false>(grad_table, lv, lc.gs[level], s_pts, g, true);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < staged_rows * C; i += kEncThreads) {
+    const float v = s_acc[i];
+    if (v != 0.f) atomicAdd(grad_table + i, v);
   }
 }
 
@@ -282,6 +378,8 @@ __global__ void __launch_bounds__(kEncThreads) k_prop_fwd(nlb_rays_t rays, nlb_t
   __shared__ PropSmem sm;
   __shared__ float4 s_pts[7][kEncThreads];
   __shared__ float s_f[L][kEncThreads];
+  __shared__ LevelCache lc;
+  fill_level_cache(lc, tab);
   load_prop_weights(sm, L, W0, b0, W1, b1);
   __syncthreads();
   const int tid = threadIdx.x;
@@ -290,9 +388,9 @@ __global__ void __launch_bounds__(kEncThreads) k_prop_fwd(nlb_rays_t rays, nlb_t
   stage_points(rays, row, s_pts);
 #pragma unroll 1
   for (int l = 0; l < L; ++l) {
-    const Level3 lv = level3(tab.offsets, l, tab.S, tab.H);
+    const Level3 lv = lc.lv[l];
     float acc[1];
-    level_feature<1>(tab.embeddings, lv, __ldg(tab.grid_sizes + l), s_pts, acc);
+    level_feature<1>(tab.embeddings, lv, lc.gs[l], s_pts, acc);
     s_f[l][tid] = acc[0];
     if (features) features[(size_t)row * L + l] = acc[0];
   }
@@ -312,101 +410,105 @@ __global__ void __launch_bounds__(kEncThreads) k_prop_fwd(nlb_rays_t rays, nlb_t
   density[row] = xin > 20.f ? xin : log1pf(expf(xin));
 }
 
-// Backward of the proposal level, one 128-row tile per block.  Phase 1: per-interval
-// MLP backward from the saved features; the tile's weight gradients are a
-// [128 x 64]^T [128 x L] product reduced through shared memory and written to a
-// per-block partial buffer (no atomics; k_prop_wgrad_reduce sums the partials).
-// Phase 2: feature gradients are scattered into the table.
+// Backward of the proposal MLP (persistent blocks over 128-row tiles): per-interval
+// data gradient from the saved features -> grad_features[rows, L] for the scatter
+// kernel; the weight gradients are a [128 x 64]^T [128 x L] product per tile reduced
+// through shared memory and accumulated in registers across the block's tiles, then
+// written as one partial per block (no atomics; k_prop_wgrad_reduce sums the partials).
 template <int L>
-__global__ void __launch_bounds__(kEncThreads) k_prop_bwd(nlb_rays_t rays, nlb_table_t tab,
-                                                          const float* __restrict__ W0, const float* __restrict__ b0,
-                                                          const float* __restrict__ W1, const float* __restrict__ b1,
-                                                          const float* __restrict__ features,
-                                                          const float* __restrict__ grad_density,
-                                                          float* __restrict__ grad_table,
-                                                          float* __restrict__ partial /*[blocks][64*L+129]*/) {
+__global__ void __launch_bounds__(kEncThreads) k_prop_mlp_bwd(int rows_total, int num_tiles,
+                                                              const float* __restrict__ W0, const float* __restrict__ b0,
+                                                              const float* __restrict__ W1, const float* __restrict__ b1,
+                                                              const float* __restrict__ features,
+                                                              const float* __restrict__ grad_density,
+                                                              float* __restrict__ grad_features,
+                                                              float* __restrict__ partial /*[blocks][64*L+129]*/) {
   __shared__ PropSmem sm;
-  // phase 1 view: relu output per row (gW1 and the relu mask); phase 2 view: the points
-  // and the per-level feature gradients (phase-1 data is dead by then)
-  __shared__ __align__(16) float s_raw[kEncThreads * (kPropHidden + 1)];
-  float (*s_h)[kPropHidden + 1] = reinterpret_cast<float (*)[kPropHidden + 1]>(s_raw);
+  __shared__ float s_h[kEncThreads][kPropHidden + 1];  // relu output per row (gW1 and the relu mask)
   __shared__ float s_f[kEncThreads][L + 1];
   __shared__ float s_graw[kEncThreads];
-  static_assert(sizeof(float4) * 7 * kEncThreads + sizeof(float) * L * kEncThreads <= sizeof(s_raw), "smem views");
   load_prop_weights(sm, L, W0, b0, W1, b1);
   __syncthreads();
   const int tid = threadIdx.x;
-  const int rows_total = rays.N * rays.S;
-  const int row = blockIdx.x * kEncThreads + tid;
-  const bool valid = row < rows_total;
-  float f[L], gf[L];
+  constexpr int kW0 = kPropHidden * L;
+  constexpr int kMine = (kW0 + kEncThreads - 1) / kEncThreads;
+  float aW0[kMine];
 #pragma unroll
-  for (int l = 0; l < L; ++l) { f[l] = valid ? __ldg(features + (size_t)row * L + l) : 0.f; gf[l] = 0.f; }
-  float raw = sm.b1;
+  for (int i = 0; i < kMine; ++i) aW0[i] = 0.f;
+  float a_b0 = 0.f, a_W1 = 0.f, a_b1 = 0.f;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int row = tile * kEncThreads + tid;
+    const bool valid = row < rows_total;
+    float f[L], gf[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) { f[l] = valid ? __ldg(features + (size_t)row * L + l) : 0.f; gf[l] = 0.f; }
+    float raw = sm.b1;
 #pragma unroll 4
-  for (int k = 0; k < kPropHidden; ++k) {
-    float h = sm.b0[k];
+    for (int k = 0; k < kPropHidden; ++k) {
+      float h = sm.b0[k];
 #pragma unroll
-    for (int l = 0; l < L; ++l) h = fmaf(sm.W0[k * L + l], f[l], h);
-    s_h[tid][k] = fmaxf(h, 0.f);
-    raw = fmaf(sm.W1[k], fmaxf(h, 0.f), raw);
-  }
-  const float xin = raw - 1.0f;
-  const float sig = xin > 20.f ? 1.0f : 1.0f / (1.0f + expf(-xin));  // d softplus
-  const float graw = valid ? __ldg(grad_density + row) * sig : 0.f;
-  s_graw[tid] = graw;
+      for (int l = 0; l < L; ++l) h = fmaf(sm.W0[k * L + l], f[l], h);
+      s_h[tid][k] = fmaxf(h, 0.f);
+      raw = fmaf(sm.W1[k], fmaxf(h, 0.f), raw);
+    }
+    const float xin = raw - 1.0f;
+    const float sig = xin > 20.f ? 1.0f : 1.0f / (1.0f + expf(-xin));  // d softplus
+    const float graw = valid ? __ldg(grad_density + row) * sig : 0.f;
+    s_graw[tid] = graw;
 #pragma unroll 4
-  for (int k = 0; k < kPropHidden; ++k) {
-    const float gh = (s_h[tid][k] > 0.f) ? graw * sm.W1[k] : 0.f;
+    for (int k = 0; k < kPropHidden; ++k) {
+      const float gh = (s_h[tid][k] > 0.f) ? graw * sm.W1[k] : 0.f;
 #pragma unroll
-    for (int l = 0; l < L; ++l) gf[l] = fmaf(gh, sm.W0[k * L + l], gf[l]);
+      for (int l = 0; l < L; ++l) gf[l] = fmaf(gh, sm.W0[k * L + l], gf[l]);
+    }
+#pragma unroll
+    for (int l = 0; l < L; ++l) s_f[tid][l] = f[l];
+    if (valid) {
+#pragma unroll
+      for (int l = 0; l < L; ++l) grad_features[(size_t)row * L + l] = gf[l];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kMine; ++i) {
+      const int e = tid + i * kEncThreads;
+      if (e < kW0) {
+        const int k = e / L, l = e - k * L;
+        const float w1k = sm.W1[k];
+        float a = 0.f;
+#pragma unroll 4
+        for (int r = 0; r < kEncThreads; ++r) a = fmaf((s_h[r][k] > 0.f) ? s_graw[r] * w1k : 0.f, s_f[r][l], a);
+        aW0[i] += a;
+      }
+    }
+    if (tid < kPropHidden) {
+      const float w1k = sm.W1[tid];
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+      for (int r = 0; r < kEncThreads; ++r) {
+        a0 += (s_h[r][tid] > 0.f) ? s_graw[r] * w1k : 0.f;
+        a1 = fmaf(s_graw[r], s_h[r][tid], a1);
+      }
+      a_b0 += a0;
+      a_W1 += a1;
+    } else if (tid == kPropHidden) {
+      float a = 0.f;
+      for (int r = 0; r < kEncThreads; ++r) a += s_graw[r];
+      a_b1 += a;
+    }
+    __syncthreads();  // every thread is done reading s_h / s_f / s_graw
   }
-#pragma unroll
-  for (int l = 0; l < L; ++l) s_f[tid][l] = f[l];
-  __syncthreads();
-  constexpr int kEntries = kPropHidden * L + 2 * kPropHidden + 1;
+  constexpr int kEntries = kW0 + 2 * kPropHidden + 1;
   float* my = partial + (size_t)blockIdx.x * kEntries;
-  for (int e = tid; e < kPropHidden * L; e += kEncThreads) {
-    const int k = e / L, l = e - k * L;
-    const float w1k = sm.W1[k];
-    float a = 0.f;
-#pragma unroll 4
-    for (int r = 0; r < kEncThreads; ++r) a = fmaf((s_h[r][k] > 0.f) ? s_graw[r] * w1k : 0.f, s_f[r][l], a);
-    my[e] = a;
+#pragma unroll
+  for (int i = 0; i < kMine; ++i) {
+    const int e = tid + i * kEncThreads;
+    if (e < kW0) my[e] = aW0[i];
   }
   if (tid < kPropHidden) {
-    const float w1k = sm.W1[tid];
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll 4
-    for (int r = 0; r < kEncThreads; ++r) {
-      a0 += (s_h[r][tid] > 0.f) ? s_graw[r] * w1k : 0.f;
-      a1 = fmaf(s_graw[r], s_h[r][tid], a1);
-    }
-    my[kPropHidden * L + tid] = a0;                // gb0
-    my[kPropHidden * L + kPropHidden + tid] = a1;  // gW1
+    my[kW0 + tid] = a_b0;                // gb0
+    my[kW0 + kPropHidden + tid] = a_W1;  // gW1
   } else if (tid == kPropHidden) {
-    float a = 0.f;
-    for (int r = 0; r < kEncThreads; ++r) a += s_graw[r];
-    my[kPropHidden * L + 2 * kPropHidden] = a;     // gb1
-  }
-  __syncthreads();  // every thread is done reading s_h / s_f / s_graw
-  if (!valid) return;
-  bool any = false;
-#pragma unroll
-  for (int l = 0; l < L; ++l) { gf[l] = gf[l] / 7.0f; any |= (gf[l] != 0.f); }
-  if (!any) return;
-  // phase 2: scatter
-  float4 (*s_pts)[kEncThreads] = reinterpret_cast<float4 (*)[kEncThreads]>(s_raw);
-  float (*s_gf)[kEncThreads] = reinterpret_cast<float (*)[kEncThreads]>(s_raw + 4 * 7 * kEncThreads);
-#pragma unroll
-  for (int l = 0; l < L; ++l) s_gf[l][tid] = gf[l];
-  stage_points(rays, row, s_pts);
-#pragma unroll 1
-  for (int l = 0; l < L; ++l) {
-    const Level3 lv = level3(tab.offsets, l, tab.S, tab.H);
-    float g1[1] = {s_gf[l][tid]};
-    if (g1[0] == 0.f) continue;
-    level_scatter<1>(grad_table, lv, __ldg(tab.grid_sizes + l), s_pts, g1);
+    my[kW0 + 2 * kPropHidden] = a_b1;    // gb1
   }
 }
 
@@ -417,27 +519,49 @@ __global__ void __launch_bounds__(256) k_prop_wgrad_reduce(const float* __restri
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= entries) return;
   float a = 0.f;
-  for (int b = 0; b < blocks; ++b) a += __ldg(partial + (size_t)b * entries + e);
+  for (int b = blockIdx.y; b < blocks; b += gridDim.y) a += __ldg(partial + (size_t)b * entries + e);
   const int n0 = kPropHidden * L;
-  if (e < n0) gW0[e] += a;
-  else if (e < n0 + kPropHidden) gb0[e - n0] += a;
-  else if (e < n0 + 2 * kPropHidden) gW1[e - n0 - kPropHidden] += a;
-  else gb1[0] += a;
+  float* dst = e < n0 ? gW0 + e : e < n0 + kPropHidden ? gb0 + (e - n0)
+             : e < n0 + 2 * kPropHidden ? gW1 + (e - n0 - kPropHidden) : gb1;
+  atomicAdd(dst, a);
 }
 
 }  // namespace nlb
 
 using namespace nlb;
 
-static int check_rays_table(const nlb_rays_t* r, const nlb_table_t* t, const char* who) {
+// Host view of the table's levels (from nlb_table_t.offsets_host), same arithmetic as the
+// kernels: resolution = ceil(2^(l*S)*H - 1) + 1, dense iff (res+1)^3 fits the level.
+struct HostLevels {
+  int rows[kMaxLevelsEnc];
+  bool dense[kMaxLevelsEnc];
+};
+
+static int check_rays_table(const nlb_rays_t* r, const nlb_table_t* t, const char* who, HostLevels* hl = nullptr) {
   if (!r || !t) { nlb_set_error("%s: null descriptor", who); return NLB_EINVAL; }
   if (r->N < 0 || r->S < 1) { nlb_set_error("%s: bad N/S", who); return NLB_EINVAL; }
+  if (t->L < 1 || t->L > kMaxLevelsEnc) { nlb_set_error("%s: num_levels %d outside [1,%d]", who, t->L, kMaxLevelsEnc); return NLB_EUNSUPPORTED; }
   if (!r->tdist || !r->origins || !r->directions || !r->radii || !r->base_x || !r->base_y || !t->embeddings ||
       !t->offsets || !t->grid_sizes) {
     nlb_set_error("%s: null pointer", who);
     return NLB_EINVAL;
   }
+  if (!t->offsets_host) { nlb_set_error("%s: nlb_table_t.offsets_host (host copy of the level offsets) is required", who); return NLB_EINVAL; }
   if ((int64_t)r->N * r->S > 0x7fffffffLL / 16) { nlb_set_error("%s: N*S too large for one launch; chunk the rays", who); return NLB_EINVAL; }
+  for (int l = 0; l < t->L; ++l) {
+    const int64_t size = (int64_t)t->offsets_host[l + 1] - t->offsets_host[l];
+    if (size < 8) { nlb_set_error("%s: level %d has %lld rows", who, l, (long long)size); return NLB_EINVAL; }
+    const float scale = exp2f(l * t->S) * t->H - 1.0f;
+    const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
+    uint32_t s1, s2;
+    const bool dense = level_is_dense(resolution, (uint32_t)size, s1, s2);
+    if (!dense && (size & (size - 1)) != 0) {
+      nlb_set_error("%s: hashed level %d has %lld rows; the fused kernels need power-of-two hashed levels "
+                    "(GridEncoder always builds them so)", who, l, (long long)size);
+      return NLB_EUNSUPPORTED;
+    }
+    if (hl) { hl->rows[l] = (int)size; hl->dense[l] = dense; }
+  }
   return NLB_OK;
 }
 
@@ -465,21 +589,82 @@ extern "C" int nlb_encode_forward(const nlb_rays_t* rays, const nlb_table_t* tab
   return nlb_check_launch("encode_forward");
 }
 
+// Persistent launch shape of k_encode_bwd: the coarse levels that fit the shared-memory
+// budget are staged per block (see the kernel comment); the grid is the number of blocks
+// the device can keep resident (a multiple of the SM count), capped by the tile count.
+static int g_sm_count = 0;
+static int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+static long env_long(const char* name, long dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atol(v) : dflt;
+}
+
+template <int C>
+static int scatter_launch(const nlb_rays_t& rays, const nlb_table_t& tab, const HostLevels& hl,
+                          const float* grad_features, float* grad_embeddings, cudaStream_t st) {
+  static const size_t kStageBudget = (size_t)env_long("NLB_SCATTER_STAGE_KB", 24) * 1024;  // >= 6 blocks/SM resident
+  static const double kL2Budget = (double)env_long("NLB_SCATTER_L2_MB", 70) * 1048576.0;
+  // coarsest dense levels accumulated per block in shared memory
+  int staged_rows = 0;
+  for (int l = 0; l < tab.L && hl.dense[l]; ++l) {
+    if ((size_t)(staged_rows + hl.rows[l]) * C * sizeof(float) > kStageBudget) break;
+    staged_rows += hl.rows[l];
+  }
+  const size_t smem = (size_t)staged_rows * C * sizeof(float);
+  const int tiles = (int)div_up(rays.N * rays.S, kEncThreads);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_encode_bwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+    attr_set = true;
+  }
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_bwd<C>, kEncThreads, smem);
+  if (per_sm < 1) per_sm = 1;
+  int blocks_staged = sm_count() * per_sm;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_bwd<C>, kEncThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  int blocks_plain = sm_count() * per_sm;
+  if (blocks_staged > tiles) blocks_staged = tiles;
+  if (blocks_plain > tiles) blocks_plain = tiles;
+  // level groups: consecutive levels whose gradient rows fit the L2 budget together, so a
+  // fine level stays L2-resident while every tile updates it (level-major order)
+  int l0 = 0;
+  while (l0 < tab.L) {
+    int l1 = l0;
+    double bytes = 0.;
+    while (l1 < tab.L && (l1 == l0 || bytes + (double)hl.rows[l1] * C * 4.0 <= kL2Budget)) bytes += (double)hl.rows[l1++] * C * 4.0;
+    const bool first = l0 == 0;
+    k_encode_bwd<C><<<first ? blocks_staged : blocks_plain, kEncThreads, first ? smem : 0, st>>>(
+        rays, tab, grad_features, grad_embeddings, first ? staged_rows : 0, tiles, l0, l1);
+    if (int e = nlb_check_launch("encode_backward")) return e;
+    l0 = l1;
+  }
+  return NLB_OK;
+}
+
 extern "C" int nlb_encode_backward(const nlb_rays_t* rays, const nlb_table_t* table, const float* grad_features,
                                    float* grad_embeddings, void* stream) {
-  if (int e = check_rays_table(rays, table, "encode_backward")) return e;
+  HostLevels hl;
+  if (int e = check_rays_table(rays, table, "encode_backward", &hl)) return e;
   const int rows = rays->N * rays->S;
   if (rows == 0) return NLB_OK;
-  dim3 grid(div_up(rows, kEncThreads));
   cudaStream_t st = (cudaStream_t)stream;
   switch (table->C) {
-    case 1: k_encode_bwd<1><<<grid, 128, 0, st>>>(*rays, *table, grad_features, grad_embeddings); break;
-    case 2: k_encode_bwd<2><<<grid, 128, 0, st>>>(*rays, *table, grad_features, grad_embeddings); break;
-    case 4: k_encode_bwd<4><<<grid, 128, 0, st>>>(*rays, *table, grad_features, grad_embeddings); break;
-    case 8: k_encode_bwd<8><<<grid, 128, 0, st>>>(*rays, *table, grad_features, grad_embeddings); break;
+    case 1: return scatter_launch<1>(*rays, *table, hl, grad_features, grad_embeddings, st);
+    case 2: return scatter_launch<2>(*rays, *table, hl, grad_features, grad_embeddings, st);
+    case 4: return scatter_launch<4>(*rays, *table, hl, grad_features, grad_embeddings, st);
+    case 8: return scatter_launch<8>(*rays, *table, hl, grad_features, grad_embeddings, st);
     default: nlb_set_error("GridEncoding: C must be 1, 2, 4, or 8."); return NLB_EINVAL;
   }
-  return nlb_check_launch("encode_backward");
 }
 
 #define NLB_PROP_DISPATCH(L, ...)                         \
@@ -505,27 +690,40 @@ extern "C" int nlb_prop_forward(const nlb_rays_t* rays, const nlb_table_t* table
   return nlb_check_launch("prop_forward");
 }
 
+static int prop_bwd_blocks(int rows) {
+  const int tiles = (int)div_up(rows, kEncThreads);
+  const int want = sm_count() * 4;
+  return tiles < want ? tiles : want;
+}
+
 extern "C" size_t nlb_prop_backward_workspace_bytes(int N, int S, int L) {
-  const size_t blocks = ((size_t)N * S + kEncThreads - 1) / kEncThreads;
-  return blocks * (size_t)(kPropHidden * L + 2 * kPropHidden + 1) * sizeof(float);
+  const size_t rows = (size_t)N * S;
+  const size_t blocks = (size_t)prop_bwd_blocks((int)rows);
+  // per-block weight-gradient partials + grad_features[rows, L]
+  return (blocks * (size_t)(kPropHidden * L + 2 * kPropHidden + 1) + rows * L + 64) * sizeof(float);
 }
 
 extern "C" int nlb_prop_backward(const nlb_rays_t* rays, const nlb_table_t* table, const float* W0, const float* b0,
                                  const float* W1, const float* b1, const float* features, const float* grad_density,
                                  float* grad_embeddings, float* gW0, float* gb0, float* gW1, float* gb1,
                                  float* workspace, void* stream) {
-  if (int e = check_rays_table(rays, table, "prop_backward")) return e;
+  HostLevels hl;
+  if (int e = check_rays_table(rays, table, "prop_backward", &hl)) return e;
   if (table->C != 1) { nlb_set_error("prop_backward: PropMLP tables have level_dim 1"); return NLB_EINVAL; }
   if (!features || !grad_density) { nlb_set_error("prop_backward: features saved by the forward are required"); return NLB_EINVAL; }
   if (!workspace) { nlb_set_error("prop_backward: workspace of nlb_prop_backward_workspace_bytes() is required"); return NLB_EINVAL; }
   const int rows = rays->N * rays->S;
   if (rows == 0) return NLB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int blocks = (int)div_up(rows, kEncThreads);
-  NLB_PROP_DISPATCH(table->L, (k_prop_bwd<L_><<<blocks, kEncThreads, 0, st>>>(
-      *rays, *table, W0, b0, W1, b1, features, grad_density, grad_embeddings, workspace)));
-  if (int e = nlb_check_launch("prop_backward")) return e;
+  const int blocks = prop_bwd_blocks(rows);
+  const int tiles = (int)div_up(rows, kEncThreads);
   const int entries = kPropHidden * table->L + 2 * kPropHidden + 1;
-  k_prop_wgrad_reduce<<<div_up(entries, 256), 256, 0, st>>>(workspace, blocks, entries, table->L, gW0, gb0, gW1, gb1);
-  return nlb_check_launch("prop_wgrad_reduce");
+  float* partial = workspace;
+  float* gfeat = workspace + (((size_t)blocks * entries + 63) / 64) * 64;  // 256-byte aligned
+  NLB_PROP_DISPATCH(table->L, (k_prop_mlp_bwd<L_><<<blocks, kEncThreads, 0, st>>>(
+      rows, tiles, W0, b0, W1, b1, features, grad_density, gfeat, partial)));
+  if (int e = nlb_check_launch("prop_mlp_backward")) return e;
+  k_prop_wgrad_reduce<<<dim3(div_up(entries, 256), 16), 256, 0, st>>>(partial, blocks, entries, table->L, gW0, gb0, gW1, gb1);
+  if (int e = nlb_check_launch("prop_wgrad_reduce")) return e;
+  return scatter_launch<1>(*rays, *table, hl, gfeat, grad_embeddings, st);
 }

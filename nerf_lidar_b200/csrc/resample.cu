@@ -57,8 +57,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_resample(
     const float* __restrict__ sdist_in, const float* __restrict__ weights_in, int n, int dilate, float dilation,
     float anneal, float pad, const float* __restrict__ u_base, const float* __restrict__ jitter, float max_jitter,
     const float* __restrict__ near, const float* __restrict__ far, float lam, int S, int N,
-    float* __restrict__ sdist_out, float* __restrict__ tdist_out, int32_t* __restrict__ sample_idx) {
+    float* __restrict__ sdist_out, float* __restrict__ tdist_out, int32_t* __restrict__ sample_idx,
+    const float* __restrict__ dyn) {
   extern __shared__ float smem[];
+  if (dyn) anneal = __ldg(dyn + NLB_DYN_ANNEAL);  // CUDA-graph replay: this step's value
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ray = blockIdx.x * kWarpsPerBlock + warp;
   if (ray >= N) return;
@@ -224,7 +226,7 @@ extern "C" int nlb_resample(const float* sdist_in, const float* weights_in, int 
   if (smem > 48 * 1024) cudaFuncSetAttribute(k_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_resample<<<div_up(N, kWarpsPerBlock), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
       sdist_in, weights_in, n_in, dilate, dilation, anneal, resample_padding, u_base, jitter, max_jitter, near, far,
-      lam, S, N, sdist_out, tdist_out, sample_idx);
+      lam, S, N, sdist_out, tdist_out, sample_idx, nlb_dynamic_scalars());
   return nlb_check_launch("resample");
 }
 

@@ -114,9 +114,20 @@ def sample_points(tdist, deg_noise, rays: RayBundle, std_scale: float = 0.35) ->
     return pts
 
 
+def host_offsets(encoder):
+    """Host copy (ctypes int32 array) of the encoder's level offsets, cached on the module."""
+    cached = getattr(encoder, '_nlb_offsets_host', None)
+    if cached is None:
+        offs = encoder.offsets.tolist()
+        cached = (C.c_int32 * len(offs))(*offs)
+        encoder._nlb_offsets_host = cached
+    return cached
+
+
 def _table_desc(encoder, embeddings: torch.Tensor) -> NlbTable:
     return NlbTable(ptr(embeddings), ptr(encoder.offsets), ptr(encoder.grid_sizes), encoder.num_levels,
-                    encoder.level_dim, int(encoder.base_resolution), float(math.log2(encoder.per_level_scale)))
+                    encoder.level_dim, int(encoder.base_resolution), float(math.log2(encoder.per_level_scale)),
+                    host_offsets(encoder))
 
 
 def _grad_buffer(param: torch.Tensor) -> Tuple[torch.Tensor, bool]:
@@ -299,8 +310,14 @@ def nerf_mlp_pack(mlp, transposed: bool = False) -> torch.Tensor:
     version = tuple((t.data_ptr(), t._version) for t in tensors)
     key = '_nlb_packed_t' if transposed else '_nlb_packed'
     cache = getattr(mlp, key, None)
-    if cache is not None and cache[0] == version:
+    dirty = getattr(mlp, '_nlb_dirty', None)  # set by Trainer.optimizer_step (raw-pointer updates bypass _version)
+    if dirty is None:
+        mlp._nlb_dirty = dirty = set()
+    if dirty is True:
+        mlp._nlb_dirty = dirty = {'_nlb_packed', '_nlb_packed_t'}
+    if cache is not None and cache[0] == version and key not in dirty:
         return cache[1]
+    dirty.discard(key)
     dev = tensors[0].device
     lib = load()
     nbytes = lib.nlb_nerf_mlp_packed_transposed_bytes() if transposed else lib.nlb_nerf_mlp_packed_bytes()

@@ -72,7 +72,8 @@ def depth_loss(pred, target, mask):
     pos = 0.9 * (n.to(torch.float32) - 1).clamp_min(0)
     lo = pos.floor().long().clamp(0, d.numel() - 1)
     hi = pos.ceil().long().clamp(0, d.numel() - 1)
-    thre = srt[lo] + (srt[hi] - srt[lo]) * (pos - pos.floor())
+    v_lo, v_hi = srt.gather(0, lo.reshape(1))[0], srt.gather(0, hi.reshape(1))[0]
+    thre = v_lo + (v_hi - v_lo) * (pos - pos.floor())
     keep = mask & (d < thre)
     return _masked_mean(torch.log(d.abs() + 1), keep)
 
@@ -268,6 +269,9 @@ class Trainer:
             off += (k + 3) // 4 * 4
         self.dense = dense
         self.decay = config.hash_decay_mults if config.hash_decay_mults > 0 else 0.
+        self.hash_decay_value = torch.zeros((), device=dev)  # persistent: written in place (CUDA-graph safe)
+        self._graphs = {}
+        self._static = None
         model.train()
         model.training = True
 
@@ -286,7 +290,9 @@ class Trainer:
                                              rand_inputs=rand_inputs)
         losses = compute_losses(batch, renderings, ray_history, c, step, num_patch)
         if 'hash_decay' in renderings[-1]:
-            losses['hash_decay'] = renderings[-1]['hash_decay']  # value only; gradient is fused into Adam
+            # value only (its gradient is fused into Adam); cloned because the optimizer pass below
+            # overwrites the persistent buffer with the updated tables' value
+            losses['hash_decay'] = renderings[-1]['hash_decay'].clone()
         loss = sum(v for k, v in losses.items() if k != 'hash_decay')
         loss.backward()
         self.optimizer_step(step)
@@ -317,7 +323,85 @@ class Trainer:
                 decay_value = v if decay_value is None else decay_value + v
         if decay_value is not None:
             # the next forward reports this as renderings[-1]['hash_decay'] without re-reading 310 MB of tables
-            self.model._hash_decay_value = self.decay * decay_value
+            self.hash_decay_value.copy_(self.decay * decay_value)
+            self.model._hash_decay_value = self.hash_decay_value
         _lib.check(lib.nlb_adam_step(self.flat.data_ptr(), self.flat_grad.data_ptr(), self.flat_m.data_ptr(),
                                      self.flat_v.data_ptr(), self.flat.numel(), float(lr), c.adam_beta1,
                                      c.adam_beta2, c.adam_eps, int(step), scale, st))
+        # the dense parameters changed through raw pointers: the packed tensor-core operand images are stale
+        for m in self.model.modules():
+            if hasattr(m, '_nlb_dirty'):
+                m._nlb_dirty = True
+
+    # ------------------------------------------------------------------------- CUDA-graph step
+    def _regime(self, step: int):
+        """Everything a captured step bakes in besides the dynamic scalars: the
+        step-dependent loss multipliers of Z/train.py:330-371 change only at the
+        pose-refinement window boundaries."""
+        c = self.config
+        refine = c.pose_refine and c.start_step < step < int(0.6 * c.end_step)
+        return (bool(refine), step > c.end_step)
+
+    def _write_dynamic(self, step: int):
+        c = self.config
+        train_frac = float(np.clip((step - 1) / (c.max_steps - 1), 0, 1))
+        slope = self.model.anneal_slope
+        anneal = (slope * train_frac) / ((slope - 1) * train_frac + 1) if slope > 0 else 1.
+        out2 = (C.c_float * 2)()
+        _lib.check(_lib.load().nlb_adam_bias_terms(float(self.lr(step)), c.adam_beta1, c.adam_beta2, int(step), out2))
+        st = self._static
+        st['dyn_host'][0], st['dyn_host'][1], st['dyn_host'][2] = float(anneal), float(out2[0]), float(out2[1])
+        st['dyn'].copy_(st['dyn_host'], non_blocking=True)
+
+    def train_step_graphed(self, batch: Dict[str, torch.Tensor], step: int, num_patch: Optional[int] = None,
+                           rand_inputs=None) -> Dict[str, torch.Tensor]:
+        """`train_step` replayed as ONE CUDA graph: the step is ~450 small launches and
+        host-bound when issued eagerly.  `batch` (device or pinned-host tensors) is copied
+        into static device buffers; the per-step scalars (anneal, learning rate, Adam bias
+        corrections) travel through the library's dynamic-scalar buffer
+        (nlb_set_dynamic_scalars); the graph is re-captured when the batch layout or the
+        loss-multiplier regime changes.  Returns the loss dictionary (static tensors,
+        overwritten by the next call)."""
+        dev = self.flat.device
+        key = (self._regime(step), num_patch, tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.items())),
+               rand_inputs is not None)
+        if self._static is None:
+            self._static = dict(dyn=torch.zeros(4, device=dev), dyn_host=torch.zeros(4).pin_memory())
+        st = self._static
+        if st.get('batch_key') != key[2]:
+            st['batch'] = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in batch.items()}
+            st['batch_key'] = key[2]
+            self._graphs.clear()
+        for k, v in batch.items():
+            st['batch'][k].copy_(v, non_blocking=True)
+        srand = None
+        if rand_inputs is not None:  # injected random draws (parity tests): static copies as well
+            if 'rand' not in st:
+                st['rand'] = [{k: torch.empty_like(v, device=dev) for k, v in r.items()} for r in rand_inputs]
+            for dst, src in zip(st['rand'], rand_inputs):
+                for k, v in src.items():
+                    dst[k].copy_(v, non_blocking=True)
+            srand = st['rand']
+        self._write_dynamic(step)
+        lib = _lib.load()
+        entry = self._graphs.get(key)
+        if entry is None:
+            # warm up eagerly on a side stream (allocator, cuBLAS handles, kernel attributes), then capture
+            lib.nlb_set_dynamic_scalars(st['dyn'].data_ptr())
+            try:
+                s = torch.cuda.Stream(device=dev)
+                s.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(s):
+                    out = self.train_step(st['batch'], step, num_patch, srand)
+                torch.cuda.current_stream(dev).wait_stream(s)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    captured = self.train_step(st['batch'], step, num_patch, srand)
+            finally:
+                lib.nlb_set_dynamic_scalars(None)
+            # capturing records the step without running it: the eager warm-up step above WAS this call's step
+            self._graphs[key] = (g, captured)
+            return out
+        g, captured = entry
+        g.replay()
+        return captured
