@@ -67,18 +67,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(',')])
 
-    def stop(self):
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0=None, t1=None):
+        """Median SM clock / throttle reasons of the samples taken in [t0, t1] (the timed
+        region; the sampler runs from before the warm-up so short regions still get samples;
+        falls back to the samples under load nearest to it)."""
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
-        mx = [int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()]
+        rows = [r[1:] for r in self.rows if t0 is None or (t0 - 0.05 <= r[0] <= t1 + 0.15)]
+        if not rows:
+            rows = [r[1:] for r in self.rows if t0 is None or r[0] >= t0 - 1.0] or [r[1:] for r in self.rows]
+        sm = sorted(int(r[1]) for r in rows if len(r) > 2 and r[1].isdigit())
+        mx = [int(r[2]) for r in rows if len(r) > 2 and r[2].isdigit()]
         reasons = set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        for r in rows:
             for i, n in enumerate(names):
                 if len(r) > 5 + i and r[5 + i].lower().startswith('active'):
                     reasons.add(n)
@@ -151,6 +160,11 @@ def run_cuda_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout carries the one JSON line
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
+        else:
+            os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     _lib.load()
     cfg = configs.nuscenes_single(use_intensity=True, instance_obj=False)
@@ -203,13 +217,14 @@ def run_cuda_arm(args):
         return float(ms.item())
 
     step0 = 6000  # steady state: past the pose-refinement window (Config.end_step = 5000)
-    timed_loop(max(3, args.warmup), step0, False)
-
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    timed_loop(max(3, args.warmup), step0, False)
+    t0 = sampler.mark()
     ms = timed_loop(args.steps, step0 + 100, False)
-    clocks = sampler.stop() if rank == 0 else None
+    t1 = sampler.mark()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
     timed_loop(2, step0 + 200, True)
     ms_e2e = timed_loop(args.steps, step0 + 300, True)
     # per-kernel device times (roofline): the same steps issued eagerly with CUDA events around every

@@ -245,6 +245,14 @@ int nlb_nerf_mlp_backward(const nlb_nerf_mlp_grad_in_t* gin, const nlb_nerf_mlp_
                           const void* packed_t, float* grad_features /*[M,40]*/,
                           const nlb_nerf_mlp_grad_out_t* gout, void* stream);
 
+/* Reductions of the bf16 pre-activation gradients written by nlb_nerf_mlp_backward:
+ * colsum: x[M, ld] (first `cols` columns; cols a power of two <= 512) -> out[cols]
+ *   (overwritten) = bias gradients;
+ * group_sum: x[groups*S, cols] -> out[groups, cols] = per-ray sums over the S samples (the
+ *   view-direction encoding is a per-ray constant, Z/internal/models.py:1192-1196). */
+int nlb_colsum_bf16(const void* x, int64_t M, int cols, int ld, float* out, void* stream);
+int nlb_group_sum_bf16(const void* x, int64_t groups, int S, int cols, float* out, void* stream);
+
 /* Dev probe: clock64() stamps of block 0's MMA thread / epilogue thread for the first two
  * tiles of nlb_nerf_mlp_forward are written to buf[128] (int64); NULL switches it off. */
 int nlb_debug_set_timeline(void* buf);

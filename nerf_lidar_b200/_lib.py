@@ -87,6 +87,8 @@ SIGNATURES = {
     'nlb_nerf_mlp_pack_transposed': (_i, [C.POINTER(NlbNerfMlpWeights), _p, _p]),
     'nlb_nerf_mlp_backward': (_i, [C.POINTER(NlbNerfMlpGradIn), C.POINTER(NlbNerfMlpSaved), _i, _p, _p,
                                    C.POINTER(NlbNerfMlpGradOut), _p]),
+    'nlb_colsum_bf16': (_i, [_p, C.c_int64, _i, _i, _p, _p]),
+    'nlb_group_sum_bf16': (_i, [_p, C.c_int64, _i, _i, _p, _p]),
     'nlb_debug_set_timeline': (_i, [_p]),
     'nlb_distortion_loss': (_i, [_p, _p, _i, _i, _p, _p, _p]),
     'nlb_interlevel_loss': (_i, [_p, _p, _i, _p, _p, _i, _f, _i, _p, _p, _p]),

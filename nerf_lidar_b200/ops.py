@@ -366,6 +366,28 @@ def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         return torch.mm(a, b).float()
 
 
+@torch.no_grad()
+def colsum_bf16(x: torch.Tensor) -> torch.Tensor:
+    """Column sums of a contiguous bf16 matrix [M, cols] -> fp32 [cols]."""
+    M, cols = x.shape
+    out = torch.empty(cols, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        with timed('mlp_bias_grad'):
+            check(load().nlb_colsum_bf16(ptr(x), M, cols, x.stride(0), ptr(out), stream()))
+    return out
+
+
+@torch.no_grad()
+def group_sum_bf16(x: torch.Tensor, S: int) -> torch.Tensor:
+    """Sums over groups of S consecutive rows of a contiguous bf16 [G*S, cols] -> fp32 [G, cols]."""
+    M, cols = x.shape
+    out = torch.empty(M // S, cols, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        with timed('mlp_ray_sum'):
+            check(load().nlb_group_sum_bf16(ptr(x), M // S, S, cols, ptr(out), stream()))
+    return out
+
+
 class _NerfMLP(Function):
     """Training path of the NerfMLP: fused tcgen05 forward that saves bf16
     activations, fused tcgen05 data-gradient chain, weight gradients as plain GEMMs."""
@@ -398,21 +420,22 @@ class _NerfMLP(Function):
                 check(load().nlb_nerf_mlp_backward(C.byref(gin), C.byref(sv), M, ptr(blob_t), ptr(g_feat),
                                                    C.byref(gout), stream()))
         # weight gradients: plain GEMMs dW = dZ^T A (bf16 operands, fp32 result)
-        colsum = lambda t: t.sum(0, dtype=torch.float32)
         de = mlp.dir_enc(viewdirs)                                   # [N,27] per-ray constant
-        ray_sum = lambda t: t.view(N, S, -1).sum(1, dtype=torch.float32)
         f0 = features.to(torch.bfloat16)
+        # bias gradients and per-ray sums: one bandwidth-bound pass each (csrc/reduce.cu)
+        cs_g, cs_hs1, cs_rgb = colsum_bf16(d_g), colsum_bf16(d_hs1), colsum_bf16(d_rgb)
         gW = {
-            'W_d0': _mm_f32(d_h0.t(), f0), 'b_d0': colsum(d_h0),
-            'W_d2': _mm_f32(d_x.t(), h0), 'b_d2': colsum(d_x),
-            'W_s0': _mm_f32(d_g[:, :64].t(), x), 'b_s0': colsum(d_g[:, :64]),
-            'W_s2': _mm_f32(d_hs1[:, :19].t(), g[:, :64]), 'b_s2': colsum(d_hs1[:, :19]),
-            'W_i0': _mm_f32(d_g[:, 64:].t(), x), 'b_i0': colsum(d_g[:, 64:]),
-            'W_i2': _mm_f32(d_hs1[:, 19:20].t(), g[:, 64:]), 'b_i2': colsum(d_hs1[:, 19:20]),
-            'W_v0': torch.cat([_mm_f32(d_v0.t(), x), ray_sum(d_v0).t() @ de], dim=1), 'b_v0': colsum(d_v0),
-            'W_v1': torch.cat([_mm_f32(d_v1.t(), h1), _mm_f32(d_v1.t(), x), ray_sum(d_v1).t() @ de], dim=1),
-            'b_v1': colsum(d_v1),
-            'W_rgb': _mm_f32(d_rgb[:, :3].t(), h2), 'b_rgb': colsum(d_rgb[:, :3]),
+            'W_d0': _mm_f32(d_h0.t(), f0), 'b_d0': colsum_bf16(d_h0),
+            'W_d2': _mm_f32(d_x.t(), h0), 'b_d2': colsum_bf16(d_x),
+            'W_s0': _mm_f32(d_g[:, :64].t(), x), 'b_s0': cs_g[:64],
+            'W_s2': _mm_f32(d_hs1[:, :19].t(), g[:, :64]), 'b_s2': cs_hs1[:19],
+            'W_i0': _mm_f32(d_g[:, 64:].t(), x), 'b_i0': cs_g[64:],
+            'W_i2': _mm_f32(d_hs1[:, 19:20].t(), g[:, 64:]), 'b_i2': cs_hs1[19:20],
+            'W_v0': torch.cat([_mm_f32(d_v0.t(), x), group_sum_bf16(d_v0, S).t() @ de], dim=1),
+            'b_v0': colsum_bf16(d_v0),
+            'W_v1': torch.cat([_mm_f32(d_v1.t(), h1), _mm_f32(d_v1.t(), x), group_sum_bf16(d_v1, S).t() @ de], dim=1),
+            'b_v1': colsum_bf16(d_v1),
+            'W_rgb': _mm_f32(d_rgb[:, :3].t(), h2), 'b_rgb': cs_rgb[:3],
         }
         grads = [gW[name] for name, _ in _NERF_WEIGHT_FIELDS]
         return (g_feat, None, None, None, *grads)

@@ -280,7 +280,7 @@ class Trainer:
         return learning_rate_decay(step, c.lr_init, c.lr_final, c.max_steps, c.lr_delay_steps, c.lr_delay_mult)
 
     def train_step(self, batch: Dict[str, torch.Tensor], step: int, num_patch: Optional[int] = None,
-                   rand_inputs=None) -> Dict[str, torch.Tensor]:
+                   rand_inputs=None, _skip_optimizer: bool = False) -> Dict[str, torch.Tensor]:
         c = self.config
         train_frac = float(np.clip((step - 1) / (c.max_steps - 1), 0, 1))
         if num_patch is None:
@@ -295,15 +295,22 @@ class Trainer:
             losses['hash_decay'] = renderings[-1]['hash_decay'].clone()
         loss = sum(v for k, v in losses.items() if k != 'hash_decay')
         loss.backward()
-        self.optimizer_step(step)
         losses['loss'] = loss.detach() + (losses['hash_decay'] if 'hash_decay' in losses else 0.)
+        if not _skip_optimizer:
+            self.optimizer_step(step)
         return losses
 
-    def optimizer_step(self, step: int):
-        c = self.config
-        lr = self.lr(step)
+    def allreduce_gradients(self):
+        """The step's only collective: sum of the three table gradients and the
+        flat dense-layer gradient over the ranks, largest first."""
         if self.world > 1:
             parallel.allreduce_grads([t['grad'] for t in self.tables] + [self.flat_grad])
+
+    def optimizer_step(self, step: int, reduce: bool = True):
+        c = self.config
+        lr = self.lr(step)
+        if reduce:
+            self.allreduce_gradients()
         scale = 1.0 / self.world
         lib = _lib.load()
         st = _lib.stream()
@@ -355,7 +362,9 @@ class Trainer:
 
     def train_step_graphed(self, batch: Dict[str, torch.Tensor], step: int, num_patch: Optional[int] = None,
                            rand_inputs=None) -> Dict[str, torch.Tensor]:
-        """`train_step` replayed as ONE CUDA graph: the step is ~450 small launches and
+        """`train_step` replayed as ONE CUDA graph (single process) or as two graphs --
+        forward + backward, then the optimizer pass -- around the eagerly issued NCCL
+        gradient all-reduce (data parallel): the step is ~450 small launches and
         host-bound when issued eagerly.  `batch` (device or pinned-host tensors) is copied
         into static device buffers; the per-step scalars (anneal, learning rate, Adam bias
         corrections) travel through the library's dynamic-scalar buffer
@@ -395,13 +404,25 @@ class Trainer:
                     out = self.train_step(st['batch'], step, num_patch, srand)
                 torch.cuda.current_stream(dev).wait_stream(s)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    captured = self.train_step(st['batch'], step, num_patch, srand)
+                g_opt = None
+                if self.world == 1:
+                    with torch.cuda.graph(g):
+                        captured = self.train_step(st['batch'], step, num_patch, srand)
+                else:
+                    # the collective stays outside the graphs: capture forward+backward and the optimizer apart
+                    with torch.cuda.graph(g):
+                        captured = self.train_step(st['batch'], step, num_patch, srand, _skip_optimizer=True)
+                    g_opt = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_opt, pool=g.pool()):
+                        self.optimizer_step(step, reduce=False)
             finally:
                 lib.nlb_set_dynamic_scalars(None)
             # capturing records the step without running it: the eager warm-up step above WAS this call's step
-            self._graphs[key] = (g, captured)
+            self._graphs[key] = (g, g_opt, captured)
             return out
-        g, captured = entry
+        g, g_opt, captured = entry
         g.replay()
+        if g_opt is not None:
+            self.allreduce_gradients()
+            g_opt.replay()
         return captured

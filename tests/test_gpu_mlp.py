@@ -101,3 +101,21 @@ def test_fused_mlp_backward_vs_autograd():
         want = p['nerf_mlp.' + name].grad
         assert prm.grad is not None, name
         assert rel_l2(prm.grad, want) < 3e-2, (name, rel_l2(prm.grad, want))
+
+
+@pytest.mark.parametrize('cols', [16, 32, 64, 128, 256])
+def test_bf16_reductions_vs_torch(cols):
+    """Bias-gradient column sums and per-ray sums (csrc/reduce.cu) against torch in fp32."""
+    from nerf_lidar_b200 import ops
+    torch.manual_seed(cols)
+    S, N = 32, 777
+    x = (torch.randn(N * S, cols, device='cuda') * 0.5).to(torch.bfloat16)
+    got = ops.colsum_bf16(x)
+    want = x.float().sum(0)
+    assert_close(got, want, 1e-4, 'colsum')
+    got = ops.group_sum_bf16(x, S)
+    want = x.float().view(N, S, cols).sum(1)
+    assert_close(got, want, 1e-5, 'group_sum')
+    # a strided view (leading dimension larger than the column count) is rejected loudly, never copied silently
+    with pytest.raises(RuntimeError):
+        ops.colsum_bf16(x[:, : cols // 2])
