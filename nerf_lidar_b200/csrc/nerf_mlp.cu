@@ -30,7 +30,11 @@ constexpr int kBlockBytes = 16384;            // [128][64] bf16
 // shared-memory A blocks
 constexpr int BX = 0, BH = 4, BD = 8, kNumABlocks = 9;
 constexpr int kStages = 4;
-constexpr int kThreads = 288;  // warps 0-3 epilogue, 4 MMA issuer, 5-8 weight producers (one per ring stage)
+// warps 0-7 epilogue (warp w and w+4 share TMEM lane quarter w%4 and split the columns),
+// warp 8 MMA issuer, warps 9-12 weight producers (one per ring stage)
+constexpr int kEpiWarps = 8, kMmaWarp = 8, kProdWarp0 = 9;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = (kProdWarp0 + kStages) * 32;
 
 struct LayerDef {
   int N, nkb;
@@ -176,6 +180,36 @@ __device__ __forceinline__ void signal_a_ready(uint64_t* bar) {
   mbar_arrive(bar);
 }
 
+// MMAs of forward layer L for one tile: for every (K block, N half) chunk wait for its
+// weights in the ring, issue the chunk's K-steps, release the ring slot when they retire;
+// finally signal the layer's accumulator.  `c` = running chunk counter (ring position).
+template <int L, class SmemT>
+__device__ __forceinline__ void issue_layer(SmemT& sm, uint8_t* a_blocks, uint8_t* w_ring, uint32_t tmem, uint32_t& c) {
+  constexpr LayerDef d = layer_def(L);
+  constexpr int nrows = layer_nrows(L), nh_count = layer_nhalves(L);
+  const uint32_t idesc = make_idesc_bf16(128, nrows);
+#pragma unroll
+  for (int kb = 0; kb < d.nkb; ++kb) {
+    const uint64_t adesc = make_desc_sw128(a_blocks + d.a_blk[kb] * kBlockBytes);
+#pragma unroll
+    for (int nh = 0; nh < nh_count; ++nh, ++c) {
+      const uint32_t st = c % kStages;
+      mbar_wait(&sm.w_full[st], (c / kStages) & 1);
+      tcgen05_fence_after();
+      const uint64_t bdesc = make_desc_sw128(w_ring + st * kBlockBytes);
+      const uint32_t dcol = tmem + d.tmem_col + nh * 128;
+      switch (d.ksteps[kb]) {
+        case 1: mma_chunk<1>(dcol, adesc, bdesc, idesc, kb != 0); break;
+        case 2: mma_chunk<2>(dcol, adesc, bdesc, idesc, kb != 0); break;
+        case 3: mma_chunk<3>(dcol, adesc, bdesc, idesc, kb != 0); break;
+        default: mma_chunk<4>(dcol, adesc, bdesc, idesc, kb != 0); break;
+      }
+      mma_commit(&sm.w_empty[st]);
+    }
+  }
+  mma_commit(&sm.acc_ready[L]);
+}
+
 __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __restrict__ features,
                                                               const float* __restrict__ viewdirs, int M,
                                                               int rows_per_ray, const uint8_t* __restrict__ blob,
@@ -194,23 +228,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
     for (int i = 0; i < kNumLayers; ++i) mbar_init(&sm.acc_ready[i], 1);
-    for (int i = 0; i < 6; ++i) mbar_init(&sm.a_ready[i], 128);
+    for (int i = 0; i < 6; ++i) mbar_init(&sm.a_ready[i], kEpiThreads);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < kBiasFloats; i += kThreads)
     sm.bias[i] = reinterpret_cast<const float*>(blob + kWeightBytes)[i];
-  if (warp == 4) tmem_alloc(&sm.tmem_base, 512);
+  if (warp == kMmaWarp) tmem_alloc(&sm.tmem_base, 512);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp >= 5) {
+  if (warp >= kProdWarp0) {
     // ===== weight producers: a 1-D bulk copy costs its issuing thread ~800 cycles whatever its
     // size and consecutive copies of one thread do not overlap (tools/bulk_probe.cu), but
     // different warps issue concurrently -> one producer warp per ring stage.
-    if (lane == 0) {
-      const int my_stage = warp - 5;
+    if (elect_one_sync()) {
+      const int my_stage = warp - kProdWarp0;
       uint32_t c = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
 #pragma unroll 1
@@ -221,71 +255,52 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
           for (int i = 0; i < n; ++i, ++c) {
             const int st = c % kStages;
             if (st != my_stage) continue;
-            mbar_wait(&sm.w_empty[st], ((c / kStages) & 1) ^ 1);
+            mbar_wait_relaxed(&sm.w_empty[st], ((c / kStages) & 1) ^ 1);
             mbar_expect_tx(&sm.w_full[st], bytes);
             bulk_g2s(w_ring + st * kBlockBytes, src + (size_t)i * bytes, bytes, &sm.w_full[st]);
           }
         }
       }
     }
-  } else if (warp == 4) {
-    // ===== MMA issuer (one thread)
-    if (lane == 0) {
+  } else if (warp == kMmaWarp) {
+    // ===== MMA issuer: one elected lane, every layer's chunk loop unrolled at compile time
+    if (elect_one_sync()) {
       uint32_t c = 0, it = 0;
-      auto run_layer = [&](int l) {
-        const LayerDef d = layer_def(l);
-        const int nrows = layer_nrows(l), nh_count = layer_nhalves(l);
-        const uint32_t idesc = make_idesc_bf16(128, nrows);
-#pragma unroll 1
-        for (int kb = 0; kb < d.nkb; ++kb) {
-          const uint64_t adesc = make_desc_sw128(a_blocks + d.a_blk[kb] * kBlockBytes);
-#pragma unroll 1
-          for (int nh = 0; nh < nh_count; ++nh, ++c) {
-            const int st = c % kStages;
-            const bool trace = (l == V1 && it == 0);
-            if (trace) stamp(32 + (kb * 2 + nh) * 3 + 0 > 95 ? 95 : 32 + (kb * 2 + nh) * 3 + 0);
-            mbar_wait(&sm.w_full[st], (c / kStages) & 1);
-            tcgen05_fence_after();
-            if (trace && kb * 2 + nh < 10) stamp(32 + (kb * 2 + nh) * 3 + 1);
-            const uint64_t bdesc = make_desc_sw128(w_ring + st * kBlockBytes);
-            const uint32_t dcol = tmem + d.tmem_col + nh * 128;
-#pragma unroll 1
-            for (int kk = 0; kk < d.ksteps[kb]; ++kk)
-              mma_bf16_ss(dcol, adesc + kk * 2, bdesc + kk * 2, idesc, (kb | kk) != 0);
-            mma_commit(&sm.w_empty[st]);
-            if (trace && kb * 2 + nh < 10) stamp(32 + (kb * 2 + nh) * 3 + 2);
-          }
-        }
-        mma_commit(&sm.acc_ready[l]);
-      };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const uint32_t ph = it & 1;
         const int tb = it < 2 ? (int)it * 16 : -1000;
         if (tb >= 0) stamp(tb + 0);
-        mbar_wait(&sm.a_ready[E_F], ph);  tcgen05_fence_after(); if (tb >= 0) stamp(tb + 1); run_layer(L0); if (tb >= 0) stamp(tb + 2);
-        mbar_wait(&sm.a_ready[E_H0], ph); tcgen05_fence_after(); if (tb >= 0) stamp(tb + 3); run_layer(L1); if (tb >= 0) stamp(tb + 4);
-        mbar_wait(&sm.a_ready[E_X], ph);  tcgen05_fence_after(); if (tb >= 0) stamp(tb + 5); run_layer(HS0); if (tb >= 0) stamp(tb + 6); run_layer(V0); if (tb >= 0) stamp(tb + 7);
-        mbar_wait(&sm.a_ready[E_G], ph);  tcgen05_fence_after(); if (tb >= 0) stamp(tb + 8); run_layer(HS1); if (tb >= 0) stamp(tb + 9);
-        mbar_wait(&sm.a_ready[E_H1], ph); tcgen05_fence_after(); if (tb >= 0) stamp(tb + 10); run_layer(V1); if (tb >= 0) stamp(tb + 11);
-        mbar_wait(&sm.a_ready[E_H2], ph); tcgen05_fence_after(); if (tb >= 0) stamp(tb + 12); run_layer(RGB); if (tb >= 0) stamp(tb + 13);
+        mbar_wait(&sm.a_ready[E_F], ph);  tcgen05_fence_after(); if (tb >= 0) stamp(tb + 1);
+        issue_layer<L0>(sm, a_blocks, w_ring, tmem, c);  if (tb >= 0) stamp(tb + 2);
+        mbar_wait(&sm.a_ready[E_H0], ph); tcgen05_fence_after(); if (tb >= 0) stamp(tb + 3);
+        issue_layer<L1>(sm, a_blocks, w_ring, tmem, c);  if (tb >= 0) stamp(tb + 4);
+        mbar_wait(&sm.a_ready[E_X], ph);  tcgen05_fence_after(); if (tb >= 0) stamp(tb + 5);
+        issue_layer<HS0>(sm, a_blocks, w_ring, tmem, c); if (tb >= 0) stamp(tb + 6);
+        issue_layer<V0>(sm, a_blocks, w_ring, tmem, c);  if (tb >= 0) stamp(tb + 7);
+        mbar_wait(&sm.a_ready[E_G], ph);  tcgen05_fence_after(); if (tb >= 0) stamp(tb + 8);
+        issue_layer<HS1>(sm, a_blocks, w_ring, tmem, c); if (tb >= 0) stamp(tb + 9);
+        mbar_wait(&sm.a_ready[E_H1], ph); tcgen05_fence_after(); if (tb >= 0) stamp(tb + 10);
+        issue_layer<V1>(sm, a_blocks, w_ring, tmem, c);  if (tb >= 0) stamp(tb + 11);
+        mbar_wait(&sm.a_ready[E_H2], ph); tcgen05_fence_after(); if (tb >= 0) stamp(tb + 12);
+        issue_layer<RGB>(sm, a_blocks, w_ring, tmem, c); if (tb >= 0) stamp(tb + 13);
       }
     }
   } else {
-    // ===== epilogue warps 0..3: thread r owns row r of the tile (TMEM lane r)
-    const int r = threadIdx.x;
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    // ===== epilogue warps 0..7: thread (q, lane) owns row r = 32 q + lane (TMEM lane r); the two
+    // warps of a lane quarter (half = 0 / 1) split every layer's columns
+    const int half = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint8_t* HB = a_blocks + BH * kBlockBytes;
     uint8_t* XB = a_blocks + BX * kBlockBytes;
     uint8_t* DB = a_blocks + BD * kBlockBytes;
-    uint8_t* myrow_off = nullptr;
-    (void)myrow_off;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
       const int row = tile * 128 + r;
       const bool valid = row < M;
-      // ---- stage features (H0) and the view-direction encoding (D)
-      {
+      // ---- stage features (H0: half 0) and the view-direction encoding (D: half 1)
+      if (half == 0) {
         float f[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) f[i] = 0.f;
@@ -305,6 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
           u.z = pack_bf16(f[q * 8 + 4], f[q * 8 + 5]); u.w = pack_bf16(f[q * 8 + 6], f[q * 8 + 7]);
           *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) * 16)) = u;
         }
+      } else {
         float d[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) d[i] = 0.f;
@@ -338,39 +354,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
 
       // ---- L0: h0 = relu(acc + b) -> H1
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 0);
-      mbar_wait(&sm.acc_ready[L0], ph);
+      mbar_wait_warp(&sm.acc_ready[L0], ph);
       tcgen05_fence_after();
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 1);
-#pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32)
+      {
+        const int c0 = half * 32;
         epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(L0) + c0, HB + 1 * kBlockBytes, r, c0, nullptr,
                                 (sv.h0 && valid) ? reinterpret_cast<__nv_bfloat16*>(sv.h0) + (size_t)row * 64 + c0 : nullptr);
+      }
       signal_a_ready(&sm.a_ready[E_H0]);
 
       // ---- L1: x = acc + b -> X0..3 ; density = softplus(x[0] - 1)
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 2);
-      mbar_wait(&sm.acc_ready[L1], ph);
+      mbar_wait_warp(&sm.acc_ready[L1], ph);
       tcgen05_fence_after();
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 3);
       float x0 = 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 256; c0 += 32)
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32)
         epi_cols_to_block<false>(tlane + 256 + c0, sm.bias + bias_offset(L1) + c0, XB + (c0 >> 6) * kBlockBytes, r,
                                  c0 & 63, c0 == 0 ? &x0 : nullptr,
                                  (sv.x && valid) ? reinterpret_cast<__nv_bfloat16*>(sv.x) + (size_t)row * 256 + c0 : nullptr);
       signal_a_ready(&sm.a_ready[E_X]);
-      if (valid) {
+      if (valid && half == 0) {
         const float xin = x0 - 1.0f;
         o_density[row] = xin > 20.f ? xin : log1pf(expf(xin));
       }
 
       // ---- HS0: hidden = relu(acc + b) -> H2, H3
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 4);
-      mbar_wait(&sm.acc_ready[HS0], ph);
+      mbar_wait_warp(&sm.acc_ready[HS0], ph);
       tcgen05_fence_after();
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 5);
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32)
+      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32)
         epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(HS0) + c0, HB + (2 + (c0 >> 6)) * kBlockBytes, r,
                                 c0 & 63, nullptr,
                                 (sv.g && valid) ? reinterpret_cast<__nv_bfloat16*>(sv.g) + (size_t)row * 128 + c0 : nullptr);
@@ -378,10 +395,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
 
       // ---- HS1: semantic softmax (19) + intensity
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 6);
-      mbar_wait(&sm.acc_ready[HS1], ph);
+      // (every warp waits: the V0 epilogue below overwrites H2/H3, which the HS1 MMAs read)
+      mbar_wait_warp(&sm.acc_ready[HS1], ph);
       tcgen05_fence_after();
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 7);
-      {
+      if (half == 0) {
         float v[32];
         tmem_ld32(tlane + 128, v);
         const float* b = sm.bias + bias_offset(HS1);
@@ -403,11 +421,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
 
       // ---- V0: h1 = relu(acc + b) -> H0..3
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 8);
-      mbar_wait(&sm.acc_ready[V0], ph);
+      mbar_wait_warp(&sm.acc_ready[V0], ph);
       tcgen05_fence_after();
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 9);
 #pragma unroll 1
-      for (int c0 = 0; c0 < 256; c0 += 32)
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32)
         epi_cols_to_block<true>(tlane + 256 + c0, sm.bias + bias_offset(V0) + c0, HB + (c0 >> 6) * kBlockBytes, r,
                                 c0 & 63, nullptr,
                                 (sv.h1 && valid) ? reinterpret_cast<__nv_bfloat16*>(sv.h1) + (size_t)row * 256 + c0 : nullptr);
@@ -415,11 +433,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
 
       // ---- V1: h2 = relu(acc + b) -> H0..3
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 10);
-      mbar_wait(&sm.acc_ready[V1], ph);
+      mbar_wait_warp(&sm.acc_ready[V1], ph);
       tcgen05_fence_after();
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 11);
 #pragma unroll 1
-      for (int c0 = 0; c0 < 256; c0 += 32)
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32)
         epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(V1) + c0, HB + (c0 >> 6) * kBlockBytes, r, c0 & 63,
                                 nullptr,
                                 (sv.h2 && valid) ? reinterpret_cast<__nv_bfloat16*>(sv.h2) + (size_t)row * 256 + c0 : nullptr);
@@ -427,10 +445,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
 
       // ---- RGB: sigmoid(acc + b) * (1 + 2 pad) - pad
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 12);
-      mbar_wait(&sm.acc_ready[RGB], ph);
+      mbar_wait_warp(&sm.acc_ready[RGB], ph);
       tcgen05_fence_after();
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 13);
-      {
+      if (half == 1) {  // (half 0 only needed the wait: the next tile's features overwrite H0)
         float v[16];
         tmem_ld16(tlane + 256, v);
         const float* b = sm.bias + bias_offset(RGB);
@@ -446,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
     }
   }
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 
 // =============================================================================
@@ -581,6 +599,38 @@ __device__ __forceinline__ void epi_masked(uint32_t taddr, const __nv_bfloat16* 
   }
 }
 
+// MMAs of backward layer L for one tile (see mlp::issue_layer).
+template <int L, class SmemT>
+__device__ __forceinline__ void issue_blayer(SmemT& sm, uint8_t* a_blocks, uint8_t* w_ring, uint32_t tmem, uint32_t& c,
+                                             uint32_t ph) {
+  constexpr BLayerDef d = blayer_def(L);
+  constexpr int nrows = bl_nrows(L), np_count = bl_nparts(L);
+  mbar_wait(&sm.a_ready[L], ph);
+  tcgen05_fence_after();
+  const uint32_t idesc = make_idesc_bf16(128, nrows);
+#pragma unroll
+  for (int kb = 0; kb < d.nkb; ++kb) {
+    const uint64_t adesc = make_desc_sw128(a_blocks + d.a_blk[kb] * kBlockBytes);
+#pragma unroll
+    for (int np = 0; np < np_count; ++np, ++c) {
+      const uint32_t st = c % kStages;
+      mbar_wait(&sm.w_full[st], (c / kStages) & 1);
+      tcgen05_fence_after();
+      const uint64_t bdesc = make_desc_sw128(w_ring + st * kBlockBytes);
+      const uint32_t dcol = tmem + d.tmem_col[np];
+      const bool acc0 = d.accumulate || kb != 0;
+      switch (d.ksteps[kb]) {
+        case 1: mma_chunk<1>(dcol, adesc, bdesc, idesc, acc0); break;
+        case 2: mma_chunk<2>(dcol, adesc, bdesc, idesc, acc0); break;
+        case 3: mma_chunk<3>(dcol, adesc, bdesc, idesc, acc0); break;
+        default: mma_chunk<4>(dcol, adesc, bdesc, idesc, acc0); break;
+      }
+      mma_commit(&sm.w_empty[st]);
+    }
+  }
+  mma_commit(&sm.acc_ready[L]);
+}
+
 __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_in_t gi, nlb_nerf_mlp_saved_t sv, int M,
                                                               const uint8_t* __restrict__ blob,
                                                               float* __restrict__ grad_features,
@@ -595,18 +645,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
-    for (int i = 0; i < kNumBLayers; ++i) { mbar_init(&sm.acc_ready[i], 1); mbar_init(&sm.a_ready[i], 128); }
+    for (int i = 0; i < kNumBLayers; ++i) { mbar_init(&sm.acc_ready[i], 1); mbar_init(&sm.a_ready[i], kEpiThreads); }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(&sm.tmem_base, 512);
+  if (warp == kMmaWarp) tmem_alloc(&sm.tmem_base, 512);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp >= 5) {
-    if (lane == 0) {
-      const int my_stage = warp - 5;
+  if (warp >= kProdWarp0) {
+    if (elect_one_sync()) {
+      const int my_stage = warp - kProdWarp0;
       uint32_t c = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
 #pragma unroll 1
@@ -617,48 +667,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
           for (int i = 0; i < n; ++i, ++c) {
             const int st = c % kStages;
             if (st != my_stage) continue;
-            mbar_wait(&sm.w_empty[st], ((c / kStages) & 1) ^ 1);
+            mbar_wait_relaxed(&sm.w_empty[st], ((c / kStages) & 1) ^ 1);
             mbar_expect_tx(&sm.w_full[st], bytes);
             bulk_g2s(w_ring + st * kBlockBytes, src + (size_t)i * bytes, bytes, &sm.w_full[st]);
           }
         }
       }
     }
-  } else if (warp == 4) {
-    if (lane == 0) {
+  } else if (warp == kMmaWarp) {
+    if (elect_one_sync()) {
       uint32_t c = 0, it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const uint32_t ph = it & 1;
-#pragma unroll 1
-        for (int l = 0; l < kNumBLayers; ++l) {
-          mbar_wait(&sm.a_ready[l], ph);
-          tcgen05_fence_after();
-          const BLayerDef d = blayer_def(l);
-          const int nrows = bl_nrows(l), np_count = bl_nparts(l);
-          const uint32_t idesc = make_idesc_bf16(128, nrows);
-#pragma unroll 1
-          for (int kb = 0; kb < d.nkb; ++kb) {
-            const uint64_t adesc = make_desc_sw128(a_blocks + d.a_blk[kb] * kBlockBytes);
-#pragma unroll 1
-            for (int np = 0; np < np_count; ++np, ++c) {
-              const int st = c % kStages;
-              mbar_wait(&sm.w_full[st], (c / kStages) & 1);
-              tcgen05_fence_after();
-              const uint64_t bdesc = make_desc_sw128(w_ring + st * kBlockBytes);
-              const uint32_t dcol = tmem + d.tmem_col[np];
-#pragma unroll 1
-              for (int kk = 0; kk < d.ksteps[kb]; ++kk)
-                mma_bf16_ss(dcol, adesc + kk * 2, bdesc + kk * 2, idesc, d.accumulate || (kb | kk) != 0);
-              mma_commit(&sm.w_empty[st]);
-            }
-          }
-          mma_commit(&sm.acc_ready[l]);
-        }
+        issue_blayer<B_RGB>(sm, a_blocks, w_ring, tmem, c, ph);
+        issue_blayer<B_V1>(sm, a_blocks, w_ring, tmem, c, ph);
+        issue_blayer<B_V0>(sm, a_blocks, w_ring, tmem, c, ph);
+        issue_blayer<B_HS1>(sm, a_blocks, w_ring, tmem, c, ph);
+        issue_blayer<B_HS0>(sm, a_blocks, w_ring, tmem, c, ph);
+        issue_blayer<B_L1>(sm, a_blocks, w_ring, tmem, c, ph);
+        issue_blayer<B_L0>(sm, a_blocks, w_ring, tmem, c, ph);
       }
     }
   } else {
-    const int r = threadIdx.x;
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const int half = warp >> 2;  // the two warps of a TMEM lane quarter split every layer's columns
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint8_t* PB = a_blocks + BP * kBlockBytes;
     uint8_t* QB = a_blocks + BQ * kBlockBytes;
     uint8_t* SB = a_blocks + BS * kBlockBytes;
@@ -671,8 +704,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
       const bool valid = row < M;
       const int crow = valid ? row : M - 1;  // clamped row: always dereferenceable
       uint8_t* srow = SB + (r >> 3) * 1024 + (r & 7) * 128;
-      // ---- dc -> S (cols 0..2)
-      {
+      // ---- dc -> S (cols 0..2): half 0
+      if (half == 0) {
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -693,25 +726,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
       signal_a_ready(&sm.a_ready[B_RGB]);
 
       // ---- dzv1 = dh2 * [h2 > 0] -> P0..3
-      mbar_wait(&sm.acc_ready[B_RGB], ph);
+      mbar_wait_warp(&sm.acc_ready[B_RGB], ph);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < 256; c0 += 32)
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32)
         epi_masked<true>(tlane + 256 + c0, cbf(sv.h2) + (size_t)crow * 256 + c0, PB + (c0 >> 6) * kBlockBytes, r,
                          c0 & 63, bf(go.d_v1) + (size_t)crow * 256 + c0, valid);
       signal_a_ready(&sm.a_ready[B_V1]);
 
       // ---- dzv0 = dh1 * [h1 > 0] -> Q0..3   (dh1 in accB, dx partial stays in accA)
-      mbar_wait(&sm.acc_ready[B_V1], ph);
+      mbar_wait_warp(&sm.acc_ready[B_V1], ph);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < 256; c0 += 32)
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32)
         epi_masked<true>(tlane + 256 + c0, cbf(sv.h1) + (size_t)crow * 256 + c0, QB + (c0 >> 6) * kBlockBytes, r,
                          c0 & 63, bf(go.d_v0) + (size_t)crow * 256 + c0, valid);
       signal_a_ready(&sm.a_ready[B_V0]);
 
-      // ---- d(sem logits) | d(intensity) -> S (cols 0..19); S is free: B_RGB completed above
-      {
+      // ---- d(sem logits) | d(intensity) -> S (cols 0..19): half 1; S is free: B_RGB completed above
+      if (half == 1) {
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -734,47 +767,53 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
       signal_a_ready(&sm.a_ready[B_HS1]);
 
       // ---- dzg = dg * [g > 0] -> Q0,Q1  (B_V0 has finished reading Q: it precedes B_HS1 on the pipe)
-      mbar_wait(&sm.acc_ready[B_HS1], ph);
+      mbar_wait_warp(&sm.acc_ready[B_HS1], ph);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32)
+      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32)
         epi_masked<true>(tlane + 256 + c0, cbf(sv.g) + (size_t)crow * 128 + c0, QB + (c0 >> 6) * kBlockBytes, r,
                          c0 & 63, bf(go.d_g) + (size_t)crow * 128 + c0, valid);
       signal_a_ready(&sm.a_ready[B_HS0]);
 
       // ---- dx = accA (+ density term on column 0) -> P0..3
-      mbar_wait(&sm.acc_ready[B_HS0], ph);
+      mbar_wait_warp(&sm.acc_ready[B_HS0], ph);
       tcgen05_fence_after();
       {
         float dterm = 0.f;
         if (valid && gi.g_density) dterm = __ldg(gi.g_density + row) * (1.0f - expf(-__ldg(gi.density + row)));
 #pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32)
+        for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32)
           epi_masked<false>(tlane + c0, nullptr, PB + (c0 >> 6) * kBlockBytes, r, c0 & 63,
                             bf(go.d_x) + (size_t)crow * 256 + c0, valid, c0 == 0 ? dterm : 0.f);
       }
       signal_a_ready(&sm.a_ready[B_L1]);
 
       // ---- dz0 = dh0 * [h0 > 0] -> Q2
-      mbar_wait(&sm.acc_ready[B_L1], ph);
+      mbar_wait_warp(&sm.acc_ready[B_L1], ph);
       tcgen05_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32)
+      {
+        const int c0 = half * 32;
         epi_masked<true>(tlane + 256 + c0, cbf(sv.h0) + (size_t)crow * 64 + c0, QB + 2 * kBlockBytes, r, c0,
                          bf(go.d_h0) + (size_t)crow * 64 + c0, valid);
+      }
       signal_a_ready(&sm.a_ready[B_L0]);
 
       // ---- grad_features = accB[64:112) (40 valid columns)
-      mbar_wait(&sm.acc_ready[B_L0], ph);
+      mbar_wait_warp(&sm.acc_ready[B_L0], ph);
       tcgen05_fence_after();
-      {
-        float v[32], t[16];
+      if (half == 0) {
+        float v[32];
         tmem_ld32(tlane + 320, v);
-        tmem_ld16(tlane + 352, t);
         if (valid) {
           float4* dst = reinterpret_cast<float4*>(grad_features + (size_t)row * kFeat);
 #pragma unroll
           for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        }
+      } else {
+        float t[16];
+        tmem_ld16(tlane + 352, t);
+        if (valid) {
+          float4* dst = reinterpret_cast<float4*>(grad_features + (size_t)row * kFeat);
           dst[8] = make_float4(t[0], t[1], t[2], t[3]);
           dst[9] = make_float4(t[4], t[5], t[6], t[7]);
         }
@@ -783,7 +822,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
     }
   }
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 
 constexpr size_t kBSmemBytes = 1024 + (kNumABlocks + kStages) * (size_t)kBlockBytes + sizeof(BSmem);

@@ -36,6 +36,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Whole-warp wait: ONE lane polls (with back-off), the rest of the warp sleeps at the
+// warp barrier.  128 epilogue threads spinning on try_wait flood the SM's memory-I/O queue
+// that tcgen05.mma issue also goes through: measured 133-140 cycles per MMA issue with
+// per-thread spinning against 64.5 (the tensor pipe's own rate) without.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+  }
+  __syncwarp();
+}
+// Single-thread wait of a non-critical role (weight producers): poll with back-off.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+}
 
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma / bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -120,6 +134,22 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
+}
+// One lane of the (converged) warp: tcgen05 instructions are issued from an elect.sync
+// region so the compiler emits them straight-line on the uniform datapath instead of
+// wrapping each one in a per-lane serialisation loop (`if (lane == 0)` did: ~16 dependent
+// uniform instructions and 133 cycles per MMA, twice the tensor pipe's 64.5).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// K-steps of one operand chunk ([128][64] x [N][64]^T), fully unrolled
+template <int KSTEPS>
+__device__ __forceinline__ void mma_chunk(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          bool accumulate_first) {
+#pragma unroll
+  for (int kk = 0; kk < KSTEPS; ++kk) mma_bf16_ss(tmem_d, desc_a + kk * 2, desc_b + kk * 2, idesc, kk ? true : accumulate_first);
 }
 // arrive on an mbarrier when all MMAs issued so far by this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

@@ -11,10 +11,10 @@ _lib.check(_lib.load().nlb_debug_set_timeline(buf.data_ptr()))
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
 e0.record(); ops.nerf_mlp_forward(mlp, feat, vd, S); e1.record(); torch.cuda.synchronize()
 print('kernel ms', e0.elapsed_time(e1))
-t = buf.cpu().tolist(); t0 = min(x for x in t if x > 0)
+t = buf.cpu().tolist(); t0 = min(x for x in t[:100] if x > 0)
 names_m = ['start','F rdy','L0 iss','H0 rdy','L1 iss','X rdy','HS0 iss','V0 iss','G rdy','HS1 iss','H1 rdy','V1 iss','H2 rdy','RGB iss']
 for tile in range(2):
     print('tile', tile, 'MMA thread:', [(n, t[tile*16+i]-t0) for i, n in enumerate(names_m)])
     en = ['L0','L1','HS0','HS1','V0','V1','RGB']
     print('tile', tile, 'EPI thread:', [(en[i], t[64+tile*16+2*i]-t0, t[64+tile*16+2*i+1]-t0) for i in range(7)], 'F staged', t[64+tile*16+14]-t0)
-print('V1 chunks (start, weights landed, committed):', [(t[32+3*i]-t0, t[32+3*i+1]-t0, t[32+3*i+2]-t0) for i in range(10)])
+print('tile 1 per layer (wait for weights, issue+commit) cycles:', [(n, t[100+2*i], t[101+2*i]) for i, n in enumerate(['L0','L1','HS0','V0','HS1','V1','RGB'])])
