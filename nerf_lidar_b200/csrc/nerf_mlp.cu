@@ -174,6 +174,71 @@ __device__ __forceinline__ void epi_cols_to_block(uint32_t taddr, const float* _
   store_cols(v, block, row, col_in_block, gdst);
 }
 
+// ---- 64-column epilogue groups ---------------------------------------------------------
+// A warp owns 32 rows of the tile; one group = those rows x one whole operand block (64
+// columns, 128 bytes per row).  Global traffic of a group is coalesced through the block
+// itself: each thread writes (reads) its own row in shared memory, and after a warp barrier
+// the warp moves 4 rows x 128 contiguous bytes per instruction to (from) the row-major
+// bf16 matrix.  (Per-thread 64-byte stores at a 512-byte row stride touched 32 lines per
+// instruction and kept the epilogue -- the critical path of the tile -- waiting on the LSU.)
+__device__ __forceinline__ uint8_t* block_row(uint8_t* block, int row) { return block + (row >> 3) * 1024 + (row & 7) * 128; }
+
+// this thread's 64 values -> bf16 -> its row of the swizzled block
+__device__ __forceinline__ void store_row64(const float (&v)[64], uint8_t* block, int row) {
+  uint8_t* rowp = block_row(block, row);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    uint4 u;
+    u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+    u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+    u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+    u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(rowp + ((q ^ (row & 7)) * 16)) = u;
+  }
+}
+
+// rows [wrow0, wrow0+32) of the block -> g[(row) * ld + 0..63] (g = tile base + column offset)
+__device__ __forceinline__ void warp_rows_to_global(const uint8_t* block, int wrow0, int lane, __nv_bfloat16* g, int ld,
+                                                    int rows_valid) {
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = wrow0 + i * 4 + (lane >> 3), ch = lane & 7;
+    const uint4 u = *reinterpret_cast<const uint4*>(block + (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) * 16));
+    if (row < rows_valid) *reinterpret_cast<uint4*>(g + (size_t)row * ld + ch * 8) = u;
+  }
+}
+
+// g[(row) * ld + 0..63] -> rows [wrow0, wrow0+32) of the block (zeros beyond rows_valid)
+__device__ __forceinline__ void warp_rows_from_global(uint8_t* block, int wrow0, int lane, const __nv_bfloat16* g, int ld,
+                                                      int rows_valid) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = wrow0 + i * 4 + (lane >> 3), ch = lane & 7;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (row < rows_valid) u = __ldg(reinterpret_cast<const uint4*>(g + (size_t)row * ld + ch * 8));
+    *reinterpret_cast<uint4*>(block + (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) * 16)) = u;
+  }
+  __syncwarp();
+}
+
+// forward group: 64 accumulator columns of this thread's row -> bias (+relu) -> block (+ saved copy)
+template <bool kRelu>
+__device__ __forceinline__ void epi_group64(uint32_t taddr, const float* __restrict__ bias, uint8_t* block, int row,
+                                            int lane, __nv_bfloat16* gsave, int ld, int rows_valid,
+                                            float* keep0 = nullptr) {
+  float v[64];
+  tmem_ld64(taddr, v);
+#pragma unroll
+  for (int i = 0; i < 64; ++i) {
+    v[i] += bias[i];
+    if (kRelu) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (keep0) *keep0 = v[0];
+  store_row64(v, block, row);
+  if (gsave) warp_rows_to_global(block, row & ~31, lane, gsave, ld, rows_valid);
+}
+
 __device__ __forceinline__ void signal_a_ready(uint64_t* bar) {
   tcgen05_fence_before();
   fence_proxy_async();
@@ -299,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
       const uint32_t ph = it & 1;
       const int row = tile * 128 + r;
       const bool valid = row < M;
+      const int rows_valid = M - tile * 128 < 128 ? M - tile * 128 : 128;
       // ---- stage features (H0: half 0) and the view-direction encoding (D: half 1)
       if (half == 0) {
         float f[64];
@@ -357,11 +423,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
       mbar_wait_warp(&sm.acc_ready[L0], ph);
       tcgen05_fence_after();
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 1);
-      {
-        const int c0 = half * 32;
-        epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(L0) + c0, HB + 1 * kBlockBytes, r, c0, nullptr,
-                                (sv.h0 && valid) ? reinterpret_cast<__nv_bfloat16*>(sv.h0) + (size_t)row * 64 + c0 : nullptr);
-      }
+      if (half == 0)
+        epi_group64<true>(tlane, sm.bias + bias_offset(L0), HB + 1 * kBlockBytes, r, lane,
+                          sv.h0 ? reinterpret_cast<__nv_bfloat16*>(sv.h0) + (size_t)tile * 128 * 64 : nullptr, 64, rows_valid);
       signal_a_ready(&sm.a_ready[E_H0]);
 
       // ---- L1: x = acc + b -> X0..3 ; density = softplus(x[0] - 1)
@@ -371,10 +435,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 3);
       float x0 = 0.f;
 #pragma unroll 1
-      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32)
-        epi_cols_to_block<false>(tlane + 256 + c0, sm.bias + bias_offset(L1) + c0, XB + (c0 >> 6) * kBlockBytes, r,
-                                 c0 & 63, c0 == 0 ? &x0 : nullptr,
-                                 (sv.x && valid) ? reinterpret_cast<__nv_bfloat16*>(sv.x) + (size_t)row * 256 + c0 : nullptr);
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
+        epi_group64<false>(tlane + 256 + c0, sm.bias + bias_offset(L1) + c0, XB + (c0 >> 6) * kBlockBytes, r, lane,
+                           sv.x ? reinterpret_cast<__nv_bfloat16*>(sv.x) + (size_t)tile * 128 * 256 + c0 : nullptr, 256,
+                           rows_valid, c0 == 0 ? &x0 : nullptr);
       signal_a_ready(&sm.a_ready[E_X]);
       if (valid && half == 0) {
         const float xin = x0 - 1.0f;
@@ -387,10 +451,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
       tcgen05_fence_after();
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 5);
 #pragma unroll 1
-      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32)
-        epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(HS0) + c0, HB + (2 + (c0 >> 6)) * kBlockBytes, r,
-                                c0 & 63, nullptr,
-                                (sv.g && valid) ? reinterpret_cast<__nv_bfloat16*>(sv.g) + (size_t)row * 128 + c0 : nullptr);
+      {
+        const int c0 = half * 64;
+        epi_group64<true>(tlane + c0, sm.bias + bias_offset(HS0) + c0, HB + (2 + half) * kBlockBytes, r, lane,
+                          sv.g ? reinterpret_cast<__nv_bfloat16*>(sv.g) + (size_t)tile * 128 * 128 + c0 : nullptr, 128,
+                          rows_valid);
+      }
       signal_a_ready(&sm.a_ready[E_G]);
 
       // ---- HS1: semantic softmax (19) + intensity
@@ -425,10 +491,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
       tcgen05_fence_after();
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 9);
 #pragma unroll 1
-      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32)
-        epi_cols_to_block<true>(tlane + 256 + c0, sm.bias + bias_offset(V0) + c0, HB + (c0 >> 6) * kBlockBytes, r,
-                                c0 & 63, nullptr,
-                                (sv.h1 && valid) ? reinterpret_cast<__nv_bfloat16*>(sv.h1) + (size_t)row * 256 + c0 : nullptr);
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
+        epi_group64<true>(tlane + 256 + c0, sm.bias + bias_offset(V0) + c0, HB + (c0 >> 6) * kBlockBytes, r, lane,
+                          sv.h1 ? reinterpret_cast<__nv_bfloat16*>(sv.h1) + (size_t)tile * 128 * 256 + c0 : nullptr, 256,
+                          rows_valid);
       signal_a_ready(&sm.a_ready[E_H1]);
 
       // ---- V1: h2 = relu(acc + b) -> H0..3
@@ -437,10 +503,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
       tcgen05_fence_after();
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 11);
 #pragma unroll 1
-      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32)
-        epi_cols_to_block<true>(tlane + c0, sm.bias + bias_offset(V1) + c0, HB + (c0 >> 6) * kBlockBytes, r, c0 & 63,
-                                nullptr,
-                                (sv.h2 && valid) ? reinterpret_cast<__nv_bfloat16*>(sv.h2) + (size_t)row * 256 + c0 : nullptr);
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
+        epi_group64<true>(tlane + c0, sm.bias + bias_offset(V1) + c0, HB + (c0 >> 6) * kBlockBytes, r, lane,
+                          sv.h2 ? reinterpret_cast<__nv_bfloat16*>(sv.h2) + (size_t)tile * 128 * 256 + c0 : nullptr, 256,
+                          rows_valid);
       signal_a_ready(&sm.a_ready[E_H2]);
 
       // ---- RGB: sigmoid(acc + b) * (1 + 2 pad) - pad
@@ -631,6 +697,39 @@ __device__ __forceinline__ void issue_blayer(SmemT& sm, uint8_t* a_blocks, uint8
   mma_commit(&sm.acc_ready[L]);
 }
 
+// backward group: 64 accumulator columns of this thread's row -> (optional) ReLU mask from
+// the saved bf16 activation -> block + row-major bf16 copy for the weight-gradient GEMMs.
+// The activation rows are first staged, coalesced, into the destination block itself (it
+// is free: it is about to be overwritten), each thread then reads its own row from there.
+//   act / gdst = tile base + column offset of the saved activation / output matrices.
+template <bool kMask>
+__device__ __forceinline__ void epi_group64_masked(uint32_t taddr, const __nv_bfloat16* __restrict__ act,
+                                                   uint8_t* block, int row, int lane, __nv_bfloat16* gdst, int ld,
+                                                   int rows_valid, float add0 = 0.f) {
+  if (kMask) warp_rows_from_global(block, row & ~31, lane, act, ld, rows_valid);
+  float v[64];
+  tmem_ld64(taddr, v);
+  v[0] += add0;
+  if (kMask) {
+    const uint8_t* rowp = block_row(block, row);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint4 m = *reinterpret_cast<const uint4*>(rowp + ((q ^ (row & 7)) * 16));
+      // post-ReLU activations are >= 0: a unit was active iff its bf16 bits are non-zero (ignoring -0)
+      if ((m.x & 0x7FFFu) == 0) v[q * 8 + 0] = 0.f;
+      if ((m.x & 0x7FFF0000u) == 0) v[q * 8 + 1] = 0.f;
+      if ((m.y & 0x7FFFu) == 0) v[q * 8 + 2] = 0.f;
+      if ((m.y & 0x7FFF0000u) == 0) v[q * 8 + 3] = 0.f;
+      if ((m.z & 0x7FFFu) == 0) v[q * 8 + 4] = 0.f;
+      if ((m.z & 0x7FFF0000u) == 0) v[q * 8 + 5] = 0.f;
+      if ((m.w & 0x7FFFu) == 0) v[q * 8 + 6] = 0.f;
+      if ((m.w & 0x7FFF0000u) == 0) v[q * 8 + 7] = 0.f;
+    }
+  }
+  store_row64(v, block, row);
+  if (gdst) warp_rows_to_global(block, row & ~31, lane, gdst, ld, rows_valid);
+}
+
 __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_in_t gi, nlb_nerf_mlp_saved_t sv, int M,
                                                               const uint8_t* __restrict__ blob,
                                                               float* __restrict__ grad_features,
@@ -702,7 +801,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
       const uint32_t ph = it & 1;
       const int row = tile * 128 + r;
       const bool valid = row < M;
-      const int crow = valid ? row : M - 1;  // clamped row: always dereferenceable
+      const int rows_valid = M - tile * 128 < 128 ? M - tile * 128 : 128;
+      const size_t trow = (size_t)tile * 128;  // first row of the tile
       uint8_t* srow = SB + (r >> 3) * 1024 + (r & 7) * 128;
       // ---- dc -> S (cols 0..2): half 0
       if (half == 0) {
@@ -729,18 +829,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
       mbar_wait_warp(&sm.acc_ready[B_RGB], ph);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32)
-        epi_masked<true>(tlane + 256 + c0, cbf(sv.h2) + (size_t)crow * 256 + c0, PB + (c0 >> 6) * kBlockBytes, r,
-                         c0 & 63, bf(go.d_v1) + (size_t)crow * 256 + c0, valid);
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
+        epi_group64_masked<true>(tlane + 256 + c0, cbf(sv.h2) + trow * 256 + c0, PB + (c0 >> 6) * kBlockBytes, r, lane,
+                                 bf(go.d_v1) + trow * 256 + c0, 256, rows_valid);
       signal_a_ready(&sm.a_ready[B_V1]);
 
       // ---- dzv0 = dh1 * [h1 > 0] -> Q0..3   (dh1 in accB, dx partial stays in accA)
       mbar_wait_warp(&sm.acc_ready[B_V1], ph);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32)
-        epi_masked<true>(tlane + 256 + c0, cbf(sv.h1) + (size_t)crow * 256 + c0, QB + (c0 >> 6) * kBlockBytes, r,
-                         c0 & 63, bf(go.d_v0) + (size_t)crow * 256 + c0, valid);
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
+        epi_group64_masked<true>(tlane + 256 + c0, cbf(sv.h1) + trow * 256 + c0, QB + (c0 >> 6) * kBlockBytes, r, lane,
+                                 bf(go.d_v0) + trow * 256 + c0, 256, rows_valid);
       signal_a_ready(&sm.a_ready[B_V0]);
 
       // ---- d(sem logits) | d(intensity) -> S (cols 0..19): half 1; S is free: B_RGB completed above
@@ -770,9 +870,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
       mbar_wait_warp(&sm.acc_ready[B_HS1], ph);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32)
-        epi_masked<true>(tlane + 256 + c0, cbf(sv.g) + (size_t)crow * 128 + c0, QB + (c0 >> 6) * kBlockBytes, r,
-                         c0 & 63, bf(go.d_g) + (size_t)crow * 128 + c0, valid);
+      {
+        const int c0 = half * 64;
+        epi_group64_masked<true>(tlane + 256 + c0, cbf(sv.g) + trow * 128 + c0, QB + half * kBlockBytes, r, lane,
+                                 bf(go.d_g) + trow * 128 + c0, 128, rows_valid);
+      }
       signal_a_ready(&sm.a_ready[B_HS0]);
 
       // ---- dx = accA (+ density term on column 0) -> P0..3
@@ -782,20 +884,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
         float dterm = 0.f;
         if (valid && gi.g_density) dterm = __ldg(gi.g_density + row) * (1.0f - expf(-__ldg(gi.density + row)));
 #pragma unroll 1
-        for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32)
-          epi_masked<false>(tlane + c0, nullptr, PB + (c0 >> 6) * kBlockBytes, r, c0 & 63,
-                            bf(go.d_x) + (size_t)crow * 256 + c0, valid, c0 == 0 ? dterm : 0.f);
+        for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
+          epi_group64_masked<false>(tlane + c0, nullptr, PB + (c0 >> 6) * kBlockBytes, r, lane,
+                                    bf(go.d_x) + trow * 256 + c0, 256, rows_valid, c0 == 0 ? dterm : 0.f);
       }
       signal_a_ready(&sm.a_ready[B_L1]);
 
       // ---- dz0 = dh0 * [h0 > 0] -> Q2
       mbar_wait_warp(&sm.acc_ready[B_L1], ph);
       tcgen05_fence_after();
-      {
-        const int c0 = half * 32;
-        epi_masked<true>(tlane + 256 + c0, cbf(sv.h0) + (size_t)crow * 64 + c0, QB + 2 * kBlockBytes, r, c0,
-                         bf(go.d_h0) + (size_t)crow * 64 + c0, valid);
-      }
+      if (half == 0)
+        epi_group64_masked<true>(tlane + 256, cbf(sv.h0) + trow * 64, QB + 2 * kBlockBytes, r, lane,
+                                 bf(go.d_h0) + trow * 64, 64, rows_valid);
       signal_a_ready(&sm.a_ready[B_L0]);
 
       // ---- grad_features = accB[64:112) (40 valid columns)

@@ -57,3 +57,26 @@ f = timeit(lambda: check(load().nlb_encode_forward(C.byref(rd), C.byref(tab), pt
 b = timeit(lambda: check(load().nlb_encode_backward(C.byref(rd), C.byref(tab), ptr(g), ptr(gt), stream())))
 out.append(f'nerf: fwd {f:.3f} bwd {b:.3f}')
 print(os.environ.get('NLB_LIB', 'default'), ' | '.join(out))
+
+# ---- NerfMLP fused kernels (training forward with saved activations, data-gradient backward)
+mlp = model.nerf_mlp
+S = 32
+M = rays.N * S
+feat = (torch.randn(M, 40, device='cuda') * 0.3)
+vd = ops.f32(batch['viewdirs'])
+import ctypes as C2
+from nerf_lidar_b200._lib import NlbNerfMlpSaved, NlbNerfMlpGradIn, NlbNerfMlpGradOut
+density, rgb, sem, inten, saved = ops._mlp_forward_raw(mlp, feat, vd, S, True)
+tf = timeit(lambda: ops._mlp_forward_raw(mlp, feat, vd, S, True))
+ti = timeit(lambda: ops._mlp_forward_raw(mlp, feat, vd, S, False))
+blob_t = ops.nerf_mlp_pack(mlp, transposed=True)
+bf = lambda cols: torch.empty(M, cols, device='cuda', dtype=torch.bfloat16)
+d_rgb, d_v1, d_v0, d_hs1, d_g, d_x, d_h0 = bf(16), bf(256), bf(256), bf(32), bf(128), bf(256), bf(64)
+g_feat = torch.empty(M, 40, device='cuda')
+gd, grgb, gsem, gint = torch.randn_like(density), torch.randn_like(rgb), torch.randn_like(sem), torch.randn_like(inten)
+gin = NlbNerfMlpGradIn(ptr(gd), ptr(grgb), ptr(gsem), ptr(gint), ptr(density), ptr(rgb), ptr(sem))
+sv = NlbNerfMlpSaved(*[ptr(saved[k]) for k in ('h0', 'x', 'g', 'h1', 'h2')])
+gout = NlbNerfMlpGradOut(ptr(d_rgb), ptr(d_v1), ptr(d_v0), ptr(d_hs1), ptr(d_g), ptr(d_x), ptr(d_h0))
+tb = timeit(lambda: check(load().nlb_nerf_mlp_backward(C.byref(gin), C.byref(sv), M, ptr(blob_t), ptr(g_feat), C.byref(gout), stream())))
+flop = 2 * 264192 * M
+print(f'mlp: fwd(train) {tf:.3f} ms = {flop / tf / 1e9:.0f} TFLOP/s | fwd(infer) {ti:.3f} ms = {flop / ti / 1e9:.0f} TFLOP/s | bwd {tb:.3f} ms = {2 * flop / tb / 1e9:.0f} TFLOP/s (data-gradient chain, 2x fwd FLOPs nominal)')
