@@ -272,6 +272,41 @@ int nlb_distortion_loss(const float* sdist, const float* weights, int N, int S, 
 int nlb_interlevel_loss(const float* c, const float* w, int Sc, const float* cp, const float* wp, int Sp,
                         float pulse_width, int N, float* loss_ray, float* grad_wp, void* stream);
 
+/* ------------------------------------------------------------------ supervision losses
+ * Value and gradient of the losses of Z/train.py:283-455 on the final rendering:
+ * losses[6] / scales[6] = {data, depth, sem, int, d_smo, s_smo} (device).  The gradient
+ * buffers receive the UNNORMALISED per-ray terms; d loss_k / d output = scales[k] * g_k
+ * (scales = multiplier / denominator, 0 where the reference's nan_to_num zeroes a term):
+ *   g_rgb[N,3] (data), g_depth[N] (depth), g_sem[N,K] (sem), g_int[N] (int),
+ *   g_depth_smo[N], g_sem_smo[N,K] (first num_patch*patch_size^2 rays: the patch rays
+ *   lead the batch, Z/internal/datasets.py:356-366; the rest is left untouched).
+ * Masks follow Z/train.py:300-327 (Config.instance_obj = True clears batch['mask']).
+ */
+typedef struct {
+  const float* rgb;         /* [N,3] rendered */
+  const float* depth;       /* [N] */
+  const float* semantic;    /* [N,K] class probabilities or NULL */
+  const float* intensity;   /* [N] or NULL */
+  const float* t_rgb;       /* [N,3] targets */
+  const float* t_depth;     /* [N] (> 0: supervised) */
+  const float* t_semantic;  /* [N] float labels, 255 = unlabelled */
+  const float* t_intensity; /* [N] */
+  const float* patch_mask;  /* [N] == 1: patch ray (smoothness only) */
+  const float* lidar_mask;  /* [N] == 1: LiDAR ray */
+  int N, K;
+  int num_patch, patch_size;
+  int lidar_supervision, only_lidar_supervision;
+  int charb;                /* 1: Charbonnier (Config.data_loss_type = 'charb'), 0: MSE */
+  float charb_padding;
+  float depth_mult, sem_mult, int_mult, smooth_mult; /* 0.4|0.1|0, 0.04|0.01|0, 0.1, 0.01 (Z/train.py:330-371) */
+  float smo_scale_x, smo_scale_y; /* filled in by the library */
+} nlb_losses_in_t;
+
+size_t nlb_render_losses_workspace_bytes(void);
+int nlb_render_losses(const nlb_losses_in_t* in, float* losses /*[6]*/, float* scales /*[6]*/, float* g_rgb,
+                      float* g_depth, float* g_sem, float* g_int, float* g_depth_smo, float* g_sem_smo,
+                      float* workspace, void* stream);
+
 /* ------------------------------------------------------------------ optimizer
  * One fused pass per table: hash-decay gradient (Model.hash_decay_loss,
  * Z/internal/models.py:203-223: d/dp of mult * mean_levels(mean_rows(p^2)))

@@ -26,6 +26,15 @@ class NlbTable(C.Structure):
                 ('H', C.c_uint32), ('S', C.c_float), ('offsets_host', C.POINTER(C.c_int32))]
 
 
+class NlbLossesIn(C.Structure):
+    _fields_ = [(n, c_f) for n in ('rgb', 'depth', 'semantic', 'intensity', 't_rgb', 't_depth', 't_semantic',
+                                   't_intensity', 'patch_mask', 'lidar_mask')] + \
+               [(n, C.c_int) for n in ('N', 'K', 'num_patch', 'patch_size', 'lidar_supervision',
+                                       'only_lidar_supervision', 'charb')] + \
+               [(n, C.c_float) for n in ('charb_padding', 'depth_mult', 'sem_mult', 'int_mult', 'smooth_mult',
+                                         'smo_scale_x', 'smo_scale_y')]
+
+
 class NlbCompositeIn(C.Structure):
     _fields_ = [('density', c_f), ('tdist', c_f), ('directions', c_f), ('rgb', c_f), ('semantic', c_f),
                 ('intensity', c_f), ('far', c_f), ('N', C.c_int), ('S', C.c_int), ('K', C.c_int),
@@ -93,6 +102,8 @@ SIGNATURES = {
     'nlb_distortion_loss': (_i, [_p, _p, _i, _i, _p, _p, _p]),
     'nlb_interlevel_loss': (_i, [_p, _p, _i, _p, _p, _i, _f, _i, _p, _p, _p]),
     'nlb_adam_table_step': (_i, [_p, _p, _p, _p, C.POINTER(C.c_int32), _i, _i, _f, _f, _f, _f, _f, _i, _f, _p, _p]),
+    'nlb_render_losses_workspace_bytes': (C.c_size_t, []),
+    'nlb_render_losses': (_i, [C.POINTER(NlbLossesIn)] + [_p] * 10),
     'nlb_set_dynamic_scalars': (_i, [_p]),
     'nlb_adam_bias_terms': (_i, [_f, _f, _f, _i, C.POINTER(C.c_float)]),
     'nlb_adam_step': (_i, [_p, _p, _p, _p, C.c_int64, _f, _f, _f, _f, _i, _f, _p]),

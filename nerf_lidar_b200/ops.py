@@ -19,7 +19,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import timed, NlbNerfMlpWeights, NlbNerfMlpSaved, NlbNerfMlpGradIn, NlbNerfMlpGradOut, NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
+from ._lib import timed, NlbLossesIn, NlbNerfMlpWeights, NlbNerfMlpSaved, NlbNerfMlpGradIn, NlbNerfMlpGradOut, NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
 
 EPS = float(torch.finfo(torch.float32).eps)
 _u_cache: Dict[Tuple, torch.Tensor] = {}
@@ -496,3 +496,65 @@ def interlevel_per_ray(c, w, cp, wp, pulse_width: float) -> torch.Tensor:
     """Sum over the proposal intervals of max(w_s - wp, 0)^2 / (wp + 1e-5) -> [N];
     (c, w) are the detached final-level histogram."""
     return _Interlevel.apply(c.detach(), w.detach(), cp.detach(), wp, pulse_width)
+
+
+# ----------------------------------------------------------------------------- supervision losses
+class _RenderLosses(Function):
+    """data / depth / sem / int / d_smo / s_smo of Z/train.py:283-455 in four launches
+    (csrc/render_losses.cu); returns the six loss values as one tensor."""
+
+    @staticmethod
+    def forward(ctx, rgb, depth, semantic, intensity, batch, cfg):
+        rgb, depth = f32(rgb), f32(depth).reshape(-1)
+        N = depth.shape[0]
+        dev = depth.device
+        sem = f32(semantic) if semantic is not None else None
+        inten = f32(intensity).reshape(-1) if intensity is not None else None
+        K = sem.shape[-1] if sem is not None else 0
+        t = {k: f32(batch[k]).reshape(-1) if k != 'rgb' else f32(batch[k][..., :3])
+             for k in ('rgb', 'depth', 'semantic', 'intensity', 'patch_mask', 'lidar_mask') if k in batch}
+        new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        losses, scales = new(6), new(6)
+        g_rgb, g_depth = new(N, 3), new(N)
+        g_sem = new(N, K) if sem is not None else None
+        g_int = new(N) if inten is not None else None
+        num_patch = int(cfg['num_patch'])
+        g_dsmo = torch.zeros(N, device=dev) if num_patch > 0 else None
+        g_ssmo = torch.zeros(N, K, device=dev) if (num_patch > 0 and sem is not None) else None
+        ws = new(load().nlb_render_losses_workspace_bytes() // 4)
+        lin = NlbLossesIn(ptr(rgb), ptr(depth), ptr(sem), ptr(inten), ptr(t['rgb']), ptr(t['depth']),
+                          ptr(t.get('semantic')), ptr(t.get('intensity')), ptr(t['patch_mask']), ptr(t['lidar_mask']),
+                          N, K, num_patch, int(cfg['patch_size']), int(cfg['lidar_supervision']),
+                          int(cfg['only_lidar_supervision']), int(cfg['charb']), float(cfg['charb_padding']),
+                          float(cfg['depth_mult']), float(cfg['sem_mult']), float(cfg['int_mult']),
+                          float(cfg['smooth_mult']), 0., 0.)
+        with torch.cuda.device(dev):
+            with timed('render_losses'):
+                check(load().nlb_render_losses(C.byref(lin), ptr(losses), ptr(scales), ptr(g_rgb), ptr(g_depth),
+                                               ptr(g_sem), ptr(g_int), ptr(g_dsmo), ptr(g_ssmo), ptr(ws), stream()))
+        ctx.save_for_backward(scales, g_rgb, g_depth, g_sem, g_int, g_dsmo, g_ssmo)
+        ctx.int_shape = None if intensity is None else intensity.shape
+        ctx.depth_shape = depth.shape
+        return losses
+
+    @staticmethod
+    def backward(ctx, go):
+        scales, g_rgb, g_depth, g_sem, g_int, g_dsmo, g_ssmo = ctx.saved_tensors
+        w = go * scales
+        o_rgb = g_rgb * w[0]
+        o_depth = g_depth * w[1]
+        if g_dsmo is not None:
+            o_depth = torch.addcmul(o_depth, g_dsmo, w[4])
+        o_sem = None
+        if g_sem is not None:
+            o_sem = g_sem * w[2]
+            if g_ssmo is not None:
+                o_sem = torch.addcmul(o_sem, g_ssmo, w[5])
+        o_int = (g_int * w[3]).reshape(ctx.int_shape) if g_int is not None else None
+        return o_rgb, o_depth, o_sem, o_int, None, None
+
+
+def render_losses(rendering: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], cfg: Dict) -> torch.Tensor:
+    """[data, depth, sem, int, d_smo, s_smo] for the final rendering (see _RenderLosses)."""
+    return _RenderLosses.apply(rendering['rgb'], rendering['depth'], rendering.get('semantic'),
+                               rendering.get('intensity'), batch, cfg)

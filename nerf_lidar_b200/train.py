@@ -184,7 +184,45 @@ def distortion_loss_torch(ray_history, config: Config):
 def compute_losses(batch: Dict[str, torch.Tensor], renderings, ray_history, config: Config, step: int,
                    num_patch: int) -> Dict[str, torch.Tensor]:
     """The loss dictionary of Z/train.py:283-455 for the nuScenes camera+LiDAR run
-    (masks as with Config.instance_obj=True: `batch['mask']` is cleared)."""
+    (masks as with Config.instance_obj=True: `batch['mask']` is cleared) on the fused
+    kernels: supervision terms in csrc/render_losses.cu, regularisers in csrc/losses.cu."""
+    from . import ops
+    final = renderings[-1]
+    refine = config.pose_refine and config.start_step < step < int(0.6 * config.end_step)
+    dep_lam = 0. if refine else (0.4 if step > config.end_step else 0.1)
+    sem_lam = 0. if refine else (0.04 if step > config.end_step else 0.01)
+    use_sem = bool(config.use_semantic) and 'semantic' in final
+    use_int = bool(config.use_intensity) and 'intensity' in final
+    rend = dict(rgb=final['rgb'], depth=final['depth'], semantic=final['semantic'] if use_sem else None,
+                intensity=final['intensity'] if use_int else None)
+    cfg = dict(num_patch=num_patch, patch_size=config.patch_size, lidar_supervision=config.lidar_supervision,
+               only_lidar_supervision=config.only_lidar_supervison, charb=config.data_loss_type != 'mse',
+               charb_padding=config.charb_padding, depth_mult=dep_lam if config.depth_loss else 0.,
+               sem_mult=sem_lam, int_mult=0.1, smooth_mult=0.01)
+    vals = ops.render_losses(rend, batch, cfg)
+    losses = {'data': vals[0]}
+    if config.depth_loss:
+        losses['depth'] = vals[1]
+    if num_patch > 0:
+        losses['d_smo'] = vals[4]
+        if use_sem:
+            losses['s_smo'] = vals[5]
+    if use_sem:
+        losses['sem'] = vals[2]
+    if use_int:
+        losses['int'] = vals[3]
+    if config.anti_interlevel_loss_mult > 0:
+        losses['interlevel'] = anti_interlevel_loss(ray_history, config)
+    if config.distortion_loss_mult > 0:
+        losses['distortion'] = distortion_loss(ray_history, config)
+    return losses
+
+
+def compute_losses_torch(batch: Dict[str, torch.Tensor], renderings, ray_history, config: Config, step: int,
+                   num_patch: int) -> Dict[str, torch.Tensor]:
+    """The loss dictionary of Z/train.py:283-455 with plain torch ops (kept for
+    cross-checking the fused kernels; masks as with Config.instance_obj=True:
+    `batch['mask']` is cleared)."""
     final = renderings[-1]
     patch_mask = batch['patch_mask'] == 1
     lidar = batch['lidar_mask'] == 1
