@@ -120,7 +120,10 @@ int nlb_sample_points(const nlb_rays_t* rays, float* points, void* stream);
 int nlb_encode_forward(const nlb_rays_t* rays, const nlb_table_t* table, float* features, void* stream);
 /* grad_features[N*S, L*C] -> grad_embeddings[rows,C] (accumulated). */
 int nlb_encode_backward(const nlb_rays_t* rays, const nlb_table_t* table, const float* grad_features,
-                        float* grad_embeddings, void* stream);
+                        float* grad_embeddings,
+                        float* workspace /*nlb_encode_backward_workspace_bytes(), or NULL: no privatised coarse rows*/,
+                        void* stream);
+size_t nlb_encode_backward_workspace_bytes(const nlb_table_t* table);
 
 /* Proposal level: the above + PropMLP Linear(L,64)-ReLU-Linear(64,1), softplus(x-1)
  * (models.py:887-889,996-997,1116) in one kernel.  W0[64,L] b0[64] W1[64] b1[1]
@@ -134,7 +137,7 @@ int nlb_prop_backward(const nlb_rays_t* rays, const nlb_table_t* table, const fl
                       const float* W1, const float* b1, const float* features, const float* grad_density,
                       float* grad_embeddings, float* gW0, float* gb0, float* gW1, float* gb1,
                       float* workspace /*nlb_prop_backward_workspace_bytes()*/, void* stream);
-size_t nlb_prop_backward_workspace_bytes(int N, int S, int L);
+size_t nlb_prop_backward_workspace_bytes(int N, int S, const nlb_table_t* table);
 
 /* ------------------------------------------------------------------ compositing
  * render.compute_alpha_weights (Z/internal/render.py:170-189) +

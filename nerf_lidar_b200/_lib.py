@@ -83,10 +83,11 @@ SIGNATURES = {
     'nlb_sorted_interp': (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
     'nlb_sample_points': (_i, [C.POINTER(NlbRays), _p, _p]),
     'nlb_encode_forward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p]),
-    'nlb_encode_backward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p, _p]),
+    'nlb_encode_backward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p, _p, _p]),
+    'nlb_encode_backward_workspace_bytes': (C.c_size_t, [C.POINTER(NlbTable)]),
     'nlb_prop_forward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p, _p, _p, _p, _p, _p]),
     'nlb_prop_backward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
-    'nlb_prop_backward_workspace_bytes': (C.c_size_t, [_i, _i, _i]),
+    'nlb_prop_backward_workspace_bytes': (C.c_size_t, [_i, _i, C.POINTER(NlbTable)]),
     'nlb_composite_forward': (_i, [C.POINTER(NlbCompositeIn), C.POINTER(NlbCompositeOut), _p]),
     'nlb_composite_backward': (_i, [C.POINTER(NlbCompositeIn), _p, C.POINTER(NlbCompositeGrad), _p, _p, _p, _p, _p]),
     'nlb_nerf_mlp_packed_bytes': (C.c_size_t, []),

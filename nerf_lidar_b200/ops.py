@@ -166,12 +166,13 @@ class _PropLevel(Function):
         gW0, gb0 = torch.zeros_like(W0), torch.zeros_like(b0)
         gW1, gb1 = torch.zeros_like(W1), torch.zeros_like(b1)
         g_density = f32(g_density)
-        ws_bytes = load().nlb_prop_backward_workspace_bytes(rays.N, tdist.shape[1] - 1, encoder.num_levels)
+        tab = _table_desc(encoder, embeddings)
+        ws_bytes = load().nlb_prop_backward_workspace_bytes(rays.N, tdist.shape[1] - 1, C.byref(tab))
         ws = torch.empty(ws_bytes // 4, device=rays.device, dtype=torch.float32)
         with torch.cuda.device(rays.device):
             with timed(f'prop{encoder.num_levels}_bwd'):
                 check(load().nlb_prop_backward(C.byref(rays.desc(tdist, deg_noise, ctx.std_scale)),
-                                               C.byref(_table_desc(encoder, embeddings)), ptr(W0), ptr(b0), ptr(W1),
+                                               C.byref(tab), ptr(W0), ptr(b0), ptr(W1),
                                                ptr(b1), ptr(feats), ptr(g_density), ptr(g_emb), ptr(gW0), ptr(gb0),
                                                ptr(gW1), ptr(gb1), ptr(ws), stream()))
         return (None, None, None if in_place else g_emb, gW0, gb0, gW1.reshape(1, -1), gb1, None, None, None, None)
@@ -204,11 +205,13 @@ class _NerfEncode(Function):
         rays, encoder = ctx.rays, ctx.encoder
         g_emb, in_place = _grad_buffer(ctx.emb_param if ctx.emb_param is not None else embeddings)
         g_feats = f32(g_feats)
+        tab = _table_desc(encoder, embeddings)
+        ws_bytes = load().nlb_encode_backward_workspace_bytes(C.byref(tab))
+        ws = torch.empty(ws_bytes // 4, device=rays.device, dtype=torch.float32) if ws_bytes else None
         with torch.cuda.device(rays.device):
             with timed('nerf_encode_bwd'):
                 check(load().nlb_encode_backward(C.byref(rays.desc(tdist, deg_noise, ctx.std_scale)),
-                                                 C.byref(_table_desc(encoder, embeddings)), ptr(g_feats), ptr(g_emb),
-                                                 stream()))
+                                                 C.byref(tab), ptr(g_feats), ptr(g_emb), ptr(ws), stream()))
         return (None, None, None if in_place else g_emb, None, None, None, None)
 
 

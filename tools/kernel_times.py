@@ -40,7 +40,7 @@ for li, mlp in enumerate([model.prop_mlp_0, model.prop_mlp_1]):
     gd = torch.randn(rays.N, S, device='cuda') * 1e-3
     gt = torch.zeros_like(enc.embeddings)
     gW0, gb0, gW1, gb1 = torch.zeros_like(W0), torch.zeros_like(b0), torch.zeros_like(W1), torch.zeros_like(b1)
-    ws = torch.empty(load().nlb_prop_backward_workspace_bytes(rays.N, S, L) // 4, device='cuda')
+    ws = torch.empty(load().nlb_prop_backward_workspace_bytes(rays.N, S, C.byref(tab)) // 4, device='cuda')
     b = timeit(lambda: check(load().nlb_prop_backward(C.byref(rd), C.byref(tab), ptr(W0), ptr(b0), ptr(W1), ptr(b1), ptr(feats), ptr(gd), ptr(gt), ptr(gW0), ptr(gb0), ptr(gW1), ptr(gb1), ptr(ws), stream())))
     out.append(f'prop{L}: fwd {f:.3f} bwd {b:.3f}')
 enc = model.nerf_mlp.encoder
@@ -54,7 +54,8 @@ feats = torch.empty(rows, 40, device='cuda')
 g = torch.randn(rows, 40, device='cuda')
 gt = torch.zeros_like(enc.embeddings)
 f = timeit(lambda: check(load().nlb_encode_forward(C.byref(rd), C.byref(tab), ptr(feats), stream())))
-b = timeit(lambda: check(load().nlb_encode_backward(C.byref(rd), C.byref(tab), ptr(g), ptr(gt), stream())))
+wsn = torch.empty(max(load().nlb_encode_backward_workspace_bytes(C.byref(tab)) // 4, 1), device='cuda')
+b = timeit(lambda: check(load().nlb_encode_backward(C.byref(rd), C.byref(tab), ptr(g), ptr(gt), ptr(wsn), stream())))
 out.append(f'nerf: fwd {f:.3f} bwd {b:.3f}')
 print(os.environ.get('NLB_LIB', 'default'), ' | '.join(out))
 

@@ -40,6 +40,7 @@ for li, enc in enumerate(encs):
         g = torch.randn(rows, L * Cc, device='cuda')
         rd = rays.desc(tdist, deg, 0.35)
         f = timeit(lambda: check(load().nlb_encode_forward(C.byref(rd), C.byref(tab), ptr(feats), stream())))
-        b = timeit(lambda: check(load().nlb_encode_backward(C.byref(rd), C.byref(tab), ptr(g), ptr(grad), stream())))
+        wsn = torch.empty(max(load().nlb_encode_backward_workspace_bytes(C.byref(tab)) // 4, 1), device='cuda')
+        b = timeit(lambda: check(load().nlb_encode_backward(C.byref(rd), C.byref(tab), ptr(g), ptr(grad), ptr(wsn), stream())))
         print(f'  L={L:2d} fwd {f:7.3f} ms (+{f - prev_f:6.3f})   bwd {b:7.3f} ms (+{b - prev_b:6.3f})')
         prev_f, prev_b = f, b
