@@ -145,7 +145,7 @@ def run_reference_arm(args):
         'e2e': {'value': rps, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------- CUDA arm
@@ -160,11 +160,9 @@ def run_cuda_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout carries the one JSON line
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'
-        else:
-            os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        # NCCL prints its version banner on STDOUT (at NCCL_DEBUG=VERSION and WARN); stdout carries the one
+        # JSON line, so NCCL's log goes to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     _lib.load()
     cfg = configs.nuscenes_single(use_intensity=True, instance_obj=False)
@@ -299,12 +297,28 @@ def run_cuda_arm(args):
         'kernels': per_kernel,
         'cpu_baseline': cpu,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line: dict):
+    """The one JSON line goes to the REAL stdout; while the run is in progress file descriptor 1 points at
+    stderr so that nothing a library prints (NCCL's version banner, ...) can precede or follow it."""
+    data = (json.dumps(line) + '\n').encode()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    sys.stdout.flush()
+    os.write(fd, data)
+
+
+_REAL_STDOUT = None
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

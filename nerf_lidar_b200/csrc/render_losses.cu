@@ -50,11 +50,20 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {  // all thre
 // ---- 0.9 quantile (linear interpolation, torch.quantile) of |pred - target| over the
 // depth-supervised rays: one block, exact k-th order statistics by a bitwise search on the
 // float bit patterns (non-negative floats order like unsigned integers).
-__global__ void __launch_bounds__(1024) k_depth_quantile(nlb_losses_in_t in, float* __restrict__ sums) {
+__global__ void __launch_bounds__(1024) k_depth_quantile(nlb_losses_in_t in, float* __restrict__ sums, int cached) {
+  extern __shared__ uint32_t s_bits[];  // [N] |d| bit patterns (0xffffffff: not supervised) when they fit
   __shared__ float s_red[32];
   const int N = in.N;
+  auto bits_of = [&](int i) -> uint32_t {
+    if (!ray_masks(in, i).depth) return 0xffffffffu;
+    return __float_as_uint(fabsf(__ldg(in.depth + i) - __ldg(in.t_depth + i)));
+  };
   float cnt = 0.f;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) cnt += ray_masks(in, i).depth ? 1.f : 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const uint32_t b = bits_of(i);
+    if (cached) s_bits[i] = b;
+    cnt += b != 0xffffffffu ? 1.f : 0.f;
+  }
   const int n = (int)block_sum(cnt, s_red);
   if (n == 0) {
     if (threadIdx.x == 0) sums[S_THRE] = INFINITY;
@@ -66,16 +75,13 @@ __global__ void __launch_bounds__(1024) k_depth_quantile(nlb_losses_in_t in, flo
 #pragma unroll 1
   for (int which = 0; which < 2; ++which) {
     const int k = which ? k_hi : k_lo;
+    if (which && k_hi == k_lo) { sel[1] = sel[0]; break; }
     uint32_t result = 0;
 #pragma unroll 1
     for (int bit = 30; bit >= 0; --bit) {
       const uint32_t trial = result | (1u << bit);
       float c = 0.f;
-      for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        if (!ray_masks(in, i).depth) continue;
-        const float a = fabsf(__ldg(in.depth + i) - __ldg(in.t_depth + i));
-        c += (__float_as_uint(a) < trial) ? 1.f : 0.f;
-      }
+      for (int i = threadIdx.x; i < N; i += blockDim.x) c += ((cached ? s_bits[i] : bits_of(i)) < trial) ? 1.f : 0.f;
       if ((int)block_sum(c, s_red) <= k) result = trial;
     }
     sel[which] = __uint_as_float(result);
@@ -274,7 +280,16 @@ extern "C" int nlb_render_losses(const nlb_losses_in_t* in_, float* losses, floa
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(workspace, 0, kNumSums * sizeof(float), st) != cudaSuccess) return nlb_check_launch("render_losses memset");
-  k_depth_quantile<<<1, 1024, 0, st>>>(in, workspace);
+  {
+    const size_t qsmem = (size_t)in.N * sizeof(uint32_t);
+    const int cached = qsmem <= 160 * 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_depth_quantile, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      attr_set = true;
+    }
+    k_depth_quantile<<<1, 1024, cached ? qsmem : 0, st>>>(in, workspace, cached);
+  }
   k_ray_losses<<<div_up(in.N, 256), 256, 0, st>>>(in, workspace, g_rgb, g_depth, g_sem, g_int);
   if (in.num_patch > 0) {
     const int pp = in.patch_size * in.patch_size;

@@ -44,6 +44,20 @@ def allreduce_grads(buffers: List[torch.Tensor], average: bool = False):
             b.div_(w)
 
 
+def allreduce_grads_async(buffers: List[torch.Tensor]):
+    """Starts the sum of the buffers over all ranks and returns the work handles (empty
+    when not distributed); the collectives run on the backend's own stream, so kernels
+    launched afterwards on the current stream overlap with them."""
+    if not is_dist() or dist.get_world_size() == 1:
+        return []
+    return [dist.all_reduce(b, op=dist.ReduceOp.SUM, async_op=True) for b in buffers]
+
+
+def wait_all(handles):
+    for h in handles:
+        h.wait()
+
+
 def gather_rendering(local: Dict, num_rays: int, world: int, rank: int) -> Dict:
     """All-gathers per-ray leaves [n_local, ...] into [num_rays, ...] with ONE
     collective: leaves are flattened to [n_local, width], concatenated along the

@@ -317,8 +317,16 @@ class Trainer:
         c = self.config
         return learning_rate_decay(step, c.lr_init, c.lr_final, c.max_steps, c.lr_delay_steps, c.lr_delay_mult)
 
-    def train_step(self, batch: Dict[str, torch.Tensor], step: int, num_patch: Optional[int] = None,
-                   rand_inputs=None, _skip_optimizer: bool = False) -> Dict[str, torch.Tensor]:
+    # The proposal networks receive gradients only from the anti-interlevel loss (the
+    # sampling weights are detached: Model.stop_level_grad) and that loss sees the final
+    # level detached, so the backward pass splits into two independent halves:
+    #   main -> NeRF table + NerfMLP        prop -> proposal tables + PropMLPs.
+    # In data-parallel runs the NeRF table's all-reduce (77 % of the gradient bytes) is
+    # issued between the two and travels while the proposal half is still computing.
+    PROP_LOSSES = ('interlevel',)
+
+    def forward_losses(self, batch, step: int, num_patch: Optional[int] = None, rand_inputs=None):
+        """Forward pass and loss dictionary; returns (losses, loss_main, loss_prop)."""
         c = self.config
         train_frac = float(np.clip((step - 1) / (c.max_steps - 1), 0, 1))
         if num_patch is None:
@@ -327,15 +335,37 @@ class Trainer:
                                              sample_m=c.sample_m_train, step=step, max_step=c.max_steps,
                                              rand_inputs=rand_inputs)
         losses = compute_losses(batch, renderings, ray_history, c, step, num_patch)
+        main = sum(v for k, v in losses.items() if k not in self.PROP_LOSSES)
+        prop = [v for k, v in losses.items() if k in self.PROP_LOSSES]
+        prop = sum(prop) if prop else None
+        total = main.detach() if prop is None else main.detach() + prop.detach()
         if 'hash_decay' in renderings[-1]:
-            # value only (its gradient is fused into Adam); cloned because the optimizer pass below
+            # value only (its gradient is fused into Adam); cloned because the optimizer pass
             # overwrites the persistent buffer with the updated tables' value
             losses['hash_decay'] = renderings[-1]['hash_decay'].clone()
-        loss = sum(v for k, v in losses.items() if k != 'hash_decay')
-        loss.backward()
-        losses['loss'] = loss.detach() + (losses['hash_decay'] if 'hash_decay' in losses else 0.)
-        if not _skip_optimizer:
+            total = total + losses['hash_decay']
+        losses['loss'] = total
+        return losses, main, prop
+
+    def _nerf_tables(self):
+        return [t for t in self.tables if 'prop' not in t['name']]
+
+    def _prop_tables(self):
+        return [t for t in self.tables if 'prop' in t['name']]
+
+    def train_step(self, batch: Dict[str, torch.Tensor], step: int, num_patch: Optional[int] = None,
+                   rand_inputs=None) -> Dict[str, torch.Tensor]:
+        losses, main, prop = self.forward_losses(batch, step, num_patch, rand_inputs)
+        if self.world == 1 or prop is None:
+            (main if prop is None else main + prop).backward()
             self.optimizer_step(step)
+            return losses
+        main.backward()
+        early = parallel.allreduce_grads_async([t['grad'] for t in self._nerf_tables()])
+        prop.backward()
+        late = parallel.allreduce_grads_async([t['grad'] for t in self._prop_tables()] + [self.flat_grad])
+        parallel.wait_all(early + late)
+        self.optimizer_step(step, reduce=False)
         return losses
 
     def allreduce_gradients(self):
@@ -400,10 +430,10 @@ class Trainer:
 
     def train_step_graphed(self, batch: Dict[str, torch.Tensor], step: int, num_patch: Optional[int] = None,
                            rand_inputs=None) -> Dict[str, torch.Tensor]:
-        """`train_step` replayed as ONE CUDA graph (single process) or as two graphs --
-        forward + backward, then the optimizer pass -- around the eagerly issued NCCL
-        gradient all-reduce (data parallel): the step is ~450 small launches and
-        host-bound when issued eagerly.  `batch` (device or pinned-host tensors) is copied
+        """`train_step` replayed as ONE CUDA graph (single process) or as three graphs --
+        forward + main backward, proposal backward, optimizer pass -- around the eagerly
+        issued NCCL gradient all-reduces (data parallel; the NeRF table's reduction overlaps
+        the proposal backward): the step is ~200 launches and host-bound when issued eagerly.  `batch` (device or pinned-host tensors) is copied
         into static device buffers; the per-step scalars (anneal, learning rate, Adam bias
         corrections) travel through the library's dynamic-scalar buffer
         (nlb_set_dynamic_scalars); the graph is re-captured when the batch layout or the
@@ -442,25 +472,35 @@ class Trainer:
                     out = self.train_step(st['batch'], step, num_patch, srand)
                 torch.cuda.current_stream(dev).wait_stream(s)
                 g = torch.cuda.CUDAGraph()
-                g_opt = None
+                g_prop = g_opt = None
                 if self.world == 1:
                     with torch.cuda.graph(g):
                         captured = self.train_step(st['batch'], step, num_patch, srand)
                 else:
-                    # the collective stays outside the graphs: capture forward+backward and the optimizer apart
+                    # the collectives stay outside the graphs: forward + main backward | proposal backward | optimizer
                     with torch.cuda.graph(g):
-                        captured = self.train_step(st['batch'], step, num_patch, srand, _skip_optimizer=True)
+                        captured, main, prop = self.forward_losses(st['batch'], step, num_patch, srand)
+                        main.backward()
+                    if prop is not None:
+                        g_prop = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g_prop, pool=g.pool()):
+                            prop.backward()
                     g_opt = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g_opt, pool=g.pool()):
                         self.optimizer_step(step, reduce=False)
+                    del main, prop
             finally:
                 lib.nlb_set_dynamic_scalars(None)
             # capturing records the step without running it: the eager warm-up step above WAS this call's step
-            self._graphs[key] = (g, g_opt, captured)
+            self._graphs[key] = (g, g_prop, g_opt, captured)
             return out
-        g, g_opt, captured = entry
+        g, g_prop, g_opt, captured = entry
         g.replay()
         if g_opt is not None:
-            self.allreduce_gradients()
+            early = parallel.allreduce_grads_async([t['grad'] for t in self._nerf_tables()])
+            if g_prop is not None:
+                g_prop.replay()
+            late = parallel.allreduce_grads_async([t['grad'] for t in self._prop_tables()] + [self.flat_grad])
+            parallel.wait_all(early + late)
             g_opt.replay()
         return captured

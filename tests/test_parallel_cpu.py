@@ -50,6 +50,12 @@ def _worker(rank, world, port, n):
         assert torch.all(a == 3.0) and torch.all(b == 30.0)
         parallel.allreduce_grads([a], average=True)
         assert torch.all(a == 3.0)
+        # split reduction used by the training step: early (NeRF table) and late (the rest) handles
+        c, d = torch.full((5,), float(rank)), torch.full((2,), 1.0)
+        early = parallel.allreduce_grads_async([c])
+        late = parallel.allreduce_grads_async([d])
+        parallel.wait_all(early + late)
+        assert torch.all(c == 1.0) and torch.all(d == 2.0)
         sh = parallel.shard_batch({'origins': torch.arange(n * 3).reshape(n, 3).float()}, world, rank)
         assert sh['origins'].shape[0] == hi - lo
     finally:
