@@ -243,6 +243,9 @@ typedef struct {
   void* d_g;   /* [M,128] bf16: d(sem_layer.0 | intensity_layer.0 pre-relu) */
   void* d_x;   /* [M,256] bf16: d(bottleneck) */
   void* d_h0;  /* [M,64]  bf16: d(density_layer.0 pre-relu) */
+  int ld_v1, ld_v0, ld_g; /* leading dimensions (elements) of d_v1 / d_v0 / d_g; 0 = dense (256 / 256 / 128).
+                             The three share the A operand `x` in the weight-gradient GEMMs: written as
+                             column slices of one [M,640] buffer they become ONE GEMM. */
 } nlb_nerf_mlp_grad_out_t;
 int nlb_nerf_mlp_backward(const nlb_nerf_mlp_grad_in_t* gin, const nlb_nerf_mlp_saved_t* saved, int M,
                           const void* packed_t, float* grad_features /*[M,40]*/,
@@ -251,10 +254,10 @@ int nlb_nerf_mlp_backward(const nlb_nerf_mlp_grad_in_t* gin, const nlb_nerf_mlp_
 /* Reductions of the bf16 pre-activation gradients written by nlb_nerf_mlp_backward:
  * colsum: x[M, ld] (first `cols` columns; cols a power of two <= 512) -> out[cols]
  *   (overwritten) = bias gradients;
- * group_sum: x[groups*S, cols] -> out[groups, cols] = per-ray sums over the S samples (the
+ * group_sum: x[groups*S, ld] (first `cols` columns) -> out[groups, cols] = per-ray sums over the S samples (the
  *   view-direction encoding is a per-ray constant, Z/internal/models.py:1192-1196). */
 int nlb_colsum_bf16(const void* x, int64_t M, int cols, int ld, float* out, void* stream);
-int nlb_group_sum_bf16(const void* x, int64_t groups, int S, int cols, float* out, void* stream);
+int nlb_group_sum_bf16(const void* x, int64_t groups, int S, int cols, int ld, float* out, void* stream);
 
 /* Dev probe: clock64() stamps of block 0's MMA thread / epilogue thread for the first two
  * tiles of nlb_nerf_mlp_forward are written to buf[128] (int64); NULL switches it off. */

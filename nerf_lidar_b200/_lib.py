@@ -65,7 +65,8 @@ class NlbNerfMlpGradIn(C.Structure):
 
 
 class NlbNerfMlpGradOut(C.Structure):
-    _fields_ = [(n, c_f) for n in ('d_rgb', 'd_v1', 'd_v0', 'd_hs1', 'd_g', 'd_x', 'd_h0')]
+    _fields_ = [(n, c_f) for n in ('d_rgb', 'd_v1', 'd_v0', 'd_hs1', 'd_g', 'd_x', 'd_h0')] + \
+               [(n, C.c_int) for n in ('ld_v1', 'ld_v0', 'ld_g')]
 
 
 _u32, _i, _f, _p = C.c_uint32, C.c_int, C.c_float, C.c_void_p
@@ -98,7 +99,7 @@ SIGNATURES = {
     'nlb_nerf_mlp_backward': (_i, [C.POINTER(NlbNerfMlpGradIn), C.POINTER(NlbNerfMlpSaved), _i, _p, _p,
                                    C.POINTER(NlbNerfMlpGradOut), _p]),
     'nlb_colsum_bf16': (_i, [_p, C.c_int64, _i, _i, _p, _p]),
-    'nlb_group_sum_bf16': (_i, [_p, C.c_int64, _i, _i, _p, _p]),
+    'nlb_group_sum_bf16': (_i, [_p, C.c_int64, _i, _i, _i, _p, _p]),
     'nlb_debug_set_timeline': (_i, [_p]),
     'nlb_distortion_loss': (_i, [_p, _p, _i, _i, _p, _p, _p]),
     'nlb_interlevel_loss': (_i, [_p, _p, _i, _p, _p, _i, _f, _i, _p, _p, _p]),

@@ -262,7 +262,7 @@ static int check_comp(const nlb_composite_in_t* in, const char* who) {
   if (!in) { nlb_set_error("%s: null descriptor", who); return NLB_EINVAL; }
   if (in->S < 1 || in->S > 256) { nlb_set_error("%s: S=%d outside [1,256]", who, in->S); return NLB_EUNSUPPORTED; }
   if (in->K < 0 || in->K > kMaxK) { nlb_set_error("%s: K=%d classes > %d", who, in->K, kMaxK); return NLB_EUNSUPPORTED; }
-  if (!in->density || !in->tdist || !in->directions) { nlb_set_error("%s: null pointer", who); return NLB_EINVAL; }
+  if (in->N > 0 && (!in->density || !in->tdist || !in->directions)) { nlb_set_error("%s: null pointer", who); return NLB_EINVAL; }
   return NLB_OK;
 }
 
@@ -281,8 +281,8 @@ extern "C" int nlb_composite_backward(const nlb_composite_in_t* in, const float*
                                       float* g_density, float* g_rgb, float* g_semantic, float* g_intensity,
                                       void* stream) {
   if (int e = check_comp(in, "composite_backward")) return e;
-  if (!weights || !g || !g_density) { nlb_set_error("composite_backward: null pointer"); return NLB_EINVAL; }
   if (in->N == 0) return NLB_OK;
+  if (!weights || !g || !g_density) { nlb_set_error("composite_backward: null pointer"); return NLB_EINVAL; }
   k_composite_bwd<<<div_up(in->N, kCompWarps), kCompWarps * 32, 0, (cudaStream_t)stream>>>(*in, weights, *g, g_density,
                                                                                          g_rgb, g_semantic, g_intensity);
   return nlb_check_launch("composite_backward");

@@ -540,6 +540,7 @@ struct HostLevels {
 static int check_rays_table(const nlb_rays_t* r, const nlb_table_t* t, const char* who, HostLevels* hl = nullptr) {
   if (!r || !t) { nlb_set_error("%s: null descriptor", who); return NLB_EINVAL; }
   if (r->N < 0 || r->S < 1) { nlb_set_error("%s: bad N/S", who); return NLB_EINVAL; }
+  if (r->N == 0) return NLB_OK;  // empty batch: the callers return before launching (pointers may be NULL)
   if (t->L < 1 || t->L > kMaxLevelsEnc) { nlb_set_error("%s: num_levels %d outside [1,%d]", who, t->L, kMaxLevelsEnc); return NLB_EUNSUPPORTED; }
   if (!r->tdist || !r->origins || !r->directions || !r->radii || !r->base_x || !r->base_y || !t->embeddings ||
       !t->offsets || !t->grid_sizes) {
@@ -756,6 +757,7 @@ extern "C" int nlb_prop_backward(const nlb_rays_t* rays, const nlb_table_t* tabl
                                  float* workspace, void* stream) {
   HostLevels hl;
   if (int e = check_rays_table(rays, table, "prop_backward", &hl)) return e;
+  if (rays->N == 0) return NLB_OK;
   if (table->C != 1) { nlb_set_error("prop_backward: PropMLP tables have level_dim 1"); return NLB_EINVAL; }
   if (!features || !grad_density) { nlb_set_error("prop_backward: features saved by the forward are required"); return NLB_EINVAL; }
   if (!workspace) { nlb_set_error("prop_backward: workspace of nlb_prop_backward_workspace_bytes() is required"); return NLB_EINVAL; }

@@ -704,9 +704,9 @@ __device__ __forceinline__ void issue_blayer(SmemT& sm, uint8_t* a_blocks, uint8
 //   act / gdst = tile base + column offset of the saved activation / output matrices.
 template <bool kMask>
 __device__ __forceinline__ void epi_group64_masked(uint32_t taddr, const __nv_bfloat16* __restrict__ act,
-                                                   uint8_t* block, int row, int lane, __nv_bfloat16* gdst, int ld,
-                                                   int rows_valid, float add0 = 0.f) {
-  if (kMask) warp_rows_from_global(block, row & ~31, lane, act, ld, rows_valid);
+                                                   uint8_t* block, int row, int lane, __nv_bfloat16* gdst, int ld_act,
+                                                   int ld_out, int rows_valid, float add0 = 0.f) {
+  if (kMask) warp_rows_from_global(block, row & ~31, lane, act, ld_act, rows_valid);
   float v[64];
   tmem_ld64(taddr, v);
   v[0] += add0;
@@ -727,7 +727,7 @@ __device__ __forceinline__ void epi_group64_masked(uint32_t taddr, const __nv_bf
     }
   }
   store_row64(v, block, row);
-  if (gdst) warp_rows_to_global(block, row & ~31, lane, gdst, ld, rows_valid);
+  if (gdst) warp_rows_to_global(block, row & ~31, lane, gdst, ld_out, rows_valid);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_in_t gi, nlb_nerf_mlp_saved_t sv, int M,
@@ -789,6 +789,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
     }
   } else {
     const int half = warp >> 2;  // the two warps of a TMEM lane quarter split every layer's columns
+    const int ld_v1 = go.ld_v1 ? go.ld_v1 : 256, ld_v0 = go.ld_v0 ? go.ld_v0 : 256, ld_g = go.ld_g ? go.ld_g : 128;
     const int r = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint8_t* PB = a_blocks + BP * kBlockBytes;
@@ -831,7 +832,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
 #pragma unroll 1
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
         epi_group64_masked<true>(tlane + 256 + c0, cbf(sv.h2) + trow * 256 + c0, PB + (c0 >> 6) * kBlockBytes, r, lane,
-                                 bf(go.d_v1) + trow * 256 + c0, 256, rows_valid);
+                                 bf(go.d_v1) + trow * ld_v1 + c0, 256, ld_v1, rows_valid);
       signal_a_ready(&sm.a_ready[B_V1]);
 
       // ---- dzv0 = dh1 * [h1 > 0] -> Q0..3   (dh1 in accB, dx partial stays in accA)
@@ -840,7 +841,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
 #pragma unroll 1
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
         epi_group64_masked<true>(tlane + 256 + c0, cbf(sv.h1) + trow * 256 + c0, QB + (c0 >> 6) * kBlockBytes, r, lane,
-                                 bf(go.d_v0) + trow * 256 + c0, 256, rows_valid);
+                                 bf(go.d_v0) + trow * ld_v0 + c0, 256, ld_v0, rows_valid);
       signal_a_ready(&sm.a_ready[B_V0]);
 
       // ---- d(sem logits) | d(intensity) -> S (cols 0..19): half 1; S is free: B_RGB completed above
@@ -873,7 +874,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
       {
         const int c0 = half * 64;
         epi_group64_masked<true>(tlane + 256 + c0, cbf(sv.g) + trow * 128 + c0, QB + half * kBlockBytes, r, lane,
-                                 bf(go.d_g) + trow * 128 + c0, 128, rows_valid);
+                                 bf(go.d_g) + trow * ld_g + c0, 128, ld_g, rows_valid);
       }
       signal_a_ready(&sm.a_ready[B_HS0]);
 
@@ -886,7 +887,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
 #pragma unroll 1
         for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
           epi_group64_masked<false>(tlane + c0, nullptr, PB + (c0 >> 6) * kBlockBytes, r, lane,
-                                    bf(go.d_x) + trow * 256 + c0, 256, rows_valid, c0 == 0 ? dterm : 0.f);
+                                    bf(go.d_x) + trow * 256 + c0, 256, 256, rows_valid, c0 == 0 ? dterm : 0.f);
       }
       signal_a_ready(&sm.a_ready[B_L1]);
 
@@ -895,7 +896,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
       tcgen05_fence_after();
       if (half == 0)
         epi_group64_masked<true>(tlane + 256, cbf(sv.h0) + trow * 64, QB + 2 * kBlockBytes, r, lane,
-                                 bf(go.d_h0) + trow * 64, 64, rows_valid);
+                                 bf(go.d_h0) + trow * 64, 64, 64, rows_valid);
       signal_a_ready(&sm.a_ready[B_L0]);
 
       // ---- grad_features = accB[64:112) (40 valid columns)

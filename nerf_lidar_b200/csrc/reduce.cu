@@ -45,17 +45,17 @@ __global__ void __launch_bounds__(kRedThreads) k_colsum_bf16(const __nv_bfloat16
 
 // x[groups * S, cols] bf16 -> out[groups, cols] fp32: sum over the S consecutive rows of a group.
 __global__ void __launch_bounds__(kRedThreads) k_group_sum_bf16(const __nv_bfloat16* __restrict__ x, int64_t groups,
-                                                                int S, int cols, float* __restrict__ out) {
+                                                                int S, int cols, int ld, float* __restrict__ out) {
   const int pairs = cols >> 1;
   const int per_block = kRedThreads / pairs;  // groups per block
   const int p = threadIdx.x % pairs;
   const int64_t g = (int64_t)blockIdx.x * per_block + threadIdx.x / pairs;
   if (g >= groups) return;
-  const __nv_bfloat16* src = x + (g * S) * cols + 2 * p;
+  const __nv_bfloat16* src = x + (g * S) * ld + 2 * p;
   float2 acc = make_float2(0.f, 0.f);
 #pragma unroll 4
   for (int s = 0; s < S; ++s) {
-    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + (int64_t)s * cols));
+    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + (int64_t)s * ld));
     acc.x += v.x;
     acc.y += v.y;
   }
@@ -80,13 +80,13 @@ extern "C" int nlb_colsum_bf16(const void* x, int64_t M, int cols, int ld, float
   return nlb_check_launch("colsum_bf16");
 }
 
-extern "C" int nlb_group_sum_bf16(const void* x, int64_t groups, int S, int cols, float* out, void* stream) {
-  if (!x || !out || groups < 0 || S < 1) { nlb_set_error("group_sum_bf16: bad arguments"); return NLB_EINVAL; }
-  if (!pow2_cols(cols)) { nlb_set_error("group_sum_bf16: cols must be a power of two in [2,512] (cols=%d)", cols); return NLB_EUNSUPPORTED; }
+extern "C" int nlb_group_sum_bf16(const void* x, int64_t groups, int S, int cols, int ld, float* out, void* stream) {
+  if (!x || !out || groups < 0 || S < 1 || ld < cols) { nlb_set_error("group_sum_bf16: bad arguments"); return NLB_EINVAL; }
+  if (!pow2_cols(cols) || (ld & 1)) { nlb_set_error("group_sum_bf16: cols must be a power of two in [2,512] (cols=%d)", cols); return NLB_EUNSUPPORTED; }
   if (groups == 0) return NLB_OK;
   const int per_block = kRedThreads / (cols >> 1);
   const int64_t blocks = (groups + per_block - 1) / per_block;
   k_group_sum_bf16<<<(unsigned)blocks, kRedThreads, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), groups, S, cols, out);
+      reinterpret_cast<const __nv_bfloat16*>(x), groups, S, cols, ld, out);
   return nlb_check_launch("group_sum_bf16");
 }

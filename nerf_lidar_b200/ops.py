@@ -370,24 +370,31 @@ def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 @torch.no_grad()
+def _bf16_rows_ptr(x: torch.Tensor):
+    """Pointer of a bf16 matrix whose rows are dense (column slices of a wider buffer are fine)."""
+    if not x.is_cuda or x.dtype != torch.bfloat16 or x.dim() != 2 or x.stride(1) != 1:
+        raise RuntimeError('nerf_lidar_b200: expected a CUDA bf16 matrix with unit column stride')
+    return C.c_void_p(x.data_ptr())
+
+
 def colsum_bf16(x: torch.Tensor) -> torch.Tensor:
-    """Column sums of a contiguous bf16 matrix [M, cols] -> fp32 [cols]."""
+    """Column sums of a bf16 matrix [M, cols] (dense rows, any row stride) -> fp32 [cols]."""
     M, cols = x.shape
     out = torch.empty(cols, device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device):
         with timed('mlp_bias_grad'):
-            check(load().nlb_colsum_bf16(ptr(x), M, cols, x.stride(0), ptr(out), stream()))
+            check(load().nlb_colsum_bf16(_bf16_rows_ptr(x), M, cols, x.stride(0), ptr(out), stream()))
     return out
 
 
 @torch.no_grad()
 def group_sum_bf16(x: torch.Tensor, S: int) -> torch.Tensor:
-    """Sums over groups of S consecutive rows of a contiguous bf16 [G*S, cols] -> fp32 [G, cols]."""
+    """Sums over groups of S consecutive rows of a bf16 [G*S, cols] (dense rows) -> fp32 [G, cols]."""
     M, cols = x.shape
     out = torch.empty(M // S, cols, device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device):
         with timed('mlp_ray_sum'):
-            check(load().nlb_group_sum_bf16(ptr(x), M // S, S, cols, ptr(out), stream()))
+            check(load().nlb_group_sum_bf16(_bf16_rows_ptr(x), M // S, S, cols, x.stride(0), ptr(out), stream()))
     return out
 
 
@@ -413,11 +420,16 @@ class _NerfMLP(Function):
         g_density, g_rgb, g_sem, g_int = c(g_density), c(g_rgb), c(g_sem), c(g_int)
         blob_t = nerf_mlp_pack(mlp, transposed=True)
         bf = lambda cols: torch.empty(M, cols, device=dev, dtype=torch.bfloat16)
-        d_rgb, d_v1, d_v0, d_hs1, d_g, d_x, d_h0 = bf(16), bf(256), bf(256), bf(32), bf(128), bf(256), bf(64)
+        d_rgb, d_hs1, d_x, d_h0 = bf(16), bf(32), bf(256), bf(64)
+        # d_g | d_v0 | d_v1 share the A operand x in the weight-gradient products: column slices of one
+        # buffer, so the three products are ONE GEMM [640, M] x [M, 256]
+        dcat = bf(640)
+        d_g, d_v0, d_v1 = dcat[:, :128], dcat[:, 128:384], dcat[:, 384:]
         g_feat = torch.empty(M, 40, device=dev, dtype=torch.float32)
         gin = NlbNerfMlpGradIn(ptr(g_density), ptr(g_rgb), ptr(g_sem), ptr(g_int), ptr(density), ptr(rgb), ptr(sem))
         sv = NlbNerfMlpSaved(ptr(h0), ptr(x), ptr(g), ptr(h1), ptr(h2))
-        gout = NlbNerfMlpGradOut(ptr(d_rgb), ptr(d_v1), ptr(d_v0), ptr(d_hs1), ptr(d_g), ptr(d_x), ptr(d_h0))
+        gout = NlbNerfMlpGradOut(ptr(d_rgb), d_v1.data_ptr(), d_v0.data_ptr(), ptr(d_hs1), d_g.data_ptr(), ptr(d_x),
+                                 ptr(d_h0), 640, 640, 640)
         with torch.cuda.device(dev):
             with timed('nerf_mlp_bwd'):
                 check(load().nlb_nerf_mlp_backward(C.byref(gin), C.byref(sv), M, ptr(blob_t), ptr(g_feat),
@@ -427,16 +439,17 @@ class _NerfMLP(Function):
         f0 = features.to(torch.bfloat16)
         # bias gradients and per-ray sums: one bandwidth-bound pass each (csrc/reduce.cu)
         cs_g, cs_hs1, cs_rgb = colsum_bf16(d_g), colsum_bf16(d_hs1), colsum_bf16(d_rgb)
+        gx = _mm_f32(dcat.t(), x)                                    # [640, 256]: W_s0 | W_i0 | W_v0[:, :256] | W_v1[:, 256:512]
         gW = {
             'W_d0': _mm_f32(d_h0.t(), f0), 'b_d0': colsum_bf16(d_h0),
             'W_d2': _mm_f32(d_x.t(), h0), 'b_d2': colsum_bf16(d_x),
-            'W_s0': _mm_f32(d_g[:, :64].t(), x), 'b_s0': cs_g[:64],
+            'W_s0': gx[:64], 'b_s0': cs_g[:64],
             'W_s2': _mm_f32(d_hs1[:, :19].t(), g[:, :64]), 'b_s2': cs_hs1[:19],
-            'W_i0': _mm_f32(d_g[:, 64:].t(), x), 'b_i0': cs_g[64:],
+            'W_i0': gx[64:128], 'b_i0': cs_g[64:],
             'W_i2': _mm_f32(d_hs1[:, 19:20].t(), g[:, 64:]), 'b_i2': cs_hs1[19:20],
-            'W_v0': torch.cat([_mm_f32(d_v0.t(), x), group_sum_bf16(d_v0, S).t() @ de], dim=1),
+            'W_v0': torch.cat([gx[128:384], group_sum_bf16(d_v0, S).t() @ de], dim=1),
             'b_v0': colsum_bf16(d_v0),
-            'W_v1': torch.cat([_mm_f32(d_v1.t(), h1), _mm_f32(d_v1.t(), x), group_sum_bf16(d_v1, S).t() @ de], dim=1),
+            'W_v1': torch.cat([_mm_f32(d_v1.t(), h1), gx[384:], group_sum_bf16(d_v1, S).t() @ de], dim=1),
             'b_v1': colsum_bf16(d_v1),
             'W_rgb': _mm_f32(d_rgb[:, :3].t(), h2), 'b_rgb': cs_rgb[:3],
         }

@@ -145,3 +145,77 @@ def test_prop_level_forward_backward(lvl, L, full_state_dict_visible):
     g_lbc = (gf * wj[..., None] / 7).reshape(-1, L, 1).permute(1, 0, 2).contiguous()
     want_ge, _ = go.grid_encode_backward(g_lbc, pts[..., :3].reshape(-1, 3), emb, sd[pre + 'encoder.offsets'], 1.0, 16)
     assert_close(mlp.encoder.embeddings.grad, want_ge, 2e-4, 'table gradient')
+
+
+def _slice_batch(batch, n):
+    return {k: v[:n].contiguous() for k, v in batch.items()}
+
+
+@pytest.mark.parametrize('n_rays,S', [(37, 5), (1, 3), (129, 33)])
+def test_encode_ragged_sizes(n_rays, S, full_state_dict_visible):
+    """Row counts that are not multiples of the warp / tile size (the scatter kernels are
+    persistent, warp-aggregated and use whole-warp shuffles): forward on the kernel's points
+    and the table gradient against the oracle scatter, NeRF table (C=4) and a proposal
+    table (C=1)."""
+    from nerf_lidar_b200 import ops
+    sd = full_state_dict_visible
+    batch, _, _ = _setup(11, S, True)
+    batch = _slice_batch(batch, n_rays)
+    g0 = torch.Generator().manual_seed(n_rays)
+    s = torch.sort(torch.rand(n_rays, S + 1, generator=g0), -1).values
+    t = zo.s_to_t(s, batch['near'], batch['far'])
+    deg = torch.rand(n_rays, S, 7, generator=g0)
+    model = _model(sd)
+    rays = ops.RayBundle({k: v.cuda() for k, v in batch.items()})
+    pts = ops.sample_points(t.cuda(), deg.cuda(), rays).cpu()
+    for pre, enc, C in (('nerf_mlp.', model.nerf_mlp.encoder, 4), ('prop_mlp_1.', model.prop_mlp_1.encoder, 1)):
+        L = enc.num_levels
+        emb, offs, gs = sd[pre + 'encoder.embeddings'], sd[pre + 'encoder.offsets'], sd[pre + 'encoder.grid_sizes']
+        enc.embeddings.grad = None
+        feat = ops.nerf_encode(t.cuda(), deg.cuda(), enc, rays, 0.35)
+        assert feat.shape == (n_rays * S, L * C)
+        want = _oracle_features_from_points(pts, emb, offs, gs, C)
+        assert_close(feat.reshape(n_rays, S, L * C), want, 1e-5, pre + 'features')
+        g = torch.randn(n_rays * S, L * C, generator=g0)
+        feat.backward(g.cuda())
+        g_pts = g.reshape(n_rays, S, 1, L, C).expand(n_rays, S, 7, L, C)
+        wj = torch.erf(1 / torch.clamp(torch.sqrt(8 * pts[..., 3][..., None] ** 2 * gs ** 2), min=1e-10))
+        g_lbc = (g_pts * wj[..., None] / 7).reshape(-1, L, C).permute(1, 0, 2).contiguous()
+        want_ge, _ = go.grid_encode_backward(g_lbc, pts[..., :3].reshape(-1, 3), emb, offs, 1.0, 16)
+        assert_close(enc.embeddings.grad, want_ge, 2e-5, pre + 'table gradient')
+
+
+def test_encode_adjoint_at_bench_size(full_state_dict_visible):
+    """Size-independent property at BASELINE's full size (10 240 rays): the fused encode is
+    linear in the table, so <g, F(e)> = <F^T g, e> must hold for the forward / scatter pair."""
+    from nerf_lidar_b200 import ops
+    sd = full_state_dict_visible
+    model = _model(sd)
+    batch = synthetic.to_torch(synthetic.make_train_batch(8192, seed=3))
+    N = batch['origins'].shape[0]
+    rays = ops.RayBundle({k: v.cuda() for k, v in batch.items()})
+    for enc, S in ((model.nerf_mlp.encoder, 32), (model.prop_mlp_0.encoder, 64), (model.prop_mlp_1.encoder, 64)):
+        g0 = torch.Generator(device='cuda').manual_seed(S)
+        s = torch.sort(torch.rand(N, S + 1, device='cuda', generator=g0), -1).values
+        t = zo.s_to_t(s.cpu(), batch['near'], batch['far']).cuda()
+        deg = torch.rand(N, S, 7, device='cuda', generator=g0)
+        enc.embeddings.grad = None
+        feat = ops.nerf_encode(t, deg, enc, rays, 0.35)
+        g = torch.randn(feat.shape, device='cuda', generator=g0)
+        feat.backward(g)
+        lhs = (g.double() * feat.detach().double()).sum()
+        rhs = (enc.embeddings.grad.double() * enc.embeddings.detach().double()).sum()
+        scale = (g.double() * feat.detach().double()).abs().sum()
+        assert float((lhs - rhs).abs()) <= 1e-5 * float(scale), (S, float(lhs), float(rhs))
+
+
+def test_empty_ray_batch():
+    """Zero rays: every op returns empty outputs without launching."""
+    from nerf_lidar_b200 import configs, models
+    model = models.Model(configs.nuscenes_single()).cuda()
+    model.load_state_dict({k: v.cuda() for k, v in synthetic.init_state_dict(seed=1).items()}, strict=False)
+    batch = {k: v[:0].cuda() for k, v in synthetic.to_torch(synthetic.make_train_batch(64, seed=1)).items()}
+    with torch.no_grad():
+        rend, hist = model(False, batch, 1.0, True)
+    assert rend[-1]['rgb'].shape == (0, 3) and rend[-1]['depth'].shape == (0,)
+    assert hist[-1]['weights'].shape == (0, 32)

@@ -116,6 +116,10 @@ def test_bf16_reductions_vs_torch(cols):
     got = ops.group_sum_bf16(x, S)
     want = x.float().view(N, S, cols).sum(1)
     assert_close(got, want, 1e-5, 'group_sum')
-    # a strided view (leading dimension larger than the column count) is rejected loudly, never copied silently
-    with pytest.raises(RuntimeError):
-        ops.colsum_bf16(x[:, : cols // 2])
+    # column slices of a wider buffer (dense rows, larger leading dimension) are read in place
+    wide = torch.cat([x, x * 2, x[:, :16] * 0], dim=1)
+    assert_close(ops.colsum_bf16(wide[:, cols:2 * cols]), (x * 2).float().sum(0), 1e-4, 'colsum of a slice')
+    assert_close(ops.group_sum_bf16(wide[:, cols:2 * cols], S), (x * 2).float().view(N, S, cols).sum(1), 1e-5,
+                 'group_sum of a slice')
+    with pytest.raises(RuntimeError):  # a transposed view has no dense rows
+        ops.colsum_bf16(x.t())
