@@ -53,6 +53,8 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {  // all thre
 __global__ void __launch_bounds__(1024) k_depth_quantile(nlb_losses_in_t in, float* __restrict__ sums, int cached) {
   extern __shared__ uint32_t s_bits[];  // [N] |d| bit patterns (0xffffffff: not supervised) when they fit
   __shared__ float s_red[32];
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_pick[2];  // chosen digit, elements below it
   const int N = in.N;
   auto bits_of = [&](int i) -> uint32_t {
     if (!ray_masks(in, i).depth) return 0xffffffffu;
@@ -74,17 +76,35 @@ __global__ void __launch_bounds__(1024) k_depth_quantile(nlb_losses_in_t in, flo
   float sel[2];
 #pragma unroll 1
   for (int which = 0; which < 2; ++which) {
-    const int k = which ? k_hi : k_lo;
     if (which && k_hi == k_lo) { sel[1] = sel[0]; break; }
-    uint32_t result = 0;
+    // radix select, 8 bits per pass: histogram of the next digit among the elements that share the
+    // prefix found so far, then the digit in which the k-th smallest falls
+    uint32_t k = which ? k_hi : k_lo, prefix = 0, prefix_mask = 0;
 #pragma unroll 1
-    for (int bit = 30; bit >= 0; --bit) {
-      const uint32_t trial = result | (1u << bit);
-      float c = 0.f;
-      for (int i = threadIdx.x; i < N; i += blockDim.x) c += ((cached ? s_bits[i] : bits_of(i)) < trial) ? 1.f : 0.f;
-      if ((int)block_sum(c, s_red) <= k) result = trial;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
+      __syncthreads();
+      for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const uint32_t b = cached ? s_bits[i] : bits_of(i);
+        if (b != 0xffffffffu && (b & prefix_mask) == prefix) atomicAdd(&s_hist[(b >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        uint32_t below = 0, d = 0;
+        for (; d < 255; ++d) {
+          if (below + s_hist[d] > k) break;
+          below += s_hist[d];
+        }
+        s_pick[0] = d;
+        s_pick[1] = below;
+      }
+      __syncthreads();
+      prefix |= s_pick[0] << shift;
+      prefix_mask |= 255u << shift;
+      k -= s_pick[1];
+      __syncthreads();
     }
-    sel[which] = __uint_as_float(result);
+    sel[which] = __uint_as_float(prefix);
   }
   if (threadIdx.x == 0) sums[S_THRE] = sel[0] + (sel[1] - sel[0]) * (pos - floorf(pos));
 }

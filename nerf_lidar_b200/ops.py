@@ -223,6 +223,7 @@ def nerf_encode(tdist, deg_noise, encoder, rays: RayBundle, std_scale: float) ->
 class _Composite(Function):
     @staticmethod
     def forward(ctx, density, rgb, semantic, intensity, tdist, directions, far, bg, opaque, extras):
+        ctx.set_materialize_grads(False)  # outputs nobody differentiates arrive as None, not as zero fills
         N, S = density.shape
         dev = density.device
         density = f32(density)
@@ -404,6 +405,7 @@ class _NerfMLP(Function):
 
     @staticmethod
     def forward(ctx, features, viewdirs, mlp, S, *weights):
+        ctx.set_materialize_grads(False)
         features, viewdirs = f32(features), f32(viewdirs)
         density, rgb, sem, inten, saved = _mlp_forward_raw(mlp, features, viewdirs, S, True)
         ctx.mlp, ctx.S = mlp, S
