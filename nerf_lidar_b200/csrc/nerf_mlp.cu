@@ -222,6 +222,19 @@ __device__ __forceinline__ void warp_rows_from_global(uint8_t* block, int wrow0,
   __syncwarp();
 }
 
+// same, asynchronously (no registers, no wait): rows beyond rows_valid are zero-filled; complete with
+// cp_async_wait_all() + __syncwarp() before reading
+__device__ __forceinline__ void warp_rows_from_global_async(uint8_t* block, int wrow0, int lane, const __nv_bfloat16* g,
+                                                            int ld, int rows_valid) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = wrow0 + i * 4 + (lane >> 3), ch = lane & 7;
+    const bool ok = row < rows_valid;
+    cp_async16(block + (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) * 16),
+               g + (size_t)(ok ? row : 0) * ld + ch * 8, ok);
+  }
+}
+
 // forward group: 64 accumulator columns of this thread's row -> bias (+relu) -> block (+ saved copy)
 template <bool kRelu>
 __device__ __forceinline__ void epi_group64(uint32_t taddr, const float* __restrict__ bias, uint8_t* block, int row,
@@ -359,60 +372,78 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
     uint8_t* HB = a_blocks + BH * kBlockBytes;
     uint8_t* XB = a_blocks + BX * kBlockBytes;
     uint8_t* DB = a_blocks + BD * kBlockBytes;
+    // staging of a tile's inputs: this thread's feature row -> registers -> H0, and the direction encoding -> D
+    auto load_features = [&](int tile_, float (&f)[kFeat]) {
+      const int row_ = tile_ * 128 + r;
+      if (tile_ < num_tiles && row_ < M) {
+        const float4* src = reinterpret_cast<const float4*>(features + (size_t)row_ * kFeat);
+#pragma unroll
+        for (int q = 0; q < kFeat / 4; ++q) {
+          const float4 t = __ldg(src + q);
+          f[q * 4] = t.x; f[q * 4 + 1] = t.y; f[q * 4 + 2] = t.z; f[q * 4 + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < kFeat; ++i) f[i] = 0.f;
+      }
+    };
+    auto store_features = [&](const float (&f)[kFeat]) {
+      uint8_t* rowp = HB + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (q < kFeat / 8) {
+          u.x = pack_bf16(f[q * 8], f[q * 8 + 1]); u.y = pack_bf16(f[q * 8 + 2], f[q * 8 + 3]);
+          u.z = pack_bf16(f[q * 8 + 4], f[q * 8 + 5]); u.w = pack_bf16(f[q * 8 + 6], f[q * 8 + 7]);
+        }
+        *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) * 16)) = u;
+      }
+    };
+    auto stage_dirs = [&](int tile_) {
+      const int row_ = tile_ * 128 + r;
+      float d[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) d[i] = 0.f;
+      if (tile_ < num_tiles && row_ < M) {
+        const int ray = row_ / rows_per_ray;
+        const float vx = __ldg(viewdirs + 3 * ray), vy = __ldg(viewdirs + 3 * ray + 1), vz = __ldg(viewdirs + 3 * ray + 2);
+        d[0] = vx; d[1] = vy; d[2] = vz;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const float sc = (float)(1 << s);
+          const float ax = vx * sc, ay = vy * sc, az = vz * sc;
+          d[3 + s * 3] = sinf(ax); d[4 + s * 3] = sinf(ay); d[5 + s * 3] = sinf(az);
+          d[15 + s * 3] = sinf(ax + 1.5707963267948966f);
+          d[16 + s * 3] = sinf(ay + 1.5707963267948966f);
+          d[17 + s * 3] = sinf(az + 1.5707963267948966f);
+        }
+      }
+      uint8_t* drow = DB + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (q < 4) {
+          u.x = pack_bf16(d[q * 8], d[q * 8 + 1]); u.y = pack_bf16(d[q * 8 + 2], d[q * 8 + 3]);
+          u.z = pack_bf16(d[q * 8 + 4], d[q * 8 + 5]); u.w = pack_bf16(d[q * 8 + 6], d[q * 8 + 7]);
+        }
+        *reinterpret_cast<uint4*>(drow + ((q ^ (r & 7)) * 16)) = u;
+      }
+    };
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
       const int row = tile * 128 + r;
       const bool valid = row < M;
       const int rows_valid = M - tile * 128 < 128 ? M - tile * 128 : 128;
-      // ---- stage features (H0: half 0) and the view-direction encoding (D: half 1)
-      if (half == 0) {
-        float f[64];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) f[i] = 0.f;
-        if (valid) {
-          const float4* src = reinterpret_cast<const float4*>(features + (size_t)row * kFeat);
-#pragma unroll
-          for (int q = 0; q < kFeat / 4; ++q) {
-            const float4 t = __ldg(src + q);
-            f[q * 4] = t.x; f[q * 4 + 1] = t.y; f[q * 4 + 2] = t.z; f[q * 4 + 3] = t.w;
-          }
-        }
-        uint8_t* rowp = HB + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          uint4 u;
-          u.x = pack_bf16(f[q * 8], f[q * 8 + 1]); u.y = pack_bf16(f[q * 8 + 2], f[q * 8 + 3]);
-          u.z = pack_bf16(f[q * 8 + 4], f[q * 8 + 5]); u.w = pack_bf16(f[q * 8 + 6], f[q * 8 + 7]);
-          *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) * 16)) = u;
-        }
-      } else {
-        float d[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) d[i] = 0.f;
-        if (valid) {
-          const int ray = row / rows_per_ray;
-          const float vx = __ldg(viewdirs + 3 * ray), vy = __ldg(viewdirs + 3 * ray + 1), vz = __ldg(viewdirs + 3 * ray + 2);
-          d[0] = vx; d[1] = vy; d[2] = vz;
-#pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            const float sc = (float)(1 << s);
-            const float ax = vx * sc, ay = vy * sc, az = vz * sc;
-            d[3 + s * 3] = sinf(ax); d[4 + s * 3] = sinf(ay); d[5 + s * 3] = sinf(az);
-            d[15 + s * 3] = sinf(ax + 1.5707963267948966f);
-            d[16 + s * 3] = sinf(ay + 1.5707963267948966f);
-            d[17 + s * 3] = sinf(az + 1.5707963267948966f);
-          }
-        }
-        uint8_t* drow = DB + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          uint4 u = make_uint4(0, 0, 0, 0);
-          if (q < 4) {
-            u.x = pack_bf16(d[q * 8], d[q * 8 + 1]); u.y = pack_bf16(d[q * 8 + 2], d[q * 8 + 3]);
-            u.z = pack_bf16(d[q * 8 + 4], d[q * 8 + 5]); u.w = pack_bf16(d[q * 8 + 6], d[q * 8 + 7]);
-          }
-          *reinterpret_cast<uint4*>(drow + ((q ^ (r & 7)) * 16)) = u;
+      // ---- features (H0: half 0) and view-direction encoding (D: half 1) of the FIRST tile; every later
+      // tile was staged during the previous one (see the end of the loop body)
+      if (it == 0) {
+        if (half == 0) {
+          float f[kFeat];
+          load_features(tile, f);
+          store_features(f);
+        } else {
+          stage_dirs(tile);
         }
       }
       signal_a_ready(&sm.a_ready[E_F]);
@@ -509,12 +540,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
                           rows_valid);
       signal_a_ready(&sm.a_ready[E_H2]);
 
+      // ---- next tile's inputs, while the RGB MMAs run: D is free (the V1 MMAs have completed), the
+      // features wait in registers until the RGB MMAs have released H0
+      const int next_tile = tile + (int)gridDim.x;
+      float fnext[kFeat];
+      if (half == 1) stage_dirs(next_tile);
+      else load_features(next_tile, fnext);
+
       // ---- RGB: sigmoid(acc + b) * (1 + 2 pad) - pad
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 12);
       mbar_wait_warp(&sm.acc_ready[RGB], ph);
       tcgen05_fence_after();
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 13);
-      if (half == 1) {  // (half 0 only needed the wait: the next tile's features overwrite H0)
+      if (half == 0) {
+        store_features(fnext);
+      } else {
         float v[16];
         tmem_ld16(tlane + 256, v);
         const float* b = sm.bias + bias_offset(RGB);
@@ -563,9 +603,9 @@ __host__ __device__ constexpr BLayerDef blayer_def(int l) {
     case B_V1:  return {512, 4, {BP, BP + 1, BP + 2, BP + 3}, {4, 4, 4, 4}, {256, 384, 0, 128}, false};
     case B_V0:  return {256, 4, {BQ, BQ + 1, BQ + 2, BQ + 3}, {4, 4, 4, 4}, {0, 128, 0, 0}, true};
     case B_HS1: return {128, 1, {BS}, {2}, {256, 0, 0, 0}, false};
-    case B_HS0: return {256, 2, {BQ, BQ + 1}, {4, 4}, {0, 128, 0, 0}, true};
+    case B_HS0: return {256, 2, {BP, BP + 1}, {4, 4}, {0, 128, 0, 0}, true};   // dzg lives in P0,P1 (free after B_V1)
     case B_L1:  return {64, 4, {BP, BP + 1, BP + 2, BP + 3}, {4, 4, 4, 4}, {256, 0, 0, 0}, false};
-    default:    return {48, 1, {BQ + 2}, {4}, {320, 0, 0, 0}, false};
+    default:    return {48, 1, {BS}, {4}, {320, 0, 0, 0}, false};                  // dz0 lives in S (free after B_HS1)
   }
 }
 __host__ __device__ constexpr int bl_nrows(int l) { return blayer_def(l).N > 128 ? 128 : blayer_def(l).N; }
@@ -702,11 +742,14 @@ __device__ __forceinline__ void issue_blayer(SmemT& sm, uint8_t* a_blocks, uint8
 // The activation rows are first staged, coalesced, into the destination block itself (it
 // is free: it is about to be overwritten), each thread then reads its own row from there.
 //   act / gdst = tile base + column offset of the saved activation / output matrices.
-template <bool kMask>
+//   kPrefetched: the activation rows are already in the block (warp_rows_from_global_async at the start
+//   of the tile, completed by the caller) -- the global-load latency of the two widest epilogues is then
+//   hidden behind the first GEMMs instead of being paid per group on the tile's critical path.
+template <bool kMask, bool kPrefetched = false>
 __device__ __forceinline__ void epi_group64_masked(uint32_t taddr, const __nv_bfloat16* __restrict__ act,
                                                    uint8_t* block, int row, int lane, __nv_bfloat16* gdst, int ld_act,
                                                    int ld_out, int rows_valid, float add0 = 0.f) {
-  if (kMask) warp_rows_from_global(block, row & ~31, lane, act, ld_act, rows_valid);
+  if (kMask && !kPrefetched) warp_rows_from_global(block, row & ~31, lane, act, ld_act, rows_valid);
   float v[64];
   tmem_ld64(taddr, v);
   v[0] += add0;
@@ -797,6 +840,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
     uint8_t* SB = a_blocks + BS * kBlockBytes;
     auto bf = [](void* p) { return reinterpret_cast<__nv_bfloat16*>(p); };
     auto cbf = [](const void* p) { return reinterpret_cast<const __nv_bfloat16*>(p); };
+    float dc_rgb[3] = {0.f, 0.f, 0.f}, dc_g[3] = {0.f, 0.f, 0.f};
+    auto load_dc_inputs = [&](int row_, bool valid_) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        dc_rgb[i] = (valid_ && gi.g_rgb) ? __ldg(gi.rgb + (size_t)row_ * 3 + i) : 0.f;
+        dc_g[i] = (valid_ && gi.g_rgb) ? __ldg(gi.g_rgb + (size_t)row_ * 3 + i) : 0.f;
+      }
+    };
+    // this warp's 32 rows x this half's two 64-column blocks of a saved [M,256] activation -> blocks dst[0..3]
+    auto prefetch_mask = [&](uint8_t* dst, const void* act, int tile_) {
+      if (tile_ >= num_tiles) return;
+      const int rv = M - tile_ * 128 < 128 ? M - tile_ * 128 : 128;
+#pragma unroll 1
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
+        warp_rows_from_global_async(dst + (c0 >> 6) * kBlockBytes, r & ~31, lane,
+                                    cbf(act) + (size_t)tile_ * 128 * 256 + c0, 256, rv);
+    };
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
@@ -805,17 +865,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
       const int rows_valid = M - tile * 128 < 128 ? M - tile * 128 : 128;
       const size_t trow = (size_t)tile * 128;  // first row of the tile
       uint8_t* srow = SB + (r >> 3) * 1024 + (r & 7) * 128;
-      // ---- dc -> S (cols 0..2): half 0
+      if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 0);
+      // ---- dc -> S (cols 0..2): half 0 (inputs were loaded at the end of the previous tile)
       if (half == 0) {
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        if (valid && gi.g_rgb) {
+        if (it == 0) load_dc_inputs(row, valid);
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const float s = (__ldg(gi.rgb + (size_t)row * 3 + i) + 0.001f) / (1.0f + 2.0f * 0.001f);
-            v[i] = __ldg(gi.g_rgb + (size_t)row * 3 + i) * (1.0f + 2.0f * 0.001f) * s * (1.0f - s);
-          }
+        for (int i = 0; i < 3; ++i) {
+          const float s = (dc_rgb[i] + 0.001f) / (1.0f + 2.0f * 0.001f);
+          v[i] = dc_g[i] * (1.0f + 2.0f * 0.001f) * s * (1.0f - s);
         }
         store_cols(v, SB, r, 0, nullptr);
         if (valid && go.d_rgb) {
@@ -826,25 +886,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
       }
       signal_a_ready(&sm.a_ready[B_RGB]);
 
+      // ReLU masks of the two widest epilogues: h2 -> P, h1 -> Q.  For the first tile they are fetched
+      // here; for every later tile they were issued during the previous one, as soon as its last reader
+      // of Q (B_V0) / P (B_L1) had completed, so they are resident when the tile starts.
+      if (it == 0) {
+        prefetch_mask(QB, sv.h1, tile);
+        prefetch_mask(PB, sv.h2, tile);
+      }
+
       // ---- dzv1 = dh2 * [h2 > 0] -> P0..3
       mbar_wait_warp(&sm.acc_ready[B_RGB], ph);
+      if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 2);
       tcgen05_fence_after();
+      cp_async_wait_all();
+      __syncwarp();
 #pragma unroll 1
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
-        epi_group64_masked<true>(tlane + 256 + c0, cbf(sv.h2) + trow * 256 + c0, PB + (c0 >> 6) * kBlockBytes, r, lane,
+        epi_group64_masked<true, true>(tlane + 256 + c0, cbf(sv.h2) + trow * 256 + c0, PB + (c0 >> 6) * kBlockBytes, r, lane,
                                  bf(go.d_v1) + trow * ld_v1 + c0, 256, ld_v1, rows_valid);
+      if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 3);
       signal_a_ready(&sm.a_ready[B_V1]);
 
-      // ---- dzv0 = dh1 * [h1 > 0] -> Q0..3   (dh1 in accB, dx partial stays in accA)
-      mbar_wait_warp(&sm.acc_ready[B_V1], ph);
-      tcgen05_fence_after();
-#pragma unroll 1
-      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
-        epi_group64_masked<true>(tlane + 256 + c0, cbf(sv.h1) + trow * 256 + c0, QB + (c0 >> 6) * kBlockBytes, r, lane,
-                                 bf(go.d_v0) + trow * ld_v0 + c0, 256, ld_v0, rows_valid);
-      signal_a_ready(&sm.a_ready[B_V0]);
-
-      // ---- d(sem logits) | d(intensity) -> S (cols 0..19): half 1; S is free: B_RGB completed above
+      // ---- d(sem logits) | d(intensity) -> S (cols 0..19): half 1, while B_V1 runs; S is free: B_RGB completed above
       if (half == 1) {
         float v[32];
 #pragma unroll
@@ -865,21 +928,46 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
         }
         store_cols(v, SB, r, 0, (valid && go.d_hs1) ? bf(go.d_hs1) + (size_t)row * 32 : nullptr);
       }
+      if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 6);
       signal_a_ready(&sm.a_ready[B_HS1]);
 
-      // ---- dzg = dg * [g > 0] -> Q0,Q1  (B_V0 has finished reading Q: it precedes B_HS1 on the pipe)
-      mbar_wait_warp(&sm.acc_ready[B_HS1], ph);
+      // ---- dzv0 = dh1 * [h1 > 0] -> Q0..3   (dh1 in accB, dx partial stays in accA)
+      mbar_wait_warp(&sm.acc_ready[B_V1], ph);
+      if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 4);
       tcgen05_fence_after();
 #pragma unroll 1
+      // B_V1 has consumed P: the ReLU mask of the sem | intensity hidden layer goes to P0 / P1 now and is
+      // there when the HS1 epilogue needs it
+      warp_rows_from_global_async(PB + half * kBlockBytes, r & ~31, lane, cbf(sv.g) + trow * 128 + half * 64, 128, rows_valid);
+#pragma unroll 1
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
+        epi_group64_masked<true, true>(tlane + 256 + c0, cbf(sv.h1) + trow * 256 + c0, QB + (c0 >> 6) * kBlockBytes, r, lane,
+                                 bf(go.d_v0) + trow * ld_v0 + c0, 256, ld_v0, rows_valid);
+      if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 5);
+      signal_a_ready(&sm.a_ready[B_V0]);
+
+
+      // ---- dzg = dg * [g > 0] -> P0,P1
+      mbar_wait_warp(&sm.acc_ready[B_HS1], ph);
+      if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 7);
+      tcgen05_fence_after();
+      cp_async_wait_all();
+      __syncwarp();
+      // B_HS1 has consumed S: the ReLU mask of density_layer.0 goes there for the last epilogue
+      if (half == 0) warp_rows_from_global_async(SB, r & ~31, lane, cbf(sv.h0) + trow * 64, 64, rows_valid);
+      // B_V0 (ahead of B_HS1 on the pipe) has consumed Q, which this tile does not touch again
+      prefetch_mask(QB, sv.h1, tile + (int)gridDim.x);
       {
         const int c0 = half * 64;
-        epi_group64_masked<true>(tlane + 256 + c0, cbf(sv.g) + trow * 128 + c0, QB + half * kBlockBytes, r, lane,
-                                 bf(go.d_g) + trow * ld_g + c0, 128, ld_g, rows_valid);
+        epi_group64_masked<true, true>(tlane + 256 + c0, cbf(sv.g) + trow * 128 + c0, PB + half * kBlockBytes, r, lane,
+                                       bf(go.d_g) + trow * ld_g + c0, 128, ld_g, rows_valid);
       }
+      if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 8);
       signal_a_ready(&sm.a_ready[B_HS0]);
 
       // ---- dx = accA (+ density term on column 0) -> P0..3
       mbar_wait_warp(&sm.acc_ready[B_HS0], ph);
+      if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 9);
       tcgen05_fence_after();
       {
         float dterm = 0.f;
@@ -889,18 +977,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
           epi_group64_masked<false>(tlane + c0, nullptr, PB + (c0 >> 6) * kBlockBytes, r, lane,
                                     bf(go.d_x) + trow * 256 + c0, 256, 256, rows_valid, c0 == 0 ? dterm : 0.f);
       }
+      if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 10);
       signal_a_ready(&sm.a_ready[B_L1]);
 
-      // ---- dz0 = dh0 * [h0 > 0] -> Q2
+      // ---- dz0 = dh0 * [h0 > 0] -> S
       mbar_wait_warp(&sm.acc_ready[B_L1], ph);
+      if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 11);
       tcgen05_fence_after();
-      if (half == 0)
-        epi_group64_masked<true>(tlane + 256, cbf(sv.h0) + trow * 64, QB + 2 * kBlockBytes, r, lane,
-                                 bf(go.d_h0) + trow * 64, 64, 64, rows_valid);
+      if (half == 0) {
+        cp_async_wait_all();
+        __syncwarp();
+        epi_group64_masked<true, true>(tlane + 256, cbf(sv.h0) + trow * 64, SB, r, lane, bf(go.d_h0) + trow * 64, 64, 64,
+                                       rows_valid);
+      }
+      if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 12);
       signal_a_ready(&sm.a_ready[B_L0]);
+      // B_L1 has consumed P (dx): next tile's h2 mask
+      prefetch_mask(PB, sv.h2, tile + (int)gridDim.x);
 
+      // next tile's rgb / g_rgb (dc staging opens the tile with nothing to overlap their latency)
+      if (half == 0) {
+        const int nrow = (tile + (int)gridDim.x) * 128 + r;
+        load_dc_inputs(nrow, nrow < M && tile + (int)gridDim.x < num_tiles);
+      }
       // ---- grad_features = accB[64:112) (40 valid columns)
       mbar_wait_warp(&sm.acc_ready[B_L0], ph);
+      if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 13);
       tcgen05_fence_after();
       if (half == 0) {
         float v[32];
