@@ -55,11 +55,11 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ param, float* 
   int cur_l = -1;
   float sq = 0.f;
   for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    // streaming (evict-first) accesses: 2.5 GB pass through L2 once per step
-    float4 p = __ldcs(reinterpret_cast<const float4*>(param) + i);
-    float4 g = __ldcs(reinterpret_cast<const float4*>(grad) + i);
-    float4 m = __ldcs(reinterpret_cast<const float4*>(exp_avg) + i);
-    float4 v = __ldcs(reinterpret_cast<const float4*>(exp_avg_sq) + i);
+    // (evict-first __ldcs / __stcs accesses were measured: 4.8 TB/s against 5.2 TB/s with plain ones)
+    float4 p = reinterpret_cast<float4*>(param)[i];
+    float4 g = reinterpret_cast<float4*>(grad)[i];
+    float4 m = reinterpret_cast<float4*>(exp_avg)[i];
+    float4 v = reinterpret_cast<float4*>(exp_avg_sq)[i];
     float coef = 0.f;
     if (kDecay) {
       const int64_t e = i << 2;  // level sizes are multiples of 8 rows, so a float4 never straddles levels
@@ -80,10 +80,10 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ param, float* 
     adam_update(p.y, gy, m.y, v.y, lr_c, rsqrt_bc2, beta1, beta2, eps);
     adam_update(p.z, gz, m.z, v.z, lr_c, rsqrt_bc2, beta1, beta2, eps);
     adam_update(p.w, gw, m.w, v.w, lr_c, rsqrt_bc2, beta1, beta2, eps);
-    __stcs(reinterpret_cast<float4*>(param) + i, p);
-    __stcs(reinterpret_cast<float4*>(exp_avg) + i, m);
-    __stcs(reinterpret_cast<float4*>(exp_avg_sq) + i, v);
-    __stcs(reinterpret_cast<float4*>(grad) + i, make_float4(0.f, 0.f, 0.f, 0.f));
+    reinterpret_cast<float4*>(param)[i] = p;
+    reinterpret_cast<float4*>(exp_avg)[i] = m;
+    reinterpret_cast<float4*>(exp_avg_sq)[i] = v;
+    reinterpret_cast<float4*>(grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (kDecay && level_sumsq) sq += p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;  // UPDATED parameters
   }
   if (kDecay && level_sumsq) {
