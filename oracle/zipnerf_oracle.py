@@ -9,7 +9,7 @@ has no tests or golden vectors for this path; this restate
 pinned against the reference's OWN Python executed in the build container:
 tests/golden/make_golden.py runs Z/internal/models.py `Model.forward` through
 oracle/ref_shims.py and stores its outputs; tests/test_oracle_golden.py checks
-this file against them (and tests/test_oracle_vs_reference.py re-runs the live
+this file against them (and tests/test_reference_import.py re-runs the live
 comparison whenever /root/reference is present).
 
 Random draws are INPUTS here (`rand_inputs`, one dict per level with 'jitter'

@@ -27,3 +27,36 @@ def test_reference_grid_py_binds_to_our_backend():
     )
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and 'ok' in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not present')
+def test_golden_fixtures_reproduce_from_the_live_reference():
+    """Re-runs the reference's own Model.forward (tests/golden/make_golden.py) and checks that the
+    committed golden fixtures are what it produces today, and the oracle against a FRESH case
+    (different seed) that has no committed fixture."""
+    code = (
+        "import sys, warnings, numpy as np, torch; warnings.filterwarnings('ignore');"
+        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests', 'golden')!r});"
+        "import make_golden as mg;"
+        "from oracle import zipnerf_oracle as zo;"
+        "from nerf_lidar_b200 import synthetic;"
+        "case = mg.CASES['train_visible'];"
+        "rend, hist = mg.run_reference(case);"
+        f"gold = np.load({os.path.join(ROOT, 'tests', 'golden', 'train_visible.npz')!r});"
+        "assert np.array_equal(gold['rend2_rgb'], rend[2]['rgb'].numpy().astype(np.float32));"
+        "assert np.array_equal(gold['hist1_sdist'], hist[1]['sdist'].numpy().astype(np.float32));"
+        "fresh = dict(batch_size=32, seed=77, table_std=0.3, rand=True, train_frac=0.25);"
+        "rend, hist = mg.run_reference(fresh);"
+        "sd = synthetic.init_state_dict(seed=77, table_std=0.3);"
+        "batch = synthetic.to_torch(synthetic.make_train_batch(32, seed=77));"
+        "rin = [{k: torch.from_numpy(v) for k, v in r.items()} for r in synthetic.make_rand_inputs(batch['origins'].shape[0], seed=77)];"
+        "orend, ohist = zo.model_forward(sd, batch, rin, 0.25);"
+        "chk = lambda a, b: float((a - b).abs().max() / (b.abs().max() + 1e-30));"
+        "errs = [chk(orend[2][k], rend[2][k]) for k in ('rgb', 'depth', 'semantic', 'intensity', 'acc')] + "
+        "[chk(ohist[i][k], hist[i][k]) for i in range(3) for k in ('sdist', 'tdist', 'weights')];"
+        "assert max(errs) <= 1e-6, errs;"
+        "print('ok', max(errs))"
+    )
+    env = dict(os.environ, TORCHDYNAMO_DISABLE='1')
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and 'ok' in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
