@@ -249,6 +249,35 @@ def run_cuda_arm(args):
     kt = _lib.TIMER.summary() if _lib.TIMER is not None else {}
     _lib.TIMER = None
 
+    # ---- rendering (BASELINE configs[2] / [4]): LiDAR sweep and one 1600x900 camera frame through
+    # models.render_image, rays sharded contiguously over the ranks, one packed gather at the end
+    render = None
+    if not args.no_render:
+        class _Acc:
+            process_index, num_processes, is_main_process = rank, world, rank == 0
+        render = {}
+        for name, make, reps in (('lidar_sweep_32x1084', synthetic.make_lidar_sweep, 5),
+                                 ('camera_frame_1600x900', synthetic.make_camera_frame, 2)):
+            rb = {k: torch.from_numpy(v).to(dev) for k, v in make(seed=0).items()}
+            n_rays = rb['origins'].shape[0]
+            with torch.no_grad():
+                models.render_image(model, _Acc, rb, False, cfg, image=False, verbose=False)  # warm-up
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    out = models.render_image(model, _Acc, rb, False, cfg, image=False, verbose=False)
+                e1.record()
+                barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            render[name] = {'rays': n_rays, 'ms': float(t.item()), 'rays_per_s': n_rays / float(t.item()) * 1e3,
+                            'outputs': sorted(k for k in out if not k.startswith('ray_'))}
+            del rb, out
+        model.train()
+        model.training = True
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -328,6 +357,7 @@ def run_cuda_arm(args):
         'gpu_launches': launches,
         'roofline': roofline,
         'roofline_mlp': roofline_mlp,
+        'render': render,
         'kernels': per_kernel,
         'cpu_baseline': cpu,
     }
@@ -359,6 +389,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-render', action='store_true', help='skip the rendering throughput measurement')
     ap.add_argument('--eager', action='store_true', help='issue the step eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
