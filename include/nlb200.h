@@ -100,6 +100,9 @@ typedef struct {
   const float* deg_noise; /* [N,S,7] or NULL */
   int N, S;
   float std_scale;        /* Model.std_scale = 0.35 */
+  float* points_cache;    /* [7, N*S, 4] grid-space sample points (x, y, z, std or -1), or NULL */
+  int points_mode;        /* 0: compute; 1: compute and write points_cache (training forward);
+                             2: read points_cache instead of computing (backward of the same level) */
 } nlb_rays_t;
 
 typedef struct {

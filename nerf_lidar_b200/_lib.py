@@ -18,7 +18,8 @@ c_f = C.c_void_p  # device pointers travel as void*
 
 class NlbRays(C.Structure):
     _fields_ = [('tdist', c_f), ('origins', c_f), ('directions', c_f), ('radii', c_f), ('base_x', c_f),
-                ('base_y', c_f), ('deg_noise', c_f), ('N', C.c_int), ('S', C.c_int), ('std_scale', C.c_float)]
+                ('base_y', c_f), ('deg_noise', c_f), ('N', C.c_int), ('S', C.c_int), ('std_scale', C.c_float),
+                ('points_cache', c_f), ('points_mode', C.c_int)]
 
 
 class NlbTable(C.Structure):

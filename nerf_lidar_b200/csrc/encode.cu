@@ -122,6 +122,13 @@ __device__ __forceinline__ void lookup(const float* __restrict__ table, const Le
 constexpr int kEncThreads = 128;
 
 __device__ __forceinline__ void stage_points(const nlb_rays_t& rays, int row, float4 (*s_pts)[kEncThreads]) {
+  const size_t rows = (size_t)rays.N * rays.S;
+  float4* cache = reinterpret_cast<float4*>(rays.points_cache);
+  if (rays.points_mode == 2) {  // backward: the forward's points, [7][rows] so a warp reads 512 contiguous bytes
+#pragma unroll
+    for (int j = 0; j < 7; ++j) s_pts[j][threadIdx.x] = __ldg(cache + j * rows + row);
+    return;
+  }
   const int ray = row / rays.S, s = row - ray * rays.S;
   const RayGeom rg = load_ray(rays.origins, rays.directions, rays.base_x, rays.base_y, rays.radii, ray);
   const float t0 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s);
@@ -133,7 +140,9 @@ __device__ __forceinline__ void stage_points(const nlb_rays_t& rays, int row, fl
     const SamplePoint p = sample_point(rg, t0, t1, j, noise, has_noise, rays.std_scale);
     // points outside the unit cube contribute zero features (kernel_grid writes zeros):
     // flag them with a negative std
-    s_pts[j][threadIdx.x] = make_float4(p.x, p.y, p.z, in_unit_cube(p.x, p.y, p.z) ? p.std : -1.0f);
+    const float4 v = make_float4(p.x, p.y, p.z, in_unit_cube(p.x, p.y, p.z) ? p.std : -1.0f);
+    s_pts[j][threadIdx.x] = v;
+    if (rays.points_mode == 1) __stcs(cache + j * rows + row, v);  // evict-first: must not displace the table in L2
   }
 }
 
@@ -571,6 +580,10 @@ static int check_rays_table(const nlb_rays_t* r, const nlb_table_t* t, const cha
   }
   if (!t->offsets_host) { nlb_set_error("%s: nlb_table_t.offsets_host (host copy of the level offsets) is required", who); return NLB_EINVAL; }
   if ((int64_t)r->N * r->S > 0x7fffffffLL / 16) { nlb_set_error("%s: N*S too large for one launch; chunk the rays", who); return NLB_EINVAL; }
+  if (r->points_mode < 0 || r->points_mode > 2 || (r->points_mode != 0 && !r->points_cache)) {
+    nlb_set_error("%s: points_mode %d needs a points_cache buffer", who, r->points_mode);
+    return NLB_EINVAL;
+  }
   for (int l = 0; l < t->L; ++l) {
     const int64_t size = (int64_t)t->offsets_host[l + 1] - t->offsets_host[l];
     if (size < 8) { nlb_set_error("%s: level %d has %lld rows", who, l, (long long)size); return NLB_EINVAL; }

@@ -98,10 +98,17 @@ class RayBundle:
         self.N = self.origins.shape[0]
         self.device = self.origins.device
 
-    def desc(self, tdist: torch.Tensor, deg_noise: Optional[torch.Tensor], std_scale: float) -> NlbRays:
+    def desc(self, tdist: torch.Tensor, deg_noise: Optional[torch.Tensor], std_scale: float,
+             points_cache: Optional[torch.Tensor] = None, points_mode: int = 0) -> NlbRays:
+        """points_cache [7, N*S, 4] fp32 + mode 1 (write, training forward) / 2 (read, backward): the
+        backward kernels reuse the forward's sample points instead of regenerating them."""
         S = tdist.shape[1] - 1
         return NlbRays(ptr(tdist), ptr(self.origins), ptr(self.directions), ptr(self.radii), ptr(self.base_x),
-                       ptr(self.base_y), ptr(deg_noise), self.N, S, float(std_scale))
+                       ptr(self.base_y), ptr(deg_noise), self.N, S, float(std_scale), ptr(points_cache),
+                       int(points_mode) if points_cache is not None else 0)
+
+    def new_points_cache(self, S: int) -> torch.Tensor:
+        return torch.empty(7, self.N * S, 4, device=self.device, dtype=torch.float32)
 
 
 @torch.no_grad()
@@ -148,19 +155,20 @@ class _PropLevel(Function):
         density = torch.empty(N, S, device=rays.device, dtype=torch.float32)
         need_grad = any(ctx.needs_input_grad)
         feats = torch.empty(N * S, encoder.num_levels, device=rays.device, dtype=torch.float32) if need_grad else None
+        pts = rays.new_points_cache(S) if need_grad else None
         W0c, b0c, W1c, b1c = f32(W0), f32(b0), f32(W1).reshape(-1), f32(b1)
         with torch.cuda.device(rays.device):
             with timed(f'prop{encoder.num_levels}_fwd'):
-                check(load().nlb_prop_forward(C.byref(rays.desc(tdist, deg_noise, std_scale)),
+                check(load().nlb_prop_forward(C.byref(rays.desc(tdist, deg_noise, std_scale, pts, 1)),
                                               C.byref(_table_desc(encoder, embeddings)), ptr(W0c), ptr(b0c), ptr(W1c),
                                               ptr(b1c), ptr(density), ptr(feats), stream()))
-        ctx.save_for_backward(tdist, deg_noise, embeddings, W0c, b0c, W1c, b1c, feats)
+        ctx.save_for_backward(tdist, deg_noise, embeddings, W0c, b0c, W1c, b1c, feats, pts)
         ctx.rays, ctx.encoder, ctx.std_scale, ctx.emb_param = rays, encoder, std_scale, emb_param
         return density
 
     @staticmethod
     def backward(ctx, g_density):
-        tdist, deg_noise, embeddings, W0, b0, W1, b1, feats = ctx.saved_tensors
+        tdist, deg_noise, embeddings, W0, b0, W1, b1, feats, pts = ctx.saved_tensors
         rays, encoder = ctx.rays, ctx.encoder
         g_emb, in_place = _grad_buffer(ctx.emb_param if ctx.emb_param is not None else embeddings)
         gW0, gb0 = torch.zeros_like(W0), torch.zeros_like(b0)
@@ -171,7 +179,7 @@ class _PropLevel(Function):
         ws = torch.empty(ws_bytes // 4, device=rays.device, dtype=torch.float32)
         with torch.cuda.device(rays.device):
             with timed(f'prop{encoder.num_levels}_bwd'):
-                check(load().nlb_prop_backward(C.byref(rays.desc(tdist, deg_noise, ctx.std_scale)),
+                check(load().nlb_prop_backward(C.byref(rays.desc(tdist, deg_noise, ctx.std_scale, pts, 2)),
                                                C.byref(tab), ptr(W0), ptr(b0), ptr(W1),
                                                ptr(b1), ptr(feats), ptr(g_density), ptr(g_emb), ptr(gW0), ptr(gb0),
                                                ptr(gW1), ptr(gb1), ptr(ws), stream()))
@@ -191,17 +199,18 @@ class _NerfEncode(Function):
     def forward(ctx, tdist, deg_noise, embeddings, rays: RayBundle, encoder, std_scale, emb_param):
         N, S = rays.N, tdist.shape[1] - 1
         feats = torch.empty(N * S, encoder.output_dim, device=rays.device, dtype=torch.float32)
+        pts = rays.new_points_cache(S) if any(ctx.needs_input_grad) else None
         with torch.cuda.device(rays.device):
             with timed('nerf_encode_fwd'):
-                check(load().nlb_encode_forward(C.byref(rays.desc(tdist, deg_noise, std_scale)),
+                check(load().nlb_encode_forward(C.byref(rays.desc(tdist, deg_noise, std_scale, pts, 1)),
                                                 C.byref(_table_desc(encoder, embeddings)), ptr(feats), stream()))
-        ctx.save_for_backward(tdist, deg_noise, embeddings)
+        ctx.save_for_backward(tdist, deg_noise, embeddings, pts)
         ctx.rays, ctx.encoder, ctx.std_scale, ctx.emb_param = rays, encoder, std_scale, emb_param
         return feats
 
     @staticmethod
     def backward(ctx, g_feats):
-        tdist, deg_noise, embeddings = ctx.saved_tensors
+        tdist, deg_noise, embeddings, pts = ctx.saved_tensors
         rays, encoder = ctx.rays, ctx.encoder
         g_emb, in_place = _grad_buffer(ctx.emb_param if ctx.emb_param is not None else embeddings)
         g_feats = f32(g_feats)
@@ -210,7 +219,7 @@ class _NerfEncode(Function):
         ws = torch.empty(ws_bytes // 4, device=rays.device, dtype=torch.float32) if ws_bytes else None
         with torch.cuda.device(rays.device):
             with timed('nerf_encode_bwd'):
-                check(load().nlb_encode_backward(C.byref(rays.desc(tdist, deg_noise, ctx.std_scale)),
+                check(load().nlb_encode_backward(C.byref(rays.desc(tdist, deg_noise, ctx.std_scale, pts, 2)),
                                                  C.byref(tab), ptr(g_feats), ptr(g_emb), ptr(ws), stream()))
         return (None, None, None if in_place else g_emb, None, None, None, None)
 
