@@ -42,17 +42,17 @@ ALG_BYTES = {
 }
 ADAM_BYTES_PER_PARAM = 32  # p,g,m,v read + p,m,v,g written
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per ABI call from the committed `ncu --set full`
-# captures of this workload (profiles/r1_s9_kernels_full.txt; nerf_encode_bwd's four level-group launches from
-# profiles/r1_s5_kernels_full.txt).  Far below the algorithmic bytes wherever a table (or one level group of it)
-# stays L2-resident: the algorithmic figure counts every corner gather / read-modify-write as HBM traffic.
+# capture of this workload (profiles/r1_s12_kernels_full.txt).  Far below the algorithmic bytes wherever a table
+# (or one level group of it) stays L2-resident: the algorithmic figure counts every corner gather /
+# read-modify-write as HBM traffic.
 NCU_DRAM_BYTES = {
-    'nerf_encode_fwd': 1.862e9 + 86.5e6,
-    'nerf_encode_bwd': (92.4 + 130.7 + 131.4 + 86.6) * 1e6 + (3.2 + 61.0 + 134.1 + 2.5) * 1e6,
-    'prop6_fwd': 40.3e6 + 1.0e6,
-    'prop8_fwd': 57.1e6 + 5.5e6,
-    'prop6_bwd': 55.4e6 + 0.1e6 + 18.4e6 + 2.7e6,   # scatter + proposal-MLP backward + reductions
-    'prop8_bwd': 77.8e6 + 1.3e6 + 23.6e6 + 2.7e6,
-    'adam_table': (0.9605 + 0.1730 + 0.1057 + 0.9033 + 0.1157 + 0.0484) * 1e9 / 3.0,
+    'nerf_encode_fwd': 1.8594e9 + 122.8e6,
+    'nerf_encode_bwd': (120.4 + 157.3 + 157.5 + 112.3) * 1e6 + (5.4 + 61.5 + 131.3 + 5.7) * 1e6,  # four level groups
+    'prop6_fwd': 40.3e6 + 42.8e6,
+    'prop8_fwd': 58.0e6 + 64.4e6,
+    'prop6_bwd': 107.3e6 + 3.9e6 + 18.4e6,   # scatter + proposal-MLP backward
+    'prop8_bwd': 129.7e6 + 3.9e6 + 23.6e6,
+    'adam_table': (0.9604 + 0.1730 + 0.1057 + 0.9026 + 0.1170 + 0.0482) * 1e9 / 3.0,
 }
 
 
