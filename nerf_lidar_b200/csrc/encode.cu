@@ -5,14 +5,14 @@
 // -> coord.contract_mean_std and /2 (coord.py:51-63, models.py:968-973) ->
 // GridEncoder (gridencoder.cu kernel_grid, outputs [L,B,C] + permute copy) ->
 // erf re-weighting and mean over the 7 samples (models.py:974-977).
-// Here a thread owns one (interval, level) [NeRF level] or one interval with all
-// levels [proposal levels] and keeps everything in registers: the only HBM traffic
-// is tdist + ray parameters in, table gathers, and features[N*S, L*C] (or the
-// proposal density) out.
-//
-// Launch order is level-major (blockIdx.y = level) for the NeRF table so one 33.5 MB
-// level is L2-resident at a time; lanes of a warp are consecutive intervals of the
-// same ray, so coarse-level gathers coalesce in L1.
+// Here a thread owns one interval: its 7 sample points are generated once into shared
+// memory (or, in the backward of a training step, read back from the forward's cache) and
+// the levels are walked with rolled loops; the only HBM traffic is tdist + ray parameters
+// in, table gathers / reductions, and features[N*S, L*C] (or the proposal density) out.
+// Lanes of a warp are consecutive intervals of the same ray, so coarse-level gathers
+// coalesce in L1 and coarse-level reductions aggregate across the warp.  Forward: one
+// launch over all levels.  Backward (scatter): persistent blocks, level groups sized to
+// L2 -- see k_encode_bwd.
 #include <stdlib.h>
 #include "common.cuh"
 #include "../../include/nlb200.h"

@@ -3,15 +3,17 @@
 // intensity 256->64->1, view branch cat[x, pos_enc(viewdirs)] (283) -> 256 ->
 // cat (539) -> 256 -> 3 sigmoid.  bf16 operands, fp32 accumulation in TMEM.
 //
-// Per CTA (one per SM, 192 threads): a 128-row tile of samples stays on chip for the
-// whole chain.  Activations live in shared memory as UMMA operand blocks
+// Per CTA (one per SM, 416 threads = 8 epilogue warps + 1 MMA warp + 4 weight-producer
+// warps): a 128-row tile of samples stays on chip for the whole chain.  Activations live in shared memory as UMMA operand blocks
 // ([128 rows][64 k] bf16, K-major, SWIZZLE_128B, 16 KB each): X0-3 (bottleneck),
 // H0-3 (layer outputs, reused), D (view-direction encoding).  Weights are pre-packed
 // (nlb_nerf_mlp_pack) into the same block format and streamed from L2 through a
-// 4 x 16 KB ring with 1-D bulk async copies (UBLKCP) by a producer warp; one MMA
-// thread issues tcgen05.mma (M=128, N<=128 per instruction) into two 256-column
-// TMEM accumulators; four epilogue warps read TMEM (LDTM), apply bias/activation
-// and write the next layer's A operand back to shared memory.  The concatenations
+// 4 x 16 KB ring with 1-D bulk async copies (UBLKCP), one producer warp per ring stage;
+// one elected thread issues tcgen05.mma (M=128, N<=128 per instruction) into two
+// 256-column TMEM accumulators; eight epilogue warps (two per TMEM lane quarter, splitting
+// the columns) read TMEM (LDTM) in 64-column groups, apply bias/activation and write the
+// next layer's A operand back to shared memory; the next tile's inputs are staged while
+// the last layer's MMAs run.  The concatenations
 // of the reference are just extra K blocks (X, D) of the next GEMM.
 // Layer order on the tensor pipe: L0, L1, HS0 (sem|int hidden), V0, HS1 (sem|int
 // out), V1, RGB; the HS0/HS1 epilogues overlap the V0 MMAs.
@@ -481,7 +483,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
       mbar_wait_warp(&sm.acc_ready[HS0], ph);
       tcgen05_fence_after();
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 5);
-#pragma unroll 1
       {
         const int c0 = half * 64;
         epi_group64<true>(tlane + c0, sm.bias + bias_offset(HS0) + c0, HB + (2 + half) * kBlockBytes, r, lane,
@@ -935,7 +936,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
       mbar_wait_warp(&sm.acc_ready[B_V1], ph);
       if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 4);
       tcgen05_fence_after();
-#pragma unroll 1
       // B_V1 has consumed P: the ReLU mask of the sem | intensity hidden layer goes to P0 / P1 now and is
       // there when the HS1 epilogue needs it
       warp_rows_from_global_async(PB + half * kBlockBytes, r & ~31, lane, cbf(sv.g) + trow * 128 + half * 64, 128, rows_valid);
