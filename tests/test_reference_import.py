@@ -60,3 +60,93 @@ def test_golden_fixtures_reproduce_from_the_live_reference():
     env = dict(os.environ, TORCHDYNAMO_DISABLE='1')
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and 'ok' in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not present')
+def test_training_oracle_against_the_reference_loss_functions():
+    """Pins oracle/train_oracle.py (the checker of the fused loss kernels) against the reference's own
+    Z/internal/train_utils.py: distortion_loss, anti_interlevel_loss, compute_data_loss and the two
+    edge-aware smoothness losses (with the all-ones patch mask of Z/train.py:374-388), values AND
+    gradients, on random step functions / renderings."""
+    code = r'''
+import sys, warnings, types, importlib
+warnings.filterwarnings('ignore')
+sys.path.insert(0, %(root)r)
+import torch
+from oracle import ref_shims, train_oracle as to, zipnerf_oracle as zo
+ref_shims.import_reference()
+
+class _Anything(types.ModuleType):       # third-party modules train_utils imports but these functions never touch
+    def __getattr__(self, name):
+        if name.startswith('__'):
+            raise AttributeError(name)
+        if name[0].isupper():
+            return type(name, (), {'__init__': lambda self, *a, **k: None})
+        sub = _Anything(self.__name__ + '.' + name)
+        sys.modules[sub.__name__] = sub
+        return sub
+for _ in range(60):
+    try:
+        tu = importlib.import_module('internal.train_utils')
+        break
+    except ModuleNotFoundError as e:
+        assert not e.name.startswith('internal'), e
+        sys.modules[e.name] = _Anything(e.name)
+
+class Cfg:
+    pulse_width = (0.03, 0.003); anti_interlevel_loss_mult = 0.01; distortion_loss_mult = 0.005
+    data_loss_type = 'charb'; charb_padding = 0.001; data_loss_mult = 1.0; data_coarse_loss_mult = 0.
+    disable_multiscale_loss = False; compute_disp_metrics = False; compute_normal_metrics = False
+
+g = torch.Generator().manual_seed(0)
+N = 96
+def hist(S):
+    s = torch.sort(torch.rand(N, S + 1, generator=g), -1).values
+    s[:, 0], s[:, -1] = 0.0, 1.0
+    dens = torch.rand(N, S, generator=g) * 30
+    near, far = torch.full((N, 1), 2 / 60.), torch.full((N, 1), 500 / 60.)
+    w, _, _ = zo.alpha_weights(dens, zo.s_to_t(s, near, far), torch.ones(N, 3), True)
+    return s, w
+def rel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+errs = {}
+levels = [hist(64), hist(64), hist(32)]
+for which in ('distortion', 'interlevel'):
+    ra = [dict(sdist=s, weights=w.clone().requires_grad_(True)) for s, w in levels]
+    rb = [dict(sdist=s, weights=w.clone().requires_grad_(True)) for s, w in levels]
+    if which == 'distortion':
+        la, lb = tu.distortion_loss(ra, Cfg), to.distortion(rb, mult=0.005)
+    else:
+        la, lb = tu.anti_interlevel_loss(ra, Cfg), to.anti_interlevel(rb)
+    la.backward(); lb.backward()
+    errs[which] = rel(lb.detach(), la.detach())
+    for a, b in zip(ra, rb):
+        if a['weights'].grad is not None:
+            errs[which + '_grad'] = max(errs.get(which + '_grad', 0.), rel(b['weights'].grad, a['weights'].grad))
+# data loss: lossmult = rgb mask (camera rays that are not patch rays)
+rgb_t = torch.rand(N, 3, generator=g)
+mask = (torch.rand(N, generator=g) < 0.7).float()
+pa = torch.rand(N, 3, generator=g).requires_grad_(True)
+pb = pa.detach().clone().requires_grad_(True)
+la, _ = tu.compute_data_loss(dict(rgb=rgb_t, mask_rgb=mask), [dict(rgb=pa)], Cfg)
+lm = mask[:, None].expand(-1, 3)
+lb = (lm * torch.sqrt((pb - rgb_t) ** 2 + 0.001 ** 2)).sum() / lm.sum()      # train_oracle.losses 'data'
+la.backward(); lb.backward()
+errs['data'], errs['data_grad'] = rel(lb.detach(), la.detach()), rel(pb.grad, pa.grad)
+# edge-aware smoothness on 2 patches of 32 x 32
+P = 2
+rgbp = torch.rand(P, 32, 32, 3, generator=g)
+ones = torch.ones(P, 32, 32, 1)
+for name, fn, ch, eps, csum in (('d_smo', tu.edge_aware_loss_v2, 1, 1e-7, False),
+                                ('s_smo', tu.edge_aware_loss_for_semantic, 19, 1e-5, True)):
+    xa = (torch.rand(P, 32, 32, ch, generator=g) + 0.05).requires_grad_(True)
+    xb = xa.detach().clone().requires_grad_(True)
+    la, lb = fn(rgbp, xa, mask=ones), to._edge_aware(rgbp, xb, eps, csum)
+    la.backward(); lb.backward()
+    errs[name], errs[name + '_grad'] = rel(lb.detach(), la.detach()), rel(xb.grad, xa.grad)
+assert max(errs.values()) <= 2e-5, errs
+print('ok', errs)
+''' % dict(root=ROOT)
+    env = dict(os.environ, TORCHDYNAMO_DISABLE='1')
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and 'ok' in r.stdout, (r.stdout[-800:], r.stderr[-2500:])
