@@ -55,6 +55,13 @@ def test_golden_fixtures_reproduce_from_the_live_reference():
         "errs = [chk(orend[2][k], rend[2][k]) for k in ('rgb', 'depth', 'semantic', 'intensity', 'acc')] + "
         "[chk(ohist[i][k], hist[i][k]) for i in range(3) for k in ('sdist', 'tdist', 'weights')];"
         "assert max(errs) <= 1e-6, errs;"
+        # Model.hash_decay_loss (Z/internal/models.py:203-223; torch_scatter.segment_coo stood in by the shim)
+        "models = mg.ref_shims.import_reference(); mg.ref_shims.apply_gin_bindings(models);"
+        "m = models.Model(config=mg.ref_shims.RefConfig()); m.load_state_dict(sd, strict=False);"
+        # (includes Config.hash_decay_mults = 0.1; the shim's fp32 index_add accumulates 2 M squares per level
+        # sequentially, hence the loose bound -- torch_scatter itself is not in the image: SURVEY 8c (i))
+        "hd = float(m.hash_decay_loss()); ohd = 0.1 * float(zo.hash_decay(sd));"
+        "assert abs(hd - ohd) <= 2e-3 * abs(hd), (hd, ohd);"
         "print('ok', max(errs))"
     )
     env = dict(os.environ, TORCHDYNAMO_DISABLE='1')
