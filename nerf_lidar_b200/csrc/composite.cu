@@ -6,12 +6,14 @@
 // per-sample tensor exactly once (warp scan for the transmittance, warp
 // reductions for the K-channel weighted sums) and writes the per-ray outputs.
 #include "common.cuh"
+#include "umma.cuh"
 #include "../../include/nlb200.h"
 
 namespace nlb {
 
 constexpr int kCompWarps = 4;
 constexpr int kMaxK = 32;  // semantic classes handled by one lane each in the column sums
+constexpr int kSemPre4 = 5;  // float4 per lane prefetched from the chunk's [32, K] class probabilities (K <= 20)
 
 __device__ __forceinline__ int upper_bound_f(const float* a, int n, float x) {
   int lo = 0, hi = n;
@@ -59,11 +61,31 @@ __global__ void __launch_bounds__(kCompWarps * 32) k_composite_fwd(nlb_composite
   for (int c0 = 0; c0 < S; c0 += 32) {
     const int s = c0 + lane;
     const bool ok = s < S;
-    float t0 = 0.f, t1 = 0.f, dd = 0.f;
+    // every global load of the chunk is issued here, before the first dependent instruction: a ray is one
+    // short dependent chain per warp, and with the loads spread along it (after the scans and the warp
+    // barriers) their latencies added up instead of overlapping
+    float t0 = 0.f, t1 = 0.f, dd = 0.f, den_s = 0.f, c_r = 0.f, c_g = 0.f, c_b = 0.f, c_i = 0.f;
+    // class probabilities of the chunk: [rows, K] contiguous, read as float4 (16-byte aligned when S*K % 4 == 0)
+    float4 semv[kSemPre4];
+    const int cnt = (in.semantic && out.semantic) ? min(32, S - c0) * K : 0;
+    const float* sp = in.semantic ? in.semantic + ((size_t)ray * S + c0) * K : nullptr;
+    const bool vec4 = cnt > 0 && K >= 4 && (S & 1) == 0 && ((S * K) & 3) == 0 && (cnt & 3) == 0 && cnt <= 128 * kSemPre4;
+    if (vec4) {
+#pragma unroll
+      for (int j = 0; j < kSemPre4; ++j)
+        semv[j] = (4 * (lane + 32 * j) < cnt) ? __ldg(reinterpret_cast<const float4*>(sp) + lane + 32 * j)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (ok) {
       t0 = __ldg(td + s);
       t1 = __ldg(td + s + 1);
-      dd = __fmul_rn(__ldg(in.density + (size_t)ray * S + s), __fmul_rn(__fsub_rn(t1, t0), dnorm));
+      den_s = __ldg(in.density + (size_t)ray * S + s);
+      if (in.rgb) {
+        const float* c = in.rgb + ((size_t)ray * S + s) * 3;
+        c_r = __ldg(c); c_g = __ldg(c + 1); c_b = __ldg(c + 2);
+      }
+      if (in.intensity) c_i = __ldg(in.intensity + (size_t)ray * S + s);
+      dd = __fmul_rn(den_s, __fmul_rn(__fsub_rn(t1, t0), dnorm));
     }
     const float dd_scan = (ok && !(in.opaque_background && s == S - 1)) ? dd : 0.f;
     if (ok && in.opaque_background && s == S - 1) dd = INFINITY;
@@ -83,12 +105,11 @@ __global__ void __launch_bounds__(kCompWarps * 32) k_composite_fwd(nlb_composite
       a_dep = fmaf(w, tm, a_dep);
       if (in.compute_extras) a_log = fmaf(w, logf(tm), a_log);
       if (in.rgb) {
-        const float* c = in.rgb + ((size_t)ray * S + s) * 3;
-        a_r = fmaf(w, __ldg(c), a_r);
-        a_g = fmaf(w, __ldg(c + 1), a_g);
-        a_b = fmaf(w, __ldg(c + 2), a_b);
+        a_r = fmaf(w, c_r, a_r);
+        a_g = fmaf(w, c_g, a_g);
+        a_b = fmaf(w, c_b, a_b);
       }
-      if (in.intensity) a_int = fmaf(w, __ldg(in.intensity + (size_t)ray * S + s), a_int);
+      if (in.intensity) a_int = fmaf(w, c_i, a_int);
     }
     wchunk[lane] = w;
     // running (unclamped) sum of the weights for the percentile CDF
@@ -99,9 +120,32 @@ __global__ void __launch_bounds__(kCompWarps * 32) k_composite_fwd(nlb_composite
     }
     __syncwarp();
     if (in.semantic && out.semantic) {
-      const int cnt = min(32, S - c0) * K;
-      const float* sp = in.semantic + ((size_t)ray * S + c0) * K;
-      for (int i = lane; i < cnt; i += 32) prod[i] = wchunk[i / K] * __ldg(sp + i);
+      // element e = row * K + class; row / class advance incrementally (no division by the run-time K)
+      if (vec4) {
+        int row = (4 * lane) / K, cls = 4 * lane - row * K;
+        const int drow = 128 / K, dcls = 128 - drow * K;
+#pragma unroll
+        for (int j = 0; j < kSemPre4; ++j) {
+          const int e = 4 * (lane + 32 * j);
+          if (e < cnt) {
+            const float w0 = wchunk[row];
+            const float w1 = wchunk[row + (cls + 1 >= K)], w2 = wchunk[row + (cls + 2 >= K)], w3 = wchunk[row + (cls + 3 >= K)];
+            *reinterpret_cast<float4*>(prod + e) = make_float4(w0 * semv[j].x, w1 * semv[j].y, w2 * semv[j].z, w3 * semv[j].w);
+          }
+          row += drow;
+          cls += dcls;
+          if (cls >= K) { cls -= K; ++row; }
+        }
+      } else {
+        int row = lane / K, cls = lane - row * K;
+        const int drow = 32 / K, dcls = 32 - drow * K;
+        for (int i = lane; i < cnt; i += 32) {
+          prod[i] = wchunk[row] * __ldg(sp + i);
+          row += drow;
+          cls += dcls;
+          if (cls >= K) { cls -= K; ++row; }
+        }
+      }
       __syncwarp();
       if (lane < K) {
         const int rows = min(32, S - c0);
@@ -145,6 +189,271 @@ __global__ void __launch_bounds__(kCompWarps * 32) k_composite_fwd(nlb_composite
       if (lane < 3) {
         const float q = (lane == 0) ? 0.05f : (lane == 1 ? 0.5f : 0.95f);
         out.distance_percentiles[(size_t)ray * 3 + lane] = interp_sorted_c(q, cw, taug, S + 2);
+      }
+    }
+  }
+}
+
+// Proposal levels (no colour / class / intensity channels): one THREAD per ray.  With a warp per ray the
+// fixed per-ray cost (two warp scans per chunk, eight warp reductions, the percentile search) is ~1000 warp
+// instructions for 820 algorithmic bytes and the kernel is issue-bound at 12 % of the HBM roofline (ncu at
+// 1 M rays); a thread walks its ray sequentially in ~60 warp instructions per ray.  Coalescing comes from
+// staging: a warp loads 32 rays x 32 samples with lane = sample into padded shared-memory rows, then every
+// thread reads its own row; the weights leave the same way.
+constexpr int kPropRays = 128;
+
+__global__ void __launch_bounds__(kPropRays) k_composite_prop_fwd(nlb_composite_in_t in, nlb_composite_out_t out) {
+  __shared__ float s_den[kPropRays][33];  // densities of the chunk, overwritten by the weights
+  __shared__ float s_t[kPropRays][34];    // fenceposts c0 .. c0 + 32
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = in.S;
+  const int ray0 = blockIdx.x * kPropRays;
+  const int ray = ray0 + tid;
+  const bool rok = ray < in.N;
+  float dnorm = 0.f;
+  if (rok) {
+    const float dx = __ldg(in.directions + 3 * ray), dy = __ldg(in.directions + 3 * ray + 1),
+                dz = __ldg(in.directions + 3 * ray + 2);
+    dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  }
+  float carry = 0.f, acc = 0.f, dep = 0.f, lg = 0.f, wsum = 0.f;
+  float prev_cw = 0.f, prev_tk = 0.f, t_first = 0.f, t_last = 0.f;
+  const float qs[3] = {0.05f, 0.5f, 0.95f};
+  float pct[3] = {0.f, 0.f, 0.f};
+  bool found[3] = {false, false, false};
+  auto knot = [&](int k, float x1, float f1) {  // interp_sorted_c between the previous knot and (x1, f1)
+    float off = __fdiv_rn(__fsub_rn(qs[k], prev_cw), __fsub_rn(x1, prev_cw));
+    if (isnan(off)) off = 0.f;
+    off = fminf(fmaxf(off, 0.f), 1.f);
+    pct[k] = __fadd_rn(prev_tk, __fmul_rn(off, __fsub_rn(f1, prev_tk)));
+    found[k] = true;
+  };
+  for (int c0 = 0; c0 < S; c0 += 32) {
+    const int n = min(32, S - c0);
+    // stage: this warp's 32 rays, lane = sample; asynchronous 4-byte copies, so the 64+ loads of a lane are
+    // all in flight together (a load -> store loop paid the global latency once per ray row)
+#pragma unroll 4
+    for (int rr = 0; rr < 32; ++rr) {
+      const int row = warp * 32 + rr, gr = ray0 + row;
+      if (gr < in.N) {
+        if (lane < n) umma::cp_async4(&s_den[row][lane], in.density + (size_t)gr * S + c0 + lane);
+        if (lane <= n) umma::cp_async4(&s_t[row][lane], in.tdist + (size_t)gr * (S + 1) + c0 + lane);
+        if (lane == 0 && n == 32) umma::cp_async4(&s_t[row][32], in.tdist + (size_t)gr * (S + 1) + c0 + 32);
+      }
+    }
+    umma::cp_async_wait_all();
+    __syncwarp();
+    if (rok) {
+      if (c0 == 0) { t_first = s_t[tid][0]; prev_tk = t_first; }
+      for (int j = 0; j < n; ++j) {
+        const float t0 = s_t[tid][j], t1 = s_t[tid][j + 1];
+        float dd = __fmul_rn(s_den[tid][j], __fmul_rn(__fsub_rn(t1, t0), dnorm));
+        const bool last = in.opaque_background && (c0 + j == S - 1);
+        const float trans = expf(-carry);
+        if (last) dd = INFINITY; else carry = __fadd_rn(carry, dd);
+        const float alpha = __fsub_rn(1.0f, expf(-dd));
+        const float w = __fmul_rn(alpha, trans);
+        s_den[tid][j] = w;
+        const float tm = __fmul_rn(0.5f, __fadd_rn(t0, t1));
+        acc += w;
+        dep = fmaf(w, tm, dep);
+        if (in.compute_extras) {
+          lg = fmaf(w, logf(tm), lg);
+          wsum = __fadd_rn(wsum, w);
+          const float cwj = fminf(wsum, 1.0f);
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            if (!found[k] && cwj > qs[k]) knot(k, cwj, t1);
+          prev_cw = cwj;
+          prev_tk = t1;
+        }
+        t_last = t1;
+      }
+    }
+    __syncwarp();
+    if (out.weights) {
+      for (int rr = 0; rr < 32; ++rr) {
+        const int row = warp * 32 + rr, gr = ray0 + row;
+        if (gr < in.N && lane < n) out.weights[(size_t)gr * S + c0 + lane] = s_den[row][lane];
+      }
+    }
+    __syncwarp();
+  }
+  if (!rok) return;
+  const float bg_w = fmaxf(__fsub_rn(1.0f, acc), 0.f);
+  const float den = fmaxf(acc, kEps);
+  if (out.rgb) {
+    const float v = fmaf(bg_w, in.bg, 0.f);
+    out.rgb[3 * (size_t)ray] = v;
+    out.rgb[3 * (size_t)ray + 1] = v;
+    out.rgb[3 * (size_t)ray + 2] = v;
+  }
+  if (out.depth) out.depth[ray] = __fdiv_rn(dep, den);
+  if (out.acc) out.acc[ray] = acc;
+  if (in.compute_extras) {
+    if (out.distance_mean) {
+      float v = expf(__fdiv_rn(lg, den));
+      if (isnan(v)) v = INFINITY;
+      out.distance_mean[ray] = fminf(fmaxf(v, t_first), t_last);
+    }
+    if (out.distance_percentiles) {
+      const float far = __ldg(in.far + ray);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (!found[k]) knot(k, 1.0f, far);  // the closing knot (cw = 1, t = far)
+        out.distance_percentiles[(size_t)ray * 3 + k] = pct[k];
+      }
+    }
+  }
+}
+
+// NeRF level with the nuScenes head layout (rgb + K = 19 class probabilities + intensity): one thread per
+// ray as well, reading its own rows straight from global memory with 16-byte loads: a ray's 8-sample chunk
+// is 608 contiguous bytes of class probabilities, 96 of colour, 32 of density and of intensity, so every
+// 32-byte sector a thread touches is fully used (its second half is an L1 hit) and a chunk's ~50 independent
+// loads are in flight together.  With K fixed at compile time the (sample, class) of every element of the
+// 152-float class block is known and the 19 class sums live in registers.  (The warp-per-ray kernel above
+// needs ~900 warp instructions per ray -- index arithmetic, a 32-step column sum in shared memory, eight warp
+// reductions -- and is issue-bound at 48 % of the HBM roofline at 1 M rays; staging the rows through shared
+// memory with cp.async cost 560 warp instructions per ray in address arithmetic and was slower still.  The
+// warp kernel remains the path for other layouts.)
+#ifndef NLB_RAYCS
+#define NLB_RAYCS 4
+#endif
+constexpr int kRayK = 19, kRayCS = NLB_RAYCS, kRayThreads = 128;
+constexpr int kSem4 = kRayCS * kRayK / 4, kRgb4 = kRayCS * 3 / 4, kVec4 = kRayCS / 4;  // float4 per chunk
+static_assert(kRayCS % 4 == 0, "chunk = whole float4 of every per-sample tensor");
+
+__global__ void __launch_bounds__(kRayThreads) k_composite_ray19_fwd(nlb_composite_in_t in, nlb_composite_out_t out) {
+  const int S = in.S;
+  const int ray = blockIdx.x * kRayThreads + threadIdx.x;
+  if (ray >= in.N) return;
+  const float dx = __ldg(in.directions + 3 * ray), dy = __ldg(in.directions + 3 * ray + 1),
+              dz = __ldg(in.directions + 3 * ray + 2);
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  float carry = 0.f, acc = 0.f, dep = 0.f, lg = 0.f, wsum = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f, a_int = 0.f;
+  float a_sem[kRayK];
+#pragma unroll
+  for (int k = 0; k < kRayK; ++k) a_sem[k] = 0.f;
+  const float* td = in.tdist + (size_t)ray * (S + 1);
+  float t_prev = __ldg(td);
+  const float t_first = t_prev;
+  float prev_cw = 0.f, prev_tk = t_first, t_last = t_first;
+  const float qs[3] = {0.05f, 0.5f, 0.95f};
+  float pct[3] = {0.f, 0.f, 0.f};
+  bool found[3] = {false, false, false};
+  auto knot = [&](int k, float x1, float f1) {
+    float off = __fdiv_rn(__fsub_rn(qs[k], prev_cw), __fsub_rn(x1, prev_cw));
+    if (isnan(off)) off = 0.f;
+    off = fminf(fmaxf(off, 0.f), 1.f);
+    pct[k] = __fadd_rn(prev_tk, __fmul_rn(off, __fsub_rn(f1, prev_tk)));
+    found[k] = true;
+  };
+#pragma unroll 1
+  for (int c0 = 0; c0 < S; c0 += kRayCS) {
+    const size_t e0 = (size_t)ray * S + c0;  // first sample of the chunk
+    // ---- all loads of the chunk first
+    const float4* sem4 = reinterpret_cast<const float4*>(in.semantic + e0 * kRayK);
+    const float4* rgb4 = reinterpret_cast<const float4*>(in.rgb + e0 * 3);
+    float4 sv[kSem4], cv[kRgb4], dv[kVec4], iv[kVec4];
+#pragma unroll
+    for (int m = 0; m < kSem4; ++m) sv[m] = __ldg(sem4 + m);
+#pragma unroll
+    for (int m = 0; m < kRgb4; ++m) cv[m] = __ldg(rgb4 + m);
+#pragma unroll
+    for (int m = 0; m < kVec4; ++m) {
+      dv[m] = __ldg(reinterpret_cast<const float4*>(in.density + e0) + m);
+      iv[m] = __ldg(reinterpret_cast<const float4*>(in.intensity + e0) + m);
+    }
+    float tt[kRayCS + 1];
+    tt[0] = t_prev;
+#pragma unroll
+    for (int j = 1; j <= kRayCS; ++j) tt[j] = __ldg(td + c0 + j);
+    t_prev = tt[kRayCS];
+    float dens[kRayCS], ints[kRayCS], w[kRayCS];
+#pragma unroll
+    for (int m = 0; m < kVec4; ++m) {
+      dens[4 * m] = dv[m].x; dens[4 * m + 1] = dv[m].y; dens[4 * m + 2] = dv[m].z; dens[4 * m + 3] = dv[m].w;
+      ints[4 * m] = iv[m].x; ints[4 * m + 1] = iv[m].y; ints[4 * m + 2] = iv[m].z; ints[4 * m + 3] = iv[m].w;
+    }
+#pragma unroll
+    for (int j = 0; j < kRayCS; ++j) {
+      const float t0 = tt[j], t1 = tt[j + 1];
+      float dd = __fmul_rn(dens[j], __fmul_rn(__fsub_rn(t1, t0), dnorm));
+      const bool last = in.opaque_background && (c0 + j == S - 1);
+      const float trans = expf(-carry);
+      if (last) dd = INFINITY; else carry = __fadd_rn(carry, dd);
+      w[j] = __fmul_rn(__fsub_rn(1.0f, expf(-dd)), trans);
+      const float tm = __fmul_rn(0.5f, __fadd_rn(t0, t1));
+      acc += w[j];
+      dep = fmaf(w[j], tm, dep);
+      a_int = fmaf(w[j], ints[j], a_int);
+      if (in.compute_extras) {
+        lg = fmaf(w[j], logf(tm), lg);
+        wsum = __fadd_rn(wsum, w[j]);
+        const float cwj = fminf(wsum, 1.0f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (!found[k] && cwj > qs[k]) knot(k, cwj, t1);
+        prev_cw = cwj;
+        prev_tk = t1;
+      }
+      t_last = t1;
+    }
+    // colours: 24 floats = samples x (r, g, b)
+#pragma unroll
+    for (int m = 0; m < kRgb4; ++m) {
+      const float e[4] = {cv[m].x, cv[m].y, cv[m].z, cv[m].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int idx = 4 * m + q, j = idx / 3, ch = idx - 3 * j;
+        if (ch == 0) a_r = fmaf(w[j], e[q], a_r);
+        else if (ch == 1) a_g = fmaf(w[j], e[q], a_g);
+        else a_b = fmaf(w[j], e[q], a_b);
+      }
+    }
+    // class probabilities: 152 floats = samples x 19 classes (weights detached: render.py:240-249)
+#pragma unroll
+    for (int m = 0; m < kSem4; ++m) {
+      const float e[4] = {sv[m].x, sv[m].y, sv[m].z, sv[m].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int idx = 4 * m + q, j = idx / kRayK, k = idx - kRayK * j;
+        a_sem[k] = fmaf(w[j], e[q], a_sem[k]);
+      }
+    }
+    if (out.weights) {
+      float4* dst = reinterpret_cast<float4*>(out.weights + e0);
+#pragma unroll
+      for (int m = 0; m < kVec4; ++m) dst[m] = make_float4(w[4 * m], w[4 * m + 1], w[4 * m + 2], w[4 * m + 3]);
+    }
+  }
+  const float bg_w = fmaxf(__fsub_rn(1.0f, acc), 0.f);
+  const float den = fmaxf(acc, kEps);
+  if (out.rgb) {
+    out.rgb[3 * (size_t)ray] = fmaf(bg_w, in.bg, a_r);
+    out.rgb[3 * (size_t)ray + 1] = fmaf(bg_w, in.bg, a_g);
+    out.rgb[3 * (size_t)ray + 2] = fmaf(bg_w, in.bg, a_b);
+  }
+  if (out.depth) out.depth[ray] = __fdiv_rn(dep, den);
+  if (out.acc) out.acc[ray] = acc;
+  if (out.intensity) out.intensity[ray] = a_int;
+  if (out.semantic) {
+#pragma unroll
+    for (int k = 0; k < kRayK; ++k) out.semantic[(size_t)ray * kRayK + k] = a_sem[k];
+  }
+  if (in.compute_extras) {
+    if (out.distance_mean) {
+      float v = expf(__fdiv_rn(lg, den));
+      if (isnan(v)) v = INFINITY;
+      out.distance_mean[ray] = fminf(fmaxf(v, t_first), t_last);
+    }
+    if (out.distance_percentiles) {
+      const float far = __ldg(in.far + ray);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (!found[k]) knot(k, 1.0f, far);
+        out.distance_percentiles[(size_t)ray * 3 + k] = pct[k];
       }
     }
   }
@@ -271,6 +580,16 @@ extern "C" int nlb_composite_forward(const nlb_composite_in_t* in, const nlb_com
   if (!out) { nlb_set_error("composite_forward: null outputs"); return NLB_EINVAL; }
   if (in->N == 0) return NLB_OK;
   if (in->compute_extras && out->distance_percentiles && !in->far) { nlb_set_error("composite_forward: far is required for the percentiles"); return NLB_EINVAL; }
+  if (!in->rgb && !in->semantic && !in->intensity) {  // proposal levels: thread per ray
+    k_composite_prop_fwd<<<div_up(in->N, kPropRays), kPropRays, 0, (cudaStream_t)stream>>>(*in, *out);
+    return nlb_check_launch("composite_forward");
+  }
+  if (in->rgb && in->semantic && in->intensity && in->K == kRayK && in->S % kRayCS == 0 && out->semantic && out->intensity &&
+      (reinterpret_cast<uintptr_t>(in->rgb) | reinterpret_cast<uintptr_t>(in->semantic) | reinterpret_cast<uintptr_t>(in->intensity) |
+       reinterpret_cast<uintptr_t>(in->density) | reinterpret_cast<uintptr_t>(out->weights)) % 16 == 0) {
+    k_composite_ray19_fwd<<<div_up(in->N, kRayThreads), kRayThreads, 0, (cudaStream_t)stream>>>(*in, *out);
+    return nlb_check_launch("composite_forward");
+  }
   size_t smem = (size_t)kCompWarps * comp_smem_floats(in->S, in->K) * sizeof(float);
   if (smem > 48 * 1024) cudaFuncSetAttribute(k_composite_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_composite_fwd<<<div_up(in->N, kCompWarps), kCompWarps * 32, smem, (cudaStream_t)stream>>>(*in, *out);

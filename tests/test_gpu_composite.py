@@ -43,15 +43,24 @@ def test_forward_vs_oracle(S):
     assert torch.allclose(got['weights'].sum(-1), torch.ones(N, device='cuda'), atol=1e-5)
 
 
-def test_proposal_level_without_colour():
+@pytest.mark.parametrize('N,S', [(100, 64), (515, 64), (131, 37), (4100, 32)])
+def test_proposal_level_without_colour(N, S):
+    """The thread-per-ray kernel of the proposal levels (no colour / class / intensity inputs): every output
+    against the oracle, incl. ragged ray counts and a sample count that is not a multiple of the chunk."""
     from nerf_lidar_b200 import ops
-    dens, t, dirs, far, *_ = _inputs(100, 64, 19, 5)
+    dens, t, dirs, far, *_ = _inputs(N, S, 19, 5 + S)
     w, _, _ = zo.alpha_weights(dens, t, dirs, True)
-    want = zo.composite(torch.zeros(100, 64, 3), w, t, far, 1.0, None, None, True)
+    want = zo.composite(torch.zeros(N, S, 3), w, t, far, 1.0, None, None, True)
     got = ops.composite(dens.cuda(), t.cuda(), dirs.cuda(), far.cuda())
     assert got['semantic'] is None and got['intensity'] is None
+    assert_close(got['weights'], w, 1e-5, 'weights')
     assert_close(got['rgb'], want['rgb'], 1e-5, 'rgb', atol=1e-6)
-    assert_close(got['depth'], want['depth'], 1e-5, 'depth')
+    for k in ('depth', 'acc', 'distance_mean'):
+        assert_close(got[k], want[k], 1e-5, k)
+    pct = got['distance_percentiles']
+    assert_close(pct[:, 0], want['distance_percentile_5'], 1e-5, 'p5')
+    assert_close(pct[:, 1], want['distance_median'], 1e-5, 'median')
+    assert_close(pct[:, 2], want['distance_percentile_95'], 1e-5, 'p95')
 
 
 @pytest.mark.parametrize('S', [32, 64])
