@@ -5,6 +5,7 @@
 // The reference runs ~60 eager kernels per level; here one kernel reads each
 // per-sample tensor exactly once (warp scan for the transmittance, warp
 // reductions for the K-channel weighted sums) and writes the per-ray outputs.
+#include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
 #include "../../include/nlb200.h"
@@ -307,6 +308,93 @@ __global__ void __launch_bounds__(kPropRays) k_composite_prop_fwd(nlb_composite_
   }
 }
 
+// Proposal levels with S % 4 == 0: the same walk with direct 16-byte loads of the densities and stores of
+// the weights (no staging instructions); only the fenceposts ([N, S+1] rows are not 16-byte aligned) are
+// scalar loads.
+__global__ void __launch_bounds__(128) k_composite_prop4_fwd(nlb_composite_in_t in, nlb_composite_out_t out) {
+  const int S = in.S;
+  const int ray = blockIdx.x * 128 + threadIdx.x;
+  if (ray >= in.N) return;
+  const float dx = __ldg(in.directions + 3 * ray), dy = __ldg(in.directions + 3 * ray + 1),
+              dz = __ldg(in.directions + 3 * ray + 2);
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  const float* td = in.tdist + (size_t)ray * (S + 1);
+  float carry = 0.f, acc = 0.f, dep = 0.f, lg = 0.f, wsum = 0.f;
+  float t_prev = __ldg(td);
+  const float t_first = t_prev;
+  float prev_cw = 0.f, prev_tk = t_first, t_last = t_first;
+  const float qs[3] = {0.05f, 0.5f, 0.95f};
+  float pct[3] = {0.f, 0.f, 0.f};
+  bool found[3] = {false, false, false};
+  auto knot = [&](int k, float x1, float f1) {
+    float off = __fdiv_rn(__fsub_rn(qs[k], prev_cw), __fsub_rn(x1, prev_cw));
+    if (isnan(off)) off = 0.f;
+    off = fminf(fmaxf(off, 0.f), 1.f);
+    pct[k] = __fadd_rn(prev_tk, __fmul_rn(off, __fsub_rn(f1, prev_tk)));
+    found[k] = true;
+  };
+#pragma unroll 2
+  for (int c0 = 0; c0 < S; c0 += 4) {
+    const float4 dv = __ldg(reinterpret_cast<const float4*>(in.density + (size_t)ray * S + c0));
+    float tt[5];
+    tt[0] = t_prev;
+#pragma unroll
+    for (int j = 1; j <= 4; ++j) tt[j] = __ldg(td + c0 + j);
+    t_prev = tt[4];
+    const float dens[4] = {dv.x, dv.y, dv.z, dv.w};
+    float w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float t0 = tt[j], t1 = tt[j + 1];
+      float dd = __fmul_rn(dens[j], __fmul_rn(__fsub_rn(t1, t0), dnorm));
+      const bool last = in.opaque_background && (c0 + j == S - 1);
+      const float trans = expf(-carry);
+      if (last) dd = INFINITY; else carry = __fadd_rn(carry, dd);
+      w[j] = __fmul_rn(__fsub_rn(1.0f, expf(-dd)), trans);
+      const float tm = __fmul_rn(0.5f, __fadd_rn(t0, t1));
+      acc += w[j];
+      dep = fmaf(w[j], tm, dep);
+      if (in.compute_extras) {
+        lg = fmaf(w[j], logf(tm), lg);
+        wsum = __fadd_rn(wsum, w[j]);
+        const float cwj = fminf(wsum, 1.0f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (!found[k] && cwj > qs[k]) knot(k, cwj, t1);
+        prev_cw = cwj;
+        prev_tk = t1;
+      }
+      t_last = t1;
+    }
+    if (out.weights) *reinterpret_cast<float4*>(out.weights + (size_t)ray * S + c0) = make_float4(w[0], w[1], w[2], w[3]);
+  }
+  const float bg_w = fmaxf(__fsub_rn(1.0f, acc), 0.f);
+  const float den = fmaxf(acc, kEps);
+  if (out.rgb) {
+    const float v = fmaf(bg_w, in.bg, 0.f);
+    out.rgb[3 * (size_t)ray] = v;
+    out.rgb[3 * (size_t)ray + 1] = v;
+    out.rgb[3 * (size_t)ray + 2] = v;
+  }
+  if (out.depth) out.depth[ray] = __fdiv_rn(dep, den);
+  if (out.acc) out.acc[ray] = acc;
+  if (in.compute_extras) {
+    if (out.distance_mean) {
+      float v = expf(__fdiv_rn(lg, den));
+      if (isnan(v)) v = INFINITY;
+      out.distance_mean[ray] = fminf(fmaxf(v, t_first), t_last);
+    }
+    if (out.distance_percentiles) {
+      const float far = __ldg(in.far + ray);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (!found[k]) knot(k, 1.0f, far);
+        out.distance_percentiles[(size_t)ray * 3 + k] = pct[k];
+      }
+    }
+  }
+}
+
 // NeRF level with the nuScenes head layout (rgb + K = 19 class probabilities + intensity): one thread per
 // ray as well, reading its own rows straight from global memory with 16-byte loads: a ray's 8-sample chunk
 // is 608 contiguous bytes of class probabilities, 96 of colour, 32 of density and of intensity, so every
@@ -581,7 +669,12 @@ extern "C" int nlb_composite_forward(const nlb_composite_in_t* in, const nlb_com
   if (in->N == 0) return NLB_OK;
   if (in->compute_extras && out->distance_percentiles && !in->far) { nlb_set_error("composite_forward: far is required for the percentiles"); return NLB_EINVAL; }
   if (!in->rgb && !in->semantic && !in->intensity) {  // proposal levels: thread per ray
-    k_composite_prop_fwd<<<div_up(in->N, kPropRays), kPropRays, 0, (cudaStream_t)stream>>>(*in, *out);
+    static const bool kDirect = getenv("NLB_PROP_COMPOSITE_STAGED") == nullptr;
+    if (kDirect && in->S % 4 == 0 &&
+        (reinterpret_cast<uintptr_t>(in->density) | reinterpret_cast<uintptr_t>(out->weights)) % 16 == 0)
+      k_composite_prop4_fwd<<<div_up(in->N, 128), 128, 0, (cudaStream_t)stream>>>(*in, *out);
+    else
+      k_composite_prop_fwd<<<div_up(in->N, kPropRays), kPropRays, 0, (cudaStream_t)stream>>>(*in, *out);
     return nlb_check_launch("composite_forward");
   }
   if (in->rgb && in->semantic && in->intensity && in->K == kRayK && in->S % kRayCS == 0 && out->semantic && out->intensity &&
