@@ -668,7 +668,10 @@ extern "C" int nlb_composite_forward(const nlb_composite_in_t* in, const nlb_com
   if (!out) { nlb_set_error("composite_forward: null outputs"); return NLB_EINVAL; }
   if (in->N == 0) return NLB_OK;
   if (in->compute_extras && out->distance_percentiles && !in->far) { nlb_set_error("composite_forward: far is required for the percentiles"); return NLB_EINVAL; }
-  if (!in->rgb && !in->semantic && !in->intensity) {  // proposal levels: thread per ray
+  // thread-per-ray kernels need >= ~32 K rays to fill the machine (148 SMs x 2048 threads / a few); a training
+  // batch (10 240 rays) is served faster by the warp-per-ray kernel (0.016 against 0.026 ms at S = 64)
+  const bool many_rays = in->N >= 32768;
+  if (many_rays && !in->rgb && !in->semantic && !in->intensity) {  // proposal levels: thread per ray
     static const bool kDirect = getenv("NLB_PROP_COMPOSITE_STAGED") == nullptr;
     if (kDirect && in->S % 4 == 0 &&
         (reinterpret_cast<uintptr_t>(in->density) | reinterpret_cast<uintptr_t>(out->weights)) % 16 == 0)
@@ -677,7 +680,7 @@ extern "C" int nlb_composite_forward(const nlb_composite_in_t* in, const nlb_com
       k_composite_prop_fwd<<<div_up(in->N, kPropRays), kPropRays, 0, (cudaStream_t)stream>>>(*in, *out);
     return nlb_check_launch("composite_forward");
   }
-  if (in->rgb && in->semantic && in->intensity && in->K == kRayK && in->S % kRayCS == 0 && out->semantic && out->intensity &&
+  if (many_rays && in->rgb && in->semantic && in->intensity && in->K == kRayK && in->S % kRayCS == 0 && out->semantic && out->intensity &&
       (reinterpret_cast<uintptr_t>(in->rgb) | reinterpret_cast<uintptr_t>(in->semantic) | reinterpret_cast<uintptr_t>(in->intensity) |
        reinterpret_cast<uintptr_t>(in->density) | reinterpret_cast<uintptr_t>(out->weights)) % 16 == 0) {
     k_composite_ray19_fwd<<<div_up(in->N, kRayThreads), kRayThreads, 0, (cudaStream_t)stream>>>(*in, *out);

@@ -304,6 +304,62 @@ class _SingleProcess:
     is_main_process = True
 
 
+def _chunk_outputs(renderings, ray_history, return_weights):
+    """What render_image keeps of one chunk (Z/internal/models.py:1440-1452): the final level's rendering, the
+    ray_* visualisation leaves of every level, and the final weights on request."""
+    out = dict(renderings[-1])
+    for k in renderings[0]:
+        if k.startswith('ray_'):
+            out[k] = [r[k] for r in renderings]
+    if return_weights:
+        out['weights'] = ray_history[-1]['weights']
+    return out
+
+
+def _forward_chunk(model, rand, chunk, train_frac, return_weights=False):
+    """One chunk of rays through Model.forward -> _chunk_outputs.  Deterministic rendering (rand=False) on CUDA is
+    replayed as a CUDA graph per chunk shape: ~60 launches per chunk are host-bound when issued eagerly (the
+    32 x 1084 LiDAR sweep is three chunks).  The anneal slope travels through the library's dynamic-scalar
+    buffer.  The returned tensors live in the graph's static buffers: the caller copies them out before the
+    next replay (stream order makes that safe)."""
+    first = next(iter(chunk.values()))
+    if rand or not first.is_cuda or first.shape[0] == 0 or not getattr(model, 'graph_render', True):
+        return _chunk_outputs(*model(rand, chunk, train_frac=train_frac, compute_extras=True, zero_glo=True),
+                              return_weights)
+    from . import _lib
+    dev = first.device
+    key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(chunk.items()))
+    cache = model.__dict__.setdefault('_render_graphs', {})
+    dyn = model.__dict__.get('_render_dyn')
+    if dyn is None:
+        dyn = model.__dict__['_render_dyn'] = (torch.zeros(4, device=dev), torch.zeros(4).pin_memory())
+    slope = model.anneal_slope
+    dyn[1][0] = (slope * train_frac) / ((slope - 1) * train_frac + 1) if slope > 0 else 1.
+    dyn[0].copy_(dyn[1], non_blocking=True)
+    entry = cache.get(key)
+    lib = _lib.load()
+    if entry is None:
+        static = {k: v.clone() for k, v in chunk.items()}
+        lib.nlb_set_dynamic_scalars(dyn[0].data_ptr())
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                model(rand, static, train_frac=train_frac, compute_extras=True, zero_glo=True)  # warm-up
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outputs = model(rand, static, train_frac=train_frac, compute_extras=True, zero_glo=True)
+        finally:
+            lib.nlb_set_dynamic_scalars(None)
+        entry = cache[key] = (graph, static, outputs)
+    graph, static, outputs = entry
+    for k, v in chunk.items():
+        static[k].copy_(v, non_blocking=True)
+    graph.replay()
+    return _chunk_outputs(*outputs, return_weights)
+
+
 @torch.no_grad()
 def render_image(model, accelerator, batch, rand, config, train_frac=1, verbose=True, return_weights=False,
                  image=True, render_instance=False, instance_id=None):
@@ -329,25 +385,20 @@ def render_image(model, accelerator, batch, rand, config, train_frac=1, verbose=
     batch = {k: v.reshape((num_rays, -1)) for k, v in batch.items() if v is not None}
     world, rank = int(acc.num_processes), int(acc.process_index)
     lo, hi = parallel.shard_range(num_rays, world, rank)
-    chunks = []
+    rendering, bundles = {}, {}
     for idx0 in range(lo, hi, config.render_chunk_size):
         idx1 = min(hi, idx0 + config.render_chunk_size)
         chunk = {k: v[idx0:idx1] for k, v in batch.items()}
-        renderings, ray_history = model(rand, chunk, train_frac=train_frac, compute_extras=True, zero_glo=True)
-        out = dict(renderings[-1])
-        for k in renderings[0]:
-            if k.startswith('ray_'):
-                out[k] = [r[k] for r in renderings]
-        if return_weights:
-            out['weights'] = ray_history[-1]['weights']
-        chunks.append(out)
-    rendering = {}
-    keys = chunks[0].keys() if chunks else []
-    for k in keys:
-        if isinstance(chunks[0][k], list):
-            rendering[k] = [torch.cat([c[k][i] for c in chunks]) for i in range(len(chunks[0][k]))]
-        else:
-            rendering[k] = torch.cat([c[k] for c in chunks])
+        out = _forward_chunk(model, rand, chunk, train_frac, return_weights)
+        for k, v in out.items():
+            if isinstance(v, list):     # ray_* bundles: vis_num_rays rays of every chunk, every level
+                bundles.setdefault(k, []).append([z.clone() for z in v])
+                continue
+            if k not in rendering:      # per-ray leaves go straight into this rank's result buffer (no cat)
+                rendering[k] = v.new_empty((hi - lo,) + tuple(v.shape[1:]))
+            rendering[k][idx0 - lo:idx1 - lo].copy_(v)
+    for k, per_chunk in bundles.items():
+        rendering[k] = [torch.cat([c[i] for c in per_chunk]) for i in range(len(per_chunk[0]))]
     if world > 1:
         rendering = parallel.gather_rendering(rendering, num_rays, world, rank)
     for k, z in rendering.items():

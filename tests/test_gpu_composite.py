@@ -24,10 +24,11 @@ def _inputs(N, S, K, seed):
     return dens, t, dirs, far, rgb, sem, inten
 
 
-@pytest.mark.parametrize('S', [32, 64, 256])
-def test_forward_vs_oracle(S):
+@pytest.mark.parametrize('S,N', [(32, 515), (64, 515), (256, 515), (32, 33001), (64, 32771)])
+def test_forward_vs_oracle(S, N):
+    """Small ray counts run the warp-per-ray kernel, >= 32768 rays the thread-per-ray kernel (K = 19)."""
     from nerf_lidar_b200 import ops
-    N, K = 515, 19
+    K = 19
     dens, t, dirs, far, rgb, sem, inten = _inputs(N, S, K, S)
     w, _, _ = zo.alpha_weights(dens, t, dirs, True)
     want = zo.composite(rgb, w, t, far, 1.0, sem, inten, True)
@@ -43,10 +44,11 @@ def test_forward_vs_oracle(S):
     assert torch.allclose(got['weights'].sum(-1), torch.ones(N, device='cuda'), atol=1e-5)
 
 
-@pytest.mark.parametrize('N,S', [(100, 64), (515, 64), (131, 37), (4100, 32)])
+@pytest.mark.parametrize('N,S', [(100, 64), (515, 64), (131, 37), (33001, 64), (32771, 37), (40000, 32)])
 def test_proposal_level_without_colour(N, S):
-    """The thread-per-ray kernel of the proposal levels (no colour / class / intensity inputs): every output
-    against the oracle, incl. ragged ray counts and a sample count that is not a multiple of the chunk."""
+    """Proposal levels (no colour / class / intensity inputs): every output against the oracle; >= 32768 rays
+    run the thread-per-ray kernels (direct 16-byte loads when S % 4 == 0, the staged variant otherwise), incl.
+    ragged ray counts and a sample count that is not a multiple of the chunk."""
     from nerf_lidar_b200 import ops
     dens, t, dirs, far, *_ = _inputs(N, S, 19, 5 + S)
     w, _, _ = zo.alpha_weights(dens, t, dirs, True)

@@ -11,6 +11,7 @@ if len(sys.argv) > 1:
     cfg.render_chunk_size = int(sys.argv[1])
 model = models.Model(cfg).cuda()
 model.load_state_dict({k: v.cuda() for k, v in synthetic.init_state_dict(seed=0, table_std=0.05).items()}, strict=False)
+model.graph_render = os.environ.get('NLB_RENDER_GRAPH', '1') != '0'   # 0: eager launches per chunk
 
 
 def timeit(fn, n):
