@@ -69,13 +69,20 @@ __device__ __forceinline__ void corner_weights(float fx, float fy, float fz, flo
 // Per-level constants, computed once per block into shared memory.
 struct LevelCache {
   Level3 lv[kMaxLevelsEnc];
-  int gs[kMaxLevelsEnc];
+  float inv_gs[kMaxLevelsEnc];  // 1 / grid_size
 };
+
+// erf re-weighting of one sample at one level (models.py:976): erf(1 / max(sqrt(8 std^2 gs^2), 1e-10)).  The
+// staged points carry a = 1 / sqrt(8 std^2) (one MUFU.RSQ per point instead of an IEEE sqrt and divide per
+// point-level: 30 of ~180 instructions of a lookup), so the argument is a * (1 / gs); std = 0 gives inf -> 1
+// like the reference's clamp.  Agreement with the reference expression: ~2 ulp of the argument.
+__device__ __forceinline__ float staged_a(float sd) { return rsqrtf(8.0f * sd * sd); }
+__device__ __forceinline__ float erf_weight_a(float a, float inv_gs) { return erff(a * inv_gs); }
 
 __device__ __forceinline__ void fill_level_cache(LevelCache& lc, const nlb_table_t& tab) {
   if (threadIdx.x < tab.L) {
     lc.lv[threadIdx.x] = level3(tab.offsets, threadIdx.x, tab.S, tab.H);
-    lc.gs[threadIdx.x] = __ldg(tab.grid_sizes + threadIdx.x);
+    lc.inv_gs[threadIdx.x] = 1.0f / (float)__ldg(tab.grid_sizes + threadIdx.x);
   }
 }
 
@@ -126,7 +133,11 @@ __device__ __forceinline__ void stage_points(const nlb_rays_t& rays, int row, fl
   float4* cache = reinterpret_cast<float4*>(rays.points_cache);
   if (rays.points_mode == 2) {  // backward: the forward's points, [7][rows] so a warp reads 512 contiguous bytes
 #pragma unroll
-    for (int j = 0; j < 7; ++j) s_pts[j][threadIdx.x] = __ldg(cache + j * rows + row);
+    for (int j = 0; j < 7; ++j) {
+      float4 v = __ldg(cache + j * rows + row);
+      if (v.w >= 0.f) v.w = staged_a(v.w);  // the cache keeps std (nlb200.h), the staged copy a
+      s_pts[j][threadIdx.x] = v;
+    }
     return;
   }
   const int ray = row / rays.S, s = row - ray * rays.S;
@@ -140,15 +151,16 @@ __device__ __forceinline__ void stage_points(const nlb_rays_t& rays, int row, fl
     const SamplePoint p = sample_point(rg, t0, t1, j, noise, has_noise, rays.std_scale);
     // points outside the unit cube contribute zero features (kernel_grid writes zeros):
     // flag them with a negative std
-    const float4 v = make_float4(p.x, p.y, p.z, in_unit_cube(p.x, p.y, p.z) ? p.std : -1.0f);
-    s_pts[j][threadIdx.x] = v;
-    if (rays.points_mode == 1) __stcs(cache + j * rows + row, v);  // evict-first: must not displace the table in L2
+    const bool inside = in_unit_cube(p.x, p.y, p.z);
+    s_pts[j][threadIdx.x] = make_float4(p.x, p.y, p.z, inside ? staged_a(p.std) : -1.0f);
+    // evict-first: must not displace the table in L2
+    if (rays.points_mode == 1) __stcs(cache + j * rows + row, make_float4(p.x, p.y, p.z, inside ? p.std : -1.0f));
   }
 }
 
 // erf-weighted sum over the 7 samples of the interpolated feature at one level
 template <int C>
-__device__ __forceinline__ void level_feature(const float* __restrict__ table, const Level3& lv, int gs,
+__device__ __forceinline__ void level_feature(const float* __restrict__ table, const Level3& lv, float inv_gs,
                                               const float4 (*s_pts)[kEncThreads], float (&acc)[C]) {
 #pragma unroll
   for (int c = 0; c < C; ++c) acc[c] = 0.f;
@@ -156,7 +168,7 @@ __device__ __forceinline__ void level_feature(const float* __restrict__ table, c
   for (int j = 0; j < 7; ++j) {
     const float4 p = s_pts[j][threadIdx.x];
     if (p.w < 0.f) continue;
-    const float wj = erf_weight(p.w, gs);
+    const float wj = erf_weight_a(p.w, inv_gs);
     float f[C];
     lookup<C>(table, lv, p.x, p.y, p.z, f);
 #pragma unroll
@@ -193,7 +205,7 @@ __device__ __forceinline__ void add_row(float* __restrict__ acc, const Level3& l
 //            Every ray of a scene starts in the same few coarse cells -- without this,
 //            L2 serialises millions of same-address atomics (measured: 0.4 ms per level).
 template <int C, bool kStaged, bool kWarpAgg>
-__device__ __forceinline__ void level_scatter(float* __restrict__ acc, const Level3& lv, int gs,
+__device__ __forceinline__ void level_scatter(float* __restrict__ acc, const Level3& lv, float inv_gs,
                                               const float4 (*s_pts)[kEncThreads], const float (&g)[C], bool has_g) {
   uint32_t cx = 0, cy = 0, cz = 0;
   float w[8];
@@ -245,7 +257,7 @@ __device__ __forceinline__ void level_scatter(float* __restrict__ acc, const Lev
     if (valid) {
       cx = nx; cy = ny; cz = nz;
       live = true;
-      const float coef = erf_weight(p.w, gs);
+      const float coef = erf_weight_a(p.w, inv_gs);
       float cw[8];
       corner_weights(fx, fy, fz, cw);
 #pragma unroll
@@ -298,7 +310,7 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_fwd(nlb_rays_t rays, nlb
   for (int level = level_begin; level < level_end; ++level) {
     const Level3 lv = lc.lv[level];
     float acc[C];
-    level_feature<C>(tab.embeddings, lv, lc.gs[level], s_pts, acc);
+    level_feature<C>(tab.embeddings, lv, lc.inv_gs[level], s_pts, acc);
     if constexpr (C == 4) {
       *reinterpret_cast<float4*>(out + level * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     } else if constexpr (C == 2) {
@@ -356,14 +368,14 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_bwd(nlb_rays_t rays, nlb
       const Level3 lv = lc.lv[level];
       if (lv.dense) {  // uniform per level: the whole warp takes the same branch
         if ((int)(lv.offset + lv.hashmap_size) <= staged_rows)
-          level_scatter<C, true, true>(s_acc, lv, lc.gs[level], s_pts, g, any);
+          level_scatter<C, true, true>(s_acc, lv, lc.inv_gs[level], s_pts, g, any);
         else if ((int)(lv.offset + lv.hashmap_size) <= priv_rows)  // privatised copy of the coarse rows
-          level_scatter<C, false, true>(priv + (size_t)(blockIdx.x % priv_copies) * priv_rows * C, lv, lc.gs[level],
+          level_scatter<C, false, true>(priv + (size_t)(blockIdx.x % priv_copies) * priv_rows * C, lv, lc.inv_gs[level],
                                         s_pts, g, any);
         else
-          level_scatter<C, false, true>(grad_table, lv, lc.gs[level], s_pts, g, any);
+          level_scatter<C, false, true>(grad_table, lv, lc.inv_gs[level], s_pts, g, any);
       } else if (any) {
-        level_scatter<C, false, false>(grad_table, lv, lc.gs[level], s_pts, g, true);
+        level_scatter<C, false, false>(grad_table, lv, lc.inv_gs[level], s_pts, g, true);
       }
     }
   }
@@ -440,7 +452,7 @@ __global__ void __launch_bounds__(kEncThreads) k_prop_fwd(nlb_rays_t rays, nlb_t
   for (int l = 0; l < L; ++l) {
     const Level3 lv = lc.lv[l];
     float acc[1];
-    level_feature<1>(tab.embeddings, lv, lc.gs[l], s_pts, acc);
+    level_feature<1>(tab.embeddings, lv, lc.inv_gs[l], s_pts, acc);
     s_f[l][tid] = acc[0];
     if (features) features[(size_t)row * L + l] = acc[0];
   }
@@ -458,6 +470,163 @@ __global__ void __launch_bounds__(kEncThreads) k_prop_fwd(nlb_rays_t rays, nlb_t
   // softplus(raw + density_bias), density_bias = -1 (torch threshold 20)
   const float xin = raw - 1.0f;
   density[row] = xin > 20.f ? xin : log1pf(expf(xin));
+}
+
+// Proposal forward with TWO lanes per interval.  ncu + a cycle model of k_prop_fwd: on the hashed C=1 levels
+// every lane of a gather instruction touches its own 128-byte line and L1 retires about one line per clock
+// per SM (wavefronts = 32 per LDG; predicted 0.43 / 0.68 ms for the 6- / 8-level tables, measured 0.42 /
+// 0.78).  The x and x+1 corners of a cell are h and h ^ (x ^ (x+1)) -- the same line for 31 of 32 cells --
+// so lane pair (2i, 2i+1) of interval i takes the four (y, z) corners at x and at x+1 respectively: the pair's
+// two addresses of one LDG coalesce into one wavefront (16 per instruction instead of 32), on dense levels
+// they are adjacent words.  Each lane also does half of the staging, of the erf weights of a level and of the
+// hidden units of the density MLP.  Summation order: per lane sum_j erf_j * (sum over its 4 corners), then the
+// two lanes are added (the reference sums the 8 corners of a sample first; agreement is to fp32 rounding,
+// the indices are the same).
+constexpr int kPairIv = kEncThreads / 2;
+
+// (floor / frac through the ALU -- pos + 2^23 trick, exact for pos < 2^22 -- instead of F2I + FRND per axis
+// was measured: 0.282 / 0.366 ms against 0.262 / 0.350, the conversion pipe is not the limit)
+__device__ __forceinline__ void stage_points_pair(const nlb_rays_t& rays, int row, int h, int iv,
+                                                  float4 (*s_pts)[kPairIv]) {
+  const size_t rows = (size_t)rays.N * rays.S;
+  float4* cache = reinterpret_cast<float4*>(rays.points_cache);
+  if (rays.points_mode == 2) {
+    for (int j = h; j < 7; j += 2) {
+      float4 v = __ldg(cache + j * rows + row);
+      if (v.w >= 0.f) v.w = staged_a(v.w);
+      s_pts[j][iv] = v;
+    }
+    return;
+  }
+  const int ray = row / rays.S, s = row - ray * rays.S;
+  const RayGeom rg = load_ray(rays.origins, rays.directions, rays.base_x, rays.base_y, rays.radii, ray);
+  const float t0 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s);
+  const float t1 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s + 1);
+  const bool has_noise = rays.deg_noise != nullptr;
+#pragma unroll 1
+  for (int j = h; j < 7; j += 2) {
+    const float noise = has_noise ? __ldg(rays.deg_noise + (size_t)row * 7 + j) : 0.f;
+    const SamplePoint p = sample_point(rg, t0, t1, j, noise, has_noise, rays.std_scale);
+    const bool inside = in_unit_cube(p.x, p.y, p.z);
+    s_pts[j][iv] = make_float4(p.x, p.y, p.z, inside ? staged_a(p.std) : -1.0f);
+    if (rays.points_mode == 1) __stcs(cache + j * rows + row, make_float4(p.x, p.y, p.z, inside ? p.std : -1.0f));
+  }
+}
+
+template <int L>
+__global__ void __launch_bounds__(kEncThreads) k_prop_fwd_pair(nlb_rays_t rays, nlb_table_t tab,
+                                                               const float* __restrict__ W0, const float* __restrict__ b0,
+                                                               const float* __restrict__ W1, const float* __restrict__ b1,
+                                                               float* __restrict__ density, float* __restrict__ features) {
+  __shared__ PropSmem sm;
+  __shared__ float4 s_pts[7][kPairIv];
+  __shared__ float s_w[7][kPairIv];
+  __shared__ float s_f[L][kPairIv];
+  __shared__ LevelCache lc;
+  fill_level_cache(lc, tab);
+  load_prop_weights(sm, L, W0, b0, W1, b1);
+  __syncthreads();
+  const int tid = threadIdx.x, iv = tid >> 1, h = tid & 1;
+  const int row = blockIdx.x * kPairIv + iv;
+  const bool ok = row < rays.N * rays.S;  // the same for both lanes of a pair; no early exit (warp shuffles below)
+  if (ok) stage_points_pair(rays, row, h, iv, s_pts);
+  __syncwarp();
+#pragma unroll 1
+  for (int l = 0; l < L; ++l) {
+    const Level3 lv = lc.lv[l];
+    const float inv_gs = lc.inv_gs[l];
+    if (ok) {
+      for (int j = h; j < 7; j += 2) {
+        const float a = s_pts[j][iv].w;
+        s_w[j][iv] = a < 0.f ? 0.f : erf_weight_a(a, inv_gs);
+      }
+    }
+    __syncwarp();
+    const float* __restrict__ emb = tab.embeddings;  // row = offset + idx in 32 bits (offsets are int32)
+    const uint32_t off = lv.offset;
+    float acc = 0.f;
+    if (ok) {
+      if (lv.dense) {  // uniform per level
+#pragma unroll 1
+        for (int j = 0; j < 7; ++j) {
+          const float4 p = s_pts[j][iv];
+          if (p.w < 0.f) continue;
+          uint32_t cx, cy, cz;
+          float fx, fy, fz;
+          cell_of(p.x, lv.scale, cx, fx);
+          cell_of(p.y, lv.scale, cy, fy);
+          cell_of(p.z, lv.scale, cz, fz);
+          const float wx = h ? fx : 1.f - fx;
+          const float wy0 = wx * (1.f - fy), wy1 = wx * fy;
+          const uint32_t i00 = off + cx + h + cy * lv.s1 + cz * lv.s2;
+          const float r0 = __ldg(emb + i00), r1 = __ldg(emb + (i00 + lv.s1));
+          const float r2 = __ldg(emb + (i00 + lv.s2)), r3 = __ldg(emb + (i00 + lv.s1 + lv.s2));
+          float f = (wy0 * (1.f - fz)) * r0;
+          f = fmaf(wy1 * (1.f - fz), r1, f);
+          f = fmaf(wy0 * fz, r2, f);
+          f = fmaf(wy1 * fz, r3, f);
+          acc = fmaf(f, s_w[j][iv], acc);
+        }
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < 7; ++j) {
+          const float4 p = s_pts[j][iv];
+          if (p.w < 0.f) continue;
+          uint32_t cx, cy, cz;
+          float fx, fy, fz;
+          cell_of(p.x, lv.scale, cx, fx);
+          cell_of(p.y, lv.scale, cy, fy);
+          cell_of(p.z, lv.scale, cz, fz);
+          const float wx = h ? fx : 1.f - fx;
+          const float wy0 = wx * (1.f - fy), wy1 = wx * fy;
+          const uint32_t vx = cx + h;
+          const uint32_t hy0 = cy * 2654435761u, hy1 = hy0 + 2654435761u;
+          const uint32_t hz0 = cz * 805459861u, hz1 = hz0 + 805459861u;
+          const float r0 = __ldg(emb + (off + ((vx ^ hy0 ^ hz0) & lv.mask))), r1 = __ldg(emb + (off + ((vx ^ hy1 ^ hz0) & lv.mask)));
+          const float r2 = __ldg(emb + (off + ((vx ^ hy0 ^ hz1) & lv.mask))), r3 = __ldg(emb + (off + ((vx ^ hy1 ^ hz1) & lv.mask)));
+          float f = (wy0 * (1.f - fz)) * r0;
+          f = fmaf(wy1 * (1.f - fz), r1, f);
+          f = fmaf(wy0 * fz, r2, f);
+          f = fmaf(wy1 * fz, r3, f);
+          acc = fmaf(f, s_w[j][iv], acc);
+        }
+      }
+    }
+    acc += __shfl_xor_sync(NLB_FULL_MASK, acc, 1);
+    if (h == 0) s_f[l][iv] = acc / 7.0f;
+    // the next level's s_w writes race with nothing: both lanes passed the shuffle above
+  }
+  __syncwarp();
+  float f[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) f[l] = s_f[l][iv];
+  if (features && ok) {
+    float* out = features + (size_t)row * L;
+    if ((L & 1) == 0 && (reinterpret_cast<uintptr_t>(features) & 7) == 0) {
+#pragma unroll
+      for (int q = 0; q < L / 2; ++q)
+        if ((q & 1) == h) *reinterpret_cast<float2*>(out + 2 * q) = make_float2(f[2 * q], f[2 * q + 1]);
+    } else {
+#pragma unroll
+      for (int l = 0; l < L; ++l)
+        if ((l & 1) == h) out[l] = f[l];
+    }
+  }
+  // density MLP: lane h takes the hidden units k = 2 i + h (interleaved: conflict-free weight reads)
+  float raw = 0.f;
+#pragma unroll 4
+  for (int i = 0; i < kPropHidden / 2; ++i) {
+    const int k = 2 * i + h;
+    float a = sm.b0[k];
+#pragma unroll
+    for (int l = 0; l < L; ++l) a = fmaf(sm.W0[k * L + l], f[l], a);
+    raw = fmaf(sm.W1[k], fmaxf(a, 0.f), raw);
+  }
+  raw += __shfl_xor_sync(NLB_FULL_MASK, raw, 1);
+  if (ok && h == 0) {
+    const float xin = (raw + sm.b1) - 1.0f;  // softplus(raw + density_bias), density_bias = -1 (torch threshold 20)
+    density[row] = xin > 20.f ? xin : log1pf(expf(xin));
+  }
 }
 
 // Backward of the proposal MLP (persistent blocks over 128-row tiles): per-interval
@@ -702,6 +871,9 @@ static int scatter_launch(const nlb_rays_t& rays, const nlb_table_t& tab, const 
                           const float* grad_features, float* grad_embeddings, float* workspace, cudaStream_t st) {
   static const size_t kStageBudget = (size_t)env_long("NLB_SCATTER_STAGE_KB", 24) * 1024;  // >= 6 blocks/SM resident
   static const double kL2Budget = (double)env_long("NLB_SCATTER_L2_MB", 70) * 1048576.0;
+  // (measured and rejected: the hashed levels of a table that fits L2 in a launch of their own without the
+  // staging buffer -- 9 instead of 6 resident blocks per SM -- 0.62 / 0.90 ms against 0.52 / 0.79 for the
+  // proposal backward: the second pass over the points costs more than the occupancy gains)
   // coarsest dense levels accumulated per block in shared memory
   int staged_rows = 0;
   for (int l = 0; l < tab.L && hl.dense[l]; ++l) {
@@ -799,7 +971,12 @@ extern "C" int nlb_prop_forward(const nlb_rays_t* rays, const nlb_table_t* table
   const int rows = rays->N * rays->S;
   if (rows == 0) return NLB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  NLB_PROP_DISPATCH(table->L, (k_prop_fwd<L_><<<div_up(rows, 128), 128, 0, st>>>(*rays, *table, W0, b0, W1, b1, density, features)));
+  static const bool kLegacy = getenv("NLB_PROP_FWD_LEGACY") != nullptr;  // one lane per interval (A/B timing)
+  if (kLegacy) {
+    NLB_PROP_DISPATCH(table->L, (k_prop_fwd<L_><<<div_up(rows, kEncThreads), kEncThreads, 0, st>>>(*rays, *table, W0, b0, W1, b1, density, features)));
+  } else {
+    NLB_PROP_DISPATCH(table->L, (k_prop_fwd_pair<L_><<<div_up(rows, kPairIv), kEncThreads, 0, st>>>(*rays, *table, W0, b0, W1, b1, density, features)));
+  }
   return nlb_check_launch("prop_forward");
 }
 
