@@ -513,6 +513,109 @@ __device__ __forceinline__ void stage_points_pair(const nlb_rays_t& rays, int ro
   }
 }
 
+// Interpolation partial of one lane of a pair: its x corner (cx + h) of the four (y, z) corners of one cell.
+// `rowbase(k)` is the table row of corner k = (y bit) + 2 (z bit).
+template <int C, class RowOf>
+__device__ __forceinline__ void pair_partial(const float* __restrict__ emb, RowOf row_of, int h, float fx, float fy,
+                                             float fz, float wj, float (&acc)[C]) {
+  const float wx = h ? fx : 1.f - fx;
+  const float wy0 = wx * (1.f - fy), wy1 = wx * fy;
+  float r[4][C];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) gather_row<C>(emb + row_of(k) * (uint32_t)C, r[k]);  // 32-bit row * C: offsets are int32
+  const float w0 = wy0 * (1.f - fz), w1 = wy1 * (1.f - fz), w2 = wy0 * fz, w3 = wy1 * fz;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float f = w0 * r[0][c];
+    f = fmaf(w1, r[1][c], f);
+    f = fmaf(w2, r[2][c], f);
+    f = fmaf(w3, r[3][c], f);
+    acc[c] = fmaf(f, wj, acc[c]);
+  }
+}
+
+// Fused encode forward (any level_dim) with two lanes per interval -- see k_prop_fwd_pair below for the why.
+// At C = 4 the x / x+1 rows of an even-x cell are one 32-byte sector, so the pair's loads also halve the
+// L2 -> L1 sector traffic of those cells.
+template <int C>
+__global__ void __launch_bounds__(kEncThreads) k_encode_fwd_pair(nlb_rays_t rays, nlb_table_t tab,
+                                                                 float* __restrict__ features, int level_begin,
+                                                                 int level_end) {
+  __shared__ float4 s_pts[7][kPairIv];
+  __shared__ float s_w[7][kPairIv];
+  __shared__ LevelCache lc;
+  fill_level_cache(lc, tab);
+  __syncthreads();
+  const int tid = threadIdx.x, iv = tid >> 1, h = tid & 1;
+  const int row = blockIdx.x * kPairIv + iv;
+  const bool ok = row < rays.N * rays.S;
+  if (ok) stage_points_pair(rays, row, h, iv, s_pts);
+  __syncwarp();
+  const float* __restrict__ emb = tab.embeddings;
+#pragma unroll 1
+  for (int level = level_begin; level < level_end; ++level) {
+    const Level3 lv = lc.lv[level];
+    const float inv_gs = lc.inv_gs[level];
+    if (ok) {
+      for (int j = h; j < 7; j += 2) {
+        const float a = s_pts[j][iv].w;
+        s_w[j][iv] = a < 0.f ? 0.f : erf_weight_a(a, inv_gs);
+      }
+    }
+    __syncwarp();
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    if (ok) {
+      const uint32_t off = lv.offset;
+      if (lv.dense) {  // uniform per level
+#pragma unroll 1
+        for (int j = 0; j < 7; ++j) {
+          const float4 p = s_pts[j][iv];
+          if (p.w < 0.f) continue;
+          uint32_t cx, cy, cz;
+          float fx, fy, fz;
+          cell_of(p.x, lv.scale, cx, fx);
+          cell_of(p.y, lv.scale, cy, fy);
+          cell_of(p.z, lv.scale, cz, fz);
+          const uint32_t i00 = off + cx + h + cy * lv.s1 + cz * lv.s2;
+          pair_partial<C>(emb, [&](int k) { return i00 + ((k & 1) ? lv.s1 : 0u) + ((k & 2) ? lv.s2 : 0u); }, h, fx, fy, fz,
+                          s_w[j][iv], acc);
+        }
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < 7; ++j) {
+          const float4 p = s_pts[j][iv];
+          if (p.w < 0.f) continue;
+          uint32_t cx, cy, cz;
+          float fx, fy, fz;
+          cell_of(p.x, lv.scale, cx, fx);
+          cell_of(p.y, lv.scale, cy, fy);
+          cell_of(p.z, lv.scale, cz, fz);
+          const uint32_t vx = cx + h;
+          const uint32_t hy0 = cy * 2654435761u, hy1 = hy0 + 2654435761u;
+          const uint32_t hz0 = cz * 805459861u, hz1 = hz0 + 805459861u;
+          pair_partial<C>(emb, [&](int k) { return off + ((vx ^ ((k & 1) ? hy1 : hy0) ^ ((k & 2) ? hz1 : hz0)) & lv.mask); },
+                          h, fx, fy, fz, s_w[j][iv], acc);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] += __shfl_xor_sync(NLB_FULL_MASK, acc[c], 1);
+    if (ok && h == 0) {
+      float* out = features + (size_t)row * (tab.L * C) + level * C;
+      if constexpr (C == 4) {
+        *reinterpret_cast<float4*>(out) = make_float4(acc[0] / 7.0f, acc[1] / 7.0f, acc[2] / 7.0f, acc[3] / 7.0f);
+      } else if constexpr (C == 2) {
+        *reinterpret_cast<float2*>(out) = make_float2(acc[0] / 7.0f, acc[1] / 7.0f);
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[c] = acc[c] / 7.0f;
+      }
+    }
+  }
+}
+
 template <int L>
 __global__ void __launch_bounds__(kEncThreads) k_prop_fwd_pair(nlb_rays_t rays, nlb_table_t tab,
                                                                const float* __restrict__ W0, const float* __restrict__ b0,
@@ -796,11 +899,16 @@ static int encode_forward_launch(const nlb_rays_t& rays_in, const nlb_table_t& t
                                  float* features, cudaStream_t st) {
   static const double kL2Budget = (double)env_long("NLB_GATHER_L2_MB", 70) * 1048576.0;
   const int rows = rays_in.N * rays_in.S;
-  dim3 grid(div_up(rows, kEncThreads));
+  static const bool kLegacy = getenv("NLB_ENC_FWD_LEGACY") != nullptr;  // one lane per interval (A/B timing)
+  dim3 grid(div_up(rows, kLegacy ? kEncThreads : kPairIv));
+  auto launch = [&](const nlb_rays_t& r, int l0, int l1) {
+    if (kLegacy) k_encode_fwd<C><<<grid, kEncThreads, 0, st>>>(r, tab, features, l0, l1);
+    else k_encode_fwd_pair<C><<<grid, kEncThreads, 0, st>>>(r, tab, features, l0, l1);
+  };
   double total = 0.;
   for (int l = 0; l < tab.L; ++l) total += (double)hl.rows[l] * C * 4.0;
   if (total <= kL2Budget || kL2Budget <= 0.) {
-    k_encode_fwd<C><<<grid, kEncThreads, 0, st>>>(rays_in, tab, features, 0, tab.L);
+    launch(rays_in, 0, tab.L);
     return nlb_check_launch("encode_forward");
   }
   nlb_rays_t rays = rays_in;
@@ -811,7 +919,7 @@ static int encode_forward_launch(const nlb_rays_t& rays_in, const nlb_table_t& t
     while (l1 < tab.L && (l1 == l0 || bytes + (double)hl.rows[l1] * C * 4.0 <= kL2Budget)) bytes += (double)hl.rows[l1++] * C * 4.0;
     // keep group boundaries on 32-byte boundaries of the feature row
     while (l1 < tab.L && (l1 * C * 4) % 32 != 0) ++l1;
-    k_encode_fwd<C><<<grid, kEncThreads, 0, st>>>(rays, tab, features, l0, l1);
+    launch(rays, l0, l1);
     if (int e = nlb_check_launch("encode_forward")) return e;
     if (rays.points_mode == 1) rays.points_mode = 2;  // the first group wrote the cache
     l0 = l1;
