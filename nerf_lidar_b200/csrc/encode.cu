@@ -616,6 +616,88 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_fwd_pair(nlb_rays_t rays
   }
 }
 
+// Scatter of a level group that holds only HASHED levels, two lanes per interval (the NeRF table's groups
+// after the dense one): lane h accumulates and reduces the four (y, z) corners at x + h, so the pair's two
+// reductions of one instruction fall into the same 128-byte line (the same 32-byte sector for even x at C = 4:
+// one L2 request instead of two).  Same per-corner values as level_scatter (weights accumulated over the
+// samples of a cell in the same order), persistent blocks over 64-interval tiles.
+template <int C>
+__global__ void __launch_bounds__(kEncThreads) k_encode_bwd_hashed_pair(nlb_rays_t rays, nlb_table_t tab,
+                                                                        const float* __restrict__ grad_features,
+                                                                        float* __restrict__ grad_table, int num_tiles,
+                                                                        int level_begin, int level_end) {
+  __shared__ float4 s_pts[7][kPairIv];
+  __shared__ LevelCache lc;
+  fill_level_cache(lc, tab);
+  __syncthreads();
+  const int tid = threadIdx.x, iv = tid >> 1, h = tid & 1;
+  const unsigned pair_mask = 3u << (tid & 30);
+  const int rows_total = rays.N * rays.S;
+  const int LC = tab.L * C;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int row = tile * kPairIv + iv;
+    const bool row_ok = row < rows_total;
+    __syncwarp(pair_mask);  // the pair is done with the previous tile's points
+    if (row_ok) stage_points_pair(rays, row, h, iv, s_pts);
+    __syncwarp(pair_mask);
+    if (!row_ok) continue;
+    const float* gin = grad_features + (size_t)row * LC;
+#pragma unroll 1
+    for (int level = level_begin; level < level_end; ++level) {
+      float g[C];
+      bool any = false;
+      gather_row<C>(gin + level * C, g);
+#pragma unroll
+      for (int c = 0; c < C; ++c) { g[c] = g[c] / 7.0f; any |= (g[c] != 0.f); }
+      if (!any) continue;
+      const Level3 lv = lc.lv[level];
+      const float inv_gs = lc.inv_gs[level];
+      uint32_t cx = 0, cy = 0, cz = 0;
+      float w[4] = {0.f, 0.f, 0.f, 0.f};
+      bool live = false;
+#pragma unroll 1
+      for (int j = 0; j <= 7; ++j) {  // the sentinel iteration flushes the last cell
+        float4 p = make_float4(0.f, 0.f, 0.f, -1.f);
+        if (j < 7) p = s_pts[j][iv];
+        const bool valid = p.w >= 0.f;
+        uint32_t nx = 0, ny = 0, nz = 0;
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        if (valid) {
+          cell_of(p.x, lv.scale, nx, fx);
+          cell_of(p.y, lv.scale, ny, fy);
+          cell_of(p.z, lv.scale, nz, fz);
+        }
+        if (live && (j == 7 || (valid && (nx != cx || ny != cy || nz != cz)))) {
+          const uint32_t vx = cx + h;
+          const uint32_t hy0 = cy * 2654435761u, hy1 = hy0 + 2654435761u;
+          const uint32_t hz0 = cz * 805459861u, hz1 = hz0 + 805459861u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t idx = (vx ^ ((k & 1) ? hy1 : hy0) ^ ((k & 2) ? hz1 : hz0)) & lv.mask;
+            float v[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c] = g[c] * w[k];
+            red_add_row<C>(grad_table + (size_t)(lv.offset + idx) * C, v);
+            w[k] = 0.f;
+          }
+          live = false;
+        }
+        if (valid) {
+          cx = nx; cy = ny; cz = nz;
+          live = true;
+          const float coef = erf_weight_a(p.w, inv_gs);
+          const float wx = h ? fx : 1.f - fx;
+          const float wy0 = wx * (1.f - fy), wy1 = wx * fy;
+          w[0] = fmaf(coef, wy0 * (1.f - fz), w[0]);
+          w[1] = fmaf(coef, wy1 * (1.f - fz), w[1]);
+          w[2] = fmaf(coef, wy0 * fz, w[2]);
+          w[3] = fmaf(coef, wy1 * fz, w[3]);
+        }
+      }
+    }
+  }
+}
+
 template <int L>
 __global__ void __launch_bounds__(kEncThreads) k_prop_fwd_pair(nlb_rays_t rays, nlb_table_t tab,
                                                                const float* __restrict__ W0, const float* __restrict__ b0,
@@ -1009,6 +1091,10 @@ static int scatter_launch(const nlb_rays_t& rays, const nlb_table_t& tab, const 
   int blocks_plain = sm_count() * per_sm;
   if (blocks_staged > tiles) blocks_staged = tiles;
   if (blocks_plain > tiles) blocks_plain = tiles;
+  static const bool kLegacyHashed = getenv("NLB_SCATTER_HASHED_LEGACY") != nullptr;  // A/B timing
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_bwd_hashed_pair<C>, kEncThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  const int blocks_pair = sm_count() * per_sm;
   // level groups: consecutive levels whose gradient rows fit the L2 budget together, so a
   // fine level stays L2-resident while every tile updates it (level-major order)
   int l0 = 0;
@@ -1017,9 +1103,25 @@ static int scatter_launch(const nlb_rays_t& rays, const nlb_table_t& tab, const 
     double bytes = 0.;
     while (l1 < tab.L && (l1 == l0 || bytes + (double)hl.rows[l1] * C * 4.0 <= kL2Budget)) bytes += (double)hl.rows[l1++] * C * 4.0;
     const bool first = l0 == 0;
-    k_encode_bwd<C><<<first ? blocks_staged : blocks_plain, kEncThreads, first ? smem : 0, st>>>(
-        rays, tab, grad_features, grad_embeddings, first ? staged_rows : 0, tiles, l0, l1, workspace, priv_rows,
-        kPrivCopies);
+    if (first && !kLegacyHashed) {
+      // a table that fits L2 as ONE group: give its hashed levels a pair launch of their own when there are
+      // enough of them to pay for the second pass over the points (measured, proposal backward: 8 levels with
+      // 5 hashed 0.804 -> 0.761 ms, 6 levels with 3 hashed 0.523 -> 0.551 ms, so the latter stays one launch)
+      int nd = 0;
+      while (nd < tab.L && hl.dense[nd]) ++nd;
+      if (nd > 0 && nd < l1 && l1 - nd >= 5) l1 = nd;
+    }
+    bool hashed_only = !kLegacyHashed;
+    for (int l = l0; l < l1; ++l) hashed_only = hashed_only && !hl.dense[l];
+    if (hashed_only) {  // two lanes per interval
+      const int tiles2 = (int)div_up(rays.N * rays.S, kPairIv);
+      k_encode_bwd_hashed_pair<C><<<blocks_pair < tiles2 ? blocks_pair : tiles2, kEncThreads, 0, st>>>(
+          rays, tab, grad_features, grad_embeddings, tiles2, l0, l1);
+    } else {
+      k_encode_bwd<C><<<first ? blocks_staged : blocks_plain, kEncThreads, first ? smem : 0, st>>>(
+          rays, tab, grad_features, grad_embeddings, first ? staged_rows : 0, tiles, l0, l1, workspace, priv_rows,
+          kPrivCopies);
+    }
     if (int e = nlb_check_launch("encode_backward")) return e;
     l0 = l1;
   }
