@@ -42,16 +42,17 @@ ALG_BYTES = {
 }
 ADAM_BYTES_PER_PARAM = 32  # p,g,m,v read + p,m,v,g written
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per ABI call from the committed `ncu --set full`
-# capture of this workload (profiles/r1_s12_kernels_full.txt).  Far below the algorithmic bytes wherever a table
-# (or one level group of it) stays L2-resident: the algorithmic figure counts every corner gather /
+# captures of this workload (profiles/r1_s14_kernels_full.txt, r1_s14_fwd_kernels_full.txt; the 6-level proposal
+# forward and the Adam pass from r1_s12_kernels_full.txt).  Far below the algorithmic bytes wherever a table (or
+# one level group of it) stays L2-resident: the algorithmic figure counts every corner gather /
 # read-modify-write as HBM traffic.
 NCU_DRAM_BYTES = {
-    'nerf_encode_fwd': 1.8594e9 + 122.8e6,
-    'nerf_encode_bwd': (120.4 + 157.3 + 157.5 + 112.3) * 1e6 + (5.4 + 61.5 + 131.3 + 5.7) * 1e6,  # four level groups
+    'nerf_encode_fwd': (95.7 + 198.1 + 234.7) * 1e6 + (61.0 + 14.6 + 18.4) * 1e6,                 # three level groups
+    'nerf_encode_bwd': (120.3 + 156.9 + 156.9 + 112.2) * 1e6 + (6.3 + 61.6 + 158.3 + 4.2) * 1e6,  # four level groups
     'prop6_fwd': 40.3e6 + 42.8e6,
-    'prop8_fwd': 58.0e6 + 64.4e6,
-    'prop6_bwd': 107.3e6 + 3.9e6 + 18.4e6,   # scatter + proposal-MLP backward
-    'prop8_bwd': 129.7e6 + 3.9e6 + 23.6e6,
+    'prop8_fwd': 58.1e6 + 62.6e6,
+    'prop6_bwd': 107.3e6 + 4.6e6 + 18.4e6,                      # scatter + proposal-MLP backward
+    'prop8_bwd': (95.5 + 4.6) * 1e6 + (128.6 + 4.0) * 1e6 + 23.6e6,  # dense launch + hashed pair launch + MLP backward
     'adam_table': (0.9604 + 0.1730 + 0.1057 + 0.9026 + 0.1170 + 0.0482) * 1e9 / 3.0,
 }
 
