@@ -215,8 +215,9 @@ __device__ __forceinline__ SamplePoint sample_point(const RayGeom& r, float t0, 
   float sn, cs;
   sincosf(deg, &sn, &cs);
   float rt = __fmul_rn(r.radius, t);
-  float lx = __fdiv_rn(__fmul_rn(rt, cs), 2.0f);
-  float ly = __fdiv_rn(__fmul_rn(rt, sn), 2.0f);
+  // x / 2 is written x * 0.5f throughout: the same correctly rounded value without the IEEE-division sequence
+  float lx = __fmul_rn(__fmul_rn(rt, cs), 0.5f);
+  float ly = __fmul_rn(__fmul_rn(rt, sn), 0.5f);
   float mx = fmaf(lx, r.bxx, fmaf(ly, r.byx, t * r.dx)) + r.ox;
   float my = fmaf(lx, r.bxy, fmaf(ly, r.byy, t * r.dy)) + r.oy;
   float mz = fmaf(lx, r.bxz, fmaf(ly, r.byz, t * r.dz)) + r.oz;
@@ -235,10 +236,10 @@ __device__ __forceinline__ SamplePoint sample_point(const RayGeom& r, float t0, 
   }
   SamplePoint p;
   // /2 (contract [-2,2] -> [-1,1]) then (x + 1) / 2
-  p.x = __fdiv_rn(__fadd_rn(__fdiv_rn(mx, 2.0f), 1.0f), 2.0f);
-  p.y = __fdiv_rn(__fadd_rn(__fdiv_rn(my, 2.0f), 1.0f), 2.0f);
-  p.z = __fdiv_rn(__fadd_rn(__fdiv_rn(mz, 2.0f), 1.0f), 2.0f);
-  p.std = __fdiv_rn(sd, 2.0f);
+  p.x = __fmul_rn(__fadd_rn(__fmul_rn(mx, 0.5f), 1.0f), 0.5f);
+  p.y = __fmul_rn(__fadd_rn(__fmul_rn(my, 0.5f), 1.0f), 0.5f);
+  p.z = __fmul_rn(__fadd_rn(__fmul_rn(mz, 0.5f), 1.0f), 0.5f);
+  p.std = __fmul_rn(sd, 0.5f);
   return p;
 }
 
