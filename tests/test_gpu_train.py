@@ -141,13 +141,17 @@ def test_fused_mlp_sees_updated_weights():
 
 def test_graphed_step_matches_eager():
     """Trainer.train_step_graphed (one CUDA graph per step) against the eager step on
-    the same batches and injected random draws, over a learning-rate / anneal change."""
+    the same batches and injected random draws, over a learning-rate / anneal change.
+    Two runs of the SAME schedule already differ: the order of the scatter's atomics moves table gradients by
+    ulps, the bf16 rounding of the MLP operands turns that into 2^-9 jumps of single activations, and Adam's
+    normalised steps turn near-zero gradients of either sign into +-lr.  So the graphed run is held to the
+    noise floor measured between two eager runs (plus loose absolute caps), not to tuned constants."""
     from nerf_lidar_b200 import configs, models, train
     B = 1024
     cfg = configs.nuscenes_single()
     sd = {k: v.cuda() for k, v in synthetic.init_state_dict(seed=5, table_std=0.1).items()}
     trainers = []
-    for _ in range(2):
+    for _ in range(3):   # eager, graphed, eager again (the noise floor)
         model = models.Model(cfg, training=True).cuda()
         model.load_state_dict(sd, strict=False)
         trainers.append(train.Trainer(model, cfg))
@@ -158,9 +162,14 @@ def test_graphed_step_matches_eager():
         step = 6000 + 700 * i   # anneal, learning rate and bias corrections all move between steps
         a = trainers[0].train_step(batches[i % 2], step, 0, rins[i % 2])
         b = trainers[1].train_step_graphed(batches[i % 2], step, 0, rins[i % 2])
+        trainers[2].train_step(batches[i % 2], step, 0, rins[i % 2])
         for k in a:
             assert abs(float(a[k]) - float(b[k])) <= 2e-3 * max(abs(float(a[k])), 1e-3), (i, k, float(a[k]), float(b[k]))
-    for (na, pa), (nb, pb) in zip(trainers[0].model.named_parameters(), trainers[1].model.named_parameters()):
-        # Adam's normalised steps amplify atomics-order noise on near-zero gradients: compare the bulk
-        diff = (pa - pb).abs().reshape(-1)
-        assert float(diff.mean()) <= 2e-4 and float((diff > 5e-3).float().mean()) < 1e-2, (na, float(diff.mean()), float(diff.max()))
+    params = [dict(t.model.named_parameters()) for t in trainers]
+    for name, pa in params[0].items():
+        graphed = (pa - params[1][name]).abs().reshape(-1)
+        floor = (pa - params[2][name]).abs().reshape(-1)
+        mean_g, mean_f = float(graphed.mean()), float(floor.mean())
+        far_g, far_f = float((graphed > 5e-3).float().mean()), float((floor > 5e-3).float().mean())
+        assert mean_g <= 2 * mean_f + 5e-5 and mean_g <= 1e-3, (name, mean_g, mean_f, float(graphed.max()))
+        assert far_g <= 2 * far_f + 5e-3 and far_g < 5e-2, (name, far_g, far_f)
