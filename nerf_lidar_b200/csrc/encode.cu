@@ -5,14 +5,17 @@
 // -> coord.contract_mean_std and /2 (coord.py:51-63, models.py:968-973) ->
 // GridEncoder (gridencoder.cu kernel_grid, outputs [L,B,C] + permute copy) ->
 // erf re-weighting and mean over the 7 samples (models.py:974-977).
-// Here a thread owns one interval: its 7 sample points are generated once into shared
-// memory (or, in the backward of a training step, read back from the forward's cache) and
-// the levels are walked with rolled loops; the only HBM traffic is tdist + ray parameters
-// in, table gathers / reductions, and features[N*S, L*C] (or the proposal density) out.
-// Lanes of a warp are consecutive intervals of the same ray, so coarse-level gathers
-// coalesce in L1 and coarse-level reductions aggregate across the warp.  Forward: one
-// launch over all levels.  Backward (scatter): persistent blocks, level groups sized to
-// L2 -- see k_encode_bwd.
+// Here one interval (7 sample points) belongs to a LANE PAIR in the forward kernels and in the scatter of
+// hashed level groups (lane h takes the four corners at x + h of every cell: the pair's two addresses of one
+// load / reduction instruction share a 128-byte line, see k_prop_fwd_pair), and to one thread in the scatter
+// of dense levels (warp aggregation over runs of equal cells along the ray).  The sample points are
+// generated once into shared memory (or, in the backward of a training step, read back from the forward's
+// cache) and the levels are walked with rolled loops; the only HBM traffic is tdist + ray parameters in,
+// table gathers / reductions, and features[N*S, L*C] (or the proposal density) out.  Lanes of a warp are
+// consecutive intervals of the same ray, so coarse-level gathers coalesce in L1 and coarse-level reductions
+// aggregate across the warp.  Forward: one launch per L2-sized level group.  Backward (scatter): persistent
+// blocks, level groups sized to L2 -- see k_encode_bwd.  The one-lane-per-interval forward kernels
+// (k_encode_fwd, k_prop_fwd) are kept for A/B timing (NLB_ENC_FWD_LEGACY / NLB_PROP_FWD_LEGACY).
 #include <stdlib.h>
 #include "common.cuh"
 #include "../../include/nlb200.h"
