@@ -354,6 +354,12 @@ def _forward_chunk(model, rand, chunk, train_frac, return_weights=False):
             lib.nlb_set_dynamic_scalars(None)
         entry = cache[key] = (graph, static, outputs)
     graph, static, outputs = entry
+    # the graph reads the NerfMLP's packed bf16 operand images, which are refreshed OUTSIDE it: repack (in place,
+    # same buffer) when the parameters changed since the last pack -- optimizer steps, load_state_dict
+    from . import ops
+    for m in model.modules():
+        if hasattr(m, '_nlb_packed'):
+            ops.nerf_mlp_pack(m)
     for k, v in chunk.items():
         static[k].copy_(v, non_blocking=True)
     graph.replay()

@@ -412,7 +412,12 @@ class Trainer:
         _lib.check(lib.nlb_adam_step(self.flat.data_ptr(), self.flat_grad.data_ptr(), self.flat_m.data_ptr(),
                                      self.flat_v.data_ptr(), self.flat.numel(), float(self.lr(step)), c.adam_beta1,
                                      c.adam_beta2, c.adam_eps, int(step), 1.0 / self.world, _lib.stream()))
-        # the dense parameters changed through raw pointers: the packed tensor-core operand images are stale
+        self._mark_packed_stale()
+
+    def _mark_packed_stale(self):
+        """The dense parameters changed through raw pointers (torch's version counters do not see it): the
+        packed tensor-core operand images are stale.  Called by the optimizer pass and after every REPLAY of a
+        captured step -- a replay runs the optimizer kernels but none of this Python."""
         for m in self.model.modules():
             if hasattr(m, '_nlb_dirty'):
                 m._nlb_dirty = True
@@ -518,4 +523,5 @@ class Trainer:
             late = parallel.allreduce_grads_async([t['grad'] for t in self._prop_tables()] + [self.flat_grad])
             parallel.wait_all(early + late)
             g_opt.replay()
+        self._mark_packed_stale()
         return captured
