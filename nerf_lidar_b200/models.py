@@ -329,18 +329,24 @@ def _forward_chunk(model, rand, chunk, train_frac, return_weights=False):
     from . import _lib
     dev = first.device
     key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(chunk.items()))
+    # a graph holds raw parameter pointers: in-place updates (optimizer, load_state_dict) are seen at replay time,
+    # re-allocated storage (model.to(...), re-assigned parameters) invalidates every captured graph
+    storage = tuple(p.data_ptr() for p in model.parameters())
+    if model.__dict__.get('_render_storage') != storage:
+        model.__dict__['_render_storage'] = storage
+        model.__dict__['_render_graphs'] = {}
+        model.__dict__['_render_dyn'] = torch.zeros(4, device=dev)
     cache = model.__dict__.setdefault('_render_graphs', {})
-    dyn = model.__dict__.get('_render_dyn')
-    if dyn is None:
-        dyn = model.__dict__['_render_dyn'] = (torch.zeros(4, device=dev), torch.zeros(4).pin_memory())
+    dyn = model.__dict__['_render_dyn']
     slope = model.anneal_slope
-    dyn[1][0] = (slope * train_frac) / ((slope - 1) * train_frac + 1) if slope > 0 else 1.
-    dyn[0].copy_(dyn[1], non_blocking=True)
+    # by value at enqueue time (a pinned staging buffer would be overwritten by the next call while this one's
+    # copies are still queued)
+    dyn[0:1].fill_(float((slope * train_frac) / ((slope - 1) * train_frac + 1) if slope > 0 else 1.))
     entry = cache.get(key)
     lib = _lib.load()
     if entry is None:
         static = {k: v.clone() for k, v in chunk.items()}
-        lib.nlb_set_dynamic_scalars(dyn[0].data_ptr())
+        lib.nlb_set_dynamic_scalars(dyn.data_ptr())
         try:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))

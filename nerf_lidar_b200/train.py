@@ -444,9 +444,11 @@ class Trainer:
         anneal = (slope * train_frac) / ((slope - 1) * train_frac + 1) if slope > 0 else 1.
         out2 = (C.c_float * 2)()
         _lib.check(_lib.load().nlb_adam_bias_terms(float(self.lr(step)), c.adam_beta1, c.adam_beta2, int(step), out2))
-        st = self._static
-        st['dyn_host'][0], st['dyn_host'][1], st['dyn_host'][2] = float(anneal), float(out2[0]), float(out2[1])
-        st['dyn'].copy_(st['dyn_host'], non_blocking=True)
+        # fill_ passes the value as a kernel argument at enqueue time.  (An asynchronous copy from ONE pinned
+        # staging buffer reads it when the copy executes: the host runs many replayed steps ahead of the device
+        # and would overwrite the scalars of a step that has not started yet.)
+        for i, v in enumerate((anneal, out2[0], out2[1])):
+            self._static['dyn'][i:i + 1].fill_(float(v))
 
     def train_step_graphed(self, batch: Dict[str, torch.Tensor], step: int, num_patch: Optional[int] = None,
                            rand_inputs=None) -> Dict[str, torch.Tensor]:
@@ -463,7 +465,7 @@ class Trainer:
         key = (self._regime(step), num_patch, tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.items())),
                rand_inputs is not None)
         if self._static is None:
-            self._static = dict(dyn=torch.zeros(4, device=dev), dyn_host=torch.zeros(4).pin_memory())
+            self._static = dict(dyn=torch.zeros(4, device=dev))
         st = self._static
         if st.get('batch_key') != key[2]:
             st['batch'] = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in batch.items()}

@@ -185,6 +185,40 @@ def test_encode_ragged_sizes(n_rays, S, full_state_dict_visible):
         assert_close(enc.embeddings.grad, want_ge, 2e-5, pre + 'table gradient')
 
 
+@pytest.mark.parametrize('C,L,log2', [(2, 7, 15), (8, 4, 14), (1, 5, 12)])
+def test_encode_other_level_dims(C, L, log2):
+    """The fused encode for tables the static zipnerf path does not use: level_dim 2 (ObjMLP's L7 x C2 grid,
+    models.py:878), level_dim 8, an odd level count; small hash maps so that most levels are hashed (the L7
+    table takes the pair-lane scatter launch, the others the mixed dense + hashed one).  Forward on the
+    kernel's points and the table gradient against the oracle, ragged row count."""
+    from nerf_lidar_b200 import ops
+    from nerf_lidar_b200.gridencoder import GridEncoder
+    n_rays, S = 53, 9
+    batch, _, _ = _setup(17, S, True)
+    batch = _slice_batch(batch, n_rays)
+    g0 = torch.Generator().manual_seed(100 * C + L)
+    s = torch.sort(torch.rand(n_rays, S + 1, generator=g0), -1).values
+    t = zo.s_to_t(s, batch['near'], batch['far'])
+    deg = torch.rand(n_rays, S, 7, generator=g0)
+    enc = GridEncoder(input_dim=3, num_levels=L, level_dim=C, base_resolution=16, log2_hashmap_size=log2).cuda()
+    with torch.no_grad():
+        enc.embeddings.copy_(torch.rand(enc.embeddings.shape, generator=g0) * 2 - 1)
+    emb, offs, gs = enc.embeddings.detach().cpu(), enc.offsets.cpu(), enc.grid_sizes.cpu()
+    rays = ops.RayBundle({k: v.cuda() for k, v in batch.items()})
+    pts = ops.sample_points(t.cuda(), deg.cuda(), rays).cpu()
+    feat = ops.nerf_encode(t.cuda(), deg.cuda(), enc, rays, 0.35)
+    assert feat.shape == (n_rays * S, L * C)
+    want = _oracle_features_from_points(pts, emb, offs, gs, C)
+    assert_close(feat.reshape(n_rays, S, L * C), want, 1e-5, 'features')
+    g = torch.randn(n_rays * S, L * C, generator=g0)
+    feat.backward(g.cuda())
+    g_pts = g.reshape(n_rays, S, 1, L, C).expand(n_rays, S, 7, L, C)
+    wj = torch.erf(1 / torch.clamp(torch.sqrt(8 * pts[..., 3][..., None] ** 2 * gs ** 2), min=1e-10))
+    g_lbc = (g_pts * wj[..., None] / 7).reshape(-1, L, C).permute(1, 0, 2).contiguous()
+    want_ge, _ = go.grid_encode_backward(g_lbc, pts[..., :3].reshape(-1, 3), emb, offs, 1.0, 16)
+    assert_close(enc.embeddings.grad, want_ge, 2e-5, 'table gradient')
+
+
 def test_encode_adjoint_at_bench_size(full_state_dict_visible):
     """Size-independent property at BASELINE's full size (10 240 rays): the fused encode is
     linear in the table, so <g, F(e)> = <F^T g, e> must hold for the forward / scatter pair."""

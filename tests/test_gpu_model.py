@@ -144,6 +144,19 @@ def test_render_image_chunked_equals_single_pass():
             a, b = out[k].reshape(n, -1), rend[-1][k].reshape(n, -1)
             assert float((a - b).abs().max()) <= 1e-3 * float(b.abs().max() + 1e-30), (train_frac, k)
     assert len(model._render_graphs) == 2          # chunk shapes: 16384 rays (twice) and 1920 rays
+    # new weights in the same model (load_state_dict / training between renders): the replayed graphs must see
+    # them, incl. the NerfMLP's packed bf16 operand images that are refreshed outside the graph
+    with torch.no_grad():
+        for name, p in model.nerf_mlp.named_parameters():
+            if p.ndim == 2 and 'embeddings' not in name:
+                p.mul_(0.8)
+    out = models.render_image(model, None, sweep, False, cfg, image=False, verbose=False)
+    with torch.no_grad():
+        rend, _ = model(False, sweep, 1.0, True)
+    assert len(model._render_graphs) == 2
+    for k in ('rgb', 'semantic', 'intensity'):
+        a, b = out[k].reshape(n, -1), rend[-1][k].reshape(n, -1)
+        assert float((a - b).abs().max()) <= 1e-3 * float(b.abs().max() + 1e-30), ('new weights', k)
     img = {k: v[:60 * 40].reshape(60, 40, *v.shape[1:]) for k, v in sweep.items()}
     out = models.render_image(model, None, img, False, cfg, image=True, verbose=False)
     assert out['rgb'].shape == (60, 40, 3) and out['depth'].shape[:2] == (60, 40)
