@@ -157,3 +157,28 @@ print('ok', errs)
     env = dict(os.environ, TORCHDYNAMO_DISABLE='1')
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and 'ok' in r.stdout, (r.stdout[-800:], r.stderr[-2500:])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not present')
+def test_state_dict_layout_equals_the_reference_model():
+    """Checkpoint compatibility: the drop-in Model and the reference's own Model
+    (Z/internal/models.py, built through oracle/ref_shims.py with the gin bindings of nuscenes_single.gin, static
+    scene) expose the same state_dict keys with the same shapes and dtypes, parameters and buffers alike."""
+    code = (
+        "import sys, warnings; warnings.filterwarnings('ignore');"
+        f"sys.path.insert(0, {ROOT!r});"
+        "from oracle import ref_shims;"
+        "ref_models = ref_shims.import_reference(); ref_shims.apply_gin_bindings(ref_models);"
+        "ref = ref_models.Model(config=ref_shims.RefConfig()).state_dict();"
+        "from nerf_lidar_b200 import configs, models;"
+        "ours = models.Model(configs.nuscenes_single()).state_dict();"
+        "a = {k: (tuple(v.shape), v.dtype) for k, v in ref.items()};"
+        "b = {k: (tuple(v.shape), v.dtype) for k, v in ours.items()};"
+        "assert a == b, (sorted(set(a) ^ set(b)), [(k, a[k], b[k]) for k in a if k in b and a[k] != b[k]]);"
+        "ours_model = models.Model(configs.nuscenes_single());"
+        "assert len(a) == 38 and sum(p.numel() for p in ours_model.parameters()) == 77656777;"
+        "print('ok')"
+    )
+    env = dict(os.environ, TORCHDYNAMO_DISABLE='1')
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and 'ok' in r.stdout, r.stderr[-2000:]
