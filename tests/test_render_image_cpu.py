@@ -110,3 +110,53 @@ def _worker(rank, world, port, n, chunk):
 @pytest.mark.parametrize('n,chunk', [(257, 50), (34688, 16384)])
 def test_sharded_render_world2(n, chunk):
     mp.spawn(_worker, args=(2, _free_port(), n, chunk), nprocs=2, join=True)
+
+
+REF = '/root/reference/NeRF_LiDAR/zipnerf'
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not present')
+def test_same_result_as_the_reference_render_image():
+    """The reference's OWN render_image (Z/internal/models.py:1379-1507, imported through oracle/ref_shims.py)
+    and this build's, driven with the same stub model, rays and RNG seed: identical leaves, ray_* bundles
+    included, for the flat LiDAR layout and the [H, W] image layout."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f'''
+import sys, contextlib, warnings
+warnings.filterwarnings('ignore')
+sys.path.insert(0, {root!r})
+import torch
+from oracle import ref_shims
+ref_models = ref_shims.import_reference()
+from nerf_lidar_b200 import models
+from tests.test_render_image_cpu import _StubModel, _batch, _cfg
+
+
+class Acc:
+    process_index, num_processes, is_main_process = 0, 1, True
+    autocast = staticmethod(contextlib.nullcontext)
+    gather = staticmethod(lambda v: v)
+
+
+for n, chunk, image in ((257, 100, False), (9 * 13, 64, True)):
+    cfg = _cfg(chunk)
+    b = _batch(n)
+    if image:
+        b = {{k: (v.reshape(9, 13, -1) if v is not None else None) for k, v in b.items()}}
+    torch.manual_seed(3)
+    want = ref_models.render_image(_StubModel(cfg), Acc(), dict(b), False, cfg, train_frac=0.5, verbose=False, image=image)
+    torch.manual_seed(3)
+    got = models.render_image(_StubModel(cfg), None, dict(b), False, cfg, train_frac=0.5, verbose=False, image=image)
+    assert sorted(got) == sorted(want), (sorted(got), sorted(want))
+    for k, v in want.items():
+        if isinstance(v, list):
+            assert len(got[k]) == len(v) and all(torch.equal(x, y) for x, y in zip(got[k], v)), k
+        else:
+            assert got[k].shape == v.shape and torch.equal(got[k], v), (k, got[k].shape, v.shape)
+print('ok')
+'''
+    env = dict(os.environ, TORCHDYNAMO_DISABLE='1')
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert r.returncode == 0 and 'ok' in r.stdout, r.stdout[-500:] + r.stderr[-3000:]
