@@ -30,6 +30,37 @@ def test_reference_grid_py_binds_to_our_backend():
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not present')
+def test_grid_encoder_module_equals_the_reference_module():
+    """gridencoder.GridEncoder of this build against the reference's own class (Z/gridencoder/grid.py:96-146) for
+    the three tables of nuscenes_single.gin and an ObjMLP-shaped one: every attribute callers read
+     and the offsets / idx / grid_sizes buffers, value for value."""
+    code = (
+        "import sys, warnings, torch; warnings.filterwarnings('ignore');"
+        f"sys.path.insert(0, {os.path.join(ROOT, 'nerf_lidar_b200')!r}); sys.path.insert(0, {REF!r});"
+        "import gridencoder.grid as ref;"
+        f"sys.path.insert(0, {ROOT!r});"
+        "from nerf_lidar_b200.gridencoder.grid import GridEncoder as Ours;"
+        "cases = [dict(num_levels=6, level_dim=1, desired_resolution=512, log2_hashmap_size=21),"
+        "         dict(num_levels=8, level_dim=1, desired_resolution=2048, log2_hashmap_size=21),"
+        "         dict(num_levels=10, level_dim=4, desired_resolution=8192, log2_hashmap_size=21),"
+        "         dict(num_levels=7, level_dim=2, desired_resolution=1024, log2_hashmap_size=19)];\n"
+        "for kw in cases:\n"
+        "    a, b = ref.GridEncoder(3, base_resolution=16, **kw), Ours(3, base_resolution=16, **kw)\n"
+        "    for name in ('input_dim', 'num_levels', 'level_dim', 'per_level_scale', 'log2_hashmap_size', 'base_resolution',"
+        "                 'output_dim', 'gridtype', 'gridtype_id', 'interpolation', 'interp_id', 'align_corners', 'init_std', 'max_params'):\n"
+        "        assert getattr(a, name) == getattr(b, name), (kw, name, getattr(a, name), getattr(b, name))\n"
+        "    for name in ('offsets', 'idx', 'grid_sizes'):\n"
+        "        x, y = getattr(a, name), getattr(b, name)\n"
+        "        assert x.dtype == y.dtype and torch.equal(x, y), (kw, name)\n"
+        "    assert a.embeddings.shape == b.embeddings.shape and float(b.embeddings.abs().max()) <= b.init_std\n"
+        "    assert [k for k, _ in a.named_buffers()] == [k for k, _ in b.named_buffers()]\n"
+        "print('ok')"
+    )
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'ok' in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not present')
 def test_golden_fixtures_reproduce_from_the_live_reference():
     """Re-runs the reference's own Model.forward (tests/golden/make_golden.py) and checks that the
     committed golden fixtures are what it produces today, and the oracle against a FRESH case
