@@ -1,9 +1,10 @@
-"""Dev tool (CPU): how often do consecutive multisamples of an interval fall into the same grid cell?
+"""Analysis script (CPU; lives under tests/ because it runs the oracle, which only test infrastructure may
+import): how often do consecutive multisamples of an interval fall into the same grid cell?
 Runs the oracle forward on the bench's synthetic rays and reports, per table and level, the share of
 (interval, j >= 1) samples whose cell equals that of sample j - 1 (lane level) and the share of
 (32-interval warp, j >= 1) steps where that holds for every lane (warp level) -- the upper bound of what
 re-using the 8 gathered corner rows across samples can save in the fused forward kernels.
-  python tools/cell_sharing.py [rays]"""
+  python tests/analysis_cell_sharing.py [rays]"""
 import os, sys
 os.environ.setdefault('TORCHDYNAMO_DISABLE', '1')
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
