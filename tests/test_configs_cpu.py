@@ -93,3 +93,24 @@ for f in dataclasses.fields(configs.Config):
 assert not bad, bad
 print('ok')
 ''')
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not present')
+def test_schedules_match_the_reference_math():
+    """train.learning_rate_decay / log_lerp against Z/internal/math.py:41-86 over the whole run (the gin's
+    lr_init 0.01 -> lr_final 0.001 with the 5000-step delay)."""
+    _run('''
+import importlib, math, sys
+sys.path.insert(0, '/root/reference/NeRF_LiDAR/zipnerf')
+rm = importlib.import_module('internal.math')
+from nerf_lidar_b200 import configs, train
+c = configs.nuscenes_single()
+for step in list(range(0, 200)) + list(range(200, 25001, 137)) + [25000, 30000]:
+    want = float(rm.learning_rate_decay(step, c.lr_init, c.lr_final, c.max_steps, c.lr_delay_steps, c.lr_delay_mult))
+    got = train.learning_rate_decay(step, c.lr_init, c.lr_final, c.max_steps, c.lr_delay_steps, c.lr_delay_mult)
+    assert abs(got - want) <= 1e-12 * max(abs(want), 1e-30), (step, got, want)
+    assert abs(train.learning_rate_decay(step, 1e-2, 1e-3, 25000) - float(rm.learning_rate_decay(step, 1e-2, 1e-3, 25000))) <= 1e-15
+for t in (-0.5, 0., 0.3, 1., 1.7):
+    assert abs(train.log_lerp(t, 0.03, 0.003) - float(rm.log_lerp(t, 0.03, 0.003))) <= 1e-15
+print('ok')
+''')
