@@ -171,5 +171,7 @@ def test_graphed_step_matches_eager():
         floor = (pa - params[2][name]).abs().reshape(-1)
         mean_g, mean_f = float(graphed.mean()), float(floor.mean())
         far_g, far_f = float((graphed > 5e-3).float().mean()), float((floor > 5e-3).float().mean())
-        assert mean_g <= 2 * mean_f + 5e-5 and mean_g <= 1e-3, (name, mean_g, mean_f, float(graphed.max()))
-        assert far_g <= 2 * far_f + 5e-3 and far_g < 5e-2, (name, far_g, far_f)
+        # (a step that is skipped or applied twice moves every entry by ~lr = 1e-2: 25x these bounds; observed
+        # noise: mean 2e-4, 1 % of the entries beyond 5e-3, with run-to-run jumps of the same size)
+        assert mean_g <= 3 * mean_f + 1e-4 and mean_g <= 1e-3, (name, mean_g, mean_f, float(graphed.max()))
+        assert far_g <= 3 * far_f + 1e-2 and far_g < 5e-2, (name, far_g, far_f)
