@@ -789,7 +789,8 @@ __global__ void __launch_bounds__(kEncThreads) k_prop_fwd_pair(nlb_rays_t rays, 
     }
     acc += __shfl_xor_sync(NLB_FULL_MASK, acc, 1);
     if (h == 0) s_f[l][iv] = acc / 7.0f;
-    // the next level's s_w writes race with nothing: both lanes passed the shuffle above
+    // the next level may overwrite s_w: every lane has passed the warp-wide shuffle above, i.e. has finished
+    // reading this level's weights
   }
   __syncwarp();
   float f[L];
