@@ -98,3 +98,28 @@ def test_argument_errors_are_reported_before_any_launch():
     # workspace queries are pure host arithmetic
     assert lib.nlb_encode_backward_workspace_bytes(ctypes.byref(tab_ok)) >= 0
     assert lib.nlb_prop_backward_workspace_bytes(4, 8, ctypes.byref(tab_ok)) > 0
+
+
+def test_gridencoder_backend_checks_like_the_reference_binding():
+    """nerf_lidar_b200/_gridencoder.py = the module Z/gridencoder/grid.py imports as `_gridencoder`: the same three
+    functions with the argument order of bindings.cpp:5-9, and the CHECK_CUDA / CHECK_CONTIGUOUS / CHECK_IS_*
+    guards of gridencoder.cu:15-18 as RuntimeError (this is what a CPU box can exercise of them)."""
+    import inspect
+    import torch
+    from nerf_lidar_b200 import _gridencoder as be
+    assert list(inspect.signature(be.grid_encode_forward).parameters) == [
+        'inputs', 'embeddings', 'offsets', 'outputs', 'B', 'D', 'C', 'L', 'S', 'H', 'dy_dx', 'gridtype',
+        'align_corners', 'interp']
+    assert list(inspect.signature(be.grid_encode_backward).parameters) == [
+        'grad', 'inputs', 'embeddings', 'offsets', 'grad_embeddings', 'B', 'D', 'C', 'L', 'S', 'H', 'dy_dx',
+        'grad_inputs', 'gridtype', 'align_corners', 'interp']
+    assert list(inspect.signature(be.grad_total_variation).parameters) == [
+        'inputs', 'embeddings', 'grad', 'offsets', 'weight', 'B', 'D', 'C', 'L', 'S', 'H', 'gridtype', 'align_corners']
+    x, emb = torch.zeros(8, 3), torch.zeros(64, 2)
+    offs, out = torch.zeros(3, dtype=torch.int32), torch.zeros(2, 8, 2)
+    with pytest.raises(RuntimeError, match='must be a CUDA tensor'):
+        be.grid_encode_forward(x, emb, offs, out, 8, 3, 2, 2, 1.0, 16, None, 0, False, 0)
+    with pytest.raises(RuntimeError, match='must be a CUDA tensor'):
+        be.grid_encode_backward(out, x, emb, offs, torch.zeros_like(emb), 8, 3, 2, 2, 1.0, 16, None, None, 0, False, 0)
+    with pytest.raises(RuntimeError, match='must be a CUDA tensor'):
+        be.grad_total_variation(x, emb, torch.zeros_like(emb), offs, 1.0, 8, 3, 2, 2, 1.0, 16, 0, False)
