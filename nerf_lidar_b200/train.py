@@ -339,6 +339,9 @@ class Trainer:
         main = sum(v for k, v in losses.items() if k not in self.PROP_LOSSES)
         prop = [v for k, v in losses.items() if k in self.PROP_LOSSES]
         prop = sum(prop) if prop else None
+        # values only from here on: the returned dictionary must not keep the autograd graph (and with it the
+        # AccumulateGrad nodes, which are bound to the stream of their first use) alive across steps / captures
+        losses = {k: v.detach() for k, v in losses.items()}
         total = main.detach() if prop is None else main.detach() + prop.detach()
         if 'hash_decay' in renderings[-1]:
             # value only (its gradient is fused into Adam); cloned because the optimizer pass
@@ -470,6 +473,7 @@ class Trainer:
         if st.get('batch_key') != key[2]:
             st['batch'] = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in batch.items()}
             st['batch_key'] = key[2]
+            st.pop('rand', None)
             self._graphs.clear()
         for k, v in batch.items():
             st['batch'][k].copy_(v, non_blocking=True)
@@ -493,6 +497,7 @@ class Trainer:
                 with torch.cuda.stream(s):
                     out = self.train_step(st['batch'], step, num_patch, srand)
                 torch.cuda.current_stream(dev).wait_stream(s)
+                out = {k: v.clone() for k, v in out.items()}
                 g = torch.cuda.CUDAGraph()
                 g_prop = g_opt = None
                 if self.world == 1:

@@ -45,3 +45,36 @@ def assert_close(a, b, rtol, name='', atol=0.0):
     err = np.abs(a.astype(np.float64) - b.astype(np.float64)).max()
     assert err <= rtol * scale + atol, f'{name}: max|d|={err:.3e} scale={scale:.3e} (rtol {rtol})'
     return err / scale
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def poisoned_empty(enable=True):
+    """torch.empty / torch.empty_like return NaN-filled (floating) or 0x7f-filled (integer) tensors: a kernel that
+    reads a byte it (or a predecessor) did not write shows up as a NaN / a changed result."""
+    if not enable:
+        yield
+        return
+    real_empty, real_like = torch.empty, torch.empty_like
+
+    def fill(t):
+        if t.is_floating_point():
+            t.fill_(float('nan'))
+        elif t.dtype == torch.uint8:
+            t.fill_(0x7f)
+        elif t.dtype != torch.bool:
+            t.fill_(0x7f7f7f7f if t.dtype in (torch.int32, torch.int64) else 0x7f)
+        return t
+
+    def empty(*a, **k):
+        return fill(real_empty(*a, **k))
+
+    def empty_like(*a, **k):
+        return fill(real_like(*a, **k))
+    torch.empty, torch.empty_like = empty, empty_like
+    try:
+        yield
+    finally:
+        torch.empty, torch.empty_like = real_empty, real_like
