@@ -289,7 +289,13 @@ int nlb_interlevel_loss(const float* c, const float* w, int Sc, const float* cp,
  *   g_rgb[N,3] (data), g_depth[N] (depth), g_sem[N,K] (sem), g_int[N] (int),
  *   g_depth_smo[N], g_sem_smo[N,K] (first num_patch*patch_size^2 rays: the patch rays
  *   lead the batch, Z/internal/datasets.py:356-366; the rest is left untouched).
- * Masks follow Z/train.py:300-327 (Config.instance_obj = True clears batch['mask']).
+ * Masks follow Z/train.py:286-327: `ray_valid` (NULL = every ray) is 1 where the loss applies, i.e. where the
+ * dataset's batch['mask'] is non-zero (Z/train.py:287,307: `mask = mask == 0`, `rgb_mask = mask == 0`); with
+ * Config.instance_obj = True the reference clears the mask (NULL here).  It gates the rgb / depth / semantic
+ * terms and, as edge_aware_loss_v2's `mask` (Z/internal/train_utils.py:341-348), the smoothness edges: an edge
+ * counts when both of its pixels are valid, and each direction is normalised by its number of counted edges.
+ * A patch_mask that does not lead the batch (== 1 exactly on the first num_patch*patch_size^2 rays) turns
+ * d_smo / s_smo into NaN instead of silently smoothing the wrong rays.
  */
 typedef struct {
   const float* rgb;         /* [N,3] rendered */
@@ -302,13 +308,14 @@ typedef struct {
   const float* t_intensity; /* [N] */
   const float* patch_mask;  /* [N] == 1: patch ray (smoothness only) */
   const float* lidar_mask;  /* [N] == 1: LiDAR ray */
+  const float* ray_valid;   /* [N] != 0: supervised (dataset mask, see above) or NULL = all */
   int N, K;
   int num_patch, patch_size;
   int lidar_supervision, only_lidar_supervision;
   int charb;                /* 1: Charbonnier (Config.data_loss_type = 'charb'), 0: MSE */
   float charb_padding;
   float depth_mult, sem_mult, int_mult, smooth_mult; /* 0.4|0.1|0, 0.04|0.01|0, 0.1, 0.01 (Z/train.py:330-371) */
-  float smo_scale_x, smo_scale_y; /* filled in by the library */
+  float smo_scale_x, smo_scale_y; /* unused (kept for layout compatibility): the edge counts are data-dependent */
 } nlb_losses_in_t;
 
 size_t nlb_render_losses_workspace_bytes(void);

@@ -29,7 +29,7 @@ class NlbTable(C.Structure):
 
 class NlbLossesIn(C.Structure):
     _fields_ = [(n, c_f) for n in ('rgb', 'depth', 'semantic', 'intensity', 't_rgb', 't_depth', 't_semantic',
-                                   't_intensity', 'patch_mask', 'lidar_mask')] + \
+                                   't_intensity', 'patch_mask', 'lidar_mask', 'ray_valid')] + \
                [(n, C.c_int) for n in ('N', 'K', 'num_patch', 'patch_size', 'lidar_supervision',
                                        'only_lidar_supervision', 'charb')] + \
                [(n, C.c_float) for n in ('charb_padding', 'depth_mult', 'sem_mult', 'int_mult', 'smooth_mult',

@@ -13,7 +13,7 @@
 namespace nlb {
 
 enum { S_DATA_NUM = 0, S_DATA_DEN, S_DEPTH_NUM, S_DEPTH_DEN, S_SEM_NUM, S_SEM_DEN, S_INT_NUM, S_INT_DEN,
-       S_DSMO_X, S_DSMO_Y, S_SSMO_X, S_SSMO_Y, S_THRE, kNumSums = 16 };
+       S_DSMO_X, S_DSMO_Y, S_SSMO_X, S_SSMO_Y, S_THRE, S_CNT_X, S_CNT_Y, S_LAYOUT_ERR, kNumSums = 16 };
 
 struct RayMasks {
   bool rgb, depth, sem, lidar;
@@ -22,9 +22,10 @@ struct RayMasks {
 __device__ __forceinline__ RayMasks ray_masks(const nlb_losses_in_t& in, int i) {
   const bool patch = __ldg(in.patch_mask + i) == 1.0f;
   const bool lidar = __ldg(in.lidar_mask + i) == 1.0f;
+  const bool valid = in.ray_valid == nullptr || __ldg(in.ray_valid + i) != 0.0f;
   RayMasks m;
   m.lidar = lidar;
-  m.rgb = !patch;
+  m.rgb = valid && !patch;
   m.depth = (__ldg(in.t_depth + i) > 0.f) && m.rgb;
   m.sem = in.semantic != nullptr && (__ldg(in.t_semantic + i) != 255.0f) && m.rgb;
   if (in.lidar_supervision) {
@@ -118,8 +119,21 @@ __global__ void __launch_bounds__(256) k_ray_losses(nlb_losses_in_t in, float* _
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  float cnt_x = 0.f, cnt_y = 0.f, layout_err = 0.f;
   if (i < in.N) {
     const RayMasks m = ray_masks(in, i);
+    // smoothness edges whose two pixels are valid (edge_aware_loss_v2's mask_x / mask_y), and the layout the
+    // patch kernel relies on: patch rays == the leading num_patch * P * P rows
+    const int P = in.patch_size, n_patch_rays = in.num_patch * P * P;
+    if ((i < n_patch_rays) != (__ldg(in.patch_mask + i) == 1.0f)) layout_err = 1.f;
+    if (i < n_patch_rays) {
+      auto ok = [&](int r) { return in.ray_valid == nullptr || __ldg(in.ray_valid + r) != 0.0f; };
+      const int t = i % (P * P), py = t / P, px = t - py * P;
+      if (ok(i)) {
+        if (px + 1 < P && ok(i + 1)) cnt_x = 1.f;
+        if (py + 1 < P && ok(i + P)) cnt_y = 1.f;
+      }
+    }
     // data
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -169,10 +183,19 @@ __global__ void __launch_bounds__(256) k_ray_losses(nlb_losses_in_t in, float* _
     const float t = block_sum(acc[k], s_red);
     if (threadIdx.x == 0 && t != 0.f) atomicAdd(sums + k, t);
   }
+  if (in.num_patch > 0) {
+    const float tx = block_sum(cnt_x, s_red), ty = block_sum(cnt_y, s_red), te = block_sum(layout_err, s_red);
+    if (threadIdx.x == 0) {
+      if (tx != 0.f) atomicAdd(sums + S_CNT_X, tx);
+      if (ty != 0.f) atomicAdd(sums + S_CNT_Y, ty);
+      if (te != 0.f) atomicAdd(sums + S_LAYOUT_ERR, te);
+    }
+  }
 }
 
 // ---- edge-aware smoothness on the patches (train_utils.edge_aware_loss_v2 /
-// edge_aware_loss_for_semantic with an all-ones mask): block = (patch, channel), thread =
+// edge_aware_loss_for_semantic with mask = ray_valid; launched after k_ray_losses, which counted the valid
+// edges into sums[S_CNT_X / S_CNT_Y]): block = (patch, channel), thread =
 // pixel.  channel 0 = depth (eps 1e-7), channel 1 + c = semantic class c (eps 1e-5, the
 // per-channel terms add up).  x_n = x / (mean + eps);  L = sum_edges exp(-mean_c |d rgb|)
 // |d x_n|;  dL/dx_k = q_k / (mean + eps) - (sum_i q_i x_i) / (n (mean + eps)^2).
@@ -186,6 +209,9 @@ __global__ void __launch_bounds__(1024) k_patch_smooth(nlb_losses_in_t in, float
   const int ray = patch * n + t;  // patch rays lead the batch (Z/internal/datasets.py:356-366)
   const bool is_depth = ch == 0;
   const float eps = is_depth ? 1e-7f : 1e-5f;
+  const float scale_x = 1.0f / fmaxf(sums[S_CNT_X], 1.0f), scale_y = 1.0f / fmaxf(sums[S_CNT_Y], 1.0f);
+  auto ok = [&](int r) { return in.ray_valid == nullptr || __ldg(in.ray_valid + r) != 0.0f; };
+  const bool v_c = ok(ray);
   const float x = is_depth ? __ldg(in.depth + ray) : __ldg(in.semantic + (size_t)ray * in.K + (ch - 1));
   const float mean = block_sum(x, s_red) / (float)n;
   const float inv = 1.0f / (mean + eps);
@@ -200,23 +226,23 @@ __global__ void __launch_bounds__(1024) k_patch_smooth(nlb_losses_in_t in, float
   };
   auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
   float q = 0.f, lx = 0.f, ly = 0.f;
-  if (px + 1 < P) {  // edge to the right neighbour: counted once, here
+  if (px + 1 < P && v_c && ok(ray + 1)) {  // edge to the right neighbour: counted once, here
     const float w = edge_w(ray + 1), d = xn - s_xn[t + 1];
     lx += w * fabsf(d);
-    q += w * sgn(d) * in.smo_scale_x;
+    q += w * sgn(d) * scale_x;
   }
-  if (px > 0) {
+  if (px > 0 && v_c && ok(ray - 1)) {
     const float w = edge_w(ray - 1), d = s_xn[t - 1] - xn;
-    q -= w * sgn(d) * in.smo_scale_x;
+    q -= w * sgn(d) * scale_x;
   }
-  if (py + 1 < P) {
+  if (py + 1 < P && v_c && ok(ray + P)) {
     const float w = edge_w(ray + P), d = xn - s_xn[t + P];
     ly += w * fabsf(d);
-    q += w * sgn(d) * in.smo_scale_y;
+    q += w * sgn(d) * scale_y;
   }
-  if (py > 0) {
+  if (py > 0 && v_c && ok(ray - P)) {
     const float w = edge_w(ray - P), d = s_xn[t - P] - xn;
-    q -= w * sgn(d) * in.smo_scale_y;
+    q -= w * sgn(d) * scale_y;
   }
   const float sqx = block_sum(q * x, s_red);
   const float g = q * inv - sqx * inv * inv / (float)n;
@@ -255,15 +281,19 @@ __global__ void k_finalize_losses(nlb_losses_in_t in, const float* __restrict__ 
     losses[3] = in.int_mult * (sums[S_INT_NUM] / den);
     scales[3] = in.int_mult / den;
   }
-  // smoothness: nan_to_num(0.01 * (sum_x / max(count_x, 1) + sum_y / max(count_y, 1))); the per-edge
-  // normalisation is already folded into the gradients (smo_scale_x / _y)
+  // smoothness: nan_to_num(0.01 * (sum_x / count_x + sum_y / count_y)) over the valid edges (a direction
+  // without valid edges is the reference's NaN -> 0); the per-edge normalisation is already folded into the
+  // gradients.  A patch_mask that does not lead the batch poisons both terms.
   {
-    const float v = in.smooth_mult * (sums[S_DSMO_X] * in.smo_scale_x + sums[S_DSMO_Y] * in.smo_scale_y);
-    losses[4] = fin(v) ? v : 0.f;
-    scales[4] = fin(v) ? in.smooth_mult : 0.f;
-    const float s = in.smooth_mult * (sums[S_SSMO_X] * in.smo_scale_x + sums[S_SSMO_Y] * in.smo_scale_y);
-    losses[5] = fin(s) ? s : 0.f;
-    scales[5] = fin(s) ? in.smooth_mult : 0.f;
+    const float sx = 1.0f / fmaxf(sums[S_CNT_X], 1.0f), sy = 1.0f / fmaxf(sums[S_CNT_Y], 1.0f);
+    const bool empty = sums[S_CNT_X] == 0.f || sums[S_CNT_Y] == 0.f;
+    const bool bad = sums[S_LAYOUT_ERR] != 0.f;
+    const float v = in.smooth_mult * (sums[S_DSMO_X] * sx + sums[S_DSMO_Y] * sy);
+    losses[4] = bad ? NAN : ((fin(v) && !empty) ? v : 0.f);
+    scales[4] = (fin(v) && !empty && !bad) ? in.smooth_mult : 0.f;
+    const float s = in.smooth_mult * (sums[S_SSMO_X] * sx + sums[S_SSMO_Y] * sy);
+    losses[5] = bad ? NAN : ((fin(s) && !empty) ? s : 0.f);
+    scales[5] = (fin(s) && !empty && !bad) ? in.smooth_mult : 0.f;
   }
 }
 
@@ -293,10 +323,6 @@ extern "C" int nlb_render_losses(const nlb_losses_in_t* in_, float* losses, floa
     }
     if (n_patch_rays > in.N) { nlb_set_error("render_losses: %d patch rays but N=%d", n_patch_rays, in.N); return NLB_EINVAL; }
     if (!g_depth_smo || (in.semantic && !g_sem_smo)) { nlb_set_error("render_losses: smoothness gradient buffers required"); return NLB_EINVAL; }
-    // all-ones mask: count = P h (w-1) (x edges), P (h-1) w (y edges); c = 1
-    const float P = (float)in.patch_size;
-    in.smo_scale_x = 1.0f / fmaxf((float)in.num_patch * P * (P - 1.0f), 1.0f);
-    in.smo_scale_y = in.smo_scale_x;
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(workspace, 0, kNumSums * sizeof(float), st) != cudaSuccess) return nlb_check_launch("render_losses memset");

@@ -20,7 +20,6 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import ops
 from .configs import Config, configurable
@@ -60,7 +59,6 @@ class MLP(nn.Module):
     no_sem_layer: bool = True
     re_weights: bool = True
     mlp_dtype = torch.bfloat16  # operand type of the dense layers (fp32 accumulation)
-    fused_mlp: bool = True      # NerfMLP on the fused tcgen05 kernels (False: plain torch GEMMs, dev/debug only)
 
     def __init__(self, **kwargs):
         super().__init__()
@@ -107,43 +105,43 @@ class MLP(nn.Module):
         sx = (viewdirs[..., None, :] * scales[:, None]).reshape(*viewdirs.shape[:-1], -1)
         return torch.cat([viewdirs, torch.sin(torch.cat([sx, sx + 0.5 * math.pi], dim=-1))], dim=-1)
 
+    def _check_fused_shapes(self):
+        """The fused tcgen05 kernels (csrc/nerf_mlp.cu) are compiled for ONE architecture -- the NerfMLP of
+        nuscenes_single.gin -- and take raw pointers: any gin binding that changes a layer shape or one of the
+        scalars baked into their epilogues must fail here, not read out of bounds or return wrong numbers."""
+        if getattr(self, '_nlb_shapes_ok', False):
+            return
+        want = {'density_layer.0.weight': (64, 40), 'density_layer.2.weight': (256, 64),
+                'sem_layer.0.weight': (64, 256), 'sem_layer.2.weight': (19, 64),
+                'intensity_layer.0.weight': (64, 256), 'intensity_layer.2.weight': (1, 64),
+                'lin_second_stage_0.weight': (256, 283), 'lin_second_stage_1.weight': (256, 539),
+                'rgb_layer.weight': (3, 256)}
+        have = {k: tuple(v.shape) for k, v in self.named_parameters()}
+        bad = [f'{k}: {have.get(k)} (built for {v})' for k, v in want.items() if have.get(k) != v]
+        scalars = dict(deg_view=4, net_depth_viewdirs=2, skip_layer_dir=0, density_bias=-1., rgb_premultiplier=1.,
+                       rgb_bias=0., rgb_padding=0.001, class_num=19)
+        bad += [f'{k}={getattr(self, k)!r} (built for {v!r})' for k, v in scalars.items() if getattr(self, k) != v]
+        if not (self.use_semantic and self.use_intensity) or self.no_sem_layer:
+            bad.append('the semantic (sem_layer) and intensity heads are required '
+                       '(Config.use_semantic, Config.use_intensity, Config.no_sem_layer=False)')
+        if self.mlp_dtype != torch.bfloat16:
+            bad.append(f'mlp_dtype={self.mlp_dtype} (the dense layers run with bf16 operands, fp32 accumulation)')
+        if bad:
+            raise NotImplementedError('NerfMLP: the fused tensor-core kernels are built for the nuscenes_single.gin '
+                                      'architecture only; unsupported: ' + '; '.join(bad))
+        self._nlb_shapes_ok = True
+
     def heads(self, feat: torch.Tensor, viewdirs: torch.Tensor, S: int) -> Dict[str, torch.Tensor]:
         """features[N*S, 40] -> density / rgb / semantic / intensity
-        (Z/internal/models.py:996-997,1116-1251).  Dense layers run with bf16
-        operands and fp32 accumulation (bf16 MLP is a build decision,
-        tolerance 1e-3 vs the fp32 reference); activations are evaluated in fp32."""
-        N = viewdirs.shape[0]
-        dt = self.mlp_dtype
-        if dt == torch.bfloat16 and self.use_semantic and self.use_intensity and self.fused_mlp:
-            # tcgen05 / TMEM kernels (forward; in training also the data-gradient chain)
-            if torch.is_grad_enabled():
-                return ops.nerf_mlp_train(self, feat, viewdirs, S)
-            return ops.nerf_mlp_forward(self, feat, viewdirs, S)
-
-        def lin(layer, x):
-            if dt == torch.float32:
-                return F.linear(x, layer.weight, layer.bias)
-            return F.linear(x.to(dt), layer.weight.to(dt), None).float() + layer.bias
-
-        x = lin(self.density_layer[2], torch.relu(lin(self.density_layer[0], feat)))
-        density = F.softplus(x[..., 0] + self.density_bias).reshape(N, S)
-        sem = inten = None
-        if self.use_semantic:
-            sem = torch.softmax(lin(self.sem_layer[2], torch.relu(lin(self.sem_layer[0], x))), dim=-1)
-            sem = sem.reshape(N, S, self.class_num)
-        if self.use_intensity:
-            inten = lin(self.intensity_layer[2], torch.relu(lin(self.intensity_layer[0], x))).reshape(N, S, 1)
-        de = self.dir_enc(viewdirs)
-        de = de[:, None, :].expand(N, S, de.shape[-1]).reshape(N * S, -1)
-        h_in = torch.cat([x, de], dim=-1)
-        h = h_in
-        for i in range(self.net_depth_viewdirs):
-            h = torch.relu(lin(self.get_submodule(f'lin_second_stage_{i}'), h))
-            if i == self.skip_layer_dir:
-                h = torch.cat([h, h_in], dim=-1)
-        rgb = torch.sigmoid(self.rgb_premultiplier * lin(self.rgb_layer, h) + self.rgb_bias)
-        rgb = (rgb * (1 + 2 * self.rgb_padding) - self.rgb_padding).reshape(N, S, 3)
-        return dict(density=density, rgb=rgb, semantic=sem, intensity=inten)
+        (Z/internal/models.py:996-997,1116-1251) on the tcgen05 / TMEM kernels: forward, and in training
+        also the data-gradient chain and the weight gradients.  Dense layers run with bf16 operands and fp32
+        accumulation (bf16 MLP is a build decision, tolerance 1e-3 vs the fp32
+        reference); activations are evaluated in fp32.  There is no other implementation in the product
+        (the plain-torch evaluation the parity tests compare with lives in tests/helpers.py)."""
+        self._check_fused_shapes()
+        if torch.is_grad_enabled():
+            return ops.nerf_mlp_train(self, feat, viewdirs, S)
+        return ops.nerf_mlp_forward(self, feat, viewdirs, S)
 
     def forward(self, *a, **k):
         raise NotImplementedError('MLP modules are evaluated through Model.forward (fused kernels); '

@@ -541,6 +541,10 @@ class _RenderLosses(Function):
         K = sem.shape[-1] if sem is not None else 0
         t = {k: f32(batch[k]).reshape(-1) if k != 'rgb' else f32(batch[k][..., :3])
              for k in ('rgb', 'depth', 'semantic', 'intensity', 'patch_mask', 'lidar_mask') if k in batch}
+        # Z/train.py:286-289,307: the loss applies where the dataset mask is non-zero; instance_obj clears it
+        valid = None
+        if not cfg.get('instance_obj', False) and batch.get('mask') is not None:
+            valid = f32(batch['mask']).reshape(-1)
         new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
         losses, scales = new(6), new(6)
         g_rgb, g_depth = new(N, 3), new(N)
@@ -552,7 +556,7 @@ class _RenderLosses(Function):
         ws = new(load().nlb_render_losses_workspace_bytes() // 4)
         lin = NlbLossesIn(ptr(rgb), ptr(depth), ptr(sem), ptr(inten), ptr(t['rgb']), ptr(t['depth']),
                           ptr(t.get('semantic')), ptr(t.get('intensity')), ptr(t['patch_mask']), ptr(t['lidar_mask']),
-                          N, K, num_patch, int(cfg['patch_size']), int(cfg['lidar_supervision']),
+                          ptr(valid), N, K, num_patch, int(cfg['patch_size']), int(cfg['lidar_supervision']),
                           int(cfg['only_lidar_supervision']), int(cfg['charb']), float(cfg['charb_padding']),
                           float(cfg['depth_mult']), float(cfg['sem_mult']), float(cfg['int_mult']),
                           float(cfg['smooth_mult']), 0., 0.)

@@ -135,8 +135,11 @@ def _finish(rays: Dict[str, np.ndarray], rng, lidar_mask: np.ndarray, labels: bo
         sem[rng.uniform(0, 1, n) < 0.05] = 255
         sem[lm] = 255
         b['semantic'] = sem
-        b['mask'] = lm.astype(np.float32)
         b['intensity'] = np.where(lm, rng.uniform(0, 1, n), 0).astype(np.float32)
+        # dataset mask (datasets.py:492,505,624): 1 = static background / LiDAR return, 0 = pixels on moving
+        # objects, which Z/train.py:287,307 exclude from the losses when Config.instance_obj is off
+        # (drawn last so that the arrays above keep the values the golden fixtures were generated with)
+        b['mask'] = np.where(lm | (rng.uniform(0, 1, n) >= 0.1), 1.0, 0.0).astype(np.float32)
     return b
 
 

@@ -3,9 +3,8 @@
 
 The forward/backward of the path itself runs on the libnlb200 kernels through
 `Model.forward`.  The loss terms are SURVEY.md section 8(f) "next #2" (training-step
-remainder): they are written with plain torch ops here, free of host
-synchronisation (no boolean indexing, no .item()), so the step can be timed
-honestly; the dense per-table passes (hash-decay gradient, NaN scrub, Adam,
+remainder): fused kernels (csrc/render_losses.cu, csrc/losses.cu), free of host
+synchronisation; the dense per-table passes (hash-decay gradient, NaN scrub, Adam,
 zero_grad) are ONE fused kernel per table (csrc/adam.cu).
 
 Data parallelism: every rank runs the step on its own rays; table and
@@ -21,7 +20,6 @@ from typing import Dict, List, Optional
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 from . import _lib, parallel
 from .configs import Config
@@ -44,97 +42,6 @@ def learning_rate_decay(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr
 
 
 # ----------------------------------------------------------------------------- losses
-def _masked_mean(x, m):
-    m = m.to(x.dtype)
-    return (x * m).sum() / m.sum().clamp_min(1.0)
-
-
-def data_loss(batch, rendering, rgb_mask, config: Config):
-    """Charbonnier / MSE on the final level (train_utils.py:55-123; the coarse
-    multiplier is 0 in every shipped config)."""
-    lossmult = rgb_mask[:, None].to(rendering['rgb'].dtype).expand_as(rendering['rgb'])
-    resid_sq = (rendering['rgb'] - batch['rgb'][..., :3]) ** 2
-    if config.data_loss_type == 'mse':
-        per = resid_sq
-    else:
-        per = torch.sqrt(resid_sq + config.charb_padding ** 2)
-    denom = lossmult.sum()
-    return torch.where(denom > 0, (lossmult * per).sum() / denom.clamp_min(1e-30), torch.zeros_like(denom))
-
-
-def depth_loss(pred, target, mask):
-    """train.py:330-339: log(|d|+1) over the depth-supervised rays whose signed
-    error is below the 0.9 quantile of |d| (torch.quantile, linear interpolation),
-    written without a host sync."""
-    d = pred - target
-    ad = torch.where(mask, d.abs(), torch.full_like(d, float('inf')))
-    srt = torch.sort(ad).values
-    n = mask.sum()
-    pos = 0.9 * (n.to(torch.float32) - 1).clamp_min(0)
-    lo = pos.floor().long().clamp(0, d.numel() - 1)
-    hi = pos.ceil().long().clamp(0, d.numel() - 1)
-    v_lo, v_hi = srt.gather(0, lo.reshape(1))[0], srt.gather(0, hi.reshape(1))[0]
-    thre = v_lo + (v_hi - v_lo) * (pos - pos.floor())
-    keep = mask & (d < thre)
-    return _masked_mean(torch.log(d.abs() + 1), keep)
-
-
-def edge_aware(rgb, x, mask, eps, per_channel_sum: bool):
-    """train_utils.edge_aware_loss_v2 / edge_aware_loss_for_semantic with a mask
-    (train_utils.py:329-345,412-431) on patches [P, h, w, c]."""
-    mean = x.mean(1, True).mean(2, True)
-    x = x / (mean + eps)
-    gx = (x[:, :, :-1] - x[:, :, 1:]).abs()
-    gy = (x[:, :-1] - x[:, 1:]).abs()
-    if per_channel_sum:
-        gx, gy = gx.sum(-1, keepdim=True), gy.sum(-1, keepdim=True)
-    mx = (mask[:, :, :-1] * mask[:, :, 1:])[..., None]
-    my = (mask[:, :-1] * mask[:, 1:])[..., None]
-    rx = (rgb[:, :, :-1] - rgb[:, :, 1:]).abs().mean(3, keepdim=True)
-    ry = (rgb[:, :-1] - rgb[:, 1:]).abs().mean(3, keepdim=True)
-    sx = gx * torch.exp(-rx)
-    sy = gy * torch.exp(-ry)
-    c = sx.shape[-1]
-    return (sx * mx).sum() / (mx.sum() * c).clamp_min(1) + (sy * my).sum() / (my.sum() * c).clamp_min(1)
-
-
-def blur_stepfun(x, y, r):
-    """Z/internal/stepfun.py:425-433."""
-    xr, idx = torch.sort(torch.cat([x - r, x + r], dim=-1))
-    z = torch.zeros_like(y[..., :1])
-    y1 = (torch.cat([y, z], dim=-1) - torch.cat([z, y], dim=-1)) / (2 * r)
-    y2 = torch.cat([y1, -y1], dim=-1).take_along_dim(idx[..., :-1], dim=-1)
-    yr = torch.cumsum((xr[..., 1:] - xr[..., :-1]) * torch.cumsum(y2, dim=-1), dim=-1).clamp_min(0)
-    return xr, torch.cat([torch.zeros_like(yr[..., :1]), yr], dim=-1)
-
-
-def interp_quad(x, xp, fpdf, fcdf):
-    """math.sorted_interp_quad (Z/internal/math.py:111-131) with a binary search
-    instead of the [N, n, m] masks (xp sorted; picks follow the reference's
-    max/min-over-mask semantics for non-decreasing xp)."""
-    n = xp.shape[-1]
-    cnt = torch.searchsorted(xp.contiguous(), x.contiguous(), right=True)
-    i0 = (cnt - 1).clamp(0, n - 1)
-    i1 = cnt.clamp(0, n - 1)
-    # the reference takes max/min of the VALUES under the mask; fpdf is not monotone,
-    # so reproduce that with running max / reversed running min
-    run_max = lambda f: torch.cummax(f, dim=-1).values
-    run_min = lambda f: torch.flip(torch.cummin(torch.flip(f, [-1]), dim=-1).values, [-1])
-    none_lo = (cnt == 0)
-    none_hi = (cnt == n)
-
-    def pick(f):
-        f0 = torch.where(none_lo, f[..., :1].expand_as(x), run_max(f).gather(-1, i0))
-        f1 = torch.where(none_hi, f[..., -1:].expand_as(x), run_min(f).gather(-1, i1))
-        return f0, f1
-
-    fpdf0, fpdf1 = pick(fpdf)
-    fcdf0, _ = pick(fcdf)
-    xp0, xp1 = pick(xp)
-    offset = torch.clip(torch.nan_to_num((x - xp0) / (xp1 - xp0), 0), 0, 1)
-    return fcdf0 + (x - xp0) * (fpdf0 + fpdf1 * offset + fpdf0 * (1 - offset)) / 2
-
-
 def anti_interlevel_loss(ray_history, config: Config):
     """train_utils.py:134-172 on the fused kernel (csrc/losses.cu)."""
     from . import ops
@@ -147,23 +54,6 @@ def anti_interlevel_loss(ray_history, config: Config):
     return config.anti_interlevel_loss_mult * total
 
 
-def anti_interlevel_loss_torch(ray_history, config: Config):
-    """The same loss with plain torch ops (kept for cross-checking the kernel)."""
-    last = ray_history[-1]
-    c = last['sdist'].detach()
-    w = last['weights'].detach()
-    w_norm = (w / (c[..., 1:] - c[..., :-1])).clamp_max(10)
-    total = 0.
-    for i, rr in enumerate(ray_history[:-1]):
-        cp, wp = rr['sdist'], rr['weights']
-        c_, w_ = blur_stepfun(c, w_norm, config.pulse_width[i])
-        area = 0.5 * (w_[..., 1:] + w_[..., :-1]) * (c_[..., 1:] - c_[..., :-1])
-        cdf = torch.cat([torch.zeros_like(area[..., :1]), torch.cumsum(area, dim=-1)], dim=-1)
-        w_s = torch.diff(interp_quad(cp, c_, w_, cdf), dim=-1)
-        total = total + ((w_s - wp).clamp_min(0) ** 2 / (wp + 1e-5)).mean()
-    return config.anti_interlevel_loss_mult * total
-
-
 def distortion_loss(ray_history, config: Config):
     """stepfun.lossfun_distortion (Z/internal/stepfun.py:297-307) on the final level,
     fused kernel (csrc/losses.cu)."""
@@ -172,21 +62,11 @@ def distortion_loss(ray_history, config: Config):
     return config.distortion_loss_mult * ops.distortion_per_ray(t, w).mean()
 
 
-def distortion_loss_torch(ray_history, config: Config):
-    """The same loss with plain torch ops (kept for cross-checking the kernel)."""
-    t, w = ray_history[-1]['sdist'], ray_history[-1]['weights']
-    ut = (t[..., 1:] + t[..., :-1]) / 2
-    dut = (ut[..., :, None] - ut[..., None, :]).abs()
-    inter = torch.sum(w * torch.sum(w[..., None, :] * dut, dim=-1), dim=-1)
-    intra = torch.sum(w ** 2 * (t[..., 1:] - t[..., :-1]), dim=-1) / 3
-    return config.distortion_loss_mult * (inter + intra).mean()
-
-
 def compute_losses(batch: Dict[str, torch.Tensor], renderings, ray_history, config: Config, step: int,
                    num_patch: int) -> Dict[str, torch.Tensor]:
-    """The loss dictionary of Z/train.py:283-455 for the nuScenes camera+LiDAR run
-    (masks as with Config.instance_obj=True: `batch['mask']` is cleared) on the fused
-    kernels: supervision terms in csrc/render_losses.cu, regularisers in csrc/losses.cu."""
+    """The loss dictionary of Z/train.py:283-455 for the nuScenes camera+LiDAR run on the fused
+    kernels: supervision terms in csrc/render_losses.cu (incl. the dataset mask `batch['mask']`,
+    Z/train.py:286-327), regularisers in csrc/losses.cu."""
     from . import ops
     final = renderings[-1]
     refine = config.pose_refine and config.start_step < step < int(0.6 * config.end_step)
@@ -199,7 +79,8 @@ def compute_losses(batch: Dict[str, torch.Tensor], renderings, ray_history, conf
     cfg = dict(num_patch=num_patch, patch_size=config.patch_size, lidar_supervision=config.lidar_supervision,
                only_lidar_supervision=config.only_lidar_supervison, charb=config.data_loss_type != 'mse',
                charb_padding=config.charb_padding, depth_mult=dep_lam if config.depth_loss else 0.,
-               sem_mult=sem_lam, int_mult=0.1, smooth_mult=0.01)
+               sem_mult=sem_lam, int_mult=0.1, smooth_mult=0.01,
+               instance_obj=bool(getattr(config, 'instance_obj', False)))
     vals = ops.render_losses(rend, batch, cfg)
     losses = {'data': vals[0]}
     if config.depth_loss:
@@ -212,54 +93,6 @@ def compute_losses(batch: Dict[str, torch.Tensor], renderings, ray_history, conf
         losses['sem'] = vals[2]
     if use_int:
         losses['int'] = vals[3]
-    if config.anti_interlevel_loss_mult > 0:
-        losses['interlevel'] = anti_interlevel_loss(ray_history, config)
-    if config.distortion_loss_mult > 0:
-        losses['distortion'] = distortion_loss(ray_history, config)
-    return losses
-
-
-def compute_losses_torch(batch: Dict[str, torch.Tensor], renderings, ray_history, config: Config, step: int,
-                   num_patch: int) -> Dict[str, torch.Tensor]:
-    """The loss dictionary of Z/train.py:283-455 with plain torch ops (kept for
-    cross-checking the fused kernels; masks as with Config.instance_obj=True:
-    `batch['mask']` is cleared)."""
-    final = renderings[-1]
-    patch_mask = batch['patch_mask'] == 1
-    lidar = batch['lidar_mask'] == 1
-    rgb_mask = ~patch_mask
-    depth_mask = (batch['depth'] > 0) & rgb_mask
-    sem_mask = (batch['semantic'] != 255) & rgb_mask
-    if config.lidar_supervision:
-        rgb_mask = rgb_mask & ~lidar
-        depth_mask = depth_mask | lidar
-        sem_mask = sem_mask & ~lidar
-        if config.only_lidar_supervison:
-            depth_mask = depth_mask & lidar
-    refine = config.pose_refine and config.start_step < step < int(0.6 * config.end_step)
-    losses = {'data': data_loss(batch, final, rgb_mask, config)}
-    if config.depth_loss:
-        dep_lam = 0. if refine else (0.4 if step > config.end_step else 0.1)
-        losses['depth'] = dep_lam * depth_loss(final['depth'], batch['depth'], depth_mask)
-    if num_patch > 0:
-        P = config.patch_size
-        n = num_patch * P * P
-        shape = (num_patch, P, P)
-        m = torch.ones(shape, device=final['depth'].device)
-        dep = final['depth'][:n].reshape(*shape, 1)   # patch rays lead the batch (datasets.py:356-366)
-        rgbp = batch['rgb'][:n].reshape(*shape, 3)
-        losses['d_smo'] = torch.nan_to_num(0.01 * edge_aware(rgbp, dep, m, 1e-7, False))
-        if config.use_semantic:
-            semp = final['semantic'][:n].reshape(*shape, -1)
-            losses['s_smo'] = torch.nan_to_num(0.01 * edge_aware(rgbp, semp, m, 1e-5, True))
-    if config.use_semantic:
-        sem_lam = 0. if refine else (0.04 if step > config.end_step else 0.01)
-        labels = torch.where(sem_mask, batch['semantic'], torch.zeros_like(batch['semantic'])).long()
-        logp = torch.log(final['semantic'] + 1e-6).gather(-1, labels[:, None])[:, 0]
-        losses['sem'] = sem_lam * _masked_mean(-logp, sem_mask)
-    if config.use_intensity:
-        diff = final['intensity'].reshape(-1) - batch['intensity'].reshape(-1)
-        losses['int'] = 0.1 * _masked_mean(diff ** 2, lidar)
     if config.anti_interlevel_loss_mult > 0:
         losses['interlevel'] = anti_interlevel_loss(ray_history, config)
     if config.distortion_loss_mult > 0:

@@ -5,8 +5,8 @@ backward, NaN scrub (train_utils.py:251-253) and torch.optim.Adam
 (train_utils.py:256-275).  Used by tests (gradient / update parity of the fused
 kernels) and by bench.py's cpu_baseline / `--impl reference` arm.
 
-Masks follow the shipped gin (Config.instance_obj=True clears batch['mask'],
-train.py:286-287); the dynamic-object branch itself is out of scope."""
+Masks follow Z/train.py:286-327: the dataset mask gates the rgb / depth / semantic terms and
+the smoothness edges (`instance_obj=True` clears it, as the shipped gin does)."""
 from __future__ import annotations
 
 import math
@@ -71,31 +71,43 @@ def distortion(history, mult=0.005):
     return mult * (inter + intra).mean()
 
 
-def _edge_aware(rgb, x, eps, channel_sum):
-    """train_utils.edge_aware_loss_v2 / _for_semantic with an all-ones mask."""
+def _edge_aware(rgb, x, eps, channel_sum, mask):
+    """train_utils.edge_aware_loss_v2 / edge_aware_loss_for_semantic with `mask` [P,h,w]
+    (Z/internal/train_utils.py:329-348,412-431)."""
     x = x / (x.mean(1, True).mean(2, True) + eps)
     gx = torch.abs(x[:, :, :-1] - x[:, :, 1:])
     gy = torch.abs(x[:, :-1] - x[:, 1:])
     if channel_sum:
-        gx, gy = gx.sum(-1, keepdim=True), gy.sum(-1, keepdim=True)
+        gx, gy = gx.sum(-1).unsqueeze(-1), gy.sum(-1).unsqueeze(-1)
+    mx = mask[:, :, :-1] * mask[:, :, 1:]
+    my = mask[:, :-1, :] * mask[:, 1:, :]
     rx = torch.mean(torch.abs(rgb[:, :, :-1] - rgb[:, :, 1:]), 3, keepdim=True)
     ry = torch.mean(torch.abs(rgb[:, :-1] - rgb[:, 1:]), 3, keepdim=True)
-    return (gx * torch.exp(-rx)).mean() + (gy * torch.exp(-ry)).mean()
+    sx = gx[mx > 0] * torch.exp(-rx[mx > 0])
+    sy = gy[my > 0] * torch.exp(-ry[my > 0])
+    return sx.mean() + sy.mean()
 
 
 def losses(batch, rend, history, step, num_patch, patch_size=32, end_step=5000, start_step=0,
-           use_intensity=True) -> Dict[str, torch.Tensor]:
-    """Z/train.py:283-455 for lidar_supervision=True, use_semantic=True, depth_loss."""
+           use_intensity=True, instance_obj=False, lidar_supervision=True, only_lidar_supervision=False,
+           pose_refine=True, regularisers=True) -> Dict[str, torch.Tensor]:
+    """Z/train.py:283-455 for use_semantic=True, depth_loss (the statements of the training loop, in order)."""
     final = rend[-1]
+    mask = batch['mask'] == 0                      # train.py:287 "only apply loss on mask == 0"
+    if instance_obj:
+        mask = torch.zeros_like(mask)              # train.py:288-289
     patch = batch['patch_mask'] == 1
     lidar = batch['lidar_mask'] == 1
-    rgb_mask = ~patch
+    rgb_mask = (mask == 0) & ~patch                # train.py:307
     depth_mask = (batch['depth'] > 0) & rgb_mask
     sem_mask = (batch['semantic'] != 255) & rgb_mask
-    rgb_mask = rgb_mask & ~lidar
-    depth_mask = depth_mask | lidar
-    sem_mask = sem_mask & ~lidar
-    refine = start_step < step < int(0.6 * end_step)
+    if lidar_supervision:                          # train.py:313-319
+        rgb_mask = rgb_mask & ~lidar
+        depth_mask = depth_mask | lidar
+        sem_mask = sem_mask & ~lidar
+        if only_lidar_supervision:
+            depth_mask = depth_mask & lidar
+    refine = pose_refine and start_step < step < int(0.6 * end_step)
     out = {}
     lm = rgb_mask[:, None].float().expand(-1, 3)
     resid = (final['rgb'] - batch['rgb'][..., :3]) ** 2
@@ -106,17 +118,22 @@ def losses(batch, rend, history, step, num_patch, patch_size=32, end_step=5000, 
     out['depth'] = dep_lam * torch.log(torch.abs(d[d < thre]) + 1).mean()
     if num_patch > 0:
         shape = (num_patch, patch_size, patch_size)
+        mask_patch = torch.where(mask[patch].reshape(*shape) > 0, 0, 1)   # train.py:363-364
         dep = final['depth'][patch].reshape(*shape, -1)
         rgbp = batch['rgb'][patch].reshape(*shape, -1)
-        out['d_smo'] = torch.nan_to_num(0.01 * _edge_aware(rgbp, dep, 1e-7, False))
+        out['d_smo'] = torch.nan_to_num(0.01 * _edge_aware(rgbp, dep, 1e-7, False, mask_patch))
         semp = final['semantic'][patch].reshape(*shape, -1)
-        out['s_smo'] = torch.nan_to_num(0.01 * _edge_aware(rgbp, semp, 1e-5, True))
+        out['s_smo'] = torch.nan_to_num(0.01 * _edge_aware(rgbp, semp, 1e-5, True, mask_patch))
     sem_lam = 0. if refine else (0.04 if step > end_step else 0.01)
-    out['sem'] = sem_lam * nn.NLLLoss()(torch.log(final['semantic'][sem_mask] + 1e-6), batch['semantic'][sem_mask].long())
+    if sem_mask.sum() > 0:
+        out['sem'] = sem_lam * nn.NLLLoss()(torch.log(final['semantic'][sem_mask] + 1e-6), batch['semantic'][sem_mask].long())
+    else:
+        out['sem'] = torch.tensor(0.) * sem_lam
     if use_intensity:
         out['int'] = 0.1 * (final['intensity'].reshape(-1) - batch['intensity'].reshape(-1))[lidar].pow(2).mean()
-    out['interlevel'] = anti_interlevel(history)
-    out['distortion'] = distortion(history)
+    if regularisers:
+        out['interlevel'] = anti_interlevel(history)
+        out['distortion'] = distortion(history)
     if 'hash_decay' in final:
         out['hash_decay'] = final['hash_decay']
     return out

@@ -78,3 +78,41 @@ def poisoned_empty(enable=True):
         yield
     finally:
         torch.empty, torch.empty_like = real_empty, real_like
+
+
+def torch_heads(mlp, feat, viewdirs, S, dtype=torch.float32):
+    """Plain-torch evaluation of the NerfMLP dense head (Z/internal/models.py:996-997,1116-1251) on the
+    module's parameters -- the reference the fused tcgen05 kernels are compared with.  dtype=float32 is the
+    reference's arithmetic; bfloat16 rounds the operands like the kernels do (fp32 accumulation)."""
+    import math
+    import torch.nn.functional as F
+    N = viewdirs.shape[0]
+
+    def lin(layer, x):
+        if dtype == torch.float32:
+            return F.linear(x, layer.weight, layer.bias)
+        return F.linear(x.to(dtype), layer.weight.to(dtype), None).float() + layer.bias
+
+    x = lin(mlp.density_layer[2], torch.relu(lin(mlp.density_layer[0], feat)))
+    density = F.softplus(x[..., 0] + mlp.density_bias).reshape(N, S)
+    sem = torch.softmax(lin(mlp.sem_layer[2], torch.relu(lin(mlp.sem_layer[0], x))), dim=-1).reshape(N, S, mlp.class_num)
+    inten = lin(mlp.intensity_layer[2], torch.relu(lin(mlp.intensity_layer[0], x))).reshape(N, S, 1)
+    de = mlp.dir_enc(viewdirs)
+    de = de[:, None, :].expand(N, S, de.shape[-1]).reshape(N * S, -1)
+    h_in = torch.cat([x, de], dim=-1)
+    h = h_in
+    for i in range(mlp.net_depth_viewdirs):
+        h = torch.relu(lin(mlp.get_submodule(f'lin_second_stage_{i}'), h))
+        if i == mlp.skip_layer_dir:
+            h = torch.cat([h, h_in], dim=-1)
+    rgb = torch.sigmoid(mlp.rgb_premultiplier * lin(mlp.rgb_layer, h) + mlp.rgb_bias)
+    rgb = (rgb * (1 + 2 * mlp.rgb_padding) - mlp.rgb_padding).reshape(N, S, 3)
+    return dict(density=density, rgb=rgb, semantic=sem, intensity=inten)
+
+
+def use_torch_heads(model, dtype=torch.float32):
+    """Routes the model's NerfMLP head through `torch_heads` (tests that need the reference's fp32 arithmetic
+    around the other kernels: teacher-forced stages, autograd comparisons of the whole step)."""
+    mlp = model.nerf_mlp
+    mlp.heads = lambda feat, viewdirs, S: torch_heads(mlp, feat, viewdirs, S, dtype)
+    return model

@@ -114,3 +114,25 @@ for t in (-0.5, 0., 0.3, 1., 1.7):
     assert abs(train.log_lerp(t, 0.03, 0.003) - float(rm.log_lerp(t, 0.03, 0.003))) <= 1e-15
 print('ok')
 ''')
+
+
+def test_fused_mlp_rejects_other_architectures():
+    """The tcgen05 NerfMLP kernels are compiled for the nuscenes_single.gin architecture and take raw pointers:
+    a gin binding that changes a layer shape or a baked-in scalar must raise before any launch."""
+    import pytest
+    import torch
+    from nerf_lidar_b200 import configs, models
+    cfg = configs.nuscenes_single()
+    ok = models.Model(cfg).nerf_mlp
+    ok._check_fused_shapes()
+    for attr, value in (('bottleneck_width', 128), ('net_width_viewdirs', 128), ('class_num', 12), ('deg_view', 2),
+                        ('density_bias', 0.0), ('rgb_padding', 0.01), ('grid_level_dim', 2), ('net_depth_viewdirs', 3),
+                        ('mlp_dtype', torch.float32)):
+        old = getattr(models.NerfMLP, attr)
+        setattr(models.NerfMLP, attr, value)
+        try:
+            mlp = models.Model(cfg).nerf_mlp
+            with pytest.raises(NotImplementedError, match='built for'):
+                mlp.heads(torch.zeros(32, mlp.encoder.output_dim), torch.zeros(1, 3), 32)
+        finally:
+            setattr(models.NerfMLP, attr, old)

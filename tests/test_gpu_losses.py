@@ -1,4 +1,5 @@
 """Fused distortion / anti-interlevel loss kernels against the oracle (autograd)."""
+import numpy as np
 import pytest
 import torch
 
@@ -50,41 +51,61 @@ def test_interlevel_value_and_gradient(Sp, pulse):
     assert_close(wpc.grad, wpr.grad, 5e-4, 'd interlevel / d wp')
 
 
-@pytest.mark.parametrize('step,lidar_sup', [(6000, True), (1000, True), (4000, False)])
-def test_fused_supervision_losses_vs_torch(step, lidar_sup):
-    """csrc/render_losses.cu (data, depth incl. the 0.9-quantile gate, semantic CE, intensity,
-    edge-aware smoothness) against the plain-torch restatement: values and gradients w.r.t.
-    the rendered rgb / depth / semantic / intensity."""
+@pytest.mark.parametrize('step,lidar_sup,only_lidar', [(6000, True, False), (1000, True, False), (4000, False, False),
+                                                       (6000, True, True)])
+def test_fused_supervision_losses_vs_oracle(step, lidar_sup, only_lidar):
+    """csrc/render_losses.cu (data, depth incl. the 0.9-quantile gate, semantic CE, intensity, edge-aware
+    smoothness, all under the dataset mask of Z/train.py:286-327) against the oracle's restatement of the
+    reference training loop (oracle/train_oracle.losses, itself pinned live against Z/internal/train_utils.py):
+    values and gradients w.r.t. the rendered rgb / depth / semantic / intensity."""
     from nerf_lidar_b200 import configs, synthetic, train
     cfg = configs.nuscenes_single()
     cfg.lidar_supervision = lidar_sup
+    cfg.only_lidar_supervison = only_lidar
     B = 8192
     num_patch = (B // 4) // 1024
-    batch = {k: v.cuda() for k, v in synthetic.to_torch(synthetic.make_train_batch(B, seed=9)).items()}
-    N = batch['origins'].shape[0]
-    g = torch.Generator(device='cuda').manual_seed(1)
-
-    def leaves():
-        rgb = torch.rand(N, 3, device='cuda', generator=g).requires_grad_(True)
-        depth = (batch['depth'] + torch.randn(N, device='cuda', generator=g) * 0.3).abs().add(0.05).requires_grad_(True)
-        sem = torch.softmax(torch.randn(N, 19, device='cuda', generator=g) * 2, dim=-1).requires_grad_(True)
-        inten = torch.rand(N, device='cuda', generator=g).requires_grad_(True)
-        return rgb, depth, sem, inten
-
-    a = leaves()
-    b = [t.detach().clone().requires_grad_(True) for t in a]
-    hist = [dict(sdist=torch.zeros(1), weights=torch.zeros(1))]
+    cpu = synthetic.to_torch(synthetic.make_train_batch(B, seed=9))
+    assert 0.05 < float((cpu['mask'] == 0).float().mean()) < 0.2        # the mask is not trivial
+    assert float((cpu['mask'][:2048] == 0).float().mean()) > 0.05       # ... on the patch rays either
+    batch = {k: v.cuda() for k, v in cpu.items()}
+    N = cpu['origins'].shape[0]
+    g = torch.Generator().manual_seed(1)
+    rgb = torch.rand(N, 3, generator=g)
+    depth = (cpu['depth'] + torch.randn(N, generator=g) * 0.3).abs().add(0.05)
+    sem = torch.softmax(torch.randn(N, 19, generator=g) * 2, dim=-1)
+    inten = torch.rand(N, generator=g)
+    a = [t.clone().requires_grad_(True) for t in (rgb, depth, sem, inten)]
+    b = [t.clone().cuda().requires_grad_(True) for t in (rgb, depth, sem, inten)]
+    want = to.losses(cpu, [dict(rgb=a[0], depth=a[1], semantic=a[2], intensity=a[3])], None, step, num_patch,
+                     end_step=cfg.end_step, start_step=cfg.start_step, lidar_supervision=lidar_sup,
+                     only_lidar_supervision=only_lidar, pose_refine=cfg.pose_refine, regularisers=False)
+    sum(want.values()).backward()
     cfg.anti_interlevel_loss_mult = 0.
     cfg.distortion_loss_mult = 0.
-    outs = []
-    for fn, (rgb, depth, sem, inten) in ((train.compute_losses_torch, a), (train.compute_losses, b)):
-        rend = [dict(rgb=rgb, depth=depth, semantic=sem, intensity=inten)]
-        ls = fn(batch, rend, hist, cfg, step, num_patch)
-        sum(ls.values()).backward()
-        outs.append(ls)
-    assert set(outs[0]) == set(outs[1])
-    for k in outs[0]:
-        want, got = float(outs[0][k]), float(outs[1][k])
-        assert abs(got - want) <= 2e-5 * max(abs(want), 1e-6), (k, got, want)
+    got = train.compute_losses(batch, [dict(rgb=b[0], depth=b[1], semantic=b[2], intensity=b[3])],
+                               [dict(sdist=torch.zeros(1), weights=torch.zeros(1))], cfg, step, num_patch)
+    sum(got.values()).backward()
+    assert set(want) == set(got)
+    for k in want:
+        assert abs(float(got[k]) - float(want[k])) <= 2e-5 * max(abs(float(want[k])), 1e-6), (k, float(got[k]), float(want[k]))
     for name, ta, tb in zip(('rgb', 'depth', 'semantic', 'intensity'), a, b):
         assert_close(tb.grad, ta.grad, 2e-5, 'grad ' + name)
+
+
+def test_patch_layout_violation_is_loud():
+    """The patch kernel smooths the LEADING num_patch * P * P rays (datasets.py:356-366); a patch_mask that says
+    otherwise must not be smoothed silently (the reference gathers by patch_mask == 1)."""
+    from nerf_lidar_b200 import configs, synthetic, train
+    cfg = configs.nuscenes_single()
+    cfg.anti_interlevel_loss_mult = 0.
+    cfg.distortion_loss_mult = 0.
+    batch = {k: v.cuda() for k, v in synthetic.to_torch(synthetic.make_train_batch(4096, seed=3)).items()}
+    N = batch['origins'].shape[0]
+    rend = [dict(rgb=torch.rand(N, 3, device='cuda'), depth=torch.rand(N, device='cuda') + 0.1,
+                 semantic=torch.softmax(torch.randn(N, 19, device='cuda'), -1), intensity=torch.rand(N, device='cuda'))]
+    hist = [dict(sdist=torch.zeros(1), weights=torch.zeros(1))]
+    ok = train.compute_losses(batch, rend, hist, cfg, 6000, 1)
+    assert np.isfinite(float(ok['d_smo'])) and float(ok['d_smo']) > 0
+    batch['patch_mask'] = batch['patch_mask'].roll(7)
+    bad = train.compute_losses(batch, rend, hist, cfg, 6000, 1)
+    assert np.isnan(float(bad['d_smo'])) and np.isnan(float(bad['s_smo']))

@@ -13,7 +13,7 @@ import torch
 
 from oracle import zipnerf_oracle as zo
 from nerf_lidar_b200 import synthetic
-from tests.helpers import CASES, load_case, assert_close
+from tests.helpers import CASES, load_case, assert_close, use_torch_heads
 
 pytestmark = pytest.mark.gpu
 
@@ -25,7 +25,8 @@ def _model(sd, dtype):
     assert not unexpected
     model.eval()
     model.training = False
-    model.nerf_mlp.mlp_dtype = dtype
+    if dtype == torch.float32:     # the reference's fp32 head arithmetic around the other kernels
+        use_torch_heads(model, torch.float32)
     return model
 
 

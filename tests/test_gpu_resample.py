@@ -57,7 +57,7 @@ def test_resample_level_vs_oracle(rand, n_in, S, power):
     from nerf_lidar_b200 import ops
     sd, w, near, far, jit = _case(n_in, S, rand, power)
     prod = n_in
-    want_s, want_idx, _, _ = zo.resample_level(sd, w, 1, S, prod, 0.5, jit)
+    want_s, want_idx, dil_s, logits = zo.resample_level(sd, w, 1, S, prod, 0.5, jit)
     want_t = zo.s_to_t(want_s, near, far)
     d = lambda x: None if x is None else x.double()
     true_s, _, _, _ = zo.resample_level(d(sd), d(w), 1, S, prod, 0.5, d(jit))
@@ -76,10 +76,17 @@ def test_resample_level_vs_oracle(rand, n_in, S, power):
     # direct comparison: the median is at rounding level, the tail is conditioning
     assert float((got_s - want_s).abs().median()) <= 5e-7
     assert_close(got_s, want_s, 1e-4 if power == 1 else 1e-3, 'sdist')
-    # a centre within rounding of a CDF knot may fall on the neighbouring interval
-    # (the value is continuous there); everything else must be identical
-    mism = (got_idx.cpu().numpy() != want_idx.numpy()).mean()
-    assert mism < 5e-3, f'sample-index mismatch rate {mism}'
+    # sample ("interval") indices: identical, except where the centre u lies within rounding of a CDF knot --
+    # the kernel sums the CDF with a warp scan, torch.cumsum sequentially, so the two CDFs differ by a few ulp of
+    # 1.0 and a centre that close to a knot may land on either side (the interpolated value is continuous there)
+    gi, wi = got_idx.cpu().numpy().astype(np.int64), want_idx.numpy().astype(np.int64)
+    cw = zo.cdf_from_logits(logits).numpy()
+    u = zo.sample_u(S, jit, sd.shape[0]).expand(sd.shape[0], S).numpy()
+    rows, cols = np.nonzero(gi != wi)
+    assert rows.size <= 5e-3 * gi.size, f'sample-index mismatch rate {rows.size / gi.size}'
+    lo, hi = np.minimum(gi, wi)[rows, cols], np.maximum(gi, wi)[rows, cols]
+    gap = np.maximum(np.abs(u[rows, cols] - cw[rows, lo + 1]), np.abs(u[rows, cols] - cw[rows, hi]))
+    assert rows.size == 0 or gap.max() <= 4 * 1.2e-7, f'{rows.size} mismatching centres, farthest {gap.max():.3e} from its knot'
     assert torch.all(got_s[:, 1:] >= got_s[:, :-1])
 
 

@@ -10,7 +10,7 @@ import torch
 from oracle import train_oracle as to
 from oracle import zipnerf_oracle as zo
 from nerf_lidar_b200 import synthetic
-from tests.helpers import assert_close
+from tests.helpers import assert_close, torch_heads, use_torch_heads
 
 pytestmark = pytest.mark.gpu
 
@@ -33,7 +33,7 @@ def test_losses_and_gradients_vs_oracle():
     cfg = configs.nuscenes_single()
     model = models.Model(cfg, training=True).cuda()
     model.load_state_dict(sd, strict=False)
-    model.nerf_mlp.mlp_dtype = torch.float32
+    use_torch_heads(model, torch.float32)
     tr = train.Trainer(model, cfg)
     cb = {k: v.cuda() for k, v in batch.items()}
     crin = [{k: v.cuda() for k, v in r.items()} for r in rin]
@@ -132,9 +132,7 @@ def test_fused_mlp_sees_updated_weights():
     vd = torch.nn.functional.normalize(torch.randn(128, 3, device='cuda'), dim=-1)
     with torch.no_grad():
         got = ops.nerf_mlp_forward(mlp, feat, vd, 32)
-        mlp.fused_mlp = False
-        want = mlp.heads(feat, vd, 32)
-        mlp.fused_mlp = True
+        want = torch_heads(mlp, feat, vd, 32, torch.bfloat16)
     for k in ('density', 'rgb', 'semantic', 'intensity'):
         assert_close(got[k].reshape(-1), want[k].reshape(-1).float(), 2e-2, 'fused vs torch after optimizer steps: ' + k)
 

@@ -104,7 +104,7 @@ def test_golden_fixtures_reproduce_from_the_live_reference():
 def test_training_oracle_against_the_reference_loss_functions():
     """Pins oracle/train_oracle.py (the checker of the fused loss kernels) against the reference's own
     Z/internal/train_utils.py: distortion_loss, anti_interlevel_loss, compute_data_loss and the two
-    edge-aware smoothness losses (with the all-ones patch mask of Z/train.py:374-388), values AND
+    edge-aware smoothness losses (with a patch mask as Z/train.py:363-388 builds it), values AND
     gradients, on random step functions / renderings."""
     code = r'''
 import sys, warnings, types, importlib
@@ -174,12 +174,12 @@ errs['data'], errs['data_grad'] = rel(lb.detach(), la.detach()), rel(pb.grad, pa
 # edge-aware smoothness on 2 patches of 32 x 32
 P = 2
 rgbp = torch.rand(P, 32, 32, 3, generator=g)
-ones = torch.ones(P, 32, 32, 1)
+pmask = (torch.rand(P, 32, 32, generator=g) < 0.85).long()      # mask_patch of Z/train.py:363-364: [P, h, w]
 for name, fn, ch, eps, csum in (('d_smo', tu.edge_aware_loss_v2, 1, 1e-7, False),
                                 ('s_smo', tu.edge_aware_loss_for_semantic, 19, 1e-5, True)):
     xa = (torch.rand(P, 32, 32, ch, generator=g) + 0.05).requires_grad_(True)
     xb = xa.detach().clone().requires_grad_(True)
-    la, lb = fn(rgbp, xa, mask=ones), to._edge_aware(rgbp, xb, eps, csum)
+    la, lb = fn(rgbp, xa, mask=pmask), to._edge_aware(rgbp, xb, eps, csum, pmask)
     la.backward(); lb.backward()
     errs[name], errs[name + '_grad'] = rel(lb.detach(), la.detach()), rel(xb.grad, xa.grad)
 assert max(errs.values()) <= 2e-5, errs
