@@ -86,27 +86,91 @@ def test_teacher_forced_stages(name):
             assert_close(comp['intensity'], G['rend2_intensity'], 1e-5, 'intensity')
 
 
-@pytest.mark.parametrize('dtype,tol', [(torch.float32, 3e-3), (torch.bfloat16, 2e-2)])
+# Bars of the free-running forward (max |d| / max |ref| per key), set from tools/parity_report.py on the B200
+# (gpurun_out/parity_report.log, round 2) with ~3x margin.  north_star: fp32 compositing 1e-5, bf16 MLP outputs and
+# rendered depth / intensity 1e-3.
+#   fp32 head: every rendered quantity is at 1e-5 or better (measured <= 1.3e-5); the exception is intensity on the
+#   "visible" random table (1.1e-4): a 1-ulp shift of a sample point is 5e-4 of a level-9 cell, i.e. ~1e-4 of a
+#   random feature, and the random-init intensity head's whole output range is 0.034.
+#   bf16 tensor-core head: depth 7e-5, rgb 5.6e-4, semantic 1.6e-4, distances 1.1e-4 -- inside 1e-3.  Intensity is
+#   3.5e-3 of its 0.044 range = 1.5e-4 ABSOLUTE: the bf16 rounding of the (shared) weights is a systematic offset of
+#   2^-9 of the head's TERMS, and at random init those terms cancel to an output 20x smaller than they are
+#   (tests/test_gpu_mlp.py holds the intensity head to 1e-3 of its term scale).
+_REND_BARS = {
+    torch.float32: dict(rgb=3e-5, depth=3e-5, semantic=3e-5, intensity=3e-4, acc=1e-5, distance_mean=3e-5,
+                        distance_median=4e-5, distance_percentile_5=3e-5, distance_percentile_95=3e-5),
+    torch.bfloat16: dict(rgb=1e-3, depth=2e-4, semantic=5e-4, intensity=6e-3, acc=1e-5, distance_mean=3e-4,
+                         distance_median=3e-4, distance_percentile_5=4e-4, distance_percentile_95=3e-4),
+}
+_INTENSITY_ABS = {torch.float32: 1.5e-5, torch.bfloat16: 3e-4}
+# per-sample history: sample positions to 6e-5 (CDF inversion conditioning); per-sample values shift with them,
+# so they are held on the MEDIAN (and loosely on the maximum)
+_HIST_POS = 6e-5
+_HIST_MED = {torch.float32: 1e-5, torch.bfloat16: 5e-4}
+_HIST_MED_INTENSITY = {torch.float32: 3e-5, torch.bfloat16: 6e-3}
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('name', list(CASES))
-def test_free_running_forward(name, dtype, tol):
+def test_free_running_forward(name, dtype):
+    """The whole Model.forward (three levels, errors compound) against the reference's own outputs.
+    float32 = the reference's head arithmetic (plain torch) around the kernels; bfloat16 = the shipped path."""
     case, golden, sd, batch, rin = load_case(name, 'cuda')
     model = _model(sd, dtype)
     with torch.no_grad():
         rend, hist = model(case['rand'], batch, case['train_frac'], True, rand_inputs=rin)
-    report = {}
     for key, ref in golden.items():
         kind, k = key.split('_', 1)
         i = int(kind[-1])
         src = hist[i] if kind.startswith('hist') else rend[i]
         got = src[k].float().cpu().numpy().reshape(ref.shape)
         scale = np.abs(ref).max() + 1e-30
-        err = np.abs(got - ref).max()
-        report[key] = err / scale
-        if kind.startswith('hist') and k in ('density', 'weights', 'rgb', 'semantic', 'intensity'):
-            # per-sample values shift with the sample positions; compare the MEDIAN error
-            assert np.median(np.abs(got - ref)) <= tol * scale, key
+        d = np.abs(got - ref)
+        if kind.startswith('rend'):
+            if k.startswith('ray_'):
+                continue
+            if k == 'rgb' and i < 2:
+                assert d.max() <= 1e-6, key            # proposal levels render black
+                continue
+            assert d.max() <= _REND_BARS[dtype][k] * scale, f'{key}: {d.max() / scale:.3e}'
+            if k == 'intensity':
+                assert d.max() <= _INTENSITY_ABS[dtype], f'{key}: abs {d.max():.3e}'
+        elif k in ('sdist', 'tdist'):
+            assert d.max() <= _HIST_POS * scale, f'{key}: {d.max() / scale:.3e}'
+        elif i < 2 and k == 'rgb':
+            assert d.max() == 0.0, key
         else:
-            assert err <= tol * scale + 1e-6, f'{key}: {err / scale:.3e}'
+            level_dtype = dtype if i == 2 else torch.float32      # the proposal levels have no bf16 stage
+            med = (_HIST_MED_INTENSITY if k == 'intensity' else _HIST_MED)[level_dtype]
+            assert np.median(d) <= med * scale, f'{key}: median {np.median(d) / scale:.3e}'
+            assert d.max() <= 1e-2 * scale, f'{key}: max {d.max() / scale:.3e}'
+
+
+def test_lidar_sweep_subset_vs_oracle():
+    """BASELINE configs[2]: 512 rays of a full 32 x 1084 LiDAR sweep rendered by the shipped path (bf16 tensor-core
+    MLP, graphs, chunking) against the oracle evaluated on the same rays: depth / intensity / rgb, and the semantic
+    argmax wherever the oracle's top-2 margin is clear of bf16 noise."""
+    from nerf_lidar_b200 import configs, models
+    cfg = configs.nuscenes_single()
+    sd = synthetic.init_state_dict(seed=41, table_std=0.3)
+    model = models.Model(cfg).cuda()
+    model.load_state_dict({k: v.cuda() for k, v in sd.items()}, strict=False)
+    sweep = synthetic.to_torch(synthetic.make_lidar_sweep(seed=41))
+    n = sweep['origins'].shape[0]
+    out = models.render_image(model, None, {k: v.cuda() for k, v in sweep.items()}, False, cfg, image=False, verbose=False)
+    pick = torch.linspace(0, n - 1, 512).long()
+    sub = {k: v[pick].contiguous() for k, v in sweep.items()}
+    want, _ = zo.model_forward(sd, sub, None, 1.0)
+    for k, tol in (('depth', 1e-3), ('rgb', 2e-3), ('acc', 1e-5)):
+        assert_close(out[k][pick.cuda()].reshape(512, -1), want[-1][k].reshape(512, -1), tol, 'sweep ' + k)
+    a, b = out['intensity'][pick.cuda()].reshape(-1).cpu(), want[-1]['intensity'].reshape(-1)
+    assert float((a - b).abs().max()) <= 3e-4, 'sweep intensity'
+    ws = want[-1]['semantic'].reshape(512, -1)
+    top2 = ws.topk(2, dim=-1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 2e-3 * float(ws.max())
+    got_label = out['semantic'][pick.cuda()].reshape(512, -1).argmax(-1).cpu()
+    assert int(clear.sum()) > 256
+    assert torch.equal(got_label[clear], ws.argmax(-1)[clear]), 'semantic argmax'
 
 
 def test_state_dict_keys_match_reference():
