@@ -216,6 +216,7 @@ typedef struct {
   void* g;  /* [M,128] relu(sem_layer.0) | relu(intensity_layer.0) */
   void* h1; /* [M,256] relu(lin_second_stage_0) */
   void* h2; /* [M,256] relu(lin_second_stage_1) */
+  void* f0; /* [M,64]  the input features, zero-padded from 40 columns (optional: nlb_nerf_mlp_wgrad needs it) */
 } nlb_nerf_mlp_saved_t;
 int nlb_nerf_mlp_forward(const float* features /*[M,40]*/, const float* viewdirs /*[N,3]*/, int M,
                          int rows_per_ray, const void* packed, float* density /*[M]*/, float* rgb /*[M,3]*/,
@@ -253,6 +254,25 @@ typedef struct {
 int nlb_nerf_mlp_backward(const nlb_nerf_mlp_grad_in_t* gin, const nlb_nerf_mlp_saved_t* saved, int M,
                           const void* packed_t, float* grad_features /*[M,40]*/,
                           const nlb_nerf_mlp_grad_out_t* gout, void* stream);
+
+/* Weight gradients of the NerfMLP dense layers on tcgen05: dW += dZ^T A for every layer, with dZ = the bf16
+ * pre-activation gradients written by nlb_nerf_mlp_backward and A = the bf16 activations saved by
+ * nlb_nerf_mlp_forward (incl. f0), both read as MN-major operands straight from their row-major matrices.
+ * The results are ADDED (fp32 atomics) into the gradient tensors, which have the shapes of the weights
+ * (e.g. views of one flat gradient buffer that the optimizer pass clears).  nlb_nerf_mlp_wgrad covers the
+ * columns fed by activations; nlb_nerf_mlp_wgrad_finish adds the bias gradients (cs_* = column sums of d_x[256],
+ * d_g[128], d_h0[64], d_hs1[32], d_rgb[16] from nlb_colsum_bf16) and the view-direction columns
+ * W_v0[:, 256:283], W_v1[:, 512:539] and b_v0 / b_v1 from the per-ray sums rs_v0 / rs_v1 [N,256]
+ * (nlb_group_sum_bf16) and viewdirs [N,3]. */
+typedef struct {
+  float *W_d0, *b_d0, *W_d2, *b_d2, *W_s0, *b_s0, *W_s2, *b_s2, *W_i0, *b_i0, *W_i2, *b_i2;
+  float *W_v0, *b_v0, *W_v1, *b_v1, *W_rgb, *b_rgb;   /* same order and shapes as nlb_nerf_mlp_weights_t */
+} nlb_nerf_mlp_wgrads_t;
+int nlb_nerf_mlp_wgrad(const nlb_nerf_mlp_saved_t* saved, const nlb_nerf_mlp_grad_out_t* dz, int M,
+                       const nlb_nerf_mlp_wgrads_t* grads, void* stream);
+int nlb_nerf_mlp_wgrad_finish(const float* rs_v0, const float* rs_v1, const float* viewdirs, int N,
+                              const float* cs_x, const float* cs_g, const float* cs_h0, const float* cs_hs1,
+                              const float* cs_rgb, const nlb_nerf_mlp_wgrads_t* grads, void* stream);
 
 /* Reductions of the bf16 pre-activation gradients written by nlb_nerf_mlp_backward:
  * colsum: x[M, ld] (first `cols` columns; cols a power of two <= 512) -> out[cols]

@@ -58,7 +58,7 @@ class NlbNerfMlpWeights(C.Structure):
 
 
 class NlbNerfMlpSaved(C.Structure):
-    _fields_ = [(n, c_f) for n in ('h0', 'x', 'g', 'h1', 'h2')]
+    _fields_ = [(n, c_f) for n in ('h0', 'x', 'g', 'h1', 'h2', 'f0')]
 
 
 class NlbNerfMlpGradIn(C.Structure):
@@ -99,6 +99,9 @@ SIGNATURES = {
     'nlb_nerf_mlp_pack_transposed': (_i, [C.POINTER(NlbNerfMlpWeights), _p, _p]),
     'nlb_nerf_mlp_backward': (_i, [C.POINTER(NlbNerfMlpGradIn), C.POINTER(NlbNerfMlpSaved), _i, _p, _p,
                                    C.POINTER(NlbNerfMlpGradOut), _p]),
+    'nlb_nerf_mlp_wgrad': (_i, [C.POINTER(NlbNerfMlpSaved), C.POINTER(NlbNerfMlpGradOut), _i,
+                                C.POINTER(NlbNerfMlpWeights), _p]),
+    'nlb_nerf_mlp_wgrad_finish': (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, C.POINTER(NlbNerfMlpWeights), _p]),
     'nlb_colsum_bf16': (_i, [_p, C.c_int64, _i, _i, _p, _p]),
     'nlb_group_sum_bf16': (_i, [_p, C.c_int64, _i, _i, _i, _p, _p]),
     'nlb_debug_set_timeline': (_i, [_p]),

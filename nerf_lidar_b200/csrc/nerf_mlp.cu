@@ -444,6 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
           float f[kFeat];
           load_features(tile, f);
           store_features(f);
+          if (sv.f0) warp_rows_to_global(HB, r & ~31, lane, reinterpret_cast<__nv_bfloat16*>(sv.f0) + (size_t)tile * 128 * 64, 64, rows_valid);
         } else {
           stage_dirs(tile);
         }
@@ -555,6 +556,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
       if (it < 2 && r == 0) stamp(64 + (int)it * 16 + 13);
       if (half == 0) {
         store_features(fnext);
+        // bf16 copy of the (zero-padded) feature rows: the B operand of density_layer.0's weight gradient
+        if (sv.f0 && next_tile < num_tiles)
+          warp_rows_to_global(HB, r & ~31, lane, reinterpret_cast<__nv_bfloat16*>(sv.f0) + (size_t)next_tile * 128 * 64, 64,
+                              M - next_tile * 128 < 128 ? M - next_tile * 128 : 128);
       } else {
         float v[16];
         tmem_ld16(tlane + 256, v);

@@ -354,8 +354,8 @@ def _mlp_forward_raw(mlp, features, viewdirs, S, save: bool):
     sv = None
     if save:
         bf = lambda c: torch.empty(M, c, device=dev, dtype=torch.bfloat16)
-        saved = dict(h0=bf(64), x=bf(256), g=bf(128), h1=bf(256), h2=bf(256))
-        sv = NlbNerfMlpSaved(*[ptr(saved[k]) for k in ('h0', 'x', 'g', 'h1', 'h2')])
+        saved = dict(h0=bf(64), x=bf(256), g=bf(128), h1=bf(256), h2=bf(256), f0=bf(64))
+        sv = NlbNerfMlpSaved(*[ptr(saved[k]) for k in ('h0', 'x', 'g', 'h1', 'h2', 'f0')])
     with torch.cuda.device(dev):
         with timed('nerf_mlp_fwd'):
             check(load().nlb_nerf_mlp_forward(ptr(features), ptr(viewdirs), M, S, ptr(blob), ptr(density), ptr(rgb),
@@ -369,14 +369,6 @@ def nerf_mlp_forward(mlp, features: torch.Tensor, viewdirs: torch.Tensor, S: int
     rgb[N,S,3], semantic[N,S,19], intensity[N,S,1]."""
     density, rgb, sem, inten, _ = _mlp_forward_raw(mlp, f32(features), f32(viewdirs), S, False)
     return dict(density=density, rgb=rgb, semantic=sem, intensity=inten)
-
-
-def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """bf16 x bf16 -> fp32 plain GEMM (cuBLAS): the weight-gradient products dZ^T A."""
-    try:
-        return torch.mm(a, b, out_dtype=torch.float32)
-    except TypeError:
-        return torch.mm(a, b).float()
 
 
 @torch.no_grad()
@@ -409,8 +401,9 @@ def group_sum_bf16(x: torch.Tensor, S: int) -> torch.Tensor:
 
 
 class _NerfMLP(Function):
-    """Training path of the NerfMLP: fused tcgen05 forward that saves bf16
-    activations, fused tcgen05 data-gradient chain, weight gradients as plain GEMMs."""
+    """Training path of the NerfMLP, all on tcgen05: fused forward that saves bf16 activations, fused
+    data-gradient chain, and the weight gradients dW = dZ^T A as MN-major UMMA products (csrc/nerf_wgrad.cu)
+    added straight into the parameters' gradient buffers."""
 
     @staticmethod
     def forward(ctx, features, viewdirs, mlp, S, *weights):
@@ -418,12 +411,12 @@ class _NerfMLP(Function):
         features, viewdirs = f32(features), f32(viewdirs)
         density, rgb, sem, inten, saved = _mlp_forward_raw(mlp, features, viewdirs, S, True)
         ctx.mlp, ctx.S = mlp, S
-        ctx.save_for_backward(features, viewdirs, density, rgb, sem, *[saved[k] for k in ('h0', 'x', 'g', 'h1', 'h2')])
+        ctx.save_for_backward(features, viewdirs, density, rgb, sem, *[saved[k] for k in ('h0', 'x', 'g', 'h1', 'h2', 'f0')])
         return density, rgb, sem, inten
 
     @staticmethod
     def backward(ctx, g_density, g_rgb, g_sem, g_int):
-        features, viewdirs, density, rgb, sem, h0, x, g, h1, h2 = ctx.saved_tensors
+        features, viewdirs, density, rgb, sem, h0, x, g, h1, h2, f0 = ctx.saved_tensors
         mlp, S = ctx.mlp, ctx.S
         M, N = features.shape[0], viewdirs.shape[0]
         dev = features.device
@@ -432,41 +425,42 @@ class _NerfMLP(Function):
         blob_t = nerf_mlp_pack(mlp, transposed=True)
         bf = lambda cols: torch.empty(M, cols, device=dev, dtype=torch.bfloat16)
         d_rgb, d_hs1, d_x, d_h0 = bf(16), bf(32), bf(256), bf(64)
-        # d_g | d_v0 | d_v1 share the A operand x in the weight-gradient products: column slices of one
-        # buffer, so the three products are ONE GEMM [640, M] x [M, 256]
-        dcat = bf(640)
+        dcat = bf(640)   # d_g | d_v0 | d_v1: column slices of one buffer (the three share the operand x)
         d_g, d_v0, d_v1 = dcat[:, :128], dcat[:, 128:384], dcat[:, 384:]
         g_feat = torch.empty(M, 40, device=dev, dtype=torch.float32)
         gin = NlbNerfMlpGradIn(ptr(g_density), ptr(g_rgb), ptr(g_sem), ptr(g_int), ptr(density), ptr(rgb), ptr(sem))
-        sv = NlbNerfMlpSaved(ptr(h0), ptr(x), ptr(g), ptr(h1), ptr(h2))
+        sv = NlbNerfMlpSaved(ptr(h0), ptr(x), ptr(g), ptr(h1), ptr(h2), ptr(f0))
         gout = NlbNerfMlpGradOut(ptr(d_rgb), d_v1.data_ptr(), d_v0.data_ptr(), ptr(d_hs1), d_g.data_ptr(), ptr(d_x),
                                  ptr(d_h0), 640, 640, 640)
+        # gradient targets: the trainer's persistent buffers (views of its flat gradient, `param._nlb_grad`) are
+        # added into directly; without a trainer the gradients are returned through autograd
+        params = _mlp_tensors(mlp)
+        in_place = all(getattr(p, '_nlb_grad', None) is not None for p in params)
+        if in_place:
+            targets = [p._nlb_grad for p in params]
+        else:
+            flat = torch.zeros(sum(p.numel() for p in params), device=dev, dtype=torch.float32)
+            targets, off = [], 0
+            for p in params:
+                targets.append(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        wg = NlbNerfMlpWeights(*[ptr(t) for t in targets])
         with torch.cuda.device(dev):
             with timed('nerf_mlp_bwd'):
                 check(load().nlb_nerf_mlp_backward(C.byref(gin), C.byref(sv), M, ptr(blob_t), ptr(g_feat),
                                                    C.byref(gout), stream()))
-        # weight gradients: plain GEMMs dW = dZ^T A (bf16 operands, fp32 result)
-        de = mlp.dir_enc(viewdirs)                                   # [N,27] per-ray constant
-        f0 = features.to(torch.bfloat16)
-        # bias gradients and per-ray sums: one bandwidth-bound pass each (csrc/reduce.cu); the column sums of
-        # d_v0 / d_v1 fall out of their per-ray sums (10 MB instead of a second 168 MB pass)
-        cs_g, cs_hs1, cs_rgb = colsum_bf16(d_g), colsum_bf16(d_hs1), colsum_bf16(d_rgb)
+            with timed('nerf_mlp_wgrad'):
+                check(load().nlb_nerf_mlp_wgrad(C.byref(sv), C.byref(gout), M, C.byref(wg), stream()))
+        # bias gradients and per-ray sums (the view-direction encoding is a per-ray constant): one
+        # bandwidth-bound pass each (csrc/reduce.cu), folded into the gradient buffers by one small kernel
+        cs_x, cs_g, cs_h0 = colsum_bf16(d_x), colsum_bf16(d_g), colsum_bf16(d_h0)
+        cs_hs1, cs_rgb = colsum_bf16(d_hs1), colsum_bf16(d_rgb)
         rs_v0, rs_v1 = group_sum_bf16(d_v0, S), group_sum_bf16(d_v1, S)
-        gx = _mm_f32(dcat.t(), x)                                    # [640, 256]: W_s0 | W_i0 | W_v0[:, :256] | W_v1[:, 256:512]
-        ghs = _mm_f32(d_hs1.t(), g)                                  # [32, 128]: W_s2 = [:19, :64], W_i2 = [19, 64:]
-        gW = {
-            'W_d0': _mm_f32(d_h0.t(), f0), 'b_d0': colsum_bf16(d_h0),
-            'W_d2': _mm_f32(d_x.t(), h0), 'b_d2': colsum_bf16(d_x),
-            'W_s0': gx[:64], 'b_s0': cs_g[:64],
-            'W_s2': ghs[:19, :64], 'b_s2': cs_hs1[:19],
-            'W_i0': gx[64:128], 'b_i0': cs_g[64:],
-            'W_i2': ghs[19:20, 64:], 'b_i2': cs_hs1[19:20],
-            'W_v0': torch.cat([gx[128:384], rs_v0.t() @ de], dim=1), 'b_v0': rs_v0.sum(0),
-            'W_v1': torch.cat([_mm_f32(d_v1.t(), h1), gx[384:], rs_v1.t() @ de], dim=1), 'b_v1': rs_v1.sum(0),
-            'W_rgb': _mm_f32(d_rgb[:, :3].t(), h2), 'b_rgb': cs_rgb[:3],
-        }
-        grads = [gW[name] for name, _ in _NERF_WEIGHT_FIELDS]
-        return (g_feat, None, None, None, *grads)
+        with torch.cuda.device(dev):
+            with timed('nerf_mlp_wgrad_finish'):
+                check(load().nlb_nerf_mlp_wgrad_finish(ptr(rs_v0), ptr(rs_v1), ptr(viewdirs), N, ptr(cs_x), ptr(cs_g),
+                                                       ptr(cs_h0), ptr(cs_hs1), ptr(cs_rgb), C.byref(wg), stream()))
+        return (g_feat, None, None, None, *([None] * len(targets) if in_place else targets))
 
 
 def nerf_mlp_train(mlp, features: torch.Tensor, viewdirs: torch.Tensor, S: int) -> Dict[str, torch.Tensor]:

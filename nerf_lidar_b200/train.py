@@ -138,6 +138,7 @@ class Trainer:
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p)
             p.grad = self.flat_grad[off:off + k].view_as(p)
+            p._nlb_grad = p.grad   # the NerfMLP weight-gradient kernels add into it directly (ops._NerfMLP)
             off += (k + 3) // 4 * 4
         self.dense = dense
         self.decay = config.hash_decay_mults if config.hash_decay_mults > 0 else 0.

@@ -103,7 +103,7 @@ static int run() {
   const size_t smem = ((Mdim + 63) / 64 + (N + 63) / 64) * (size_t)KROWS * 128 + 1024;
   cudaFuncSetAttribute(probe<Mdim, N, KROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int ok_any = 0;
-  for (int swap = 0; swap < 2; ++swap) {
+  for (int swap = 0; swap < 1; ++swap) {   // (the swapped reading faults: LBO = slab stride, SBO = 1024 it is)
     cudaMemset(dout, 0xff, 128 * N * 4);
     probe<Mdim, N, KROWS><<<1, 160, smem>>>(da, db, dout, swap);
     cudaError_t e = cudaDeviceSynchronize();
@@ -132,8 +132,7 @@ int main() {
   bad += run<128, 128, 32>();
   bad += run<128, 16, 128>();
   bad += run<128, 32, 128>();
-  bad += run<64, 64, 128>();
-  bad += run<64, 256, 64>();
+  // (M = 64 places the accumulator rows on other TMEM lanes than this probe reads back: the kernels use M = 128 only)
   printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
   return bad;
 }
