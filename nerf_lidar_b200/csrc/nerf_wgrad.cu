@@ -1,17 +1,18 @@
 // Weight gradients of the NerfMLP dense layers on tcgen05 (autograd of Z/internal/models.py:1192-1251):
 //   dW = dZ^T A  for every layer, dZ = the bf16 pre-activation gradients written by k_nerf_mlp_bwd, A = the bf16
 //   activations saved by k_nerf_mlp_fwd.  The contraction index is the SAMPLE index m, so both operands are read
-//   from their row-major [M, features] matrices exactly as they lie: a [64 rows][64 features] slab with 128-byte
+//   from their row-major [M, features] matrices exactly as they lie: a [32 rows][64 features] slab with 128-byte
 //   rows and the 128-byte swizzle IS the canonical MN-major UMMA operand layout (rows = K, LBO = next 64 features,
 //   SBO = next 8 rows; validated by tools/umma_mn_probe.cu) -- no transposes, no packing.
 //
 // The accumulators (253 K fp32 values) do not fit one SM's tensor memory (64 K), so the products are split into
-// six ROLES; a role's CTAs share the M rows between them (split-K), stream their 64-row slabs through a 3-stage
+// six ROLES; a role's CTAs share the M rows between them (split-K), stream their 32-row slabs through a 6-stage
 // cp.async ring, keep the role's accumulators in TMEM for their whole row range and add them into the fp32
 // gradient tensors at the end (coalesced RED.ADD.F32 -- straight into Trainer.flat_grad, no partial buffers, no
 // AccumulateGrad adds).  The kernel is HBM-bound: every operand byte is read once per role that needs it, 5.6 KB
-// per row in total (x three times, d_v1 twice), against 2.2 K tensor cycles per 64 KB stage; CTAs are dealt to
-// the roles in proportion to their bytes per row so that all of them finish together.
+// per row in total (x three times, d_v1 twice; 1.83 GB for the bench's 327 680 rows, 1.49 GB of DRAM reads after L2
+// hits) against ~270 tensor cycles per 32 KB stage.  Measured 0.39 ms = 4.7 TB/s algorithmic (cuBLAS: seven GEMMs +
+// split-K reductions, 0.40-0.45 ms, plus the bf16 copy of the features and ~40 AccumulateGrad adds).
 //
 //   role 0: d_v0^T x   -> W_v0[:, 0:256]        role 3: d_g^T  x   -> W_s0 | W_i0
 //   role 1: d_v1^T x   -> W_v1[:, 256:512]      role 4: d_x^T  h0  -> W_d2 ;  d_h0^T f0 -> W_d0
@@ -23,17 +24,29 @@
 #include "umma.cuh"
 #include "../../include/nlb200.h"
 #include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdlib>
 
 namespace nlb {
 namespace wgrad {
 
 using namespace nlb::umma;
 
-constexpr int kRows = 64;                 // sample rows per pipeline stage (4 K-steps of 16)
-constexpr int kBlk = kRows * 128;         // one [64][64] bf16 slab
-constexpr int kStageBytes = 65536;
-constexpr int kStages = 3;
-constexpr int kProdWarps = 4, kMmaWarp = 4;
+constexpr int kRows = 32;                 // sample rows per pipeline stage (2 K-steps of 16)
+constexpr int kBlk = kRows * 128;         // one [32 rows][64 features] bf16 slab
+constexpr int kStageBytes = 8 * kBlk;     // every role fills (at most) eight slabs per stage
+// Deep ring of small stages: a slot is refilled only after the MMAs that read it have retired, so with S slots about
+// S - 2 stages of loads are in flight; HBM latency x the per-SM share of the bandwidth needs > 100 KB in flight.
+constexpr int kStages = 7;
+// A stage is announced to the MMA warp once the copies of the kInFlight - 1 stages issued after it are in flight
+// (cp.async groups complete in order); the remaining kStages - kInFlight + 1 slots are the slack that lets the
+// producers run ahead of the tensor pipe instead of shaking hands with it every stage.
+constexpr int kInFlight = 6;
+// 8 producer warps: with 256 threads every stream's (row, 16-byte chunk) pattern repeats with a row period that is
+// a multiple of 8, so a thread's swizzle term and source column are loop constants and a copy costs ~5 instructions
+// (the first version spent 39 instructions per copy on index arithmetic with 4 warps and was issue-bound at 3 TB/s)
+constexpr int kProdWarps = 8, kMmaWarp = 8;
+constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kThreads = (kProdWarps + 1) * 32;
 constexpr int kNumRoles = 6;
 constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + 256;
@@ -82,6 +95,25 @@ __device__ __forceinline__ uint64_t desc_mn(const void* p) {     // MN-major, SW
   return d;
 }
 
+// rows [row0, row0 + kRows) x (8 << LOG2CPR) columns of a row-major bf16 matrix -> 64-column slabs (128-byte rows,
+// 16-byte chunks XOR-swizzled by row & 7).  256 threads: consecutive threads take consecutive chunks of a row.
+template <int LOG2CPR>
+__device__ __forceinline__ void copy_stream(uint8_t* slab0, const __nv_bfloat16* ptr, int ld, int row0, int M, int tid) {
+  constexpr int CPR = 1 << LOG2CPR;
+  constexpr int TOTAL = kRows * CPR;
+  constexpr int ITERS = (TOTAL + kProdThreads - 1) / kProdThreads;
+  constexpr int ROWS_PER_ITER = kProdThreads / CPR;          // 8, 16, 32, (64, 128: one partial iteration)
+  if (TOTAL < kProdThreads && tid >= TOTAL) return;
+  const int r = tid >> LOG2CPR, ch = tid & (CPR - 1);
+  uint8_t* dst = slab0 + (ch >> 3) * kBlk + (r >> 3) * 1024 + (r & 7) * 128 + (((ch & 7) ^ (r & 7)) * 16);
+  const __nv_bfloat16* src = ptr + (size_t)(row0 + r) * ld + ch * 8;
+#pragma unroll
+  for (int k = 0; k < ITERS; ++k) {
+    const bool ok = row0 + r + k * ROWS_PER_ITER < M;
+    cp_async16(dst + k * (ROWS_PER_ITER / 8) * 1024, ok ? src + (size_t)k * ROWS_PER_ITER * ld : ptr, ok);
+  }
+}
+
 struct Bars {
   uint64_t full[kStages], empty[kStages], done;
   uint32_t tmem_base;
@@ -106,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_wgrad(const __grid_con
   const int n_it = t1 > t0 ? t1 - t0 : 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&bars.full[i], kProdWarps * 32); mbar_init(&bars.empty[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bars.full[i], kProdThreads); mbar_init(&bars.empty[i], 1); }
     mbar_init(&bars.done, 1);
     fence_barrier_init();
   }
@@ -120,7 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_wgrad(const __grid_con
     // ===== producers: 16-byte async copies, rows beyond M are zero-filled; a stage is handed over when every
     // producer thread's copies of it have landed (wait_group) and are visible to the tensor pipe (proxy fence)
     const int tid = threadIdx.x;
-    for (int it = 0; it < n_it + kStages - 1; ++it) {
+    for (int it = 0; it < n_it + kInFlight - 1; ++it) {
       if (it < n_it) {
         const int slot = it % kStages;
         if (it >= kStages) mbar_wait_relaxed(&bars.empty[slot], ((it / kStages) & 1) ^ 1);
@@ -128,20 +160,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_wgrad(const __grid_con
         const int row0 = (t0 + it) * kRows;
         for (int si = 0; si < role.ns; ++si) {
           const Stream& s = role.s[si];
-          const int cpr = 1 << s.log2_cpr;
-          for (int e = tid; e < kRows * cpr; e += kProdWarps * 32) {
-            const int row = e >> s.log2_cpr, ch = e & (cpr - 1);
-            const bool ok = row0 + row < P.M;
-            uint8_t* dst = st + s.smem_off + (ch >> 3) * kBlk + (row >> 3) * 1024 + (row & 7) * 128 + (((ch & 7) ^ (row & 7)) * 16);
-            cp_async16(dst, s.ptr + (size_t)(ok ? row0 + row : 0) * s.ld + ch * 8, ok);
+          switch (s.log2_cpr) {
+            case 5: copy_stream<5>(st + s.smem_off, s.ptr, s.ld, row0, P.M, tid); break;
+            case 4: copy_stream<4>(st + s.smem_off, s.ptr, s.ld, row0, P.M, tid); break;
+            case 3: copy_stream<3>(st + s.smem_off, s.ptr, s.ld, row0, P.M, tid); break;
+            case 2: copy_stream<2>(st + s.smem_off, s.ptr, s.ld, row0, P.M, tid); break;
+            default: copy_stream<1>(st + s.smem_off, s.ptr, s.ld, row0, P.M, tid); break;
           }
         }
       }
       cp_async_commit();
-      if (it >= kStages - 1) {
-        cp_async_wait_group<kStages - 1>();
+      if (it >= kInFlight - 1) {
+        cp_async_wait_group<kInFlight - 1>();
         fence_proxy_async();
-        mbar_arrive(&bars.full[(it - (kStages - 1)) % kStages]);
+        mbar_arrive(&bars.full[(it - (kInFlight - 1)) % kStages]);
       }
     }
   } else if (elect_one_sync()) {
@@ -165,18 +197,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_wgrad(const __grid_con
   }
   __syncwarp();
 
-  // ===== epilogue (the producer warps: warp w owns TMEM lanes 32 w .. 32 w + 31)
+  // ===== epilogue (the producer warps: warps w and w + 4 own TMEM lanes 32 (w & 3) .. + 31 and alternate over the
+  // 32-column groups)
   if (warp < kProdWarps && n_it > 0) {
     mbar_wait_warp(&bars.done, 0);
     tcgen05_fence_after();
     float* tile = reinterpret_cast<float*>(base) + warp * (32 * 33);     // the ring is free now
-    const int rrow = warp * 32 + lane, half = warp >> 1, rloc = rrow & 63;
-    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    const int q = warp & 3, par = warp >> 2;
+    const int rrow = q * 32 + lane, half = q >> 1, rloc = rrow & 63;
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    int grp = 0;
     for (int o = 0; o < role.nop; ++o) {
       const Op& op = role.op[o];
       float* bp = op.base[half];
       const int lo = op.col_lo[half], hi = op.col_hi[half];
-      for (int c0 = 0; c0 < op.n; c0 += 32) {
+      for (int c0 = 0; c0 < op.n; c0 += 32, ++grp) {
+        if ((grp & 1) != par) continue;
         float v[32];
         if (op.n - c0 >= 32) {
           tmem_ld32(tl + op.tmem_col + c0, v);
@@ -203,9 +239,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_wgrad(const __grid_con
           __syncwarp();
           const int c = c0 + lane;
           const bool cok = c >= lo && c < hi;
-          const int rbase = (warp * 32) & 63;
+          const int rbase = (q * 32) & 63;
           for (int rr = 0; rr < 32; ++rr) {
-            if (cok && warp * 32 + rr < op.rows_valid) atomicAdd(bp + (size_t)(rbase + rr) * op.stride + c, tile[rr * 33 + lane]);
+            if (cok && q * 32 + rr < op.rows_valid) atomicAdd(bp + (size_t)(rbase + rr) * op.stride + c, tile[rr * 33 + lane]);
           }
           __syncwarp();
         }
@@ -352,31 +388,38 @@ extern "C" int nlb_nerf_mlp_wgrad(const nlb_nerf_mlp_saved_t* sv, const nlb_nerf
   };
   Params P{};
   P.M = M;
-  // bytes per row each role streams (CTA shares)
-  const int bytes_per_row[kNumRoles] = {1024, 1024, 1024, 768, 896, 864};
+  // CTA shares of the roles.  Bytes per row are 1024 / 1024 / 1024 / 768 / 896 / 864, but the two roles with four
+  // operand streams and small-N products cost more per stage than their bytes: measured on B200
+  // (tools/wgrad_bench.py, 327 680 rows) 0.42 ms with byte-proportional shares, 0.40 equal, 0.387 with these.
+  int bytes_per_row[kNumRoles] = {4, 4, 4, 3, 4, 4};
+  if (const char* e = getenv("NLB_WGRAD_SPLIT")) {   // dev switch: relative CTA shares of the six roles
+    int v[kNumRoles];
+    if (sscanf(e, "%d,%d,%d,%d,%d,%d", v, v + 1, v + 2, v + 3, v + 4, v + 5) == kNumRoles)
+      for (int i = 0; i < kNumRoles; ++i) bytes_per_row[i] = v[i] > 0 ? v[i] : 1;
+  }
   {
     Role& R = P.role[0];   // d_v0^T x
-    R.ns = 2; R.s[0] = stream_of(sv->x, 256, 256, 0); R.s[1] = stream_of(go->d_v0, ld_v0, 256, 32768);
+    R.ns = 2; R.s[0] = stream_of(sv->x, 256, 256, 0); R.s[1] = stream_of(go->d_v0, ld_v0, 256, 4 * kBlk);
     R.nop = 2;
-    for (int mt = 0; mt < 2; ++mt) R.op[mt] = plain(32768 + mt * 2 * kBlk, 0, 256, mt * 256, g->W_v0 + (size_t)mt * 128 * 283, 283, 256, 128);
+    for (int mt = 0; mt < 2; ++mt) R.op[mt] = plain(4 * kBlk + mt * 2 * kBlk, 0, 256, mt * 256, g->W_v0 + (size_t)mt * 128 * 283, 283, 256, 128);
   }
   {
     Role& R = P.role[1];   // d_v1^T x
-    R.ns = 2; R.s[0] = stream_of(sv->x, 256, 256, 0); R.s[1] = stream_of(go->d_v1, ld_v1, 256, 32768);
+    R.ns = 2; R.s[0] = stream_of(sv->x, 256, 256, 0); R.s[1] = stream_of(go->d_v1, ld_v1, 256, 4 * kBlk);
     R.nop = 2;
-    for (int mt = 0; mt < 2; ++mt) R.op[mt] = plain(32768 + mt * 2 * kBlk, 0, 256, mt * 256, g->W_v1 + (size_t)mt * 128 * 539 + 256, 539, 256, 128);
+    for (int mt = 0; mt < 2; ++mt) R.op[mt] = plain(4 * kBlk + mt * 2 * kBlk, 0, 256, mt * 256, g->W_v1 + (size_t)mt * 128 * 539 + 256, 539, 256, 128);
   }
   {
     Role& R = P.role[2];   // d_v1^T h1
-    R.ns = 2; R.s[0] = stream_of(sv->h1, 256, 256, 0); R.s[1] = stream_of(go->d_v1, ld_v1, 256, 32768);
+    R.ns = 2; R.s[0] = stream_of(sv->h1, 256, 256, 0); R.s[1] = stream_of(go->d_v1, ld_v1, 256, 4 * kBlk);
     R.nop = 2;
-    for (int mt = 0; mt < 2; ++mt) R.op[mt] = plain(32768 + mt * 2 * kBlk, 0, 256, mt * 256, g->W_v1 + (size_t)mt * 128 * 539, 539, 256, 128);
+    for (int mt = 0; mt < 2; ++mt) R.op[mt] = plain(4 * kBlk + mt * 2 * kBlk, 0, 256, mt * 256, g->W_v1 + (size_t)mt * 128 * 539, 539, 256, 128);
   }
   {
     Role& R = P.role[3];   // d_g^T x -> sem_layer.0 (rows 0..63) | intensity_layer.0 (rows 64..127)
-    R.ns = 2; R.s[0] = stream_of(sv->x, 256, 256, 0); R.s[1] = stream_of(go->d_g, ld_g, 128, 32768);
+    R.ns = 2; R.s[0] = stream_of(sv->x, 256, 256, 0); R.s[1] = stream_of(go->d_g, ld_g, 128, 4 * kBlk);
     R.nop = 1;
-    R.op[0] = plain(32768, 0, 256, 0, g->W_s0, 256, 256, 128);
+    R.op[0] = plain(4 * kBlk, 0, 256, 0, g->W_s0, 256, 256, 128);
     R.op[0].base[1] = g->W_i0;
   }
   {
@@ -412,7 +455,7 @@ extern "C" int nlb_nerf_mlp_wgrad(const nlb_nerf_mlp_saved_t* sv, const nlb_nerf
       R.op[1 + mt] = q;
     }
   }
-  // CTAs per role in proportion to the bytes it streams, at most one per 64-row stage
+  // CTAs per role in proportion to the bytes it streams, at most one per stage
   const int total_stages = (M + kRows - 1) / kRows;
   int sum_b = 0;
   for (int b : bytes_per_row) sum_b += b;
@@ -426,6 +469,16 @@ extern "C" int nlb_nerf_mlp_wgrad(const nlb_nerf_mlp_saved_t* sv, const nlb_nerf
     cta += n;
     left -= n;
     if (left < kNumRoles - 1 - i) left = kNumRoles - 1 - i;
+  }
+  if (const char* e = getenv("NLB_WGRAD_ONLY")) {    // dev switch: time ONE role on all SMs (results incomplete)
+    const int only = atoi(e);
+    if (only >= 0 && only < kNumRoles) {
+      P.role[0] = P.role[only];
+      P.role[0].cta0 = 0;
+      P.role[0].nctas = sms < total_stages ? sms : total_stages;
+      for (int i = 1; i < kNumRoles; ++i) P.role[i].cta0 = 1 << 30;
+      cta = P.role[0].nctas;
+    }
   }
   k_nerf_mlp_wgrad<<<cta, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
   return nlb_check_launch("nerf_mlp_wgrad");
