@@ -110,12 +110,22 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference / CPU arm
-def cpu_reference_steps(steps, warmup, sample_rays):
-    """Times the oracle port of the reference training step (oracle/train_oracle.py)
-    on the host cores with all threads, on a bounded sample of the workload."""
+def workload_config(world):
+    """`config` of BOTH arms: the workload is the same, the CPU arm times a bounded sample of it."""
+    return {'workload': 'zipnerf nuscenes_single.gin camera+LiDAR training step (BASELINE configs[1])',
+            'rays_per_step_nominal_per_gpu': BATCH, 'rays_through_model_per_gpu': BATCH + BATCH // 4,
+            'global_batch': BATCH * world, 'samples': list(SAMPLES), 'multisamples': 7, 'params': 77656777,
+            'parallelism': f'dp{world}'}
+
+
+def cpu_reference_steps(steps, warmup, sample_rays, forward_only=False):
+    """Times the oracle port of the reference path (oracle/train_oracle.py, oracle/zipnerf_oracle.py: the
+    reference's Python restated on torch-CPU with a torch-gather grid) on the host cores
+    with all threads, on a bounded sample of the workload: a full training step, or the forward only
+    (rand=False: rendering)."""
     import torch
     from nerf_lidar_b200 import synthetic
-    from oracle import train_oracle
+    from oracle import train_oracle, zipnerf_oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = synthetic.init_state_dict(seed=0, table_std=1e-4)
@@ -131,7 +141,11 @@ def cpu_reference_steps(steps, warmup, sample_rays):
     for i in range(warmup + steps):
         b, rin = batches[i % 2]
         t0 = time.perf_counter()
-        tr.step(b, rin, 6000 + i, num_patch)
+        if forward_only:
+            with torch.no_grad():
+                zipnerf_oracle.model_forward(sd, b, None, 1.0)
+        else:
+            tr.step(b, rin, 6000 + i, num_patch)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     times.sort()
@@ -140,22 +154,23 @@ def cpu_reference_steps(steps, warmup, sample_rays):
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU path (kind "port": the reference's grid encoder is CUDA-only and its
+    Python cannot travel to the GPU box) on this arm's config / metric / unit, every step a
+    bounded 1024-ray sample of the 8192-ray workload, --steps / --warmup as given."""
     rank = _env_int('RANK', 0)
     if rank != 0:
         return
     sample = 1024
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     rps, med, cores, threads = cpu_reference_steps(steps, warmup, sample)
     line = {
         'impl': 'reference', 'metric': 'train_rays_per_sec', 'value': rps, 'unit': 'rays/s', 'n_gpus': args.gpus,
         'steps': steps, 'warmup': warmup, 'ms_per_step': med * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'zipnerf nuscenes_single.gin camera+LiDAR training step (BASELINE configs[1]); '
-                               'reference path = oracle port on host cores', 'rays_per_step_nominal': sample,
-                   'rays_through_model': sample + sample // 4, 'samples': list(SAMPLES)},
+        'config': workload_config(max(1, args.gpus)),
         'cpu_baseline': {'value': rps, 'unit': 'rays/s', 'cores': threads, 'kind': 'port',
-                         'sample': f'{sample}-ray (+{sample // 4} LiDAR) training steps, median of {steps}, '
-                                   f'{cores} host cores'},
+                         'sample': f'{sample}-ray (+{sample // 4} LiDAR) sample of the {BATCH}-ray training step per '
+                                   f'timed step, median of {steps}, {cores} host cores'},
         'e2e': {'value': rps, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -250,32 +265,53 @@ def run_cuda_arm(args):
     kt = _lib.TIMER.summary() if _lib.TIMER is not None else {}
     _lib.TIMER = None
 
-    # ---- rendering (BASELINE configs[2] / [4]): LiDAR sweep and one 1600x900 camera frame through
-    # models.render_image, rays sharded contiguously over the ranks, one packed gather at the end
+    # ---- rendering (BASELINE configs[2] / [4]) through models.render_image: rays sharded contiguously over the
+    # ranks, local chunks replayed as CUDA graphs, one packed gather at the end.  configs[4] = 4 cameras at
+    # 1600 x 900 with the video sampling num_prop_samples = (256, 64) (Z/render_video.py:130) + one LiDAR sweep.
     render = None
     if not args.no_render:
+        import copy
+
         class _Acc:
             process_index, num_processes, is_main_process = rank, world, rank == 0
-        render = {}
-        for name, make, reps in (('lidar_sweep_32x1084', synthetic.make_lidar_sweep, 5),
-                                 ('camera_frame_1600x900', synthetic.make_camera_frame, 2)):
-            rb = {k: torch.from_numpy(v).to(dev) for k, v in make(seed=0).items()}
-            n_rays = rb['origins'].shape[0]
+        rcfg = copy.copy(cfg)
+        rcfg.render_chunk_size = 65536      # the 34 688-ray sweep is one chunk per rank (Config default: 16384)
+        enc_bytes = lambda samples: sum(b * 7 * s_ for b, s_ in zip((228, 300, 1452), samples))
+
+        def timed_render(batches, reps, samples):
+            model.num_prop_samples = tuple(samples[:2])
             with torch.no_grad():
-                models.render_image(model, _Acc, rb, False, cfg, image=False, verbose=False)  # warm-up
+                for rb in batches[:1] + batches[-1:]:                                   # warm-up: graph capture
+                    models.render_image(model, _Acc, rb, False, rcfg, image=False, verbose=False)
                 barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for _ in range(reps):
-                    out = models.render_image(model, _Acc, rb, False, cfg, image=False, verbose=False)
+                    for rb in batches:
+                        out = models.render_image(model, _Acc, rb, False, rcfg, image=False, verbose=False)
                 e1.record()
                 barrier()
             t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            render[name] = {'rays': n_rays, 'ms': float(t.item()), 'rays_per_s': n_rays / float(t.item()) * 1e3,
-                            'outputs': sorted(k for k in out if not k.startswith('ray_'))}
-            del rb, out
+            model.num_prop_samples = (SAMPLES[0], SAMPLES[1])
+            return float(t.item()), sorted(k for k in out if not k.startswith('ray_'))
+
+        to_dev = lambda b: {k: torch.from_numpy(v).to(dev) for k, v in b.items()}
+        sweep = to_dev(synthetic.make_lidar_sweep(seed=0))
+        frames = [to_dev(synthetic.make_camera_frame(seed=s_)) for s_ in range(4)]
+        n_sweep, n_frame = sweep['origins'].shape[0], frames[0]['origins'].shape[0]
+        render = {}
+        for name, batches, reps, samples in (
+                ('lidar_sweep_32x1084', [sweep], 5, SAMPLES),
+                ('camera_frame_1600x900', frames[:1], 2, SAMPLES),
+                ('sensor_fusion_4x1600x900_plus_sweep', frames + [sweep], 1, (256, 64, 32))):
+            n_rays = sum(b['origins'].shape[0] for b in batches)
+            ms_r, outs = timed_render(batches, reps, samples)
+            render[name] = {'rays': n_rays, 'ms': ms_r, 'rays_per_s': n_rays / ms_r * 1e3, 'samples': list(samples),
+                            'chunk_rays': rcfg.render_chunk_size, 'outputs': outs,
+                            'encode_alg_bytes_per_ray': enc_bytes(samples)}
+        del sweep, frames
         model.train()
         model.training = True
 
@@ -322,7 +358,9 @@ def run_cuda_arm(args):
     roofline_mlp = None
     tf_peak = float(peaks.get('bf16_tflops_sustained', 1356.8))
     rows_mlp = rays_model * SAMPLES[-1]
-    for name, macs in (('nerf_mlp_fwd', 264192), ('nerf_mlp_bwd', 257024)):
+    if 'nerf_mlp_wgrad' in per_kernel:   # HBM-bound: 5.6 KB of bf16 operands per row (csrc/nerf_wgrad.cu)
+        per_kernel['nerf_mlp_wgrad']['alg_gbs'] = 5600.0 * rows_mlp / (per_kernel['nerf_mlp_wgrad']['avg_ms'] * 1e-3) / 1e9
+    for name, macs in (('nerf_mlp_fwd', 264192), ('nerf_mlp_bwd', 257024), ('nerf_mlp_wgrad', 253184)):
         if name in per_kernel:
             t = 2.0 * macs * rows_mlp / (per_kernel[name]['avg_ms'] * 1e-3) / 1e12
             per_kernel[name]['tflops'] = t
@@ -332,39 +370,122 @@ def run_cuda_arm(args):
                                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if 'bf16_tflops_sustained'
                                 in peaks else 'fallback 1356.8 TFLOP/s', 'avg_launch_ms': per_kernel[name]['avg_ms'],
                                 'flops_per_row': 2 * macs, 'rows': rows_mlp}
+    # forward-only roofline of the renders: hash-grid algorithmic bytes per ray against the measured HBM rate
+    if render:
+        for r in render.values():
+            roof = hbm_peak * 1e9 / r['encode_alg_bytes_per_ray'] * world
+            r['encode_roofline_rays_per_s'] = roof
+            r['frac_of_encode_roofline'] = r['rays_per_s'] / roof
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rps, med, cores, threads = cpu_reference_steps(3, 1, 512)
+        # 4096 rays, training step (forward + backward + Adam) and forward only (render),
+        # the oracle port on all host cores; one timed iteration each after a small warm-up (~15-20 s of CPU work)
+        cpu_reference_steps(1, 0, 256)
+        rps, med, cores, threads = cpu_reference_steps(1, 0, 4096)
+        rps_f, med_f, _, _ = cpu_reference_steps(1, 0, 4096, forward_only=True)
         cpu = {'value': rps, 'unit': 'rays/s', 'cores': threads, 'kind': 'port',
-               'sample': f'512-ray (+128 LiDAR) training steps of the oracle port, median of 3, {cores} host cores'}
+               'sample': f'one 4096-ray (+1024 LiDAR) training step of the oracle port ({med:.1f} s) on {cores} host '
+                         f'cores; forward only (render): {rps_f:.0f} rays/s ({med_f:.1f} s)',
+               'render_value': rps_f}
+    ref_kernel = None
+    if world == 1 and not args.no_reference_kernel:
+        ref_kernel = reference_kernel_leg(model, resident[0], per_kernel)
     value = BATCH * world * args.steps / (ms * 1e-3)
     e2e = BATCH * world * args.steps / (ms_e2e * 1e-3)
+    if roofline is not None:
+        # (nested so that the driver, which keeps `roofline` and `config`, records them)
+        roofline['mlp'] = roofline_mlp
+        roofline['reference_kernel'] = ref_kernel
+        roofline['kernels'] = {k: {'avg_ms': round(v['avg_ms'], 4), 'launches_per_step': v['launches'] // n_prof,
+                                   'share_of_step': round(v['share_of_step'], 4),
+                                   **({'alg_gbs': round(v['alg_gbs'], 1)} if v.get('alg_gbs') else {}),
+                                   **({'tflops': round(v['tflops'], 1)} if v.get('tflops') else {})}
+                               for k, v in per_kernel.items()}
+    config = workload_config(world)
+    config.update({'launch': 'eager' if args.eager else 'whole training step replayed as one CUDA graph',
+                   'eager_ms_per_step': ms_eager / n_prof,
+                   'l2_policy': 'inputs larger than L2: 1.24 GB of table + optimizer state streamed every step, '
+                                'batches rotate over a pool of 4',
+                   'render': render})
     line = {
         'metric': 'train_rays_per_sec', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32 grid/compositing, bf16 MLP operands (fp32 accumulate)',
         'data': 'synthetic',
-        'config': {'workload': 'zipnerf nuscenes_single.gin camera+LiDAR training step (BASELINE configs[1])',
-                   'rays_per_step_nominal_per_gpu': BATCH, 'rays_through_model_per_gpu': rays_model,
-                   'global_batch': BATCH * world, 'samples': list(SAMPLES), 'multisamples': 7,
-                   'params': 77656777, 'parallelism': f'dp{world}',
-                   'launch': 'eager' if args.eager else 'whole training step replayed as one CUDA graph',
-                   'eager_ms_per_step': ms_eager / n_prof,
-                   'l2_policy': 'inputs larger than L2: 1.24 GB of table + optimizer state streamed every step, '
-                                'batches rotate over a pool of 4'},
+        'config': config,
         'clocks': clocks,
         'e2e': {'value': e2e, 'unit': 'rays/s', 'ms_per_step': ms_e2e / args.steps,
                 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
         'gpu_launches': launches,
         'roofline': roofline,
-        'roofline_mlp': roofline_mlp,
-        'render': render,
-        'kernels': per_kernel,
         'cpu_baseline': cpu,
     }
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def reference_kernel_leg(model, batch, per_kernel):
+    """The kernel to beat for subsystem (1): the reference's own gridencoder.cu, compiled
+    unmodified into oracle/_ref (oracle/build_ref.py), timed on this workload's sample points as the chain the
+    fused kernels replace -- forward: kernel_grid `[L,B,C]` + the permute copy (Z/gridencoder/grid.py:54-57) + erf
+    re-weighting and multisample mean (Z/internal/models.py:974-977); backward: autograd of that mean, the permute
+    copy, zeros_like(embeddings) and kernel_grid_backward (Z/gridencoder/grid.py:65-89).  The fused kernels'
+    times beside it also contain cast_rays + contract (and the PropMLP on the proposal levels).  A baseline leg:
+    nothing of it is on the product path."""
+    import torch
+    try:
+        from oracle import ref_grid
+        if not ref_grid.available():
+            return {'unavailable': 'oracle/_ref/_gridencoder_ref.so not built (python oracle/build_ref.py)'}
+        ref_grid.backend()
+    except Exception as e:   # noqa: BLE001
+        return {'unavailable': f'{type(e).__name__}: {e}'[:200]}
+    from nerf_lidar_b200 import ops
+    rays = ops.RayBundle(batch)
+    out = {}
+    with torch.no_grad():
+        for name, mlp, S in (('prop6', model.prop_mlp_0, SAMPLES[0]), ('prop8', model.prop_mlp_1, SAMPLES[1]),
+                             ('nerf_encode', model.nerf_mlp, SAMPLES[2])):
+            enc = mlp.encoder
+            L, C = enc.num_levels, enc.level_dim
+            _, tdist = ops.resample_level(None, None, batch['near'], batch['far'], S, False, 0.5, 1.0, None, False)
+            pts = ops.sample_points(tdist, None, rays)
+            x = pts[..., :3].reshape(-1, 3).contiguous()
+            stds = pts[..., 3].reshape(-1, 7).contiguous()
+            del pts
+            Mrows = stds.shape[0]
+            g = torch.randn(Mrows, L * C, device=x.device)
+            emb = enc.embeddings.detach()
+
+            def fwd():
+                f, _ = ref_grid.encode_forward(x, emb, enc.offsets, enc.per_level_scale, enc.base_resolution)
+                return ref_grid.erf_mean(f.reshape(Mrows, 7, L * C), stds, enc.grid_sizes, L)
+
+            def bwd():
+                w = torch.erf(1 / torch.clamp(torch.sqrt(8 * stds[..., None] ** 2 * enc.grid_sizes ** 2), min=1e-10))
+                g7 = (g.view(Mrows, 1, L, C) * w[..., None] / 7).reshape(Mrows * 7, L * C)
+                return ref_grid.encode_backward(g7, x, emb, enc.offsets, enc.per_level_scale, enc.base_resolution)[0]
+
+            res = {'points': int(x.shape[0])}
+            for tag, fn in (('fwd', fwd), ('bwd', bwd)):
+                fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ref_ms = e0.elapsed_time(e1) / 3
+                ours = per_kernel.get(f'{name}_{tag}', {}).get('avg_ms')
+                res[f'reference_{tag}_ms'] = round(ref_ms, 4)
+                res[f'fused_{tag}_ms'] = round(ours, 4) if ours else None
+                res[f'speedup_{tag}'] = round(ref_ms / ours, 2) if ours else None
+            out[name] = res
+            del x, stds, g
+            torch.cuda.empty_cache()
+    return out
 
 
 def _emit(line: dict):
@@ -391,6 +512,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-render', action='store_true', help='skip the rendering throughput measurement')
+    ap.add_argument('--no-reference-kernel', action='store_true', help='skip timing the reference grid kernel (oracle/_ref)')
     ap.add_argument('--eager', action='store_true', help='issue the step eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
