@@ -354,6 +354,14 @@ int nlb_adam_table_step(float* param, float* grad, float* exp_avg, float* exp_av
                         float beta2, float eps, int step, float grad_scale,
                         float* level_sumsq /*[L] += per-level sum of squares of the UPDATED table, or NULL*/,
                         void* stream);
+/* The same pass over the float range [first, first + count) of the table only (both multiples of 4): the slice of
+ * the optimizer pass one rank owns in data-parallel runs (reduce-scatter of the gradients -> this -> all-gather of
+ * the parameters).  param / grad point at the START of the table, exp_avg / exp_avg_sq at the slice-local moments;
+ * level_sumsq receives the slice's contribution. */
+int nlb_adam_table_step_range(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                              const int32_t* offsets_host, int L, int C, float decay_mult, float lr, float beta1,
+                              float beta2, float eps, int step, float grad_scale, float* level_sumsq,
+                              int64_t first, int64_t count, void* stream);
 /* CUDA-graph support.  The scalars that change every training step -- the resampling
  * anneal (Z/internal/models.py:343-349) and Adam's learning rate / bias corrections --
  * are by-value arguments above, which a captured graph would freeze.  When a device buffer

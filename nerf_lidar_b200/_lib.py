@@ -108,6 +108,8 @@ SIGNATURES = {
     'nlb_distortion_loss': (_i, [_p, _p, _i, _i, _p, _p, _p]),
     'nlb_interlevel_loss': (_i, [_p, _p, _i, _p, _p, _i, _f, _i, _p, _p, _p]),
     'nlb_adam_table_step': (_i, [_p, _p, _p, _p, C.POINTER(C.c_int32), _i, _i, _f, _f, _f, _f, _f, _i, _f, _p, _p]),
+    'nlb_adam_table_step_range': (_i, [_p, _p, _p, _p, C.POINTER(C.c_int32), _i, _i, _f, _f, _f, _f, _f, _i, _f, _p,
+                                       C.c_int64, C.c_int64, _p]),
     'nlb_render_losses_workspace_bytes': (C.c_size_t, []),
     'nlb_render_losses': (_i, [C.POINTER(NlbLossesIn)] + [_p] * 10),
     'nlb_set_dynamic_scalars': (_i, [_p]),

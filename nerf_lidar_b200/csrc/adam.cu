@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ param, float* 
                                               float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int64_t n,
                                               DecayTable dt, float lr_c, float rsqrt_bc2, float beta1, float beta2,
                                               float eps, float grad_scale, float* __restrict__ level_sumsq,
-                                              const float* __restrict__ dyn) {
+                                              const float* __restrict__ dyn, int64_t first) {
   __shared__ float s_sum[kMaxLevels];
   if (dyn) {  // CUDA-graph replay: this step's learning rate and bias corrections
     lr_c = __ldg(dyn + NLB_DYN_LR_C);
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ param, float* 
     float4 v = reinterpret_cast<float4*>(exp_avg_sq)[i];
     float coef = 0.f;
     if (kDecay) {
-      const int64_t e = i << 2;  // level sizes are multiples of 8 rows, so a float4 never straddles levels
+      const int64_t e = first + (i << 2);  // level sizes are multiples of 8 rows, so a float4 never straddles levels
       int l = cur_l < 0 ? 0 : cur_l;
       while (l < dt.L - 1 && e >= dt.end[l]) ++l;
       coef = dt.coef[l];
@@ -117,6 +117,15 @@ extern "C" int nlb_adam_table_step(float* param, float* grad, float* exp_avg, fl
                                    const int32_t* offsets_host, int L, int C, float decay_mult, float lr, float beta1,
                                    float beta2, float eps, int step, float grad_scale, float* level_sumsq,
                                    void* stream) {
+  if (!offsets_host || L < 1) { nlb_set_error("adam_table_step: null pointer"); return NLB_EINVAL; }
+  return nlb_adam_table_step_range(param, grad, exp_avg, exp_avg_sq, offsets_host, L, C, decay_mult, lr, beta1, beta2, eps,
+                                   step, grad_scale, level_sumsq, 0, (int64_t)offsets_host[L] * C, stream);
+}
+
+extern "C" int nlb_adam_table_step_range(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                                         const int32_t* offsets_host, int L, int C, float decay_mult, float lr,
+                                         float beta1, float beta2, float eps, int step, float grad_scale,
+                                         float* level_sumsq, int64_t first, int64_t count, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || !offsets_host) { nlb_set_error("adam_table_step: null pointer"); return NLB_EINVAL; }
   if (L < 1 || L > kMaxLevels) { nlb_set_error("adam_table_step: L=%d outside [1,%d]", L, kMaxLevels); return NLB_EINVAL; }
   if (step < 1) { nlb_set_error("adam_table_step: step counts from 1"); return NLB_EINVAL; }
@@ -127,15 +136,24 @@ extern "C" int nlb_adam_table_step(float* param, float* grad, float* exp_avg, fl
     dt.end[l] = (int64_t)offsets_host[l + 1] * C;
     dt.coef[l] = (float)(2.0 * (double)decay_mult / ((double)L * C * (double)rows));
   }
-  const int64_t n = (int64_t)offsets_host[L] * C;
-  if (n % 4 != 0) { nlb_set_error("adam_table_step: table size must be a multiple of 4 floats"); return NLB_EINVAL; }
+  const int64_t total = (int64_t)offsets_host[L] * C;
+  if (total % 4 != 0) { nlb_set_error("adam_table_step: table size must be a multiple of 4 floats"); return NLB_EINVAL; }
+  if (first < 0 || count < 0 || first + count > total || (first | count) % 4 != 0) {
+    nlb_set_error("adam_table_step: range [%lld, +%lld) must lie inside the table and be a multiple of 4 floats", (long long)first, (long long)count);
+    return NLB_EINVAL;
+  }
+  if (count == 0) return NLB_OK;
+  // this rank's slice of the table (data-parallel runs shard the optimizer pass; the moments are slice-local)
+  float* p = param + first;
+  float* g = grad + first;
   float lr_c, rs;
   bias_terms(lr, beta1, beta2, step, lr_c, rs);
-  const int blocks = 148 * 8;
+  int64_t want = (count / 4 + 255) / 256;
+  const int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
   if (decay_mult != 0.f)
-    k_adam<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale, level_sumsq, nlb_dynamic_scalars());
+    k_adam<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, exp_avg, exp_avg_sq, count, dt, lr_c, rs, beta1, beta2, eps, grad_scale, level_sumsq, nlb_dynamic_scalars(), first);
   else
-    k_adam<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale, nullptr, nlb_dynamic_scalars());
+    k_adam<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, exp_avg, exp_avg_sq, count, dt, lr_c, rs, beta1, beta2, eps, grad_scale, nullptr, nlb_dynamic_scalars(), first);
   return nlb_check_launch("adam_table_step");
 }
 
@@ -154,6 +172,6 @@ extern "C" int nlb_adam_step(float* param, float* grad, float* exp_avg, float* e
   bias_terms(lr, beta1, beta2, step, lr_c, rs);
   int64_t want = (n / 4 + 255) / 256;
   const int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
-  k_adam<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale, nullptr, nlb_dynamic_scalars());
+  k_adam<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale, nullptr, nlb_dynamic_scalars(), 0);
   return nlb_check_launch("adam_step");
 }

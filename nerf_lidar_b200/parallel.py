@@ -1,6 +1,9 @@
 """Data parallelism over rays: one process per GPU, parameters
-replicated, rays sharded.  Training = one gradient all-reduce per step over NCCL
-(what DDP does for the reference at Z/train.py:459); rendering = contiguous ray
+replicated, rays sharded.  Training = the gradient sum DDP does for the reference at
+Z/train.py:459, split into its two halves around a sharded optimizer pass: reduce-scatter of
+the gradients, fused hash-decay + Adam on this rank's 1/world slice, all-gather of the updated
+parameters (same bytes on the wire as the all-reduce, 1/world of the optimizer work and of
+the Adam moments per GPU); rendering = contiguous ray
 ranges per rank and one final gather of the packed per-ray outputs (instead of
 the reference's per-chunk, per-leaf all-gathers, Z/internal/models.py:1426-1476).
 Works with the gloo backend on CPU tensors for the host-logic tests."""
@@ -51,6 +54,40 @@ def allreduce_grads_async(buffers: List[torch.Tensor]):
     if not is_dist() or dist.get_world_size() == 1:
         return []
     return [dist.all_reduce(b, op=dist.ReduceOp.SUM, async_op=True) for b in buffers]
+
+
+def shard_chunk(n: int, world: int, align: int = 4) -> int:
+    """Elements per rank when a buffer of n elements is cut into `world` equal, `align`-element-aligned
+    chunks (the buffer is padded to chunk * world)."""
+    per = (n + world - 1) // world
+    return (per + align - 1) // align * align
+
+
+def reduce_scatter_async(arena: torch.Tensor, chunk: int, rank: int):
+    """Sum over the ranks of the padded 1-D buffer `arena` (chunk * world elements), leaving this rank's chunk
+    arena[rank * chunk : (rank + 1) * chunk] reduced IN PLACE (the other chunks hold partial garbage afterwards
+    and are cleared by the caller).  Returns the work handles.  gloo has no reduce-scatter: the host-logic
+    tests run the equivalent all-reduce."""
+    if not is_dist() or dist.get_world_size() == 1:
+        return []
+    mine = arena[rank * chunk:(rank + 1) * chunk]
+    if dist.get_backend() == 'gloo':
+        return [dist.all_reduce(arena, op=dist.ReduceOp.SUM, async_op=True)]
+    return [dist.reduce_scatter_tensor(mine, arena, op=dist.ReduceOp.SUM, async_op=True)]
+
+
+def all_gather_async(arena: torch.Tensor, chunk: int, rank: int):
+    """Every rank's chunk of the padded 1-D buffer -> all ranks, in place."""
+    if not is_dist() or dist.get_world_size() == 1:
+        return []
+    mine = arena[rank * chunk:(rank + 1) * chunk]
+    if dist.get_backend() == 'gloo':
+        parts = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+        h = dist.all_gather(parts, mine.clone(), async_op=True)
+        h.wait()
+        arena.copy_(torch.cat(parts))
+        return []
+    return [dist.all_gather_into_tensor(arena, mine, async_op=True)]
 
 
 def wait_all(handles):

@@ -111,15 +111,27 @@ class Trainer:
         self.model, self.config, self.world, self.rank = model, config, world, rank
         self.tables = []
         dense = []
+
+        def arena_for(n, dev):
+            """Padded flat buffers of a parameter group: parameters and gradients whole (chunk * world floats,
+            the collectives exchange equal 16-byte-aligned chunks), Adam moments for this rank's chunk only."""
+            chunk = parallel.shard_chunk(n, world)
+            lo = min(rank * chunk, n)
+            cnt = min(chunk, n - lo)
+            z = lambda k: torch.zeros(k, device=dev)
+            return dict(n=n, chunk=chunk, lo=lo, cnt=cnt, param=z(chunk * world), grad=z(chunk * world), m=z(chunk), v=z(chunk))
+
         for name, p in model.named_parameters():
             if name.endswith('encoder.embeddings'):
                 enc = model.get_submodule(name.rsplit('.', 2)[0]).encoder
-                p._nlb_grad = torch.zeros_like(p)
+                ar = arena_for(p.numel(), p.device)
+                ar['param'][:ar['n']].copy_(p.data.reshape(-1))
+                p.data = ar['param'][:ar['n']].view_as(p)
+                p._nlb_grad = ar['grad'][:ar['n']].view_as(p)
                 offs = enc.offsets.tolist()
                 counts = torch.tensor([(offs[i + 1] - offs[i]) * enc.level_dim for i in range(enc.num_levels)],
                                       dtype=torch.float32, device=p.device)
-                self.tables.append(dict(name=name, param=p, enc=enc, grad=p._nlb_grad,
-                                        m=torch.zeros_like(p), v=torch.zeros_like(p),
+                self.tables.append(dict(name=name, param=p, enc=enc, grad=p._nlb_grad, arena=ar, m=ar['m'], v=ar['v'],
                                         sumsq=torch.zeros(enc.num_levels, device=p.device), counts=counts,
                                         offsets=(C.c_int32 * (enc.num_levels + 1))(*offs)))
             else:
@@ -128,10 +140,10 @@ class Trainer:
         self.tables.sort(key=lambda t: -t['param'].numel())
         n = sum((p.numel() + 3) // 4 * 4 for p in dense)
         dev = dense[0].device
-        self.flat = torch.zeros(n, device=dev)
-        self.flat_grad = torch.zeros(n, device=dev)
-        self.flat_m = torch.zeros(n, device=dev)
-        self.flat_v = torch.zeros(n, device=dev)
+        self.flat_arena = arena_for(n, dev)
+        self.flat = self.flat_arena['param'][:n]
+        self.flat_grad = self.flat_arena['grad'][:n]
+        self.flat_m, self.flat_v = self.flat_arena['m'], self.flat_arena['v']   # this rank's chunk
         off = 0
         for p in dense:
             k = p.numel()
@@ -143,6 +155,12 @@ class Trainer:
         self.dense = dense
         self.decay = config.hash_decay_mults if config.hash_decay_mults > 0 else 0.
         self.hash_decay_value = torch.zeros((), device=dev)  # persistent: written in place (CUDA-graph safe)
+        # per-level sums of squares of all tables in one buffer: ONE small all-reduce per step in data-parallel runs
+        self._sumsq_all = torch.zeros(sum(t['enc'].num_levels for t in self.tables), device=dev)
+        o = 0
+        for t in self.tables:
+            t['sumsq'] = self._sumsq_all[o:o + t['enc'].num_levels]
+            o += t['enc'].num_levels
         self._graphs = {}
         self._static = None
         model.train()
@@ -194,62 +212,97 @@ class Trainer:
     def train_step(self, batch: Dict[str, torch.Tensor], step: int, num_patch: Optional[int] = None,
                    rand_inputs=None) -> Dict[str, torch.Tensor]:
         losses, main, prop = self.forward_losses(batch, step, num_patch, rand_inputs)
-        if prop is None:
-            main.backward()
-            self.optimizer_step(step)
-            return losses
         if self.world == 1:
             # (running the NeRF table's optimizer pass on a side stream beside the proposal backward was
             # measured: 7.30-7.35 ms per step against 7.23 ms in order -- the two contend for L2)
-            (main + prop).backward()
+            (main if prop is None else main + prop).backward()
             self.optimizer_step(step)
             return losses
         main.backward()
-        early = parallel.allreduce_grads_async([t['grad'] for t in self._nerf_tables()])
-        prop.backward()
-        late = parallel.allreduce_grads_async([t['grad'] for t in self._prop_tables()] + [self.flat_grad])
+        early = self.reduce_scatter_gradients(self._nerf_tables())
+        if prop is not None:
+            prop.backward()
+        late = self.reduce_scatter_gradients(self._prop_tables(), dense=True)
         parallel.wait_all(early + late)
         self.optimizer_step(step, reduce=False)
         return losses
 
-    def allreduce_gradients(self):
-        """The step's only collective: sum of the three table gradients and the
-        flat dense-layer gradient over the ranks, largest first."""
-        if self.world > 1:
-            parallel.allreduce_grads([t['grad'] for t in self.tables] + [self.flat_grad])
+    # ---- data parallel: reduce-scatter of the gradients -> this rank's slice of the optimizer pass -> all-gather
+    def _arenas(self, tables, dense=False):
+        return [t['arena'] for t in tables] + ([self.flat_arena] if dense else [])
+
+    def reduce_scatter_gradients(self, tables, dense=False):
+        """Starts the gradient sums (what DDP's all-reduce does at Z/train.py:459, first half) and returns the
+        handles.  Afterwards only this rank's chunk of each gradient buffer holds the sum."""
+        h = []
+        for ar in self._arenas(tables, dense):
+            h += parallel.reduce_scatter_async(ar['grad'], ar['chunk'], self.rank)
+        return h
+
+    def all_gather_parameters(self, tables, dense=False):
+        h = []
+        for ar in self._arenas(tables, dense):
+            h += parallel.all_gather_async(ar['param'], ar['chunk'], self.rank)
+        return h
 
     def optimizer_tables(self, step: int, tables):
-        """Fused hash-decay + NaN scrub + Adam + zero-grad pass over the given tables."""
+        """Fused hash-decay + NaN scrub + Adam + zero-grad pass over this rank's slice of the given tables."""
         c = self.config
         lr = self.lr(step)
         scale = 1.0 / self.world
         lib = _lib.load()
         st = _lib.stream()
         for t in tables:
-            enc = t['enc']
+            enc, ar = t['enc'], t['arena']
             decay = 0. if (c.obj_nodecay and 'obj' in t['name']) else self.decay
+            t['decay'] = decay
             t['sumsq'].zero_()
+            if self.world > 1:
+                # the chunks of the other ranks hold their own partial sums: clear them for the next step's scatter
+                g = ar['grad']
+                g[:ar['lo']].zero_()
+                g[ar['lo'] + ar['cnt']:].zero_()
             with _lib.timed('adam_table'):
-                _lib.check(lib.nlb_adam_table_step(t['param'].data_ptr(), t['grad'].data_ptr(), t['m'].data_ptr(),
-                                                   t['v'].data_ptr(), t['offsets'], enc.num_levels, enc.level_dim,
-                                                   float(decay), float(lr), c.adam_beta1, c.adam_beta2, c.adam_eps,
-                                                   int(step), scale, t['sumsq'].data_ptr(), st))
-            # Model.hash_decay_loss of the UPDATED table: mean over levels of the per-level mean square
-            t['decay_value'] = (t['sumsq'] / t['counts']).mean() if decay > 0 else None
+                _lib.check(lib.nlb_adam_table_step_range(
+                    ar['param'].data_ptr(), ar['grad'].data_ptr(), ar['m'].data_ptr(), ar['v'].data_ptr(), t['offsets'],
+                    enc.num_levels, enc.level_dim, float(decay), float(lr), c.adam_beta1, c.adam_beta2, c.adam_eps,
+                    int(step), scale, t['sumsq'].data_ptr(), ar['lo'], ar['cnt'], st))
 
     def optimizer_finish(self, step: int):
-        """Dense-layer Adam pass and the bookkeeping after all table passes."""
+        """Dense-layer Adam pass (this rank's slice), the all-gather of the updated parameters and the
+        bookkeeping after all table passes."""
         c = self.config
         lib = _lib.load()
-        vals = [t['decay_value'] for t in self.tables if t.get('decay_value') is not None]
+        fa = self.flat_arena
+        if self.world > 1:
+            g = fa['grad']
+            g[:fa['lo']].zero_()
+            g[fa['lo'] + fa['cnt']:].zero_()
+        if fa['cnt'] > 0:
+            _lib.check(lib.nlb_adam_step(fa['param'].data_ptr() + 4 * fa['lo'], fa['grad'].data_ptr() + 4 * fa['lo'],
+                                         fa['m'].data_ptr(), fa['v'].data_ptr(), fa['cnt'], float(self.lr(step)),
+                                         c.adam_beta1, c.adam_beta2, c.adam_eps, int(step), 1.0 / self.world,
+                                         _lib.stream()))
+        self._mark_packed_stale()
+
+    def publish(self, capture_safe_only: bool = False):
+        """After the optimizer pass of a data-parallel step: all-gather of the updated parameters (and of the
+        per-level sums of squares behind the reported hash-decay value)."""
+        if self.world > 1:
+            h = self.all_gather_parameters(self.tables, dense=True)
+            if parallel.is_dist():
+                import torch.distributed as dist
+                h.append(dist.all_reduce(self._sumsq_all, async_op=True))
+            parallel.wait_all(h)
+        self._update_hash_decay_value()
+
+    def _update_hash_decay_value(self):
+        # Model.hash_decay_loss of the UPDATED tables (mean over levels of the per-level mean square): the next
+        # forward reports it as renderings[-1]['hash_decay'] without re-reading 310 MB of tables
+        vals = [(t['sumsq'] / t['counts']).mean() for t in self.tables if t.get('decay', 0) > 0]
         if vals:
-            # the next forward reports this as renderings[-1]['hash_decay'] without re-reading 310 MB of tables
             self.hash_decay_value.copy_(self.decay * sum(vals))
             self.model._hash_decay_value = self.hash_decay_value
-        _lib.check(lib.nlb_adam_step(self.flat.data_ptr(), self.flat_grad.data_ptr(), self.flat_m.data_ptr(),
-                                     self.flat_v.data_ptr(), self.flat.numel(), float(self.lr(step)), c.adam_beta1,
-                                     c.adam_beta2, c.adam_eps, int(step), 1.0 / self.world, _lib.stream()))
-        self._mark_packed_stale()
 
     def _mark_packed_stale(self):
         """The dense parameters changed through raw pointers (torch's version counters do not see it): the
@@ -259,11 +312,13 @@ class Trainer:
             if hasattr(m, '_nlb_dirty'):
                 m._nlb_dirty = True
 
-    def optimizer_step(self, step: int, reduce: bool = True):
-        if reduce:
-            self.allreduce_gradients()
+    def optimizer_step(self, step: int, reduce: bool = True, publish: bool = True):
+        if reduce and self.world > 1:
+            parallel.wait_all(self.reduce_scatter_gradients(self.tables, dense=True))
         self.optimizer_tables(step, self.tables)
         self.optimizer_finish(step)
+        if publish:
+            self.publish()
 
     # ------------------------------------------------------------------------- CUDA-graph step
     def _regime(self, step: int):
@@ -348,7 +403,7 @@ class Trainer:
                             prop.backward()
                     g_opt = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g_opt, pool=g.pool()):
-                        self.optimizer_step(step, reduce=False)
+                        self.optimizer_step(step, reduce=False, publish=False)
                     del main, prop
             finally:
                 lib.nlb_set_dynamic_scalars(None)
@@ -358,11 +413,12 @@ class Trainer:
         g, g_prop, g_opt, captured = entry
         g.replay()
         if g_opt is not None:
-            early = parallel.allreduce_grads_async([t['grad'] for t in self._nerf_tables()])
+            early = self.reduce_scatter_gradients(self._nerf_tables())
             if g_prop is not None:
                 g_prop.replay()
-            late = parallel.allreduce_grads_async([t['grad'] for t in self._prop_tables()] + [self.flat_grad])
+            late = self.reduce_scatter_gradients(self._prop_tables(), dense=True)
             parallel.wait_all(early + late)
             g_opt.replay()
+            self.publish()
         self._mark_packed_stale()
         return captured

@@ -56,6 +56,21 @@ def _worker(rank, world, port, n):
         late = parallel.allreduce_grads_async([d])
         parallel.wait_all(early + late)
         assert torch.all(c == 1.0) and torch.all(d == 2.0)
+        # sharded optimizer: reduce-scatter of a padded gradient buffer, "update" of this rank's chunk, all-gather
+        nel = 1003
+        chunk = parallel.shard_chunk(nel, world)
+        assert chunk % 4 == 0 and chunk * world >= nel
+        grad = torch.zeros(chunk * world)
+        grad[:nel] = torch.arange(nel).float() * (rank + 1)
+        parallel.wait_all(parallel.reduce_scatter_async(grad, chunk, rank))
+        mine = slice(rank * chunk, (rank + 1) * chunk)
+        want = torch.zeros(chunk * world)
+        want[:nel] = torch.arange(nel).float() * 3
+        assert torch.equal(grad[mine], want[mine])
+        param = torch.zeros(chunk * world)
+        param[mine] = -grad[mine]
+        parallel.wait_all(parallel.all_gather_async(param, chunk, rank))
+        assert torch.equal(param, -want)
         sh = parallel.shard_batch({'origins': torch.arange(n * 3).reshape(n, 3).float()}, world, rank)
         assert sh['origins'].shape[0] == hi - lo
     finally:
