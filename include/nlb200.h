@@ -375,6 +375,36 @@ int nlb_adam_bias_terms(float lr, float beta1, float beta2, int step, float* out
 int nlb_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------ on-GPU ray generation
+ * Replaces the host-side numpy ray construction of the reference's data layer (the 8-worker DataLoader,
+ * Z/train.py:111-118).  float64 arithmetic in the reference's operation order, ONE rounding to float32 at the
+ * store (the reference casts the finished batch with `.float()`, Z/internal/datasets.py `_make_ray_batch`).
+ * Outputs follow the batch schema Model.forward reads (Z/internal/camera_utils.py:603-617): every pointer is
+ * [n,3] fp32 except radii [n] and imageplane [n,2] (optional, may be NULL).
+ */
+typedef struct {
+  float* origins; float* directions; float* viewdirs; float* radii; float* imageplane; float* base_x; float* base_y;
+} nlb_ray_out_t;
+
+/* camera_utils.pixels_to_rays / cast_ray_batch (Z/internal/camera_utils.py:454-564,567-617) for a perspective
+ * camera without distortion or NDC (the nuScenes loader).  pixtocams [n_pixtocams,3,3] and camtoworlds
+ * [n_camtoworlds,3,4] are row-major float64; a count of 1 shares the matrix between all rays (`batch_index`,
+ * camera_utils.py:591), otherwise cam_idx[n] selects it. */
+int nlb_camera_rays(const int32_t* pix_x, const int32_t* pix_y, const int32_t* cam_idx /*or NULL*/,
+                    const double* pixtocams, int n_pixtocams, const double* camtoworlds, int n_camtoworlds,
+                    int64_t n, const nlb_ray_out_t* out, void* stream);
+
+/* lidar_utils.get_directions (Z/internal/lidar_utils.py:559-568): out[n_beams*width,3] fp32, beam-major,
+ * (cos t sin p, cos t cos p, sin t) with t = elevation in DEGREES, p = azimuth in radians. */
+int nlb_lidar_directions(const double* elev_deg, int n_beams, const double* azim_rad, int width, float* out,
+                         void* stream);
+
+/* lidar_utils.cast_lidar_ray_batch (Z/internal/lidar_utils.py:8-33) incl. its quirks: viewdirs = directions /
+ * the GLOBAL Frobenius norm of the whole [n,3] array, base_x = base_y = directions, radii = 5e-4.
+ * workspace: 8 bytes of device memory (the sum of squares). */
+int nlb_lidar_rays(const float* origins, const float* directions, int64_t n, double* workspace,
+                   const nlb_ray_out_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,10 @@ class NlbNerfMlpGradOut(C.Structure):
                [(n, C.c_int) for n in ('ld_v1', 'ld_v0', 'ld_g')]
 
 
+class NlbRayOut(C.Structure):
+    _fields_ = [(n, c_f) for n in ('origins', 'directions', 'viewdirs', 'radii', 'imageplane', 'base_x', 'base_y')]
+
+
 _u32, _i, _f, _p = C.c_uint32, C.c_int, C.c_float, C.c_void_p
 
 # name -> (restype, argtypes); mirrors include/nlb200.h one to one
@@ -115,6 +119,9 @@ SIGNATURES = {
     'nlb_set_dynamic_scalars': (_i, [_p]),
     'nlb_adam_bias_terms': (_i, [_f, _f, _f, _i, C.POINTER(C.c_float)]),
     'nlb_adam_step': (_i, [_p, _p, _p, _p, C.c_int64, _f, _f, _f, _f, _i, _f, _p]),
+    'nlb_camera_rays': (_i, [_p, _p, _p, _p, _i, _p, _i, C.c_int64, C.POINTER(NlbRayOut), _p]),
+    'nlb_lidar_directions': (_i, [_p, _i, _p, _i, _p, _p]),
+    'nlb_lidar_rays': (_i, [_p, _p, C.c_int64, _p, C.POINTER(NlbRayOut), _p]),
 }
 
 _lib: Optional[C.CDLL] = None

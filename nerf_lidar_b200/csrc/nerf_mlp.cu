@@ -21,6 +21,7 @@
 #include "umma.cuh"
 #include "../../include/nlb200.h"
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace nlb {
 namespace mlp {
@@ -580,6 +581,385 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_fwd(const float* __res
 }
 
 // =============================================================================
+// Forward, two tiles in flight per CTA (default).  The one-tile kernel above leaves the tensor pipe
+// idle during five dependent epilogues and the staging of the next tile (clock64 timeline: 34 K cycles
+// per tile against 14 K of MMA issue).  A second 128-row tile cannot be resident (144 KB of operand
+// blocks each), but the TRUNK of the next tile can: its features, h0 and x live in the X blocks, which
+// the current tile stops reading when its V1 MMAs complete.  So the roles are
+//   warps 0-7   main epilogue warps (two per TMEM lane quarter): HS0, V0, V1, RGB of tile i
+//   warps 8-11  front warps (one per lane quarter): stage features / view-direction encoding of tile
+//               i+1, its L0 and L1 epilogues (-> X, density), and the semantic / intensity head
+//               outputs of tile i+1 while the main warps are in its view branch
+//   warp 12     MMA issuer: HS0 V0 HS1 V1 (tile i) | L0 L1 (tile i+1) | RGB (tile i)
+//   warps 13-16 weight producers (one per ring stage), streaming in that order
+// TMEM: V1 / HS0 (0) / HS1 (128) / RGB (224) share columns 0-255, V0 / L0 / L1 share 256-511; every
+// reuse is ordered by an mbarrier that the previous reader arrives on (see the hazard notes inline).
+namespace v2 {
+
+constexpr int kMainWarps = 8, kFrontWarp0 = 8, kFrontWarps = 4, kMmaWarp2 = 12, kProdWarp2 = 13;
+constexpr int kMainThreads = kMainWarps * 32, kFrontThreads = kFrontWarps * 32;
+constexpr int kThreads2 = (kProdWarp2 + kStages) * 32;
+
+__host__ __device__ constexpr LayerDef layer_def2(int l) {
+  LayerDef d = layer_def(l);
+  switch (l) {
+    case L0:  d.a_blk[0] = BX + 0; d.tmem_col = 256; break;   // features of the next tile in X0
+    case L1:  d.a_blk[0] = BX + 1; d.tmem_col = 256; break;   // h0 in X1
+    case HS0: d.tmem_col = 0; break;
+    case V0:  d.tmem_col = 256; break;
+    case HS1: d.tmem_col = 128; break;
+    // h1 / h2 column block j lives in H block hperm(j) = {2, 0, 3, 1}[j]: each main warp then only ever
+    // overwrites rows of blocks it wrote itself (g in H2 / H3 by column half), so its global saves can
+    // trail its "ready" signal with program order as the only hazard protection
+    case V1:  d.tmem_col = 0; d.a_blk[0] = BH + 2; d.a_blk[1] = BH + 0; d.a_blk[2] = BH + 3; d.a_blk[3] = BH + 1; break;
+    default:  d.tmem_col = 224; d.a_blk[0] = BH + 2; d.a_blk[1] = BH + 0; d.a_blk[2] = BH + 3; d.a_blk[3] = BH + 1; break;  // RGB
+  }
+  return d;
+}
+
+__host__ __device__ constexpr int hperm(int j) { return j == 0 ? 2 : (j == 1 ? 0 : (j == 2 ? 3 : 1)); }
+
+struct Smem2 {
+  uint64_t w_full[kStages], w_empty[kStages];
+  uint64_t acc_ready[kNumLayers];
+  uint64_t f_ready, h0_ready, x_ready, hs1_free;   // front warps arrive (128)
+  uint64_t g_ready, h1_ready, h2_ready;            // main warps arrive (256)
+  uint32_t tmem_base;
+  float bias[kBiasFloats];
+};
+
+template <int L>
+__device__ __forceinline__ void issue_layer2(Smem2& sm, uint8_t* a_blocks, uint8_t* w_ring, uint32_t tmem, uint32_t& c) {
+  constexpr LayerDef d = layer_def2(L);
+  constexpr int nrows = layer_nrows(L), nh_count = layer_nhalves(L);
+  const uint32_t idesc = make_idesc_bf16(128, nrows);
+#pragma unroll
+  for (int kb = 0; kb < d.nkb; ++kb) {
+    const uint64_t adesc = make_desc_sw128(a_blocks + d.a_blk[kb] * kBlockBytes);
+#pragma unroll
+    for (int nh = 0; nh < nh_count; ++nh, ++c) {
+      const uint32_t st = c % kStages;
+      mbar_wait(&sm.w_full[st], (c / kStages) & 1);
+      tcgen05_fence_after();
+      const uint64_t bdesc = make_desc_sw128(w_ring + st * kBlockBytes);
+      const uint32_t dcol = tmem + d.tmem_col + nh * 128;
+      switch (d.ksteps[kb]) {
+        case 1: mma_chunk<1>(dcol, adesc, bdesc, idesc, kb != 0); break;
+        case 2: mma_chunk<2>(dcol, adesc, bdesc, idesc, kb != 0); break;
+        case 3: mma_chunk<3>(dcol, adesc, bdesc, idesc, kb != 0); break;
+        default: mma_chunk<4>(dcol, adesc, bdesc, idesc, kb != 0); break;
+      }
+      mma_commit(&sm.w_empty[st]);
+    }
+  }
+  mma_commit(&sm.acc_ready[L]);
+}
+
+__device__ __forceinline__ void wait_then_fence(uint64_t* bar, uint32_t parity) {
+  mbar_wait(bar, parity);
+  tcgen05_fence_after();
+}
+
+__global__ void __launch_bounds__(kThreads2, 1) k_nerf_mlp_fwd2(const float* __restrict__ features,
+                                                                const float* __restrict__ viewdirs, int M,
+                                                                int rows_per_ray, const uint8_t* __restrict__ blob,
+                                                                float* __restrict__ o_density, float* __restrict__ o_rgb,
+                                                                float* __restrict__ o_sem, float* __restrict__ o_int,
+                                                                nlb_nerf_mlp_saved_t sv) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_blocks = base;                                  // 9 x 16 KB
+  uint8_t* w_ring = base + kNumABlocks * kBlockBytes;        // 4 x 16 KB
+  Smem2& sm = *reinterpret_cast<Smem2*>(w_ring + kStages * kBlockBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (M + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
+    for (int i = 0; i < kNumLayers; ++i) mbar_init(&sm.acc_ready[i], 1);
+    mbar_init(&sm.f_ready, kFrontThreads); mbar_init(&sm.h0_ready, kFrontThreads);
+    mbar_init(&sm.x_ready, kFrontThreads); mbar_init(&sm.hs1_free, kFrontThreads);
+    mbar_init(&sm.g_ready, kMainThreads); mbar_init(&sm.h1_ready, kMainThreads); mbar_init(&sm.h2_ready, kMainThreads);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < kBiasFloats; i += kThreads2)
+    sm.bias[i] = reinterpret_cast<const float*>(blob + kWeightBytes)[i];
+  if (warp == kMmaWarp2) tmem_alloc(&sm.tmem_base, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  if (g_timeline && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_timeline[120] = clock64(); g_timeline[122] = (long long)gt;
+    g_timeline[124] = (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
+  }
+
+  if (warp >= kProdWarp2) {
+    // ===== weight producers: chunks in the MMA issuer's consumption order
+    if (elect_one_sync()) {
+      const int my_stage = warp - kProdWarp2;
+      uint32_t c = 0;
+      auto stream_layer = [&](int l) {
+        const int n = layer_chunks(l), bytes = layer_chunk_bytes(l);
+        const uint8_t* src = blob + layer_offset(l);
+#pragma unroll 1
+        for (int i = 0; i < n; ++i, ++c) {
+          const int st = c % kStages;
+          if (st != my_stage) continue;
+          mbar_wait_relaxed(&sm.w_empty[st], ((c / kStages) & 1) ^ 1);
+          mbar_expect_tx(&sm.w_full[st], bytes);
+          bulk_g2s(w_ring + st * kBlockBytes, src + (size_t)i * bytes, bytes, &sm.w_full[st]);
+        }
+      };
+      if ((int)blockIdx.x < num_tiles) { stream_layer(L0); stream_layer(L1); }
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const bool has_next = tile + (int)gridDim.x < num_tiles;
+        stream_layer(HS0); stream_layer(V0); stream_layer(HS1); stream_layer(V1);
+        if (has_next) { stream_layer(L0); stream_layer(L1); }
+        stream_layer(RGB);
+      }
+    }
+  } else if (warp == kMmaWarp2) {
+    // ===== MMA issuer
+    if (elect_one_sync()) {
+      uint32_t c = 0, it = 0;
+      if ((int)blockIdx.x < num_tiles) {
+        wait_then_fence(&sm.f_ready, 0);  issue_layer2<L0>(sm, a_blocks, w_ring, tmem, c);
+        wait_then_fence(&sm.h0_ready, 0); issue_layer2<L1>(sm, a_blocks, w_ring, tmem, c);
+      }
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t ph = it & 1, nph = ph ^ 1;
+        const bool has_next = tile + (int)gridDim.x < num_tiles;
+        wait_then_fence(&sm.x_ready, ph);
+        issue_layer2<HS0>(sm, a_blocks, w_ring, tmem, c);
+        issue_layer2<V0>(sm, a_blocks, w_ring, tmem, c);
+        wait_then_fence(&sm.g_ready, ph);
+        issue_layer2<HS1>(sm, a_blocks, w_ring, tmem, c);
+        // V1 overwrites columns 0-255: the HS0 accumulator was read before g_ready / h1_ready, the HS1
+        // accumulator (128-159) is read by the front warps -> hs1_free
+        wait_then_fence(&sm.h1_ready, ph);
+        wait_then_fence(&sm.hs1_free, ph);
+        issue_layer2<V1>(sm, a_blocks, w_ring, tmem, c);
+        if (has_next) {
+          // trunk of the next tile (X blocks and columns 256-511 are free: V0 was read before h1_ready,
+          // f_ready is only signalled after this tile's V1 MMAs have completed)
+          wait_then_fence(&sm.f_ready, nph);  issue_layer2<L0>(sm, a_blocks, w_ring, tmem, c);
+          wait_then_fence(&sm.h0_ready, nph); issue_layer2<L1>(sm, a_blocks, w_ring, tmem, c);
+        }
+        wait_then_fence(&sm.h2_ready, ph);
+        issue_layer2<RGB>(sm, a_blocks, w_ring, tmem, c);
+      }
+    }
+  } else if (warp >= kFrontWarp0) {
+    // ===== front warps: thread (q, lane) owns row r = 32 q + lane of the tile it prepares
+    const int q = warp - kFrontWarp0;
+    const int r = q * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    uint8_t* XB = a_blocks + BX * kBlockBytes;
+    uint8_t* DB = a_blocks + BD * kBlockBytes;
+    uint32_t k = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
+      const uint32_t ph = k & 1;
+      const int row = tile * 128 + r;
+      const bool valid = row < M;
+      const int rows_valid = M - tile * 128 < 128 ? M - tile * 128 : 128;
+      // ---- inputs of this tile into registers (bf16 pairs), before waiting for the blocks
+      uint32_t fp[kFeat / 2], dp[16];
+      if (valid) {
+        const float4* src = reinterpret_cast<const float4*>(features + (size_t)row * kFeat);
+#pragma unroll
+        for (int i = 0; i < kFeat / 4; ++i) {
+          const float4 t = __ldg(src + i);
+          fp[2 * i] = pack_bf16(t.x, t.y); fp[2 * i + 1] = pack_bf16(t.z, t.w);
+        }
+        const int ray = row / rows_per_ray;
+        const float vx = __ldg(viewdirs + 3 * ray), vy = __ldg(viewdirs + 3 * ray + 1), vz = __ldg(viewdirs + 3 * ray + 2);
+        float d[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) d[i] = 0.f;
+        d[0] = vx; d[1] = vy; d[2] = vz;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const float sc = (float)(1 << s);
+          const float ax = vx * sc, ay = vy * sc, az = vz * sc;
+          d[3 + s * 3] = sinf(ax); d[4 + s * 3] = sinf(ay); d[5 + s * 3] = sinf(az);
+          d[15 + s * 3] = sinf(ax + 1.5707963267948966f);
+          d[16 + s * 3] = sinf(ay + 1.5707963267948966f);
+          d[17 + s * 3] = sinf(az + 1.5707963267948966f);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dp[i] = pack_bf16(d[2 * i], d[2 * i + 1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kFeat / 2; ++i) fp[i] = 0u;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dp[i] = 0u;
+      }
+      // X and D are read by the previous tile's HS0 / V0 / V1 MMAs: free once V1 has completed
+      if (k > 0) mbar_wait_warp(&sm.acc_ready[V1], (k - 1) & 1);
+      {
+        uint8_t* frow = block_row(XB, r);
+        uint8_t* drow = block_row(DB, r);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint4 u = make_uint4(0, 0, 0, 0), w = make_uint4(0, 0, 0, 0);
+          if (c8 < kFeat / 8) u = make_uint4(fp[c8 * 4], fp[c8 * 4 + 1], fp[c8 * 4 + 2], fp[c8 * 4 + 3]);
+          if (c8 < 4) w = make_uint4(dp[c8 * 4], dp[c8 * 4 + 1], dp[c8 * 4 + 2], dp[c8 * 4 + 3]);
+          *reinterpret_cast<uint4*>(frow + ((c8 ^ (r & 7)) * 16)) = u;
+          *reinterpret_cast<uint4*>(drow + ((c8 ^ (r & 7)) * 16)) = w;
+        }
+      }
+      signal_a_ready(&sm.f_ready);
+      // Global copies for the backward pass trail the signals: the blocks stay valid until this same warp
+      // overwrites its rows (program order), so the stores run while the tensor pipe works.
+      // bf16 copy of the (zero-padded) feature rows: the B operand of density_layer.0's weight gradient
+      if (sv.f0) warp_rows_to_global(XB, r & ~31, lane, reinterpret_cast<__nv_bfloat16*>(sv.f0) + (size_t)tile * 128 * 64, 64, rows_valid);
+
+      // ---- L0: h0 = relu(acc + b) -> X1
+      mbar_wait_warp(&sm.acc_ready[L0], ph);
+      tcgen05_fence_after();
+      epi_group64<true>(tlane + 256, sm.bias + bias_offset(L0), XB + 1 * kBlockBytes, r, lane, nullptr, 64, rows_valid);
+      signal_a_ready(&sm.h0_ready);
+      if (sv.h0) warp_rows_to_global(XB + 1 * kBlockBytes, r & ~31, lane, reinterpret_cast<__nv_bfloat16*>(sv.h0) + (size_t)tile * 128 * 64, 64, rows_valid);
+
+      // ---- L1: x = acc + b -> X0..3 (the L0 / L1 MMAs, readers of X0 / X1, have completed); density
+      mbar_wait_warp(&sm.acc_ready[L1], ph);
+      tcgen05_fence_after();
+      float x0 = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 64)
+        epi_group64<false>(tlane + 256 + c0, sm.bias + bias_offset(L1) + c0, XB + (c0 >> 6) * kBlockBytes, r, lane,
+                           nullptr, 256, rows_valid, c0 == 0 ? &x0 : nullptr);
+      signal_a_ready(&sm.x_ready);
+      if (sv.x) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 64)
+          warp_rows_to_global(XB + (c0 >> 6) * kBlockBytes, r & ~31, lane,
+                              reinterpret_cast<__nv_bfloat16*>(sv.x) + (size_t)tile * 128 * 256 + c0, 256, rows_valid);
+      }
+      if (valid) {
+        const float xin = x0 - 1.0f;
+        o_density[row] = xin > 20.f ? xin : log1pf(expf(xin));
+      }
+
+      // ---- HS1 of this tile (the main warps are in its view branch): semantic softmax (19) + intensity
+      mbar_wait_warp(&sm.acc_ready[HS1], ph);
+      tcgen05_fence_after();
+      {
+        float v[32];
+        tmem_ld32(tlane + 128, v);
+        tcgen05_fence_before();
+        mbar_arrive(&sm.hs1_free);
+        const float* b = sm.bias + bias_offset(HS1);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < kSem; ++i) { v[i] += b[i]; mx = fmaxf(mx, v[i]); }
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < kSem; ++i) { v[i] = expf(v[i] - mx); sum += v[i]; }
+        const float inv = 1.0f / sum;
+        if (valid) {
+          if (o_sem) {
+#pragma unroll
+            for (int i = 0; i < kSem; ++i) o_sem[(size_t)row * kSem + i] = v[i] * inv;
+          }
+          if (o_int) o_int[row] = v[kSem] + b[kSem];
+        }
+      }
+    }
+  } else {
+    // ===== main epilogue warps 0..7: thread (q, lane) owns row r = 32 q + lane; the two warps of a
+    // lane quarter (half = 0 / 1) split every layer's columns
+    const int half = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    uint8_t* HB = a_blocks + BH * kBlockBytes;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const int row = tile * 128 + r;
+      const bool valid = row < M;
+      const int rows_valid = M - tile * 128 < 128 ? M - tile * 128 : 128;
+      // ---- HS0: hidden = relu(acc + b) -> H2, H3  (H is free: every warp waited for the previous RGB)
+      mbar_wait_warp(&sm.acc_ready[HS0], ph);
+      tcgen05_fence_after();
+      {
+        const int c0 = half * 64;
+        epi_group64<true>(tlane + c0, sm.bias + bias_offset(HS0) + c0, HB + (2 + half) * kBlockBytes, r, lane, nullptr, 128,
+                          rows_valid);
+      }
+      signal_a_ready(&sm.g_ready);
+      // (global copies trail the signals, see the front warps)
+      if (sv.g) warp_rows_to_global(HB + (2 + half) * kBlockBytes, r & ~31, lane,
+                                    reinterpret_cast<__nv_bfloat16*>(sv.g) + (size_t)tile * 128 * 128 + half * 64, 128, rows_valid);
+
+      // ---- V0: h1 = relu(acc + b) -> H0..3 (overwrites H2 / H3, which the HS1 MMAs read)
+      mbar_wait_warp(&sm.acc_ready[HS1], ph);
+      mbar_wait_warp(&sm.acc_ready[V0], ph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
+        epi_group64<true>(tlane + 256 + c0, sm.bias + bias_offset(V0) + c0, HB + hperm(c0 >> 6) * kBlockBytes, r, lane,
+                          nullptr, 256, rows_valid);
+      signal_a_ready(&sm.h1_ready);
+      if (sv.h1) {
+#pragma unroll 1
+        for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
+          warp_rows_to_global(HB + hperm(c0 >> 6) * kBlockBytes, r & ~31, lane,
+                              reinterpret_cast<__nv_bfloat16*>(sv.h1) + (size_t)tile * 128 * 256 + c0, 256, rows_valid);
+      }
+
+      // ---- V1: h2 = relu(acc + b) -> H0..3
+      mbar_wait_warp(&sm.acc_ready[V1], ph);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
+        epi_group64<true>(tlane + c0, sm.bias + bias_offset(V1) + c0, HB + hperm(c0 >> 6) * kBlockBytes, r, lane,
+                          nullptr, 256, rows_valid);
+      signal_a_ready(&sm.h2_ready);
+      if (sv.h2) {
+#pragma unroll 1
+        for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
+          warp_rows_to_global(HB + hperm(c0 >> 6) * kBlockBytes, r & ~31, lane,
+                              reinterpret_cast<__nv_bfloat16*>(sv.h2) + (size_t)tile * 128 * 256 + c0, 256, rows_valid);
+      }
+
+      // ---- RGB: sigmoid(acc + b) * (1 + 2 pad) - pad   (every warp waits: the next HS0 epilogue
+      // overwrites H2 / H3, which the RGB MMAs read)
+      mbar_wait_warp(&sm.acc_ready[RGB], ph);
+      tcgen05_fence_after();
+      if (half == 1) {
+        float v[16];
+        tmem_ld16(tlane + 224, v);
+        const float* b = sm.bias + bias_offset(RGB);
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float s = 1.0f / (1.0f + expf(-(v[i] + b[i])));
+            o_rgb[(size_t)row * 3 + i] = s * (1.0f + 2.0f * 0.001f) - 0.001f;
+          }
+        }
+      }
+      tcgen05_fence_before();
+    }
+  }
+  __syncthreads();
+  if (g_timeline && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_timeline[121] = clock64(); g_timeline[123] = (long long)gt;
+  }
+  if (warp == kMmaWarp2) tmem_dealloc(tmem, 512);
+}
+
+constexpr size_t kSmemBytes2 = 1024 + (kNumABlocks + kStages) * (size_t)kBlockBytes + sizeof(Smem2);
+
+}  // namespace v2
+
+// =============================================================================
 // Backward data-gradient chain (same machinery, transposed weights).
 //   dc   = g_rgb * 1.002 * s(1-s)                       [16]   (S block)
 //   dzv1 = (dc  . Wrgb)        * [h2 > 0]               [256]  (P blocks)
@@ -1072,18 +1452,26 @@ extern "C" int nlb_nerf_mlp_forward(const float* features, const float* viewdirs
     return NLB_EINVAL;
   }
   static int sms = 0;
+  static bool legacy = false;
   if (!sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(mlp::k_nerf_mlp_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp::kSmemBytes);
+    cudaFuncSetAttribute(mlp::v2::k_nerf_mlp_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp::v2::kSmemBytes2);
+    const char* e = getenv("NLB_MLP_FWD_LEGACY");   // development switch (A/B timing): one tile in flight
+    legacy = e && e[0] == '1';
   }
   const int tiles = (M + 127) / 128;
   const int grid = tiles < sms ? tiles : sms;
   nlb_nerf_mlp_saved_t sv = {};
   if (saved) sv = *saved;
-  mlp::k_nerf_mlp_fwd<<<grid, mlp::kThreads, mlp::kSmemBytes, (cudaStream_t)stream>>>(
-      features, viewdirs, M, rows_per_ray, reinterpret_cast<const uint8_t*>(packed), density, rgb, semantic, intensity, sv);
+  if (legacy)
+    mlp::k_nerf_mlp_fwd<<<grid, mlp::kThreads, mlp::kSmemBytes, (cudaStream_t)stream>>>(
+        features, viewdirs, M, rows_per_ray, reinterpret_cast<const uint8_t*>(packed), density, rgb, semantic, intensity, sv);
+  else
+    mlp::v2::k_nerf_mlp_fwd2<<<grid, mlp::v2::kThreads2, mlp::v2::kSmemBytes2, (cudaStream_t)stream>>>(
+        features, viewdirs, M, rows_per_ray, reinterpret_cast<const uint8_t*>(packed), density, rgb, semantic, intensity, sv);
   return nlb_check_launch("nerf_mlp_forward");
 }
 
