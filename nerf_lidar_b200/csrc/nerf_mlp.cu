@@ -733,24 +733,29 @@ __global__ void __launch_bounds__(kThreads2, 1) k_nerf_mlp_fwd2(const float* __r
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const uint32_t ph = it & 1, nph = ph ^ 1;
         const bool has_next = tile + (int)gridDim.x < num_tiles;
-        wait_then_fence(&sm.x_ready, ph);
-        issue_layer2<HS0>(sm, a_blocks, w_ring, tmem, c);
-        issue_layer2<V0>(sm, a_blocks, w_ring, tmem, c);
-        wait_then_fence(&sm.g_ready, ph);
-        issue_layer2<HS1>(sm, a_blocks, w_ring, tmem, c);
+        const int tb = (it == 2 || it == 3) ? ((int)it - 2) * 32 : -1;   // dev timeline (nlb_debug_set_timeline)
+#define NLB_TS(j) do { if (tb >= 0) stamp(tb + (j)); } while (0)
+        wait_then_fence(&sm.x_ready, ph); NLB_TS(0);
+        issue_layer2<HS0>(sm, a_blocks, w_ring, tmem, c); NLB_TS(1);
+        issue_layer2<V0>(sm, a_blocks, w_ring, tmem, c); NLB_TS(2);
+        wait_then_fence(&sm.g_ready, ph); NLB_TS(3);
+        issue_layer2<HS1>(sm, a_blocks, w_ring, tmem, c); NLB_TS(4);
         // V1 overwrites columns 0-255: the HS0 accumulator was read before g_ready / h1_ready, the HS1
         // accumulator (128-159) is read by the front warps -> hs1_free
-        wait_then_fence(&sm.h1_ready, ph);
-        wait_then_fence(&sm.hs1_free, ph);
-        issue_layer2<V1>(sm, a_blocks, w_ring, tmem, c);
+        wait_then_fence(&sm.h1_ready, ph); NLB_TS(5);
+        wait_then_fence(&sm.hs1_free, ph); NLB_TS(6);
+        issue_layer2<V1>(sm, a_blocks, w_ring, tmem, c); NLB_TS(7);
         if (has_next) {
           // trunk of the next tile (X blocks and columns 256-511 are free: V0 was read before h1_ready,
           // f_ready is only signalled after this tile's V1 MMAs have completed)
-          wait_then_fence(&sm.f_ready, nph);  issue_layer2<L0>(sm, a_blocks, w_ring, tmem, c);
-          wait_then_fence(&sm.h0_ready, nph); issue_layer2<L1>(sm, a_blocks, w_ring, tmem, c);
+          wait_then_fence(&sm.f_ready, nph); NLB_TS(8);
+          issue_layer2<L0>(sm, a_blocks, w_ring, tmem, c); NLB_TS(9);
+          wait_then_fence(&sm.h0_ready, nph); NLB_TS(10);
+          issue_layer2<L1>(sm, a_blocks, w_ring, tmem, c); NLB_TS(11);
         }
-        wait_then_fence(&sm.h2_ready, ph);
-        issue_layer2<RGB>(sm, a_blocks, w_ring, tmem, c);
+        wait_then_fence(&sm.h2_ready, ph); NLB_TS(12);
+        issue_layer2<RGB>(sm, a_blocks, w_ring, tmem, c); NLB_TS(13);
+#undef NLB_TS
       }
     }
   } else if (warp >= kFrontWarp0) {
@@ -766,6 +771,9 @@ __global__ void __launch_bounds__(kThreads2, 1) k_nerf_mlp_fwd2(const float* __r
       const int row = tile * 128 + r;
       const bool valid = row < M;
       const int rows_valid = M - tile * 128 < 128 ? M - tile * 128 : 128;
+      const int tb = ((k == 2 || k == 3) && threadIdx.x == kFrontWarp0 * 32) ? 64 + ((int)k - 2) * 16 : -1;
+#define NLB_TS(j) do { if (tb >= 0) stamp(tb + (j)); } while (0)
+      NLB_TS(0);
       // ---- inputs of this tile into registers (bf16 pairs), before waiting for the blocks
       uint32_t fp[kFeat / 2], dp[16];
       if (valid) {
@@ -799,7 +807,9 @@ __global__ void __launch_bounds__(kThreads2, 1) k_nerf_mlp_fwd2(const float* __r
         for (int i = 0; i < 16; ++i) dp[i] = 0u;
       }
       // X and D are read by the previous tile's HS0 / V0 / V1 MMAs: free once V1 has completed
+      NLB_TS(1);
       if (k > 0) mbar_wait_warp(&sm.acc_ready[V1], (k - 1) & 1);
+      NLB_TS(2);
       {
         uint8_t* frow = block_row(XB, r);
         uint8_t* drow = block_row(DB, r);
@@ -812,28 +822,28 @@ __global__ void __launch_bounds__(kThreads2, 1) k_nerf_mlp_fwd2(const float* __r
           *reinterpret_cast<uint4*>(drow + ((c8 ^ (r & 7)) * 16)) = w;
         }
       }
-      signal_a_ready(&sm.f_ready);
+      signal_a_ready(&sm.f_ready); NLB_TS(3);
       // Global copies for the backward pass trail the signals: the blocks stay valid until this same warp
       // overwrites its rows (program order), so the stores run while the tensor pipe works.
       // bf16 copy of the (zero-padded) feature rows: the B operand of density_layer.0's weight gradient
       if (sv.f0) warp_rows_to_global(XB, r & ~31, lane, reinterpret_cast<__nv_bfloat16*>(sv.f0) + (size_t)tile * 128 * 64, 64, rows_valid);
 
       // ---- L0: h0 = relu(acc + b) -> X1
-      mbar_wait_warp(&sm.acc_ready[L0], ph);
+      mbar_wait_warp(&sm.acc_ready[L0], ph); NLB_TS(4);
       tcgen05_fence_after();
       epi_group64<true>(tlane + 256, sm.bias + bias_offset(L0), XB + 1 * kBlockBytes, r, lane, nullptr, 64, rows_valid);
-      signal_a_ready(&sm.h0_ready);
+      signal_a_ready(&sm.h0_ready); NLB_TS(5);
       if (sv.h0) warp_rows_to_global(XB + 1 * kBlockBytes, r & ~31, lane, reinterpret_cast<__nv_bfloat16*>(sv.h0) + (size_t)tile * 128 * 64, 64, rows_valid);
 
       // ---- L1: x = acc + b -> X0..3 (the L0 / L1 MMAs, readers of X0 / X1, have completed); density
-      mbar_wait_warp(&sm.acc_ready[L1], ph);
+      mbar_wait_warp(&sm.acc_ready[L1], ph); NLB_TS(6);
       tcgen05_fence_after();
       float x0 = 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < 256; c0 += 64)
         epi_group64<false>(tlane + 256 + c0, sm.bias + bias_offset(L1) + c0, XB + (c0 >> 6) * kBlockBytes, r, lane,
                            nullptr, 256, rows_valid, c0 == 0 ? &x0 : nullptr);
-      signal_a_ready(&sm.x_ready);
+      signal_a_ready(&sm.x_ready); NLB_TS(7);
       if (sv.x) {
 #pragma unroll 1
         for (int c0 = 0; c0 < 256; c0 += 64)
@@ -845,8 +855,9 @@ __global__ void __launch_bounds__(kThreads2, 1) k_nerf_mlp_fwd2(const float* __r
         o_density[row] = xin > 20.f ? xin : log1pf(expf(xin));
       }
 
+      NLB_TS(8);
       // ---- HS1 of this tile (the main warps are in its view branch): semantic softmax (19) + intensity
-      mbar_wait_warp(&sm.acc_ready[HS1], ph);
+      mbar_wait_warp(&sm.acc_ready[HS1], ph); NLB_TS(9);
       tcgen05_fence_after();
       {
         float v[32];
@@ -869,6 +880,8 @@ __global__ void __launch_bounds__(kThreads2, 1) k_nerf_mlp_fwd2(const float* __r
           if (o_int) o_int[row] = v[kSem] + b[kSem];
         }
       }
+      NLB_TS(10);
+#undef NLB_TS
     }
   } else {
     // ===== main epilogue warps 0..7: thread (q, lane) owns row r = 32 q + lane; the two warps of a
@@ -883,28 +896,30 @@ __global__ void __launch_bounds__(kThreads2, 1) k_nerf_mlp_fwd2(const float* __r
       const int row = tile * 128 + r;
       const bool valid = row < M;
       const int rows_valid = M - tile * 128 < 128 ? M - tile * 128 : 128;
+      const int tb = ((it == 2 || it == 3) && threadIdx.x == 0) ? 96 + ((int)it - 2) * 12 : -1;
+#define NLB_TS(j) do { if (tb >= 0) stamp(tb + (j)); } while (0)
       // ---- HS0: hidden = relu(acc + b) -> H2, H3  (H is free: every warp waited for the previous RGB)
-      mbar_wait_warp(&sm.acc_ready[HS0], ph);
+      mbar_wait_warp(&sm.acc_ready[HS0], ph); NLB_TS(0);
       tcgen05_fence_after();
       {
         const int c0 = half * 64;
         epi_group64<true>(tlane + c0, sm.bias + bias_offset(HS0) + c0, HB + (2 + half) * kBlockBytes, r, lane, nullptr, 128,
                           rows_valid);
       }
-      signal_a_ready(&sm.g_ready);
+      signal_a_ready(&sm.g_ready); NLB_TS(1);
       // (global copies trail the signals, see the front warps)
       if (sv.g) warp_rows_to_global(HB + (2 + half) * kBlockBytes, r & ~31, lane,
                                     reinterpret_cast<__nv_bfloat16*>(sv.g) + (size_t)tile * 128 * 128 + half * 64, 128, rows_valid);
 
       // ---- V0: h1 = relu(acc + b) -> H0..3 (overwrites H2 / H3, which the HS1 MMAs read)
-      mbar_wait_warp(&sm.acc_ready[HS1], ph);
-      mbar_wait_warp(&sm.acc_ready[V0], ph);
+      mbar_wait_warp(&sm.acc_ready[HS1], ph); NLB_TS(2);
+      mbar_wait_warp(&sm.acc_ready[V0], ph); NLB_TS(3);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
         epi_group64<true>(tlane + 256 + c0, sm.bias + bias_offset(V0) + c0, HB + hperm(c0 >> 6) * kBlockBytes, r, lane,
                           nullptr, 256, rows_valid);
-      signal_a_ready(&sm.h1_ready);
+      signal_a_ready(&sm.h1_ready); NLB_TS(4);
       if (sv.h1) {
 #pragma unroll 1
         for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
@@ -912,14 +927,15 @@ __global__ void __launch_bounds__(kThreads2, 1) k_nerf_mlp_fwd2(const float* __r
                               reinterpret_cast<__nv_bfloat16*>(sv.h1) + (size_t)tile * 128 * 256 + c0, 256, rows_valid);
       }
 
+      NLB_TS(5);
       // ---- V1: h2 = relu(acc + b) -> H0..3
-      mbar_wait_warp(&sm.acc_ready[V1], ph);
+      mbar_wait_warp(&sm.acc_ready[V1], ph); NLB_TS(6);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
         epi_group64<true>(tlane + c0, sm.bias + bias_offset(V1) + c0, HB + hperm(c0 >> 6) * kBlockBytes, r, lane,
                           nullptr, 256, rows_valid);
-      signal_a_ready(&sm.h2_ready);
+      signal_a_ready(&sm.h2_ready); NLB_TS(7);
       if (sv.h2) {
 #pragma unroll 1
         for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
@@ -927,9 +943,10 @@ __global__ void __launch_bounds__(kThreads2, 1) k_nerf_mlp_fwd2(const float* __r
                               reinterpret_cast<__nv_bfloat16*>(sv.h2) + (size_t)tile * 128 * 256 + c0, 256, rows_valid);
       }
 
+      NLB_TS(8);
       // ---- RGB: sigmoid(acc + b) * (1 + 2 pad) - pad   (every warp waits: the next HS0 epilogue
       // overwrites H2 / H3, which the RGB MMAs read)
-      mbar_wait_warp(&sm.acc_ready[RGB], ph);
+      mbar_wait_warp(&sm.acc_ready[RGB], ph); NLB_TS(9);
       tcgen05_fence_after();
       if (half == 1) {
         float v[16];
@@ -944,6 +961,8 @@ __global__ void __launch_bounds__(kThreads2, 1) k_nerf_mlp_fwd2(const float* __r
         }
       }
       tcgen05_fence_before();
+      NLB_TS(10);
+#undef NLB_TS
     }
   }
   __syncthreads();
@@ -986,14 +1005,18 @@ struct BLayerDef {
 __host__ __device__ constexpr BLayerDef blayer_def(int l) {
   switch (l) {
     case B_RGB: return {256, 1, {BS}, {1}, {256, 384, 0, 0}, false};
-    case B_V1:  return {512, 4, {BP, BP + 1, BP + 2, BP + 3}, {4, 4, 4, 4}, {256, 384, 0, 128}, false};
+    // 256-wide quantities staged in P (dzv1, dx): column block j lives in P block pperm(j) = {0, 2, 1, 3}[j], so
+    // the warps of column half h only ever touch P(h) and P(h + 2) -- the g mask / dzg (P(h)) included -- and
+    // their global saves can trail the "ready" signal with program order as the only hazard protection
+    case B_V1:  return {512, 4, {BP, BP + 2, BP + 1, BP + 3}, {4, 4, 4, 4}, {256, 384, 0, 128}, false};
     case B_V0:  return {256, 4, {BQ, BQ + 1, BQ + 2, BQ + 3}, {4, 4, 4, 4}, {0, 128, 0, 0}, true};
     case B_HS1: return {128, 1, {BS}, {2}, {256, 0, 0, 0}, false};
     case B_HS0: return {256, 2, {BP, BP + 1}, {4, 4}, {0, 128, 0, 0}, true};   // dzg lives in P0,P1 (free after B_V1)
-    case B_L1:  return {64, 4, {BP, BP + 1, BP + 2, BP + 3}, {4, 4, 4, 4}, {256, 0, 0, 0}, false};
+    case B_L1:  return {64, 4, {BP, BP + 2, BP + 1, BP + 3}, {4, 4, 4, 4}, {256, 0, 0, 0}, false};
     default:    return {48, 1, {BS}, {4}, {320, 0, 0, 0}, false};                  // dz0 lives in S (free after B_HS1)
   }
 }
+__host__ __device__ constexpr int pperm(int j) { return j == 1 ? 2 : (j == 2 ? 1 : j); }
 __host__ __device__ constexpr int bl_nrows(int l) { return blayer_def(l).N > 128 ? 128 : blayer_def(l).N; }
 __host__ __device__ constexpr int bl_nparts(int l) { return (blayer_def(l).N + 127) / 128; }
 __host__ __device__ constexpr int bl_chunks(int l) { return blayer_def(l).nkb * bl_nparts(l); }
@@ -1235,13 +1258,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
       }
     };
     // this warp's 32 rows x this half's two 64-column blocks of a saved [M,256] activation -> blocks dst[0..3]
-    auto prefetch_mask = [&](uint8_t* dst, const void* act, int tile_) {
+    auto prefetch_mask = [&](uint8_t* dst, const void* act, int tile_, bool permuted) {
       if (tile_ >= num_tiles) return;
       const int rv = M - tile_ * 128 < 128 ? M - tile_ * 128 : 128;
 #pragma unroll 1
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
-        warp_rows_from_global_async(dst + (c0 >> 6) * kBlockBytes, r & ~31, lane,
+        warp_rows_from_global_async(dst + (permuted ? pperm(c0 >> 6) : (c0 >> 6)) * kBlockBytes, r & ~31, lane,
                                     cbf(act) + (size_t)tile_ * 128 * 256 + c0, 256, rv);
+    };
+    // global copy of this warp's rows of a staged 64-column block (for the weight-gradient GEMMs); issued AFTER
+    // the block's "ready" signal so that the stores run under the next GEMM
+    auto save_block = [&](const uint8_t* block, void* g, size_t trow_, int ld, int c0, int rv) {
+      if (g) warp_rows_to_global(block, r & ~31, lane, bf(g) + trow_ * ld + c0, ld, rv);
     };
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -1276,8 +1304,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
       // here; for every later tile they were issued during the previous one, as soon as its last reader
       // of Q (B_V0) / P (B_L1) had completed, so they are resident when the tile starts.
       if (it == 0) {
-        prefetch_mask(QB, sv.h1, tile);
-        prefetch_mask(PB, sv.h2, tile);
+        prefetch_mask(QB, sv.h1, tile, false);
+        prefetch_mask(PB, sv.h2, tile, true);
       }
 
       // ---- dzv1 = dh2 * [h2 > 0] -> P0..3
@@ -1288,10 +1316,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
       __syncwarp();
 #pragma unroll 1
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
-        epi_group64_masked<true, true>(tlane + 256 + c0, cbf(sv.h2) + trow * 256 + c0, PB + (c0 >> 6) * kBlockBytes, r, lane,
-                                 bf(go.d_v1) + trow * ld_v1 + c0, 256, ld_v1, rows_valid);
+        epi_group64_masked<true, true>(tlane + 256 + c0, cbf(sv.h2) + trow * 256 + c0, PB + pperm(c0 >> 6) * kBlockBytes, r, lane,
+                                 nullptr, 256, ld_v1, rows_valid);
       if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 3);
       signal_a_ready(&sm.a_ready[B_V1]);
+#pragma unroll 1
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
+        save_block(PB + pperm(c0 >> 6) * kBlockBytes, go.d_v1, trow, ld_v1, c0, rows_valid);
 
       // ---- d(sem logits) | d(intensity) -> S (cols 0..19): half 1, while B_V1 runs; S is free: B_RGB completed above
       if (half == 1) {
@@ -1327,9 +1358,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
 #pragma unroll 1
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
         epi_group64_masked<true, true>(tlane + 256 + c0, cbf(sv.h1) + trow * 256 + c0, QB + (c0 >> 6) * kBlockBytes, r, lane,
-                                 bf(go.d_v0) + trow * ld_v0 + c0, 256, ld_v0, rows_valid);
+                                 nullptr, 256, ld_v0, rows_valid);
       if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 5);
       signal_a_ready(&sm.a_ready[B_V0]);
+#pragma unroll 1
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
+        save_block(QB + (c0 >> 6) * kBlockBytes, go.d_v0, trow, ld_v0, c0, rows_valid);
 
 
       // ---- dzg = dg * [g > 0] -> P0,P1
@@ -1341,14 +1375,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
       // B_HS1 has consumed S: the ReLU mask of density_layer.0 goes there for the last epilogue
       if (half == 0) warp_rows_from_global_async(SB, r & ~31, lane, cbf(sv.h0) + trow * 64, 64, rows_valid);
       // B_V0 (ahead of B_HS1 on the pipe) has consumed Q, which this tile does not touch again
-      prefetch_mask(QB, sv.h1, tile + (int)gridDim.x);
+      prefetch_mask(QB, sv.h1, tile + (int)gridDim.x, false);
       {
         const int c0 = half * 64;
         epi_group64_masked<true, true>(tlane + 256 + c0, cbf(sv.g) + trow * 128 + c0, PB + half * kBlockBytes, r, lane,
-                                       bf(go.d_g) + trow * ld_g + c0, 128, ld_g, rows_valid);
+                                       nullptr, 128, ld_g, rows_valid);
       }
       if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 8);
       signal_a_ready(&sm.a_ready[B_HS0]);
+      save_block(PB + half * kBlockBytes, go.d_g, trow, ld_g, half * 64, rows_valid);
 
       // ---- dx = accA (+ density term on column 0) -> P0..3
       mbar_wait_warp(&sm.acc_ready[B_HS0], ph);
@@ -1359,11 +1394,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
         if (valid && gi.g_density) dterm = __ldg(gi.g_density + row) * (1.0f - expf(-__ldg(gi.density + row)));
 #pragma unroll 1
         for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
-          epi_group64_masked<false>(tlane + c0, nullptr, PB + (c0 >> 6) * kBlockBytes, r, lane,
-                                    bf(go.d_x) + trow * 256 + c0, 256, 256, rows_valid, c0 == 0 ? dterm : 0.f);
+          epi_group64_masked<false>(tlane + c0, nullptr, PB + pperm(c0 >> 6) * kBlockBytes, r, lane,
+                                    nullptr, 256, 256, rows_valid, c0 == 0 ? dterm : 0.f);
       }
       if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 10);
       signal_a_ready(&sm.a_ready[B_L1]);
+#pragma unroll 1
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64)
+        save_block(PB + pperm(c0 >> 6) * kBlockBytes, go.d_x, trow, 256, c0, rows_valid);
 
       // ---- dz0 = dh0 * [h0 > 0] -> S
       mbar_wait_warp(&sm.acc_ready[B_L1], ph);
@@ -1372,13 +1410,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_bwd(nlb_nerf_mlp_grad_
       if (half == 0) {
         cp_async_wait_all();
         __syncwarp();
-        epi_group64_masked<true, true>(tlane + 256, cbf(sv.h0) + trow * 64, SB, r, lane, bf(go.d_h0) + trow * 64, 64, 64,
-                                       rows_valid);
+        epi_group64_masked<true, true>(tlane + 256, cbf(sv.h0) + trow * 64, SB, r, lane, nullptr, 64, 64, rows_valid);
       }
       if (it < 2 && warp == 0 && lane == 0) mlp::stamp((int)it * 20 + 12);
       signal_a_ready(&sm.a_ready[B_L0]);
+      if (half == 0) save_block(SB, go.d_h0, trow, 64, 0, rows_valid);
       // B_L1 has consumed P (dx): next tile's h2 mask
-      prefetch_mask(PB, sv.h2, tile + (int)gridDim.x);
+      prefetch_mask(PB, sv.h2, tile + (int)gridDim.x, true);
 
       // next tile's rgb / g_rgb (dc staging opens the tile with nothing to overlap their latency)
       if (half == 0) {

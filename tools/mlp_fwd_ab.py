@@ -35,4 +35,15 @@ t = buf.cpu().tolist()
 if t[124] > 0:
     cyc, ns = t[121] - t[120], t[123] - t[122]
     print(f'block 0: {t[124]} tiles, {cyc} cycles = {cyc / t[124]:.0f} per tile, {ns} ns -> SM clock {cyc / ns * 1000:.0f} MHz')
+
+if t[124] > 0 and t[0] > 0:
+    t0 = min(x for x in t[:120] if x > 0)
+    rel = lambda i: (t[i] - t0) if t[i] > 0 else None
+    mm = ['x_rdy', 'HS0 iss', 'V0 iss', 'g_rdy', 'HS1 iss', 'h1_rdy', 'hs1_free', 'V1 iss', 'f_rdy', 'L0 iss', 'h0_rdy', 'L1 iss', 'h2_rdy', 'RGB iss']
+    fr = ['top', 'inputs', 'V1 done', 'f sig', 'L0 acc', 'h0 sig', 'L1 acc', 'x sig', 'x saved', 'HS1 acc', 'end']
+    ma = ['HS0 acc', 'g sig', 'HS1 acc', 'V0 acc', 'h1 sig', 'h1 saved', 'V1 acc', 'h2 sig', 'h2 saved', 'RGB acc', 'end']
+    for j in range(2):
+        print('MMA  it', 2 + j, [(n, rel(j * 32 + i)) for i, n in enumerate(mm)])
+        print('front k', 2 + j, [(n, rel(64 + j * 16 + i)) for i, n in enumerate(fr)])
+        print('main it', 2 + j, [(n, rel(96 + j * 12 + i)) for i, n in enumerate(ma)])
 _lib.check(_lib.load().nlb_debug_set_timeline(0))
