@@ -163,6 +163,12 @@ class Trainer:
             o += t['enc'].num_levels
         self._graphs = {}
         self._static = None
+        # Every training step -- eager, warm-up or captured -- is issued on this stream.  Autograd binds a
+        # leaf's AccumulateGrad node to the stream of its first use (the PropMLP weight gradients still travel
+        # through autograd); a step first run eagerly on the legacy default stream and later captured on
+        # another one made the engine join the default stream into the capture
+        # (cudaErrorStreamCaptureIsolation: tests/dp_worker.py, eager step followed by the graphed one).
+        self.stream = torch.cuda.Stream(device=dev)
         model.train()
         model.training = True
 
@@ -211,6 +217,18 @@ class Trainer:
 
     def train_step(self, batch: Dict[str, torch.Tensor], step: int, num_patch: Optional[int] = None,
                    rand_inputs=None) -> Dict[str, torch.Tensor]:
+        """One eager training step, issued on the trainer's own stream (the caller's stream waits for it)."""
+        dev = self.flat.device
+        cur = torch.cuda.current_stream(dev)
+        if cur == self.stream or torch.cuda.is_current_stream_capturing():
+            return self._train_step(batch, step, num_patch, rand_inputs)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            out = self._train_step(batch, step, num_patch, rand_inputs)
+        cur.wait_stream(self.stream)
+        return out
+
+    def _train_step(self, batch, step, num_patch=None, rand_inputs=None):
         losses, main, prop = self.forward_losses(batch, step, num_patch, rand_inputs)
         if self.world == 1:
             # (running the NeRF table's optimizer pass on a side stream beside the proposal backward was
@@ -381,28 +399,24 @@ class Trainer:
             # warm up eagerly on a side stream (allocator, cuBLAS handles, kernel attributes), then capture
             lib.nlb_set_dynamic_scalars(st['dyn'].data_ptr())
             try:
-                s = torch.cuda.Stream(device=dev)
-                s.wait_stream(torch.cuda.current_stream(dev))
-                with torch.cuda.stream(s):
-                    out = self.train_step(st['batch'], step, num_patch, srand)
-                torch.cuda.current_stream(dev).wait_stream(s)
+                out = self.train_step(st['batch'], step, num_patch, srand)   # on self.stream
                 out = {k: v.clone() for k, v in out.items()}
                 g = torch.cuda.CUDAGraph()
                 g_prop = g_opt = None
                 if self.world == 1:
-                    with torch.cuda.graph(g):
-                        captured = self.train_step(st['batch'], step, num_patch, srand)
+                    with torch.cuda.graph(g, stream=self.stream):
+                        captured = self._train_step(st['batch'], step, num_patch, srand)
                 else:
                     # the collectives stay outside the graphs: forward + main backward | proposal backward | optimizer
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, stream=self.stream):
                         captured, main, prop = self.forward_losses(st['batch'], step, num_patch, srand)
                         main.backward()
                     if prop is not None:
                         g_prop = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g_prop, pool=g.pool()):
+                        with torch.cuda.graph(g_prop, pool=g.pool(), stream=self.stream):
                             prop.backward()
                     g_opt = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g_opt, pool=g.pool()):
+                    with torch.cuda.graph(g_opt, pool=g.pool(), stream=self.stream):
                         self.optimizer_step(step, reduce=False, publish=False)
                     del main, prop
             finally:

@@ -38,10 +38,23 @@ def main():
         halves.append({k: v.to(dev) for k, v in synthetic.to_torch(synthetic.make_train_batch(B, seed=80 + r)).items()})
         n = halves[-1]['origins'].shape[0]
         rins.append([{k: torch.from_numpy(v).to(dev) for k, v in x.items()} for x in synthetic.make_rand_inputs(n, seed=90 + r)])
-    for i, fn in enumerate((dp.train_step, dp.train_step_graphed, dp.train_step_graphed)):
+    seq = {'e': dp.train_step, 'g': dp.train_step_graphed}
+    for i, fn in enumerate([seq[c] for c in os.environ.get('DPW_SEQ', 'egg')]):   # eager, capture, replay
         step = 6000 + 500 * i
         # identical state on both sides (free-running trainers drift apart chaotically, see test_gpu_train.py)
         if i > 0:
+            # ONE source for the state: the single-GPU references of the two ranks are independent computations
+            # whose gradients differ in the last bits (atomics order), and Adam with eps = 1e-15 turns a
+            # near-zero gradient of either sign into a +-lr step -- copied rank-locally, the "replicated"
+            # parameters of the data-parallel trainer would differ between the ranks (measured: 1e-4-level
+            # moment differences at the next step).  Rank 0's reference state goes to every rank.
+            with torch.no_grad():
+                for t in ref.tables:
+                    for x in (t['param'].data, t['m'], t['v']):
+                        dist.broadcast(x, 0)
+                for x in (ref.flat, ref.flat_m, ref.flat_v, ref.hash_decay_value):
+                    dist.broadcast(x, 0)
+            ref._mark_packed_stale()
             for a, b in zip(ref.tables, dp.tables):
                 b['param'].data.copy_(a['param'].data)
                 lo, cnt = b['arena']['lo'], b['arena']['cnt']
@@ -64,28 +77,34 @@ def main():
             t['grad'].mul_(1.0 / world)
         ref.optimizer_step(step)
         torch.cuda.synchronize()
-        for k in ref_losses[rank]:
-            if k in ('loss', 'hash_decay'):
-                continue
-            a, b = float(out[k]), float(ref_losses[rank][k])
-            assert abs(a - b) <= 1e-5 * max(abs(b), 1e-3), (i, rank, k, a, b)
-        for a, b in zip(ref.tables, dp.tables):
-            lo, cnt = b['arena']['lo'], b['arena']['cnt']
-            assert rel(b['m'][:cnt], a['m'][lo:lo + cnt]) <= 1e-5, (i, rank, a['name'], 'm')
-            assert rel(b['v'][:cnt], a['v'][lo:lo + cnt]) <= 1e-5, (i, rank, a['name'], 'v')
-            assert float((b['param'] - a['param']).abs().mean()) <= 1e-8, (i, rank, a['name'], 'param')
-            assert float(b['grad'].abs().max()) == 0.0 and float(b['arena']['grad'].abs().max()) == 0.0
-        fa = dp.flat_arena
-        assert rel(dp.flat_m[:fa['cnt']], ref.flat_m[fa['lo']:fa['lo'] + fa['cnt']]) <= 1e-4, (i, rank, 'flat m')
-        assert rel(dp.flat_v[:fa['cnt']], ref.flat_v[fa['lo']:fa['lo'] + fa['cnt']]) <= 1e-4, (i, rank, 'flat v')
-        assert float((dp.flat - ref.flat).abs().mean()) <= 1e-6, (i, rank, 'flat params')
-        assert float(fa['grad'].abs().max()) == 0.0
-        assert abs(float(dp.hash_decay_value) - float(ref.hash_decay_value)) <= 1e-5 * float(ref.hash_decay_value)
-        # parameters identical on every rank after the all-gather
-        chk = torch.stack([dp.flat.double().sum()] + [t['param'].double().sum() for t in dp.tables])
-        lst = [torch.empty_like(chk) for _ in range(world)]
-        dist.all_gather(lst, chk)
-        assert all(torch.equal(lst[0], x) for x in lst), (i, rank, 'ranks disagree after the all-gather')
+        # Verification under no_grad: `t['param']` are Parameters, and an autograd graph built over them HERE (on the
+        # default stream) that stays alive -- `chk` survives into the next iteration -- keeps their AccumulateGrad nodes
+        # bound to the default stream; the next captured backward then joins that stream into the capture
+        # (cudaErrorStreamCaptureIsolation in GraphTask::exec_post_processing).
+        with torch.no_grad():
+            for k in ref_losses[rank]:
+                if k in ('loss', 'hash_decay'):
+                    continue
+                a, b = float(out[k]), float(ref_losses[rank][k])
+                assert abs(a - b) <= 1e-5 * max(abs(b), 1e-3), (i, rank, k, a, b)
+            for a, b in zip(ref.tables, dp.tables):
+                lo, cnt = b['arena']['lo'], b['arena']['cnt']
+                rm, rv = rel(b['m'][:cnt], a['m'][lo:lo + cnt]), rel(b['v'][:cnt], a['v'][lo:lo + cnt])
+                print(f'step {i} rank {rank} {a["name"]}: rel m {rm:.2e} v {rv:.2e}', flush=True)
+                assert rm <= 1e-5 and rv <= 1e-5, (i, rank, a['name'], rm, rv)
+                assert float((b['param'] - a['param']).abs().mean()) <= 1e-8, (i, rank, a['name'], 'param')
+                assert float(b['grad'].abs().max()) == 0.0 and float(b['arena']['grad'].abs().max()) == 0.0
+            fa = dp.flat_arena
+            assert rel(dp.flat_m[:fa['cnt']], ref.flat_m[fa['lo']:fa['lo'] + fa['cnt']]) <= 1e-4, (i, rank, 'flat m')
+            assert rel(dp.flat_v[:fa['cnt']], ref.flat_v[fa['lo']:fa['lo'] + fa['cnt']]) <= 1e-4, (i, rank, 'flat v')
+            assert float((dp.flat - ref.flat).abs().mean()) <= 1e-6, (i, rank, 'flat params')
+            assert float(fa['grad'].abs().max()) == 0.0
+            assert abs(float(dp.hash_decay_value) - float(ref.hash_decay_value)) <= 1e-5 * float(ref.hash_decay_value)
+            # parameters identical on every rank after the all-gather
+            chk = torch.stack([dp.flat.double().sum()] + [t['param'].double().sum() for t in dp.tables])
+            lst = [torch.empty_like(chk) for _ in range(world)]
+            dist.all_gather(lst, chk)
+            assert all(torch.equal(lst[0], x) for x in lst), (i, rank, 'ranks disagree after the all-gather')
     dist.barrier()
     if rank == 0:
         print('dp ok')
