@@ -405,6 +405,39 @@ int nlb_lidar_directions(const double* elev_deg, int n_beams, const double* azim
 int nlb_lidar_rays(const float* origins, const float* directions, int64_t n, double* workspace,
                    const nlb_ray_out_t* out, void* stream);
 
+/* ------------------------------------------------------------------ dynamic-object branch
+ * Replaces, inside Model.forward (Z/internal/models.py:306-315,401-477): obj_utils.get_pose
+ * (Z/internal/obj_utils.py:431-475), obj_utils.box_pts / world2object / rotate_yaw_z / scale_frames
+ * (:196-234,116-194,76-111,5-29), the boolean-index compaction with its host synchronisation
+ * (`intersect_idx.sum() == 0`), the per-class ObjMLP evaluation (Z/internal/models.py:1000-1034,1036-1263 with
+ * warp_fn=None, re_weights=False, fixed_semantic=True, split shape / texture latent) and the masked merge of
+ * every result key (zeros_like + masked assignment + where).
+ */
+/* pose[N,n_obj,9] = per ray, per track: the two track entries closest to the ray's timestamp, blended
+ * (get_pose).  tracks[n_obj,T,9] = centre(3), yaw about z, wlh(3), timestamp, track id; T >= 2. */
+int nlb_obj_pose(const float* time /*[N]*/, const float* tracks, int N, int n_obj, int T, float* pose, void* stream);
+
+typedef struct {
+  const float *W_d0, *b_d0;   /* density_layer.0 [hidden, L*C + latent_shape] */
+  const float *W_d2, *b_d2;   /* density_layer.2 [bottleneck, hidden] */
+  const float *W_v0, *b_v0;   /* lin_second_stage_0 [view_width, bottleneck + dir + latent_tex] */
+  const float *W_v1, *b_v1;   /* lin_second_stage_1 [view_width, view_width + bottleneck + dir + latent_tex] */
+  const float *W_rgb, *b_rgb; /* rgb_layer [3, view_width] */
+  const float* latent;        /* [latent_shape + latent_tex] (split_latent) or NULL */
+  int hidden, bottleneck, view_width, deg_view, latent_shape, latent_tex;
+  float density_bias, rgb_premultiplier, rgb_bias, rgb_padding;
+  int class_type, class_num;  /* fixed_semantic one-hot; class 255 = all zeros */
+} nlb_obj_mlp_t;
+
+/* One track at one sampling level: every sample midpoint of every ray is tested against the track's box; hits
+ * are evaluated by the ObjMLP and OVERWRITE density[N,S] (and rgb[N,S,3], semantic[N,S,class_num] when given:
+ * NULL at the proposal levels) in place; obj_mask[N,S] (bytes) is set to 1 on hits.  Tracks are applied by
+ * calling this once per track in track order, as the reference's loop does. */
+int nlb_obj_forward(const float* tdist /*[N,S+1]*/, const float* origins, const float* directions,
+                    const float* viewdirs, const float* pose /*[N,n_obj,9]*/, int n_obj, int track, int N, int S,
+                    const nlb_table_t* table, const nlb_obj_mlp_t* mlp, float* density, float* rgb, float* semantic,
+                    uint8_t* obj_mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,14 @@ class NlbRayOut(C.Structure):
     _fields_ = [(n, c_f) for n in ('origins', 'directions', 'viewdirs', 'radii', 'imageplane', 'base_x', 'base_y')]
 
 
+class NlbObjMlp(C.Structure):
+    _fields_ = [(n, c_f) for n in ('W_d0', 'b_d0', 'W_d2', 'b_d2', 'W_v0', 'b_v0', 'W_v1', 'b_v1', 'W_rgb', 'b_rgb',
+                                   'latent')] + \
+               [(n, C.c_int) for n in ('hidden', 'bottleneck', 'view_width', 'deg_view', 'latent_shape', 'latent_tex')] + \
+               [(n, C.c_float) for n in ('density_bias', 'rgb_premultiplier', 'rgb_bias', 'rgb_padding')] + \
+               [(n, C.c_int) for n in ('class_type', 'class_num')]
+
+
 _u32, _i, _f, _p = C.c_uint32, C.c_int, C.c_float, C.c_void_p
 
 # name -> (restype, argtypes); mirrors include/nlb200.h one to one
@@ -122,6 +130,8 @@ SIGNATURES = {
     'nlb_camera_rays': (_i, [_p, _p, _p, _p, _i, _p, _i, C.c_int64, C.POINTER(NlbRayOut), _p]),
     'nlb_lidar_directions': (_i, [_p, _i, _p, _i, _p, _p]),
     'nlb_lidar_rays': (_i, [_p, _p, C.c_int64, _p, C.POINTER(NlbRayOut), _p]),
+    'nlb_obj_pose': (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    'nlb_obj_forward': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, C.POINTER(NlbTable), C.POINTER(NlbObjMlp), _p, _p, _p, _p, _p]),
 }
 
 _lib: Optional[C.CDLL] = None

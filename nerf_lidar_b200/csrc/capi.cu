@@ -37,10 +37,10 @@ extern "C" int nlb_device_ok(void) {
 }
 
 // ---------------------------------------------------------------- CUDA-graph support
-// Scalars that change every training step (see include/nlb200.h).  The pointer is
-// process-global host state; kernels receive it as an argument at launch/capture time
-// and read the values at execution time.
-static const float* g_dyn = nullptr;
+// Scalars that change every training step (see include/nlb200.h).  The pointer is host state of the CALLING
+// THREAD (two trainers capturing on two threads must not see each other's buffer); kernels receive it as an
+// argument at launch / capture time and read the values at execution time.
+static thread_local const float* g_dyn = nullptr;
 const float* nlb_dynamic_scalars() { return g_dyn; }
 
 extern "C" int nlb_set_dynamic_scalars(const float* dev) {
@@ -55,4 +55,18 @@ extern "C" int nlb_adam_bias_terms(float lr, float beta1, float beta2, int step,
   out2[0] = (float)((double)lr / bc1);
   out2[1] = (float)(1.0 / sqrt(bc2));
   return NLB_OK;
+}
+
+// SM count of the CURRENT device (cached per device: a process may drive several GPUs)
+int nlb_sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cache[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = n > 0 ? n : 148;
+  }
+  return cache[dev];
 }

@@ -283,4 +283,6 @@ void nlb_set_error(const char* fmt, ...);
 int nlb_check_launch(const char* what);
 // device buffer of step-varying scalars {anneal, lr_c, rsqrt_bc2} or nullptr (nlb_set_dynamic_scalars)
 const float* nlb_dynamic_scalars();
+// SM count of the current device (per-device cache, capi.cu)
+int nlb_sm_count();
 enum { NLB_DYN_ANNEAL = 0, NLB_DYN_LR_C = 1, NLB_DYN_RSQRT_BC2 = 2 };

@@ -1038,16 +1038,7 @@ extern "C" int nlb_encode_forward(const nlb_rays_t* rays, const nlb_table_t* tab
 // Persistent launch shape of k_encode_bwd: the coarse levels that fit the shared-memory
 // budget are staged per block (see the kernel comment); the grid is the number of blocks
 // the device can keep resident (a multiple of the SM count), capped by the tile count.
-static int g_sm_count = 0;
-static int sm_count() {
-  if (g_sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
-  }
-  return g_sm_count;
-}
+static int sm_count() { return nlb_sm_count(); }
 
 
 constexpr int kPrivCopies = 16;
@@ -1088,10 +1079,14 @@ static int scatter_launch(const nlb_rays_t& rays, const nlb_table_t& tab, const 
       cudaMemsetAsync(workspace, 0, (size_t)kPrivCopies * priv_rows * C * sizeof(float), st) != cudaSuccess)
     return nlb_check_launch("encode_backward memset");
   const int tiles = (int)div_up(rays.N * rays.S, kEncThreads);
-  static bool attr_set = false;
-  if (!attr_set) {
+  // per device (function attributes are device state): a process may drive several GPUs
+  static bool attr_set[64] = {false};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  if (dev_ < 0 || dev_ >= 64) dev_ = 0;
+  if (!attr_set[dev_]) {
     cudaFuncSetAttribute(k_encode_bwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_bwd<C>, kEncThreads, smem);

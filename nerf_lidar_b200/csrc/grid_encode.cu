@@ -378,6 +378,7 @@ extern "C" int nlb_grad_total_variation(const float* inputs, const float* embedd
                                         void* stream) {
   if (int e = check_dc(D, C)) return e;
   if (B == 0 || L == 0) return NLB_OK;
+  if (!inputs || !embeddings || !grad || !offsets) { nlb_set_error("grad_total_variation: null pointer"); return NLB_EINVAL; }
   dim3 grid(div_up(B, 256), L);
   NLB_DISPATCH_DC(D, C, (k_grad_tv<D_, C_><<<grid, 256, 0, (cudaStream_t)stream>>>(
       inputs, embeddings, grad, offsets, weight, B, L, S, H, gridtype, align_corners != 0)));
@@ -389,6 +390,7 @@ extern "C" int nlb_grid_corner_indices(const float* inputs, const int32_t* offse
                                        int align_corners, void* stream) {
   if (int e = check_dc(D, 1)) return e;
   if (B == 0 || L == 0) return NLB_OK;
+  if (!inputs || !offsets || !indices) { nlb_set_error("grid_corner_indices: null pointer"); return NLB_EINVAL; }
   dim3 grid(div_up(B, 256), L);
   if (D == 3)
     k_corner_indices<3><<<grid, 256, 0, (cudaStream_t)stream>>>(inputs, offsets, indices, B, L, S, H, gridtype, align_corners != 0);

@@ -81,11 +81,11 @@ __device__ float packed_weight(const nlb_nerf_mlp_weights_t& w, int l, int n, in
   switch (l) {
     case L0:  return (n < 64 && k < kFeat) ? w.W_d0[n * kFeat + k] : 0.f;
     case L1:  return w.W_d2[n * 64 + k];
-    case HS0: return n < 64 ? w.W_s0[n * 256 + k] : w.W_i0[(n - 64) * 256 + k];
+    case HS0: return n < 64 ? w.W_s0[n * 256 + k] : (w.W_i0 ? w.W_i0[(n - 64) * 256 + k] : 0.f);   // no intensity head: zeros
     case V0:  return k < 256 ? w.W_v0[n * 283 + k] : (k - 256 < kDir ? w.W_v0[n * 283 + k] : 0.f);
     case HS1:
       if (n < kSem) return k < 64 ? w.W_s2[n * 64 + k] : 0.f;
-      if (n == kSem) return k >= 64 ? w.W_i2[k - 64] : 0.f;
+      if (n == kSem) return (k >= 64 && w.W_i2) ? w.W_i2[k - 64] : 0.f;
       return 0.f;
     case V1:  return k < 512 ? w.W_v1[n * 539 + k] : (k - 512 < kDir ? w.W_v1[n * 539 + k] : 0.f);
     default:  return n < 3 ? w.W_rgb[n * 256 + k] : 0.f;
@@ -95,9 +95,9 @@ __device__ float packed_bias(const nlb_nerf_mlp_weights_t& w, int l, int n) {
   switch (l) {
     case L0:  return w.b_d0[n];
     case L1:  return w.b_d2[n];
-    case HS0: return n < 64 ? w.b_s0[n] : w.b_i0[n - 64];
+    case HS0: return n < 64 ? w.b_s0[n] : (w.b_i0 ? w.b_i0[n - 64] : 0.f);
     case V0:  return w.b_v0[n];
-    case HS1: return n < kSem ? w.b_s2[n] : (n == kSem ? w.b_i2[0] : 0.f);
+    case HS1: return n < kSem ? w.b_s2[n] : ((n == kSem && w.b_i2) ? w.b_i2[0] : 0.f);
     case V1:  return w.b_v1[n];
     default:  return n < 3 ? w.b_rgb[n] : 0.f;
   }
@@ -1471,9 +1471,11 @@ extern "C" int nlb_nerf_mlp_pack(const nlb_nerf_mlp_weights_t* w, void* packed, 
     // the intensity head is optional in the reference (Config.use_intensity)
     if (!p[i] && !(i >= 8 && i < 12)) { nlb_set_error("nerf_mlp_pack: null weight pointer %zu", i); return NLB_EINVAL; }
   }
-  if (!w->W_i0 || !w->b_i0 || !w->W_i2 || !w->b_i2) {
-    nlb_set_error("nerf_mlp_pack: the intensity head is required (Config.use_intensity=True)");
-    return NLB_EUNSUPPORTED;
+  // Config.use_intensity=False: the intensity head's rows of the fused sem | intensity layers are packed as zeros
+  // and nlb_nerf_mlp_forward is called with intensity == NULL (inference; the training kernels need the head)
+  if ((!w->W_i0) != (!w->b_i0) || (!w->W_i0) != (!w->W_i2) || (!w->W_i0) != (!w->b_i2)) {
+    nlb_set_error("nerf_mlp_pack: the intensity head must be given completely or not at all");
+    return NLB_EINVAL;
   }
   mlp::k_pack<<<148, 256, 0, (cudaStream_t)stream>>>(*w, reinterpret_cast<uint8_t*>(packed));
   return nlb_check_launch("nerf_mlp_pack");
@@ -1489,17 +1491,17 @@ extern "C" int nlb_nerf_mlp_forward(const float* features, const float* viewdirs
     nlb_set_error("nerf_mlp_forward: features / packed weights must be 16-byte aligned");
     return NLB_EINVAL;
   }
-  static int sms = 0;
-  static bool legacy = false;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static bool attr_set[64] = {false};   // per device: function attributes are device state
+  static const bool legacy = [] { const char* e = getenv("NLB_MLP_FWD_LEGACY"); return e && e[0] == '1'; }();  // A/B timing
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
     cudaFuncSetAttribute(mlp::k_nerf_mlp_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp::kSmemBytes);
     cudaFuncSetAttribute(mlp::v2::k_nerf_mlp_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp::v2::kSmemBytes2);
-    const char* e = getenv("NLB_MLP_FWD_LEGACY");   // development switch (A/B timing): one tile in flight
-    legacy = e && e[0] == '1';
+    attr_set[dev] = true;
   }
+  const int sms = nlb_sm_count();
   const int tiles = (M + 127) / 128;
   const int grid = tiles < sms ? tiles : sms;
   nlb_nerf_mlp_saved_t sv = {};
@@ -1530,17 +1532,27 @@ extern "C" int nlb_nerf_mlp_backward(const nlb_nerf_mlp_grad_in_t* gin, const nl
   if (M == 0) return NLB_OK;
   if (!gin || !saved || !packed_t || !grad_features || !gout) { nlb_set_error("nerf_mlp_backward: null pointer"); return NLB_EINVAL; }
   if (!saved->h0 || !saved->g || !saved->h1 || !saved->h2) { nlb_set_error("nerf_mlp_backward: the activations saved by the forward are required"); return NLB_EINVAL; }
+  if (!gout->d_rgb || !gout->d_v1 || !gout->d_v0 || !gout->d_hs1 || !gout->d_g || !gout->d_x || !gout->d_h0) {
+    nlb_set_error("nerf_mlp_backward: every pre-activation gradient buffer of nlb_nerf_mlp_grad_out_t is required");
+    return NLB_EINVAL;
+  }
+  if ((gout->ld_v1 && gout->ld_v1 < 256) || (gout->ld_v0 && gout->ld_v0 < 256) || (gout->ld_g && gout->ld_g < 128)) {
+    nlb_set_error("nerf_mlp_backward: leading dimensions smaller than the matrices");
+    return NLB_EINVAL;
+  }
   if ((gin->g_rgb && !gin->rgb) || (gin->g_semantic && !gin->semantic) || (gin->g_density && !gin->density)) {
     nlb_set_error("nerf_mlp_backward: forward outputs are required next to their gradients");
     return NLB_EINVAL;
   }
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
     cudaFuncSetAttribute(mlp::bwd::k_nerf_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp::bwd::kBSmemBytes);
+    attr_set[dev] = true;
   }
+  const int sms = nlb_sm_count();
   const int tiles = (M + 127) / 128;
   const int grid = tiles < sms ? tiles : sms;
   mlp::bwd::k_nerf_mlp_bwd<<<grid, mlp::kThreads, mlp::bwd::kBSmemBytes, (cudaStream_t)stream>>>(

@@ -329,10 +329,13 @@ extern "C" int nlb_render_losses(const nlb_losses_in_t* in_, float* losses, floa
   {
     const size_t qsmem = (size_t)in.N * sizeof(uint32_t);
     const int cached = qsmem <= 160 * 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};   // per device
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (dev_ < 0 || dev_ >= 64) dev_ = 0;
+    if (!attr_set[dev_]) {
       cudaFuncSetAttribute(k_depth_quantile, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      attr_set = true;
+      attr_set[dev_] = true;
     }
     k_depth_quantile<<<1, 1024, cached ? qsmem : 0, st>>>(in, workspace, cached);
   }

@@ -4,9 +4,9 @@ render_image) on the B200 kernels.
 
 Scope: the static-scene zipnerf path of nuscenes_single.gin --
 3 sampling levels, hash-grid PropMLPs, NerfMLP with semantic + intensity heads,
-opaque background, power-transformation ray warp.  The dynamic-object branch
-(Config.instance_obj, Z/internal/models.py:306-315,401-477) is section 8(f) "next" and
-raises NotImplementedError here.
+opaque background, power-transformation ray warp -- and, with Config.instance_obj, the dynamic-object
+branch (Z/internal/models.py:92-177 ctor, :306-315,401-477 forward; ObjMLP per class with split shape /
+texture latents) on csrc/obj.cu, forward (rendering) only.
 
 State-dict keys are the reference's (nerf_mlp.encoder.embeddings,
 nerf_mlp.density_layer.0.weight, prop_mlp_0.encoder.offsets, ...), so reference
@@ -58,6 +58,13 @@ class MLP(nn.Module):
     use_intensity: bool = False
     no_sem_layer: bool = True
     re_weights: bool = True
+    density_init: bool = False
+    fixed_semantic: bool = False
+    class_type: int = 255
+    obj_mode: bool = False
+    complex_decoder: bool = False
+    latent_size: int = 0
+    split_latent: bool = False
     mlp_dtype = torch.bfloat16  # operand type of the dense layers (fp32 accumulation)
 
     def __init__(self, **kwargs):
@@ -66,9 +73,12 @@ class MLP(nn.Module):
         if not self.disable_density_normals:
             raise NotImplementedError('density normals (Ref-NeRF options) are outside the zipnerf hot path; '
                                       'bind disable_density_normals=True as nuscenes_single.gin does')
-        if self.use_semantic and self.no_sem_layer and not self.disable_rgb:
+        if self.use_semantic and self.no_sem_layer and not self.disable_rgb and not self.fixed_semantic:
             raise NotImplementedError('no_sem_layer=True (semantic = bottleneck slice) is not built; '
                                       'nuscenes_single.gin binds Config.no_sem_layer=False')
+        if self.obj_mode or self.complex_decoder:
+            raise NotImplementedError('obj_mode / complex_decoder density heads are not built '
+                                      '(nuscenes_single.gin binds ObjMLP.obj_mode=False)')
         self.grid_num_levels = int(np.log(self.grid_disired_resolution / self.grid_base_resolution)
                                    / np.log(self.grid_level_interval)) + 1
         self.encoder = GridEncoder(input_dim=3, num_levels=self.grid_num_levels, level_dim=self.grid_level_dim,
@@ -77,11 +87,19 @@ class MLP(nn.Module):
                                    log2_hashmap_size=self.grid_log2_hashmap_size, gridtype='hash',
                                    align_corners=False)
         width = self.encoder.output_dim
+        # latent codes of the per-class object networks (Z/internal/models.py:907-912,953-955): with
+        # split_latent the first half (shape) joins the grid features, the second (texture) the view branch
+        if self.latent_size > 0:
+            width += self.latent_size // 2 if self.split_latent else self.latent_size
         self.density_layer = nn.Sequential(nn.Linear(width, 64), nn.ReLU(),
                                            nn.Linear(64, 1 if self.disable_rgb else self.bottleneck_width))
+        if self.density_init:
+            self.density_layer[2].bias.data[0] = self.density_layer[2].bias.data[0] + 0.1
         if not self.disable_rgb:
             dim_dir_enc = 3 + 2 * 3 * self.deg_view
             in_rgb = self.bottleneck_width + dim_dir_enc
+            if self.split_latent:
+                in_rgb += self.latent_size // 2
             last = in_rgb
             for i in range(self.net_depth_viewdirs):
                 lin = nn.Linear(last, self.net_width_viewdirs)
@@ -91,7 +109,7 @@ class MLP(nn.Module):
                 if i == self.skip_layer_dir:
                     last += in_rgb
             self.rgb_layer = nn.Linear(last, self.num_rgb_channels)
-            if not self.no_sem_layer:
+            if not self.no_sem_layer and not self.fixed_semantic:
                 self.sem_layer = nn.Sequential(nn.Linear(self.bottleneck_width, 64), nn.ReLU(),
                                                nn.Linear(64, self.class_num))
             if self.use_intensity:
@@ -117,19 +135,23 @@ class MLP(nn.Module):
                 'lin_second_stage_0.weight': (256, 283), 'lin_second_stage_1.weight': (256, 539),
                 'rgb_layer.weight': (3, 256)}
         have = {k: tuple(v.shape) for k, v in self.named_parameters()}
+        if not self.use_intensity and not torch.is_grad_enabled():
+            # rendering without the intensity head (the configuration of the dynamic-object branch): its rows
+            # of the fused sem | intensity layers are packed as zeros
+            want = {k: v for k, v in want.items() if not k.startswith('intensity_layer')}
         bad = [f'{k}: {have.get(k)} (built for {v})' for k, v in want.items() if have.get(k) != v]
         scalars = dict(deg_view=4, net_depth_viewdirs=2, skip_layer_dir=0, density_bias=-1., rgb_premultiplier=1.,
                        rgb_bias=0., rgb_padding=0.001, class_num=19)
         bad += [f'{k}={getattr(self, k)!r} (built for {v!r})' for k, v in scalars.items() if getattr(self, k) != v]
-        if not (self.use_semantic and self.use_intensity) or self.no_sem_layer:
-            bad.append('the semantic (sem_layer) and intensity heads are required '
-                       '(Config.use_semantic, Config.use_intensity, Config.no_sem_layer=False)')
+        if not self.use_semantic or self.no_sem_layer or (not self.use_intensity and torch.is_grad_enabled()):
+            bad.append('the semantic head (sem_layer) is required, and for training the intensity head '
+                       '(Config.use_semantic, Config.no_sem_layer=False, Config.use_intensity)')
         if self.mlp_dtype != torch.bfloat16:
             bad.append(f'mlp_dtype={self.mlp_dtype} (the dense layers run with bf16 operands, fp32 accumulation)')
         if bad:
             raise NotImplementedError('NerfMLP: the fused tensor-core kernels are built for the nuscenes_single.gin '
                                       'architecture only; unsupported: ' + '; '.join(bad))
-        self._nlb_shapes_ok = True
+        self._nlb_shapes_ok = self.use_intensity   # (without the head the check depends on the grad mode)
 
     def heads(self, feat: torch.Tensor, viewdirs: torch.Tensor, S: int) -> Dict[str, torch.Tensor]:
         """features[N*S, 40] -> density / rgb / semantic / intensity
@@ -159,6 +181,26 @@ class PropMLP(MLP):
 
 
 @configurable
+class ObjMLP(MLP):
+    """Per-class (or per-instance) network of a dynamic object (Z/internal/models.py:1271-1273): evaluated by
+    csrc/obj.cu on the sample points that fall inside the object's box."""
+    pass
+
+
+def query_class(class_name: str) -> int:
+    """obj_utils.query_class (Z/internal/obj_utils.py:498-508)."""
+    if 'human' in class_name:
+        return 11
+    if 'truck' in class_name or 'trailer' in class_name or 'construction' in class_name:
+        return 14
+    if 'bus' in class_name:
+        return 15
+    if 'car' in class_name:
+        return 13
+    return 255
+
+
+@configurable
 class Model(nn.Module):
     """Z/internal/models.py:30-58 class attributes (gin-configurable)."""
     num_prop_samples = (64, 64)
@@ -183,15 +225,14 @@ class Model(nn.Module):
     std_scale: float = 0.35
     prop_desired_grid_size = [512, 2048]
     training: bool = False
+    bboxes = None               # (obj_info {track: [T, 9]}, obj_type_info {track: class name}), datasets.py:1457
+    latent_vector_dict = None   # {'obj_latent_<track>': Parameter[latent_size]}, train_utils.create_latent
 
     def __init__(self, config: Optional[Config] = None, **kwargs):
         super().__init__()
         set_kwargs(self, kwargs)
         self.config = config if config is not None else Config()
         config = self.config
-        if getattr(config, 'instance_obj', False):
-            raise NotImplementedError('Config.instance_obj (dynamic-object branch) is SURVEY 8(f) "next"; '
-                                      'bind Config.instance_obj=False for the static-scene hot path')
         if self.raydist_fn != 'power_transformation' or self.single_mlp or not self.distinct_prop \
                 or self.num_glo_features > 0 or not self.single_jitter or self.near_anneal_rate is not None \
                 or not self.stop_level_grad or self.bg_intensity_range[0] != self.bg_intensity_range[1]:
@@ -203,6 +244,49 @@ class Model(nn.Module):
         for i in range(self.num_levels - 1):
             self.register_module(f'prop_mlp_{i}', PropMLP(grid_disired_resolution=self.prop_desired_grid_size[i]))
         self.instance_obj = False
+        self.tracks = None
+        if getattr(config, 'instance_obj', False):
+            self._init_objects(config)
+
+    def _init_objects(self, config):
+        """Z/internal/models.py:92-177: one ObjMLP per class (latent mode: a latent code per track) or per track
+        (instance mode), and the track table [n_obj, T, 9]."""
+        if self.bboxes is None:
+            raise ValueError('Config.instance_obj=True needs Model(bboxes=(obj_info, obj_type_info)) as Z/train.py:88 passes it')
+        if config.symmetrize:
+            raise NotImplementedError('Config.symmetrize (training-time symmetry loss of the object branch) is not built')
+        if config.use_intensity:
+            raise NotImplementedError(
+                'Config.instance_obj with Config.use_intensity: ObjMLP has no intensity head, and the reference\'s '
+                'merge loop (Z/internal/models.py:461-472) cannot overwrite the intensity key with None')
+        obj_info, self.obj_type_info = self.bboxes
+        latent_mode = not (config.latent_size == 0 and not config.fuse_render)
+        self.mlp_type = ['latent' if latent_mode else 'instance' for _ in obj_info]
+        tracks = []
+        for track_id, bbox_infos in obj_info.items():
+            class_type = self.obj_type_info[track_id]
+            class_id = query_class(class_type)
+            obj_mlp = ObjMLP(deg_view=2, grid_level_interval=2, grid_base_resolution=16, warp_fn=None,
+                             re_weights=False, fixed_semantic=True, use_semantic=config.use_semantic,
+                             class_type=class_id, latent_size=config.latent_size if latent_mode else 0,
+                             **({'grid_level_dim': 2} if latent_mode else {}))
+            if self.mlp_type[track_id] == 'instance':
+                self.register_module(f'obj_mlp_{track_id}', obj_mlp)
+            self.register_module(f'obj_mlp_{class_id}_fusion' if 'fusion' in class_type else f'obj_mlp_{class_id}', obj_mlp)
+            tracks.append(np.asarray(bbox_infos))
+        self.tracks = torch.from_numpy(np.stack(tracks)).float()          # init_tracks (models.py:180-183)
+        self.instance_obj = True
+        if self.latent_vector_dict is not None:
+            self.latent_vector_dict = nn.ParameterDict(self.latent_vector_dict)
+
+    def _obj_network(self, track_id: int):
+        """(ObjMLP, latent or None) of a track (Z/internal/models.py:425-437)."""
+        if self.mlp_type[track_id] == 'instance':
+            return self.get_submodule(f'obj_mlp_{track_id}'), None
+        class_type = self.obj_type_info[track_id]
+        class_id = query_class(class_type)
+        name = f'obj_mlp_{class_id}_fusion' if 'fusion' in class_type else f'obj_mlp_{class_id}'
+        return self.get_submodule(name), self.latent_vector_dict[f'obj_latent_{track_id}']
 
     # Z/internal/models.py:203-223 (value only: its gradient is applied analytically
     # inside the fused optimizer pass, see train.py / csrc/adam.cu)
@@ -237,6 +321,14 @@ class Model(nn.Module):
         anneal = (self.anneal_slope * train_frac) / ((self.anneal_slope - 1) * train_frac + 1) \
             if self.anneal_slope > 0 else 1.
         bg = float(self.bg_intensity_range[0])
+        obj_pose = None
+        if self.instance_obj:
+            if torch.is_grad_enabled():
+                raise NotImplementedError('the dynamic-object branch is built for rendering (no_grad); its training '
+                                          'backward (ObjMLP / latent / track gradients) is not')
+            track = curr_track if curr_track is not None else self.tracks
+            if track is not None:     # obj_utils.get_pose: per ray, per track
+                obj_pose = ops.obj_pose(batch['timestamp'], track.to(dev))
         for i_level in range(self.num_levels):
             is_prop = i_level < (self.num_levels - 1)
             S = self.num_prop_samples[i_level] if is_prop else self.num_nerf_samples
@@ -259,6 +351,9 @@ class Model(nn.Module):
             else:
                 feat = ops.nerf_encode(tdist, deg, self.nerf_mlp.encoder, rays, self.std_scale)
                 res = self.nerf_mlp.heads(feat, viewdirs, S)
+            obj_mask = None
+            if obj_pose is not None:
+                obj_mask = ops.obj_apply(self, res, tdist, rays, viewdirs, obj_pose, is_prop)
             sem = res['semantic'] if (not is_prop and self.config.use_semantic) else None
             inten = res['intensity'] if (not is_prop and self.config.use_intensity) else None
             comp = ops.composite(res['density'], tdist, rays.directions, far, res['rgb'], sem, inten, bg,
@@ -282,6 +377,9 @@ class Model(nn.Module):
                 rendering['ray_sdist'] = sdist[:n]
                 rendering['ray_weights'] = weights[:n]
                 rendering['ray_rgbs'] = res['rgb'][:n]
+            if obj_mask is not None:   # Z/internal/models.py:543-545
+                res['obj_mask'] = res['instance_mask'] = obj_mask
+                rendering['obj_mask'] = rendering['instance_mask'] = obj_mask.sum(-1) > 0
             renderings.append(rendering)
             res['sdist'], res['weights'], res['tdist'] = sdist, weights, tdist
             ray_history.append(res)

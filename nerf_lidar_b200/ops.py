@@ -19,7 +19,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import timed, NlbLossesIn, NlbNerfMlpWeights, NlbNerfMlpSaved, NlbNerfMlpGradIn, NlbNerfMlpGradOut, NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
+from ._lib import timed, NlbObjMlp, NlbLossesIn, NlbNerfMlpWeights, NlbNerfMlpSaved, NlbNerfMlpGradIn, NlbNerfMlpGradOut, NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
 
 EPS = float(torch.finfo(torch.float32).eps)
 _u_cache: Dict[Tuple, torch.Tensor] = {}
@@ -309,8 +309,10 @@ _NERF_WEIGHT_FIELDS = (('W_d0', 'density_layer.0.weight'), ('b_d0', 'density_lay
 
 
 def _mlp_tensors(mlp):
+    """Dense-layer parameters in nlb_nerf_mlp_weights_t order; None for the intensity head of a network built
+    without it (Config.use_intensity=False: inference only, see nlb_nerf_mlp_pack)."""
     params = dict(mlp.named_parameters())
-    return [params[name] for _, name in _NERF_WEIGHT_FIELDS]
+    return [params.get(name) if name.startswith('intensity_layer') else params[name] for _, name in _NERF_WEIGHT_FIELDS]
 
 
 @torch.no_grad()
@@ -320,7 +322,9 @@ def nerf_mlp_pack(mlp, transposed: bool = False) -> torch.Tensor:
     refreshed when any parameter has been modified in place (optimizer step,
     load_state_dict)."""
     tensors = _mlp_tensors(mlp)
-    version = tuple((t.data_ptr(), t._version) for t in tensors)
+    if transposed and any(t is None for t in tensors):
+        raise NotImplementedError('NerfMLP training kernels need the intensity head (Config.use_intensity=True)')
+    version = tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
     key = '_nlb_packed_t' if transposed else '_nlb_packed'
     cache = getattr(mlp, key, None)
     dirty = getattr(mlp, '_nlb_dirty', None)  # set by Trainer.optimizer_step (raw-pointer updates bypass _version)
@@ -335,7 +339,7 @@ def nerf_mlp_pack(mlp, transposed: bool = False) -> torch.Tensor:
     lib = load()
     nbytes = lib.nlb_nerf_mlp_packed_transposed_bytes() if transposed else lib.nlb_nerf_mlp_packed_bytes()
     blob = cache[1] if cache is not None else torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    keep = [f32(t.detach()) for t in tensors]
+    keep = [None if t is None else f32(t.detach()) for t in tensors]
     w = NlbNerfMlpWeights(*[ptr(t) for t in keep])
     with torch.cuda.device(dev):
         fn = lib.nlb_nerf_mlp_pack_transposed if transposed else lib.nlb_nerf_mlp_pack
@@ -350,6 +354,10 @@ def _mlp_forward_raw(mlp, features, viewdirs, S, save: bool):
     blob = nerf_mlp_pack(mlp)
     new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
     density, rgb, sem, inten = new(N, S), new(N, S, 3), new(N, S, 19), new(N, S, 1)
+    if getattr(mlp, 'intensity_layer', None) is None:
+        if save:
+            raise NotImplementedError('NerfMLP training kernels need the intensity head (Config.use_intensity=True)')
+        inten = None
     saved = None
     sv = None
     if save:
@@ -584,3 +592,79 @@ def render_losses(rendering: Dict[str, torch.Tensor], batch: Dict[str, torch.Ten
     """[data, depth, sem, int, d_smo, s_smo] for the final rendering (see _RenderLosses)."""
     return _RenderLosses.apply(rendering['rgb'], rendering['depth'], rendering.get('semantic'),
                                rendering.get('intensity'), batch, cfg)
+
+
+# ----------------------------------------------------------------------------- dynamic objects (csrc/obj.cu)
+@torch.no_grad()
+def obj_pose(timestamp: torch.Tensor, tracks: torch.Tensor) -> torch.Tensor:
+    """obj_utils.get_pose (Z/internal/obj_utils.py:431-475): timestamp [N,1], tracks [n_obj,T,9] -> [N,n_obj,9]."""
+    t, tr = f32(timestamp).reshape(-1), f32(tracks)
+    if tr.dim() != 3 or tr.shape[-1] != 9:
+        raise RuntimeError(f'tracks must be [n_obj, T, 9], got {tuple(tr.shape)}')
+    N, n_obj, T = t.shape[0], tr.shape[0], tr.shape[1]
+    pose = torch.empty(N, n_obj, 9, device=t.device, dtype=torch.float32)
+    with torch.cuda.device(t.device):
+        check(load().nlb_obj_pose(ptr(t), ptr(tr), N, n_obj, T, ptr(pose), stream()))
+    return pose
+
+
+def _obj_mlp_desc(mlp, latent):
+    """Pointers / sizes of an ObjMLP for the kernel; keeps the fp32 tensors alive through the returned list."""
+    if mlp.net_depth_viewdirs != 2 or mlp.skip_layer_dir != 0 or mlp.disable_rgb or not mlp.fixed_semantic \
+            or mlp.re_weights or mlp.warp_fn is not None:
+        raise NotImplementedError('ObjMLP: only the nuscenes_single.gin object network is built (two view layers with a '
+                                  'skip after the first, fixed semantic class, no contraction, no re-weighting)')
+    d0, d2 = mlp.density_layer[0], mlp.density_layer[2]
+    v0, v1 = mlp.lin_second_stage_0, mlp.lin_second_stage_1
+    keep = [f32(x.detach()) for x in (d0.weight, d0.bias, d2.weight, d2.bias, v0.weight, v0.bias, v1.weight, v1.bias,
+                                      mlp.rgb_layer.weight, mlp.rgb_layer.bias)]
+    lat = None
+    shape_n = tex_n = 0
+    if latent is not None:
+        lat = f32(latent.detach())
+        if mlp.split_latent:
+            shape_n = mlp.latent_size // 2
+            tex_n = mlp.latent_size - shape_n
+        else:
+            shape_n = mlp.latent_size
+        keep.append(lat)
+    F = mlp.encoder.output_dim
+    dir_dim = 3 + 6 * mlp.deg_view
+    want = {'density_layer.0': (d0.weight, (64, F + shape_n)), 'lin_second_stage_0': (v0.weight, (mlp.net_width_viewdirs, mlp.bottleneck_width + dir_dim + tex_n)),
+            'lin_second_stage_1': (v1.weight, (mlp.net_width_viewdirs, mlp.net_width_viewdirs + mlp.bottleneck_width + dir_dim + tex_n)),
+            'rgb_layer': (mlp.rgb_layer.weight, (3, mlp.net_width_viewdirs))}
+    for name, (w, shp) in want.items():
+        if tuple(w.shape) != shp:
+            raise RuntimeError(f'ObjMLP.{name}: weight {tuple(w.shape)}, expected {shp}')
+    desc = NlbObjMlp(*[ptr(x) for x in keep[:10]], ptr(lat), d0.weight.shape[0], mlp.bottleneck_width,
+                     mlp.net_width_viewdirs, mlp.deg_view, shape_n, tex_n, float(mlp.density_bias),
+                     float(mlp.rgb_premultiplier), float(mlp.rgb_bias), float(mlp.rgb_padding), int(mlp.class_type),
+                     int(mlp.class_num))
+    return desc, keep
+
+
+@torch.no_grad()
+def obj_apply(model, res: Dict[str, torch.Tensor], tdist: torch.Tensor, rays: RayBundle, viewdirs: torch.Tensor,
+              pose: torch.Tensor, is_prop: bool) -> torch.Tensor:
+    """The per-track loop of Z/internal/models.py:415-477 for one sampling level: box test, ObjMLP on the hits,
+    masked overwrite of density (and rgb / semantic at the final level), in track order, without leaving the
+    device.  Returns obj_mask [N,S] (bool)."""
+    N, S = rays.N, tdist.shape[1] - 1
+    if res.get('intensity') is not None:
+        raise NotImplementedError('object branch with an intensity head (see Model._init_objects)')
+    density = res['density']
+    rgb = res['rgb'] if (not is_prop and res.get('rgb') is not None) else None
+    sem = res['semantic'] if (not is_prop and res.get('semantic') is not None) else None
+    mask = torch.zeros(N, S, device=rays.device, dtype=torch.uint8)
+    n_obj = pose.shape[1]
+    lib = load()
+    with torch.cuda.device(rays.device):
+        for track_id in range(n_obj):
+            mlp, latent = model._obj_network(track_id)
+            desc, keep = _obj_mlp_desc(mlp, latent)
+            tab = _table_desc(mlp.encoder, mlp.encoder.embeddings.detach())
+            with timed('obj_forward'):
+                check(lib.nlb_obj_forward(ptr(tdist), ptr(rays.origins), ptr(rays.directions), ptr(viewdirs), ptr(pose),
+                                          n_obj, track_id, N, S, C.byref(tab), C.byref(desc), ptr(density), ptr(rgb),
+                                          ptr(sem), ptr(mask), stream()))
+    return mask.bool()
