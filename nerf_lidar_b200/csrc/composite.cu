@@ -311,6 +311,10 @@ __global__ void __launch_bounds__(kPropRays) k_composite_prop_fwd(nlb_composite_
 // Proposal levels with S % 4 == 0: the same walk with direct 16-byte loads of the densities and stores of
 // the weights (no staging instructions); only the fenceposts ([N, S+1] rows are not 16-byte aligned) are
 // scalar loads.
+// CS = samples per iteration: with CS = 8 a thread consumes (and writes) one whole 32-byte sector of its density /
+// weight row per iteration instead of relying on L1 to keep the second half of the sector until the next one
+// (the working set of a resident SM, 2048 rays x 772 B, is six times L1).
+template <int CS>
 __global__ void __launch_bounds__(128) k_composite_prop4_fwd(nlb_composite_in_t in, nlb_composite_out_t out) {
   const int S = in.S;
   const int ray = blockIdx.x * 128 + threadIdx.x;
@@ -333,18 +337,22 @@ __global__ void __launch_bounds__(128) k_composite_prop4_fwd(nlb_composite_in_t 
     pct[k] = __fadd_rn(prev_tk, __fmul_rn(off, __fsub_rn(f1, prev_tk)));
     found[k] = true;
   };
-#pragma unroll 2
-  for (int c0 = 0; c0 < S; c0 += 4) {
-    const float4 dv = __ldg(reinterpret_cast<const float4*>(in.density + (size_t)ray * S + c0));
-    float tt[5];
+#pragma unroll(CS == 4 ? 2 : 1)
+  for (int c0 = 0; c0 < S; c0 += CS) {
+    float dens[CS];
+#pragma unroll
+    for (int q = 0; q < CS / 4; ++q) {
+      const float4 dv = __ldg(reinterpret_cast<const float4*>(in.density + (size_t)ray * S + c0 + 4 * q));
+      dens[4 * q] = dv.x; dens[4 * q + 1] = dv.y; dens[4 * q + 2] = dv.z; dens[4 * q + 3] = dv.w;
+    }
+    float tt[CS + 1];
     tt[0] = t_prev;
 #pragma unroll
-    for (int j = 1; j <= 4; ++j) tt[j] = __ldg(td + c0 + j);
-    t_prev = tt[4];
-    const float dens[4] = {dv.x, dv.y, dv.z, dv.w};
-    float w[4];
+    for (int j = 1; j <= CS; ++j) tt[j] = __ldg(td + c0 + j);
+    t_prev = tt[CS];
+    float w[CS];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < CS; ++j) {
       const float t0 = tt[j], t1 = tt[j + 1];
       float dd = __fmul_rn(dens[j], __fmul_rn(__fsub_rn(t1, t0), dnorm));
       const bool last = in.opaque_background && (c0 + j == S - 1);
@@ -366,7 +374,11 @@ __global__ void __launch_bounds__(128) k_composite_prop4_fwd(nlb_composite_in_t 
       }
       t_last = t1;
     }
-    if (out.weights) *reinterpret_cast<float4*>(out.weights + (size_t)ray * S + c0) = make_float4(w[0], w[1], w[2], w[3]);
+    if (out.weights) {
+#pragma unroll
+      for (int q = 0; q < CS / 4; ++q)
+        *reinterpret_cast<float4*>(out.weights + (size_t)ray * S + c0 + 4 * q) = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    }
   }
   const float bg_w = fmaxf(__fsub_rn(1.0f, acc), 0.f);
   const float den = fmaxf(acc, kEps);
@@ -675,7 +687,13 @@ extern "C" int nlb_composite_forward(const nlb_composite_in_t* in, const nlb_com
     static const bool kDirect = getenv("NLB_PROP_COMPOSITE_STAGED") == nullptr;
     if (kDirect && in->S % 4 == 0 &&
         (reinterpret_cast<uintptr_t>(in->density) | reinterpret_cast<uintptr_t>(out->weights)) % 16 == 0)
-      k_composite_prop4_fwd<<<div_up(in->N, 128), 128, 0, (cudaStream_t)stream>>>(*in, *out);
+    {
+      static const int kChunk = [] { const char* e = getenv("NLB_PROP_COMPOSITE_CHUNK"); return e ? atoi(e) : 8; }();  // A/B timing
+      if (kChunk == 8 && in->S % 8 == 0)
+        k_composite_prop4_fwd<8><<<div_up(in->N, 128), 128, 0, (cudaStream_t)stream>>>(*in, *out);
+      else
+        k_composite_prop4_fwd<4><<<div_up(in->N, 128), 128, 0, (cudaStream_t)stream>>>(*in, *out);
+    }
     else
       k_composite_prop_fwd<<<div_up(in->N, kPropRays), kPropRays, 0, (cudaStream_t)stream>>>(*in, *out);
     return nlb_check_launch("composite_forward");

@@ -225,8 +225,9 @@ class Model(nn.Module):
     std_scale: float = 0.35
     prop_desired_grid_size = [512, 2048]
     training: bool = False
-    bboxes = None               # (obj_info {track: [T, 9]}, obj_type_info {track: class name}), datasets.py:1457
-    latent_vector_dict = None   # {'obj_latent_<track>': Parameter[latent_size]}, train_utils.create_latent
+    # kwargs of the dynamic-object branch (no class attributes: a registered ParameterDict must not be shadowed):
+    #   bboxes = (obj_info {track: [T, 9]}, obj_type_info {track: class name})      datasets.py:1457
+    #   latent_vector_dict = {'obj_latent_<track>': Parameter[latent_size]}         train_utils.create_latent
 
     def __init__(self, config: Optional[Config] = None, **kwargs):
         super().__init__()
@@ -251,7 +252,7 @@ class Model(nn.Module):
     def _init_objects(self, config):
         """Z/internal/models.py:92-177: one ObjMLP per class (latent mode: a latent code per track) or per track
         (instance mode), and the track table [n_obj, T, 9]."""
-        if self.bboxes is None:
+        if getattr(self, 'bboxes', None) is None:
             raise ValueError('Config.instance_obj=True needs Model(bboxes=(obj_info, obj_type_info)) as Z/train.py:88 passes it')
         if config.symmetrize:
             raise NotImplementedError('Config.symmetrize (training-time symmetry loss of the object branch) is not built')
@@ -276,8 +277,10 @@ class Model(nn.Module):
             tracks.append(np.asarray(bbox_infos))
         self.tracks = torch.from_numpy(np.stack(tracks)).float()          # init_tracks (models.py:180-183)
         self.instance_obj = True
-        if self.latent_vector_dict is not None:
-            self.latent_vector_dict = nn.ParameterDict(self.latent_vector_dict)
+        latents = self.__dict__.pop('latent_vector_dict', None)
+        if latent_mode and latents is None:
+            raise ValueError('latent mode (Config.latent_size > 0) needs Model(latent_vector_dict=...) as Z/train.py:82-88 builds it')
+        self.latent_vector_dict = nn.ParameterDict(latents) if latents is not None else None
 
     def _obj_network(self, track_id: int):
         """(ObjMLP, latent or None) of a track (Z/internal/models.py:425-437)."""
