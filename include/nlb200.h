@@ -438,6 +438,36 @@ int nlb_obj_forward(const float* tdist /*[N,S+1]*/, const float* origins, const 
                     const nlb_table_t* table, const nlb_obj_mlp_t* mlp, float* density, float* rgb, float* semantic,
                     uint8_t* obj_mask, void* stream);
 
+/* ------------------------------------------------------------------ stage-3 ray-drop: around the U-Net
+ * `R/` = NeRF_LiDAR/NeRF_Lidar_code/.  The U-Net (R/src/unet/) is not part of the library: its [2,H,W] logits are
+ * an input of nlb_raydrop_select.
+ */
+/* R/src/depth_filter.py:4-31: points[H,W,3] (beam-major sweep), semantic[H*W] or NULL -> mask[H*W] (bytes). */
+int nlb_depth_filter(const float* points, const float* semantic, int H, int W, int width, float radius, int threshold,
+                     uint8_t* mask, void* stream);
+
+/* LaserScan.do_range_projection (R/src/lidar_utils.py:209-275).  Images are [H,W] (xyz / rgb [H,W,3]); any pointer
+ * may be NULL.  Empty pixels: range / xyz / semantic = -1, rgb = 0, idx = -1; proj_mask = (proj_idx > 0). */
+typedef struct {
+  float* proj_range; float* proj_xyz; float* proj_semantic; float* proj_rgb; int32_t* proj_idx; float* proj_mask;
+} nlb_range_image_t;
+size_t nlb_range_projection_workspace_bytes(int H, int W);
+int nlb_range_projection(const float* points /*[n,3]*/, const float* semantic /*[n] or NULL*/, const float* rgb /*[n,3] or NULL*/,
+                         int n, int H, int W, float fov_up_deg, float fov_down_deg, int32_t* proj_x /*[n]*/,
+                         int32_t* proj_y /*[n]*/, float* unproj_range /*[n]*/, const nlb_range_image_t* image,
+                         void* workspace, void* stream);
+
+/* The drop selection of R/src/drop_simulation_rays.py:104-140 (save_near=False): a point survives when the
+ * softmax probability of class 1 at its pixel exceeds mask_thre, its pixel is occupied (proj_mask), the depth filter
+ * kept it (filter_mask, or NULL), and it is neither sky (label 10) nor a road outlier (label 0, z < -3).  Survivors
+ * are written in their original order to remain_points[*,3] / remain_labels[*] (capacity n); *remain_count (device
+ * int) receives their number. */
+size_t nlb_raydrop_select_workspace_bytes(int n);
+int nlb_raydrop_select(const float* logits /*[2,H,W]*/, float mask_thre, const float* proj_mask, const int32_t* proj_x,
+                       const int32_t* proj_y, const uint8_t* filter_mask, const float* points, const float* labels, int n,
+                       int H, int W, float* remain_points, float* remain_labels, int* remain_count, void* workspace,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,10 @@ class NlbObjMlp(C.Structure):
                [(n, C.c_int) for n in ('class_type', 'class_num')]
 
 
+class NlbRangeImage(C.Structure):
+    _fields_ = [(n, c_f) for n in ('proj_range', 'proj_xyz', 'proj_semantic', 'proj_rgb', 'proj_idx', 'proj_mask')]
+
+
 _u32, _i, _f, _p = C.c_uint32, C.c_int, C.c_float, C.c_void_p
 
 # name -> (restype, argtypes); mirrors include/nlb200.h one to one
@@ -130,6 +134,11 @@ SIGNATURES = {
     'nlb_camera_rays': (_i, [_p, _p, _p, _p, _i, _p, _i, C.c_int64, C.POINTER(NlbRayOut), _p]),
     'nlb_lidar_directions': (_i, [_p, _i, _p, _i, _p, _p]),
     'nlb_lidar_rays': (_i, [_p, _p, C.c_int64, _p, C.POINTER(NlbRayOut), _p]),
+    'nlb_depth_filter': (_i, [_p, _p, _i, _i, _i, _f, _i, _p, _p]),
+    'nlb_range_projection_workspace_bytes': (C.c_size_t, [_i, _i]),
+    'nlb_range_projection': (_i, [_p, _p, _p, _i, _i, _i, _f, _f, _p, _p, _p, C.POINTER(NlbRangeImage), _p, _p]),
+    'nlb_raydrop_select_workspace_bytes': (C.c_size_t, [_i]),
+    'nlb_raydrop_select': (_i, [_p, _f, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
     'nlb_obj_pose': (_i, [_p, _p, _i, _i, _i, _p, _p]),
     'nlb_obj_forward': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, C.POINTER(NlbTable), C.POINTER(NlbObjMlp), _p, _p, _p, _p, _p]),
 }

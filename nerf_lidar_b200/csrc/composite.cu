@@ -407,6 +407,126 @@ __global__ void __launch_bounds__(128) k_composite_prop4_fwd(nlb_composite_in_t 
   }
 }
 
+// Proposal levels, S % 8 == 0, 16-byte loads for the fenceposts as well.  The [N, S+1] fencepost rows are not
+// 16-byte aligned (a row starts 4 * (ray mod 4) bytes past a 16-byte boundary), so the kernel above reads them
+// with S scalar loads per ray -- and with a thread per ray every load instruction touches 32 different lines,
+// which L1 retires at one per clock whatever the access width (tools/gather_probe.cu): 81 load + 16 store
+// instructions x 32 cycles per 32 rays = 0.29 ms per 1 M rays, the measured time.  Here a row is covered by 17
+// ALIGNED float4 loads (two new ones per 8-sample chunk, the third carried) and the lane's misalignment
+// A = ray mod 4 is resolved in registers with selects: 33 loads + 16 stores per ray.  (Making A a compile-time
+// constant per warp -- warp w of a block takes the rays with ray mod 4 == w -- was measured first: 0.50 ms, the
+// interleaved rays of a warp cost more in DRAM / L2 locality than the selects cost in issue slots.)
+__device__ __forceinline__ void composite_prop_aligned(const nlb_composite_in_t& in, const nlb_composite_out_t& out, int ray) {
+  const int S = in.S;
+  const int A = ray & 3;
+  const float dx = __ldg(in.directions + 3 * ray), dy = __ldg(in.directions + 3 * ray + 1),
+              dz = __ldg(in.directions + 3 * ray + 2);
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  // float4 view of the fencepost matrix: this row's element j sits at float index row0 + j = 4 * g0 + A + j
+  const size_t row0 = (size_t)ray * (S + 1);
+  const size_t g0 = (row0 - A) >> 2;
+  const size_t total = (size_t)in.N * (S + 1);
+  const float4* t4 = reinterpret_cast<const float4*>(in.tdist);
+  auto load_group = [&](size_t g) -> float4 {
+    if ((g + 1) * 4 <= total) return __ldg(t4 + g);
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);   // the very last group of the matrix: element-wise, bounded
+    if (g * 4 + 0 < total) r.x = __ldg(in.tdist + g * 4 + 0);
+    if (g * 4 + 1 < total) r.y = __ldg(in.tdist + g * 4 + 1);
+    if (g * 4 + 2 < total) r.z = __ldg(in.tdist + g * 4 + 2);
+    return r;
+  };
+  float carry = 0.f, acc = 0.f, dep = 0.f, lg = 0.f, wsum = 0.f;
+  float4 q0 = load_group(g0);
+  const float t_first = A == 0 ? q0.x : (A == 1 ? q0.y : (A == 2 ? q0.z : q0.w));
+#define NLB_SEL(k) (A == 0 ? f[(k)] : (A == 1 ? f[(k) + 1] : (A == 2 ? f[(k) + 2] : f[(k) + 3])))
+  float prev_cw = 0.f, prev_tk = t_first, t_last = t_first;
+  const float qs[3] = {0.05f, 0.5f, 0.95f};
+  float pct[3] = {0.f, 0.f, 0.f};
+  bool found[3] = {false, false, false};
+  auto knot = [&](int k, float x1, float f1) {
+    float off = __fdiv_rn(__fsub_rn(qs[k], prev_cw), __fsub_rn(x1, prev_cw));
+    if (isnan(off)) off = 0.f;
+    off = fminf(fmaxf(off, 0.f), 1.f);
+    pct[k] = __fadd_rn(prev_tk, __fmul_rn(off, __fsub_rn(f1, prev_tk)));
+    found[k] = true;
+  };
+#pragma unroll 1
+  for (int c0 = 0; c0 < S; c0 += 8) {
+    const float4 q1 = load_group(g0 + (c0 >> 2) + 1), q2 = load_group(g0 + (c0 >> 2) + 2);
+    const float f[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+    q0 = q2;
+    float dens[8];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float4 dv = __ldg(reinterpret_cast<const float4*>(in.density + (size_t)ray * S + c0 + 4 * q));
+      dens[4 * q] = dv.x; dens[4 * q + 1] = dv.y; dens[4 * q + 2] = dv.z; dens[4 * q + 3] = dv.w;
+    }
+    float tt[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) tt[j] = NLB_SEL(j);
+    float w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t0 = tt[j], t1 = tt[j + 1];
+      float dd = __fmul_rn(dens[j], __fmul_rn(__fsub_rn(t1, t0), dnorm));
+      const bool last = in.opaque_background && (c0 + j == S - 1);
+      const float trans = expf(-carry);
+      if (last) dd = INFINITY; else carry = __fadd_rn(carry, dd);
+      w[j] = __fmul_rn(__fsub_rn(1.0f, expf(-dd)), trans);
+      const float tm = __fmul_rn(0.5f, __fadd_rn(t0, t1));
+      acc += w[j];
+      dep = fmaf(w[j], tm, dep);
+      if (in.compute_extras) {
+        lg = fmaf(w[j], logf(tm), lg);
+        wsum = __fadd_rn(wsum, w[j]);
+        const float cwj = fminf(wsum, 1.0f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (!found[k] && cwj > qs[k]) knot(k, cwj, t1);
+        prev_cw = cwj;
+        prev_tk = t1;
+      }
+      t_last = t1;
+    }
+    if (out.weights) {
+      *reinterpret_cast<float4*>(out.weights + (size_t)ray * S + c0) = make_float4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<float4*>(out.weights + (size_t)ray * S + c0 + 4) = make_float4(w[4], w[5], w[6], w[7]);
+    }
+  }
+  const float bg_w = fmaxf(__fsub_rn(1.0f, acc), 0.f);
+  const float den = fmaxf(acc, kEps);
+  if (out.rgb) {
+    const float v = fmaf(bg_w, in.bg, 0.f);
+    out.rgb[3 * (size_t)ray] = v;
+    out.rgb[3 * (size_t)ray + 1] = v;
+    out.rgb[3 * (size_t)ray + 2] = v;
+  }
+  if (out.depth) out.depth[ray] = __fdiv_rn(dep, den);
+  if (out.acc) out.acc[ray] = acc;
+  if (in.compute_extras) {
+    if (out.distance_mean) {
+      float v = expf(__fdiv_rn(lg, den));
+      if (isnan(v)) v = INFINITY;
+      out.distance_mean[ray] = fminf(fmaxf(v, t_first), t_last);
+    }
+    if (out.distance_percentiles) {
+      const float far = __ldg(in.far + ray);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (!found[k]) knot(k, 1.0f, far);
+        out.distance_percentiles[(size_t)ray * 3 + k] = pct[k];
+      }
+    }
+  }
+}
+
+#undef NLB_SEL
+__global__ void __launch_bounds__(128) k_composite_prop_aligned_fwd(nlb_composite_in_t in, nlb_composite_out_t out) {
+  const int ray = blockIdx.x * 128 + threadIdx.x;
+  if (ray >= in.N) return;
+  composite_prop_aligned(in, out, ray);
+}
+
 // NeRF level with the nuScenes head layout (rgb + K = 19 class probabilities + intensity): one thread per
 // ray as well, reading its own rows straight from global memory with 16-byte loads: a ray's 8-sample chunk
 // is 608 contiguous bytes of class probabilities, 96 of colour, 32 of density and of intensity, so every
@@ -689,7 +809,9 @@ extern "C" int nlb_composite_forward(const nlb_composite_in_t* in, const nlb_com
         (reinterpret_cast<uintptr_t>(in->density) | reinterpret_cast<uintptr_t>(out->weights)) % 16 == 0)
     {
       static const int kChunk = [] { const char* e = getenv("NLB_PROP_COMPOSITE_CHUNK"); return e ? atoi(e) : 8; }();  // A/B timing
-      if (kChunk == 8 && in->S % 8 == 0)
+      if (kChunk == 8 && in->S % 8 == 0 && reinterpret_cast<uintptr_t>(in->tdist) % 16 == 0)
+        k_composite_prop_aligned_fwd<<<div_up(in->N, 128), 128, 0, (cudaStream_t)stream>>>(*in, *out);
+      else if (kChunk == 16 && in->S % 8 == 0)
         k_composite_prop4_fwd<8><<<div_up(in->N, 128), 128, 0, (cudaStream_t)stream>>>(*in, *out);
       else
         k_composite_prop4_fwd<4><<<div_up(in->N, 128), 128, 0, (cudaStream_t)stream>>>(*in, *out);
