@@ -390,6 +390,7 @@ def run_cuda_arm(args):
     ref_kernel = None
     if world == 1 and not args.no_reference_kernel:
         ref_kernel = reference_kernel_leg(model, resident[0], per_kernel)
+    extras = stream_kernel_leg(dev, hbm_peak) if world == 1 else None
     value = BATCH * world * args.steps / (ms * 1e-3)
     e2e = BATCH * world * args.steps / (ms_e2e * 1e-3)
     if roofline is not None:
@@ -406,7 +407,10 @@ def run_cuda_arm(args):
                    'eager_ms_per_step': ms_eager / n_prof,
                    'l2_policy': 'inputs larger than L2: 1.24 GB of table + optimizer state streamed every step, '
                                 'batches rotate over a pool of 4',
-                   'render': render})
+                   'render': render,
+                   # bandwidth-bound kernels at 1 M rays (launch-bound at the 10 240-ray batch) and the
+                   # device-resident data layer
+                   'stream_kernels_1M_rays': extras})
     line = {
         'metric': 'train_rays_per_sec', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -423,6 +427,52 @@ def run_cuda_arm(args):
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def stream_kernel_leg(dev, hbm_peak, n=1 << 20):
+    """Compositing (3464 B/ray at the NeRF level, 820 B/ray at a proposal level), resampling and the
+    on-GPU ray generation at 1 M rays, where they are bandwidth- rather than launch-bound: algorithmic GB/s against
+    the measured HBM rate.  Inputs (0.5 GB per case) exceed L2."""
+    import torch
+    from nerf_lidar_b200 import ops, raygen, synthetic as sy
+
+    def timeit(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    g = torch.Generator(device=dev).manual_seed(0)
+    out = {}
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, device=dev, generator=g), dim=-1)
+    far = torch.full((n,), 8.33, device=dev)
+    with torch.no_grad():
+        for S, K, name, alg in ((32, 19, 'composite_nerf_level', 3464), (64, 0, 'composite_proposal_level', 820)):
+            t = torch.sort(torch.rand(n, S + 1, device=dev, generator=g) * 8 + 0.05, -1).values
+            dens = torch.rand(n, S, device=dev, generator=g) * 5
+            rgb = torch.rand(n, S, 3, device=dev, generator=g) if K else None
+            sem = torch.softmax(torch.randn(n, S, K, device=dev, generator=g), -1) if K else None
+            inten = torch.rand(n, S, device=dev, generator=g) if K else None
+            ms = timeit(lambda: ops.composite(dens, t, dirs, far, rgb, sem, inten, 1.0, True, True))
+            out[name] = {'ms': round(ms, 4), 'alg_bytes_per_ray': alg, 'alg_gbs': round(alg * n / ms / 1e6, 1),
+                         'frac_of_hbm': round(alg * n / ms / 1e6 / hbm_peak, 3)}
+            del t, dens, rgb, sem, inten
+        # camera rays: 12 B of pixel / camera indices in, 76 B of ray fields out (float64 arithmetic inside)
+        px = torch.randint(0, sy.IMG_W, (n,), device=dev, generator=g)
+        py = torch.randint(0, sy.IMG_H, (n,), device=dev, generator=g)
+        cam = torch.randint(0, 64, (n,), device=dev, generator=g)
+        K3 = torch.tensor([[sy.FOCAL, 0, sy.IMG_W / 2], [0, sy.FOCAL, sy.IMG_H / 2], [0, 0, 1.]], dtype=torch.float64)
+        p2c = torch.linalg.inv(K3).to(dev)
+        c2w = torch.eye(3, 4, dtype=torch.float64, device=dev).repeat(64, 1, 1)
+        ms = timeit(lambda: raygen.pixels_to_rays(px, py, p2c, c2w, cam_idx=cam))
+        out['camera_rays'] = {'ms': round(ms, 4), 'rays_per_s': round(n / ms * 1e3), 'alg_gbs': round(88 * n / ms / 1e6, 1)}
+    torch.cuda.empty_cache()
+    return out
 
 
 def reference_kernel_leg(model, batch, per_kernel):

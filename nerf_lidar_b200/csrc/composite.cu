@@ -813,6 +813,10 @@ extern "C" int nlb_composite_forward(const nlb_composite_in_t* in, const nlb_com
         k_composite_prop_aligned_fwd<<<div_up(in->N, 128), 128, 0, (cudaStream_t)stream>>>(*in, *out);
       else if (kChunk == 16 && in->S % 8 == 0)
         k_composite_prop4_fwd<8><<<div_up(in->N, 128), 128, 0, (cudaStream_t)stream>>>(*in, *out);
+      else if (kChunk == 116 && in->S % 16 == 0)
+        k_composite_prop4_fwd<16><<<div_up(in->N, 128), 128, 0, (cudaStream_t)stream>>>(*in, *out);
+      else if (kChunk == 132 && in->S % 32 == 0)
+        k_composite_prop4_fwd<32><<<div_up(in->N, 128), 128, 0, (cudaStream_t)stream>>>(*in, *out);
       else
         k_composite_prop4_fwd<4><<<div_up(in->N, 128), 128, 0, (cudaStream_t)stream>>>(*in, *out);
     }
