@@ -86,6 +86,16 @@ class NlbRangeImage(C.Structure):
     _fields_ = [(n, c_f) for n in ('proj_range', 'proj_xyz', 'proj_semantic', 'proj_rgb', 'proj_idx', 'proj_mask')]
 
 
+class NlbUnetConv(C.Structure):
+    _fields_ = [('weight', c_f), ('scale', c_f), ('shift', c_f)]
+
+
+class NlbUnetWeights(C.Structure):
+    _fields_ = [('inc', NlbUnetConv * 2), ('down', (NlbUnetConv * 2) * 4), ('up', (NlbUnetConv * 2) * 4),
+                ('up_weight', c_f * 4), ('up_bias', c_f * 4), ('outc_weight', c_f), ('outc_bias', c_f),
+                ('bilinear', C.c_int), ('n_classes', C.c_int)]
+
+
 _u32, _i, _f, _p = C.c_uint32, C.c_int, C.c_float, C.c_void_p
 
 # name -> (restype, argtypes); mirrors include/nlb200.h one to one
@@ -139,6 +149,8 @@ SIGNATURES = {
     'nlb_range_projection': (_i, [_p, _p, _p, _i, _i, _i, _f, _f, _p, _p, _p, C.POINTER(NlbRangeImage), _p, _p]),
     'nlb_raydrop_select_workspace_bytes': (C.c_size_t, [_i]),
     'nlb_raydrop_select': (_i, [_p, _f, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    'nlb_unet_workspace_bytes': (C.c_size_t, [_i, _i, _i]),
+    'nlb_unet_forward': (_i, [_p, C.POINTER(NlbUnetWeights), _i, _i, _i, _i, _p, _p, _p]),
     'nlb_obj_pose': (_i, [_p, _p, _i, _i, _i, _p, _p]),
     'nlb_obj_forward': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, C.POINTER(NlbTable), C.POINTER(NlbObjMlp), _p, _p, _p, _p, _p]),
 }

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libnlb200.so')
-SOURCES = ['capi.cu', 'grid_encode.cu', 'resample.cu', 'encode.cu', 'composite.cu', 'adam.cu', 'nerf_mlp.cu', 'nerf_wgrad.cu', 'losses.cu', 'reduce.cu', 'render_losses.cu', 'raygen.cu', 'obj.cu', 'raydrop.cu']
+SOURCES = ['capi.cu', 'grid_encode.cu', 'resample.cu', 'encode.cu', 'composite.cu', 'adam.cu', 'nerf_mlp.cu', 'nerf_wgrad.cu', 'losses.cu', 'reduce.cu', 'render_losses.cu', 'raygen.cu', 'obj.cu', 'raydrop.cu', 'unet.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

@@ -1,0 +1,248 @@
+// Stage-3 ray-drop U-Net, inference (`R/` = NeRF_LiDAR/NeRF_Lidar_code/): R/src/unet/unet_model.py:6-47,
+// R/src/unet/unet_parts.py:8-77 -- DoubleConv (3x3 conv, no bias -> BatchNorm (eval) -> ReLU, twice), Down (2x2 max pool +
+// DoubleConv), Up (bilinear x2 upsampling with align_corners or a 2x2 stride-2 transposed convolution, concatenation
+// with the skip tensor, DoubleConv), OutConv (1x1 conv with bias) -- on the 32 x 1024 range-image features.
+//
+// fp32 throughout, as the reference computes it (the drop mask is a hard threshold on these logits).  The 3x3
+// convolution is a register-tiled direct convolution: a block owns 64 output channels x (4 rows x 32 columns) of
+// pixels, a thread 8 channels x 4 pixels; input channels are walked in chunks of 8 through shared memory; the
+// concatenation of an Up block is never materialised (the kernel reads its input channels from two tensors); the
+// folded BatchNorm scale / shift and the ReLU are the epilogue.
+#include "common.cuh"
+#include "../../include/nlb200.h"
+
+namespace nlb {
+namespace unet {
+
+constexpr int kOcTile = 64, kRows = 4, kCols = 32, kIcChunk = 8;
+constexpr int kConvThreads = 256;   // 32 pixel threads (4 px each) x 8 channel threads (8 oc each)
+
+// out[n, oc, y, x] = act(scale[oc] * sum_{ic,ky,kx} in[n, ic, y+ky-1, x+kx-1] * W[oc, ic, ky, kx] + shift[oc])
+// `in` = channels [0, CA) of inA followed by [0, CB) of inB (torch.cat([x2, x1], dim=1) of Up.forward).
+__global__ void __launch_bounds__(kConvThreads) k_conv3x3(const float* __restrict__ inA, int CA, const float* __restrict__ inB,
+                                                          int CB, const float* __restrict__ W, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, int OC, int H, int Wd, int relu,
+                                                          float* __restrict__ out) {
+  __shared__ float s_in[kIcChunk][kRows + 2][kCols + 2];
+  __shared__ __align__(16) float s_w[kIcChunk][9][kOcTile];
+  const int C = CA + CB;
+  const int tiles_x = (Wd + kCols - 1) / kCols;
+  const int tile = blockIdx.x, tx0 = (tile % tiles_x) * kCols, ty0 = (tile / tiles_x) * kRows;
+  const int oc0 = blockIdx.y * kOcTile, n = blockIdx.z;
+  const int pt = threadIdx.x & 31, ct = threadIdx.x >> 5;      // pixel thread, channel thread
+  const int py = pt >> 3, px = (pt & 7) * 4;                    // this thread's 4 pixels: row py, columns px..px+3
+  float acc[8][4];
+#pragma unroll
+  for (int o = 0; o < 8; ++o)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc[o][p] = 0.f;
+  const size_t plane = (size_t)H * Wd;
+  for (int ic0 = 0; ic0 < C; ic0 += kIcChunk) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < kIcChunk * (kRows + 2) * (kCols + 2); e += kConvThreads) {
+      const int c = e / ((kRows + 2) * (kCols + 2)), r = (e / (kCols + 2)) % (kRows + 2), q = e % (kCols + 2);
+      const int ic = ic0 + c, y = ty0 + r - 1, x = tx0 + q - 1;
+      float v = 0.f;
+      if (ic < C && y >= 0 && y < H && x >= 0 && x < Wd) {
+        const float* src = ic < CA ? inA + ((size_t)n * CA + ic) * plane : inB + ((size_t)n * CB + (ic - CA)) * plane;
+        v = __ldg(src + (size_t)y * Wd + x);
+      }
+      s_in[c][r][q] = v;
+    }
+    for (int e = threadIdx.x; e < kIcChunk * 9 * kOcTile; e += kConvThreads) {
+      const int o = e % kOcTile, k = (e / kOcTile) % 9, c = e / (kOcTile * 9);
+      const int ic = ic0 + c, oc = oc0 + o;
+      s_w[c][k][o] = (ic < C && oc < OC) ? __ldg(W + ((size_t)oc * C + ic) * 9 + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int c = 0; c < kIcChunk; ++c) {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        float v[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) v[q] = s_in[c][py + ky][px + q];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4 w0 = *reinterpret_cast<const float4*>(&s_w[c][ky * 3 + kx][ct * 8]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&s_w[c][ky * 3 + kx][ct * 8 + 4]);
+          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int o = 0; o < 8; ++o)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[o][p] = fmaf(w[o], v[p + kx], acc[o][p]);
+        }
+      }
+    }
+  }
+  const int y = ty0 + py;
+  if (y >= H) return;
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const int oc = oc0 + ct * 8 + o;
+    if (oc >= OC) continue;
+    const float sc = scale ? __ldg(scale + oc) : 1.f, sh = shift ? __ldg(shift + oc) : 0.f;
+    float* dst = out + (((size_t)n * OC + oc) * H + y) * Wd + tx0 + px;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (tx0 + px + p < Wd) {
+        const float r = fmaf(acc[o][p], sc, sh);
+        dst[p] = relu ? fmaxf(r, 0.f) : r;
+      }
+    }
+  }
+}
+
+__global__ void k_maxpool2(const float* __restrict__ in, int planes, int H, int Wd, float* __restrict__ out) {
+  const int Ho = H / 2, Wo = Wd / 2;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)planes * Ho * Wo) return;
+  const int x = i % Wo, y = (i / Wo) % Ho;
+  const size_t p = i / ((size_t)Wo * Ho);
+  const float* s = in + (p * H + 2 * y) * Wd + 2 * x;
+  out[i] = fmaxf(fmaxf(__ldg(s), __ldg(s + 1)), fmaxf(__ldg(s + Wd), __ldg(s + Wd + 1)));
+}
+
+// nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True): src = dst * (in - 1) / (out - 1)
+__global__ void k_upsample2_bilinear(const float* __restrict__ in, int planes, int H, int Wd, float* __restrict__ out) {
+  const int Ho = 2 * H, Wo = 2 * Wd;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)planes * Ho * Wo) return;
+  const int x = i % Wo, y = (i / Wo) % Ho;
+  const size_t p = i / ((size_t)Wo * Ho);
+  const float ry = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f, rx = Wo > 1 ? (float)(Wd - 1) / (float)(Wo - 1) : 0.f;
+  const float sy = ry * y, sx = rx * x;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < Wd - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  const float* s = in + p * H * Wd;
+  const float v00 = __ldg(s + (size_t)y0 * Wd + x0), v01 = __ldg(s + (size_t)y0 * Wd + x1);
+  const float v10 = __ldg(s + (size_t)y1 * Wd + x0), v11 = __ldg(s + (size_t)y1 * Wd + x1);
+  out[i] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+}
+
+// nn.ConvTranspose2d(C, OC, kernel_size=2, stride=2): out[n, oc, 2y+dy, 2x+dx] = b[oc] + sum_ic in[n, ic, y, x] W[ic, oc, dy, dx]
+__global__ void k_convtranspose2(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
+                                 int C, int OC, int H, int Wd, float* __restrict__ out) {
+  const int Ho = 2 * H, Wo = 2 * Wd;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (i >= (size_t)OC * Ho * Wo) return;
+  const int xo = i % Wo, yo = (i / Wo) % Ho, oc = i / ((size_t)Wo * Ho);
+  const int x = xo >> 1, y = yo >> 1, k = (yo & 1) * 2 + (xo & 1);
+  float acc = bias ? __ldg(bias + oc) : 0.f;
+  const float* s = in + (size_t)n * C * H * Wd + (size_t)y * Wd + x;
+  for (int ic = 0; ic < C; ++ic) acc = fmaf(__ldg(s + (size_t)ic * H * Wd), __ldg(W + ((size_t)ic * OC + oc) * 4 + k), acc);
+  out[(size_t)n * OC * Ho * Wo + i] = acc;
+}
+
+// OutConv: 1x1 convolution with bias
+__global__ void k_conv1x1(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias, int C,
+                          int OC, size_t plane, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (i >= plane) return;
+  for (int oc = 0; oc < OC; ++oc) {
+    float acc = bias ? __ldg(bias + oc) : 0.f;
+    for (int ic = 0; ic < C; ++ic) acc = fmaf(__ldg(in + ((size_t)n * C + ic) * plane + i), __ldg(W + (size_t)oc * C + ic), acc);
+    out[((size_t)n * OC + oc) * plane + i] = acc;
+  }
+}
+
+static int conv3x3(const float* inA, int CA, const float* inB, int CB, const nlb_unet_conv_t& L, int OC, int N, int H, int Wd,
+                   float* out, cudaStream_t st) {
+  if (!inA || !L.weight || !L.scale || !L.shift || !out || (CB > 0 && !inB)) { nlb_set_error("unet: null pointer in a 3x3 layer"); return NLB_EINVAL; }
+  const int tiles = ((Wd + kCols - 1) / kCols) * ((H + kRows - 1) / kRows);
+  dim3 grid(tiles, (OC + kOcTile - 1) / kOcTile, N);
+  k_conv3x3<<<grid, kConvThreads, 0, st>>>(inA, CA, inB, CB, L.weight, L.scale, L.shift, OC, H, Wd, 1, out);
+  return nlb_check_launch("unet conv3x3");
+}
+
+}  // namespace unet
+}  // namespace nlb
+
+using namespace nlb;
+
+// activations of one forward pass, in floats: x1..x5 (encoder), one pooled / upsampled scratch, one mid tensor and
+// one decoder output per level (sized for the finest level), for N images
+extern "C" size_t nlb_unet_workspace_bytes(int N, int H, int W) {
+  const size_t px = (size_t)N * H * W;
+  // x1 64, x2 128/4, x3 256/16, x4 512/64, x5 1024/256 pixel-equivalents of floats + four scratch tensors (pooled /
+  // upsampled input, mid tensor, two ping-pong decoder outputs) of at most 64 channels at full resolution (96 reserved)
+  return (64 + 32 + 16 + 8 + 4 + 4 * 96) * px * sizeof(float) + 1024;
+}
+
+extern "C" int nlb_unet_forward(const float* image, const nlb_unet_weights_t* w, int N, int Cin, int H, int W, float* logits,
+                                float* workspace, void* stream) {
+  if (N == 0) return NLB_OK;
+  if (N < 0 || Cin < 1 || !image || !w || !logits || !workspace) { nlb_set_error("unet_forward: bad argument"); return NLB_EINVAL; }
+  if (H < 16 || W < 16 || H % 16 || W % 16) {
+    nlb_set_error("unet_forward: H and W must be multiples of 16 (four 2x2 poolings without padding), got %d x %d", H, W);
+    return NLB_EUNSUPPORTED;
+  }
+  if (w->n_classes < 1 || !w->outc_weight) { nlb_set_error("unet_forward: the output layer is required"); return NLB_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int bil = w->bilinear != 0;
+  const int f = bil ? 2 : 1;
+  const size_t px = (size_t)N * H * W;
+  float* x1 = workspace;                 // [N, 64, H, W]
+  float* x2 = x1 + 64 * px;              // [N, 128, H/2, W/2]
+  float* x3 = x2 + 32 * px;              // [N, 256, H/4, W/4]
+  float* x4 = x3 + 16 * px;              // [N, 512, H/8, W/8]
+  float* x5 = x4 + 8 * px;               // [N, 1024/f, H/16, W/16]
+  float* s0 = x5 + 4 * px;               // scratch: pooled / upsampled input
+  float* s1 = s0 + 96 * px;              // scratch: mid tensor of a DoubleConv
+  float* s2 = s1 + 96 * px;              // scratch: decoder level outputs (ping-pong)
+  float* s3 = s2 + 96 * px;
+  auto double_conv = [&](const float* inA, int CA, const float* inB, int CB, const nlb_unet_conv_t* L, int mid, int oc, int h,
+                         int wd, float* out) -> int {
+    if (int e = unet::conv3x3(inA, CA, inB, CB, L[0], mid, N, h, wd, s1, st)) return e;
+    return unet::conv3x3(s1, mid, nullptr, 0, L[1], oc, N, h, wd, out, st);
+  };
+  auto pool = [&](const float* in, int C, int h, int wd) {
+    const size_t total = (size_t)N * C * (h / 2) * (wd / 2);
+    unet::k_maxpool2<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, N * C, h, wd, s0);
+  };
+  // encoder
+  if (int e = double_conv(image, Cin, nullptr, 0, w->inc, 64, 64, H, W, x1)) return e;
+  pool(x1, 64, H, W);
+  if (int e = double_conv(s0, 64, nullptr, 0, w->down[0], 128, 128, H / 2, W / 2, x2)) return e;
+  pool(x2, 128, H / 2, W / 2);
+  if (int e = double_conv(s0, 128, nullptr, 0, w->down[1], 256, 256, H / 4, W / 4, x3)) return e;
+  pool(x3, 256, H / 4, W / 4);
+  if (int e = double_conv(s0, 256, nullptr, 0, w->down[2], 512, 512, H / 8, W / 8, x4)) return e;
+  pool(x4, 512, H / 8, W / 8);
+  if (int e = double_conv(s0, 512, nullptr, 0, w->down[3], 1024 / f, 1024 / f, H / 16, W / 16, x5)) return e;
+  // decoder: Up(in, out): x1' = up(x_low); DoubleConv(cat[x_skip, x1'], out, mid)
+  const float* low = x5;
+  int c_low = 1024 / f;
+  const float* skips[4] = {x4, x3, x2, x1};
+  const int c_skip[4] = {512, 256, 128, 64};
+  const int c_out[4] = {512 / f, 256 / f, 128 / f, 64};
+  int h = H / 16, wd = W / 16;
+  float* outs[2] = {s2, s3};
+  for (int u = 0; u < 4; ++u) {
+    int c_up;
+    if (bil) {
+      c_up = c_low;
+      const size_t total = (size_t)N * c_low * (2 * h) * (2 * wd);
+      unet::k_upsample2_bilinear<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(low, N * c_low, h, wd, s0);
+    } else {
+      c_up = c_low / 2;
+      if (!w->up_weight[u]) { nlb_set_error("unet_forward: transposed-convolution weights of up%d are required", u + 1); return NLB_EINVAL; }
+      const size_t total = (size_t)c_up * (2 * h) * (2 * wd);
+      unet::k_convtranspose2<<<dim3((unsigned)((total + 255) / 256), N), 256, 0, st>>>(low, w->up_weight[u], w->up_bias[u], c_low,
+                                                                                      c_up, h, wd, s0);
+    }
+    h *= 2; wd *= 2;
+    const int cin = c_skip[u] + c_up;
+    const int mid = bil ? cin / 2 : c_out[u];
+    float* dst = outs[u & 1];   // never aliases its inputs: s0 (upsampled), s1 (mid), the skip tensor, `low` = the other one
+    if (int e = double_conv(skips[u], c_skip[u], s0, c_up, w->up[u], mid, c_out[u], h, wd, dst)) return e;
+    low = dst;
+    c_low = c_out[u];
+  }
+  unet::k_conv1x1<<<dim3((unsigned)(((size_t)H * W + 255) / 256), N), 256, 0, st>>>(low, w->outc_weight, w->outc_bias, 64,
+                                                                                    w->n_classes, (size_t)H * W, logits);
+  return nlb_check_launch("unet_forward");
+}

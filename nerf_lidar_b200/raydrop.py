@@ -91,3 +91,110 @@ def drop_rays(pred_logits: torch.Tensor, laser_scan: LaserScan, points: torch.Te
                                      ptr(count), ptr(ws), stream()))
     m = int(count.item())
     return out_p[:m], out_l[:m]
+
+
+# ----------------------------------------------------------------------------- the U-Net (R/src/unet/)
+import torch.nn as nn
+
+from ._lib import NlbUnetConv, NlbUnetWeights
+
+
+class DoubleConv(nn.Module):
+    """R/src/unet/unet_parts.py:8-26 (parameter container; evaluated by csrc/unet.cu)."""
+
+    def __init__(self, in_channels, out_channels, mid_channels=None):
+        super().__init__()
+        mid_channels = mid_channels or out_channels
+        self.double_conv = nn.Sequential(
+            nn.Conv2d(in_channels, mid_channels, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(mid_channels),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(mid_channels, out_channels, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(out_channels),
+            nn.ReLU(inplace=True))
+
+
+class Down(nn.Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), DoubleConv(in_channels, out_channels))
+
+
+class Up(nn.Module):
+    def __init__(self, in_channels, out_channels, bilinear=True):
+        super().__init__()
+        if bilinear:
+            self.up = nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True)
+            self.conv = DoubleConv(in_channels, out_channels, in_channels // 2)
+        else:
+            self.up = nn.ConvTranspose2d(in_channels, in_channels // 2, kernel_size=2, stride=2)
+            self.conv = DoubleConv(in_channels, out_channels)
+
+
+class OutConv(nn.Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=1)
+
+
+class UNet(nn.Module):
+    """R/src/unet/unet_model.py:6-47: same constructor, sub-module names and state-dict keys (reference checkpoints
+    load as they are); `forward` is inference only (BatchNorm running statistics), on csrc/unet.cu."""
+
+    def __init__(self, n_channels, n_classes, bilinear=False, regression=False):
+        super().__init__()
+        if regression:
+            raise NotImplementedError('UNet(regression=True): the range-regression head is not built')
+        self.n_channels, self.n_classes, self.bilinear, self.regression = n_channels, n_classes, bilinear, regression
+        self.inc = DoubleConv(n_channels, 64)
+        self.down1 = Down(64, 128)
+        self.down2 = Down(128, 256)
+        self.down3 = Down(256, 512)
+        factor = 2 if bilinear else 1
+        self.down4 = Down(512, 1024 // factor)
+        self.up1 = Up(1024, 512 // factor, bilinear)
+        self.up2 = Up(512, 256 // factor, bilinear)
+        self.up3 = Up(256, 128 // factor, bilinear)
+        self.up4 = Up(128, 64, bilinear)
+        self.outc = OutConv(64, n_classes)
+
+    @staticmethod
+    def _fold(dc: DoubleConv, keep):
+        """(conv weight, BatchNorm folded to scale / shift) of both halves of a DoubleConv."""
+        out = []
+        for ci, bi in ((0, 1), (3, 4)):
+            conv, bn = dc.double_conv[ci], dc.double_conv[bi]
+            scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+            shift = bn.bias.detach() - bn.running_mean * scale
+            t = [f32(conv.weight.detach()), f32(scale), f32(shift)]
+            keep += t
+            out.append(NlbUnetConv(*[ptr(x) for x in t]))
+        return out
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            raise NotImplementedError('UNet: inference only (call .eval(); training the ray-drop network is not built)')
+        x = f32(x)
+        N, cin, H, W = x.shape
+        if cin != self.n_channels:
+            raise RuntimeError(f'UNet: expected {self.n_channels} input channels, got {cin}')
+        keep = []
+        w = NlbUnetWeights()
+        w.inc[0], w.inc[1] = self._fold(self.inc, keep)
+        for i, d in enumerate((self.down1, self.down2, self.down3, self.down4)):
+            w.down[i][0], w.down[i][1] = self._fold(d.maxpool_conv[1], keep)
+        for i, u in enumerate((self.up1, self.up2, self.up3, self.up4)):
+            w.up[i][0], w.up[i][1] = self._fold(u.conv, keep)
+            if not self.bilinear:
+                t = [f32(u.up.weight.detach()), f32(u.up.bias.detach())]
+                keep += t
+                w.up_weight[i], w.up_bias[i] = ptr(t[0]), ptr(t[1])
+        t = [f32(self.outc.conv.weight.detach().reshape(self.n_classes, 64)), f32(self.outc.conv.bias.detach())]
+        keep += t
+        w.outc_weight, w.outc_bias = ptr(t[0]), ptr(t[1])
+        w.bilinear, w.n_classes = int(bool(self.bilinear)), int(self.n_classes)
+        lib = load()
+        ws = torch.empty(lib.nlb_unet_workspace_bytes(N, H, W) // 4, device=x.device)
+        out = torch.empty(N, self.n_classes, H, W, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.nlb_unet_forward(ptr(x), C.byref(w), N, cin, H, W, ptr(out), ptr(ws), stream()))
+        return out
