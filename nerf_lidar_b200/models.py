@@ -313,6 +313,9 @@ class Model(nn.Module):
         parity tests see the reference's jitter."""
         if sample_n != 7 or sample_m != 3:
             raise NotImplementedError('the fused kernels implement the n=7, m=3 hexagonal multisample')
+        sync = self.__dict__.get('_nlb_sync')     # a data-parallel trainer may still be gathering the NeRF table
+        if sync is not None and not (batch['origins'].is_cuda and torch.cuda.is_current_stream_capturing()):
+            sync()
         rays = ops.RayBundle(batch)
         N, dev = rays.N, rays.device
         near, far = batch['near'], batch['far']
@@ -352,6 +355,9 @@ class Model(nn.Module):
                 density = ops.prop_level(tdist, deg, mlp, rays, self.std_scale)
                 res = dict(density=density, rgb=None, semantic=None, intensity=None)
             else:
+                hook = self.__dict__.get('_nlb_before_nerf_table')   # data-parallel trainer: see Trainer.train_step_graphed
+                if hook is not None:
+                    hook()
                 feat = ops.nerf_encode(tdist, deg, self.nerf_mlp.encoder, rays, self.std_scale)
                 res = self.nerf_mlp.heads(feat, viewdirs, S)
             obj_mask = None

@@ -169,6 +169,11 @@ class Trainer:
         # another one made the engine join the default stream into the capture
         # (cudaErrorStreamCaptureIsolation: tests/dp_worker.py, eager step followed by the graphed one).
         self.stream = torch.cuda.Stream(device=dev)
+        # data parallel: collectives still in flight when a step returns (the all-gather of the NeRF table's
+        # updated rows travels under the next step's proposal levels); Model.forward and every trainer entry
+        # point wait for them first
+        self._pending = []
+        model.__dict__['_nlb_sync'] = self.sync
         model.train()
         model.training = True
 
@@ -215,9 +220,17 @@ class Trainer:
     def _prop_tables(self):
         return [t for t in self.tables if 'prop' in t['name']]
 
+    def sync(self):
+        """Waits (on the current stream) for the collectives a data-parallel step left in flight: afterwards the
+        replicated parameters are complete on this rank."""
+        if self._pending:
+            parallel.wait_all(self._pending)
+            self._pending = []
+
     def train_step(self, batch: Dict[str, torch.Tensor], step: int, num_patch: Optional[int] = None,
                    rand_inputs=None) -> Dict[str, torch.Tensor]:
         """One eager training step, issued on the trainer's own stream (the caller's stream waits for it)."""
+        self.sync()
         dev = self.flat.device
         cur = torch.cuda.current_stream(dev)
         if cur == self.stream or torch.cuda.is_current_stream_capturing():
@@ -303,15 +316,20 @@ class Trainer:
                                          _lib.stream()))
         self._mark_packed_stale()
 
-    def publish(self, capture_safe_only: bool = False):
+    def publish(self, capture_safe_only: bool = False, defer_nerf: bool = False):
         """After the optimizer pass of a data-parallel step: all-gather of the updated parameters (and of the
-        per-level sums of squares behind the reported hash-decay value)."""
+        per-level sums of squares behind the reported hash-decay value).  With `defer_nerf` the NeRF table's
+        gather (77 % of the bytes) is issued last and left in flight: the next step reads that table only after its
+        two proposal levels, so the transfer hides under them (`sync()` waits for it)."""
         if self.world > 1:
-            h = self.all_gather_parameters(self.tables, dense=True)
+            first = self._prop_tables() if defer_nerf else self.tables
+            h = self.all_gather_parameters(first, dense=True)
             if parallel.is_dist():
                 import torch.distributed as dist
                 h.append(dist.all_reduce(self._sumsq_all, async_op=True))
             parallel.wait_all(h)
+            if defer_nerf:
+                self._pending += self.all_gather_parameters(self._nerf_tables())
         self._update_hash_decay_value()
 
     def _update_hash_decay_value(self):
@@ -402,15 +420,35 @@ class Trainer:
                 out = self.train_step(st['batch'], step, num_patch, srand)   # on self.stream
                 out = {k: v.clone() for k, v in out.items()}
                 g = torch.cuda.CUDAGraph()
-                g_prop = g_opt = None
+                g_prop = g_opt = g_nerf = None
                 if self.world == 1:
                     with torch.cuda.graph(g, stream=self.stream):
                         captured = self._train_step(st['batch'], step, num_patch, srand)
                 else:
-                    # the collectives stay outside the graphs: forward + main backward | proposal backward | optimizer
-                    with torch.cuda.graph(g, stream=self.stream):
+                    # the collectives stay outside the graphs: proposal levels | NeRF level + main backward |
+                    # proposal backward | optimizer.  The first cut sits where the forward first reads the NeRF
+                    # table (Model.forward calls the hook): the previous step's all-gather of that table is
+                    # waited for between the two replays.
+                    g_nerf = torch.cuda.CUDAGraph()
+                    ctx = [torch.cuda.graph(g, stream=self.stream)]
+                    cut = []
+
+                    def hook():
+                        if not cut:
+                            ctx.pop().__exit__(None, None, None)
+                            ctx.append(torch.cuda.graph(g_nerf, pool=g.pool(), stream=self.stream))
+                            ctx[0].__enter__()
+                            cut.append(True)
+                    self.model.__dict__['_nlb_before_nerf_table'] = hook
+                    ctx[0].__enter__()
+                    try:
                         captured, main, prop = self.forward_losses(st['batch'], step, num_patch, srand)
                         main.backward()
+                    finally:
+                        self.model.__dict__.pop('_nlb_before_nerf_table', None)
+                        ctx.pop().__exit__(None, None, None)
+                    if not cut:
+                        raise RuntimeError('train_step_graphed: the forward never reached the NeRF level')
                     if prop is not None:
                         g_prop = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g_prop, pool=g.pool(), stream=self.stream):
@@ -422,17 +460,21 @@ class Trainer:
             finally:
                 lib.nlb_set_dynamic_scalars(None)
             # capturing records the step without running it: the eager warm-up step above WAS this call's step
-            self._graphs[key] = (g, g_prop, g_opt, captured)
+            self._graphs[key] = (g, g_nerf if self.world > 1 else None, g_prop, g_opt, captured)
             return out
-        g, g_prop, g_opt, captured = entry
-        g.replay()
-        if g_opt is not None:
+        g, g_nerf, g_prop, g_opt, captured = entry
+        if g_opt is None:
+            g.replay()
+        else:
+            g.replay()                      # proposal levels: prop tables + dense parameters (gathered, waited)
+            self.sync()                     # the NeRF table's rows of the previous step have arrived
+            g_nerf.replay()                 # NeRF level, losses, main backward
             early = self.reduce_scatter_gradients(self._nerf_tables())
             if g_prop is not None:
                 g_prop.replay()
             late = self.reduce_scatter_gradients(self._prop_tables(), dense=True)
             parallel.wait_all(early + late)
             g_opt.replay()
-            self.publish()
+            self.publish(defer_nerf=True)
         self._mark_packed_stale()
         return captured

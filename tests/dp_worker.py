@@ -66,6 +66,7 @@ def main():
             dp.hash_decay_value.copy_(ref.hash_decay_value)
             dp._mark_packed_stale()
         out = fn(halves[rank], step, 0, rins[rank])
+        dp.sync()   # a replayed step leaves the NeRF table's all-gather in flight (it hides under the next step)
         # one GPU: both halves' gradients accumulate in the buffers, then their mean drives the same optimizer pass
         ref_losses = []
         for r in range(world):
