@@ -177,21 +177,28 @@ class UNet(nn.Module):
         N, cin, H, W = x.shape
         if cin != self.n_channels:
             raise RuntimeError(f'UNet: expected {self.n_channels} input channels, got {cin}')
-        keep = []
-        w = NlbUnetWeights()
-        w.inc[0], w.inc[1] = self._fold(self.inc, keep)
-        for i, d in enumerate((self.down1, self.down2, self.down3, self.down4)):
-            w.down[i][0], w.down[i][1] = self._fold(d.maxpool_conv[1], keep)
-        for i, u in enumerate((self.up1, self.up2, self.up3, self.up4)):
-            w.up[i][0], w.up[i][1] = self._fold(u.conv, keep)
-            if not self.bilinear:
-                t = [f32(u.up.weight.detach()), f32(u.up.bias.detach())]
-                keep += t
-                w.up_weight[i], w.up_bias[i] = ptr(t[0]), ptr(t[1])
-        t = [f32(self.outc.conv.weight.detach().reshape(self.n_classes, 64)), f32(self.outc.conv.bias.detach())]
-        keep += t
-        w.outc_weight, w.outc_bias = ptr(t[0]), ptr(t[1])
-        w.bilinear, w.n_classes = int(bool(self.bilinear)), int(self.n_classes)
+        # folded BatchNorm terms / weight pointers, rebuilt only when a parameter or buffer changed (18 layers x a
+        # handful of tiny launches would otherwise cost more than the convolutions)
+        version = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        cached = self.__dict__.get('_nlb_folded')
+        if cached is None or cached[0] != version:
+            keep = []
+            w = NlbUnetWeights()
+            w.inc[0], w.inc[1] = self._fold(self.inc, keep)
+            for i, d in enumerate((self.down1, self.down2, self.down3, self.down4)):
+                w.down[i][0], w.down[i][1] = self._fold(d.maxpool_conv[1], keep)
+            for i, u in enumerate((self.up1, self.up2, self.up3, self.up4)):
+                w.up[i][0], w.up[i][1] = self._fold(u.conv, keep)
+                if not self.bilinear:
+                    t = [f32(u.up.weight.detach()), f32(u.up.bias.detach())]
+                    keep += t
+                    w.up_weight[i], w.up_bias[i] = ptr(t[0]), ptr(t[1])
+            t = [f32(self.outc.conv.weight.detach().reshape(self.n_classes, 64)), f32(self.outc.conv.bias.detach())]
+            keep += t
+            w.outc_weight, w.outc_bias = ptr(t[0]), ptr(t[1])
+            w.bilinear, w.n_classes = int(bool(self.bilinear)), int(self.n_classes)
+            self.__dict__['_nlb_folded'] = cached = (version, w, keep)
+        w = cached[1]
         lib = load()
         ws = torch.empty(lib.nlb_unet_workspace_bytes(N, H, W) // 4, device=x.device)
         out = torch.empty(N, self.n_classes, H, W, device=x.device)
