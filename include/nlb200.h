@@ -436,7 +436,21 @@ typedef struct {
 int nlb_obj_forward(const float* tdist /*[N,S+1]*/, const float* origins, const float* directions,
                     const float* viewdirs, const float* pose /*[N,n_obj,9]*/, int n_obj, int track, int N, int S,
                     const nlb_table_t* table, const nlb_obj_mlp_t* mlp, float* density, float* rgb, float* semantic,
-                    uint8_t* obj_mask, void* stream);
+                    uint8_t* obj_mask, int32_t* owner /*[N,S] or NULL: the track that wrote each sample*/, void* stream);
+
+/* Training backward of one track at the final level: gradients of the ObjMLP weights, the track's latent code and
+ * the object table (all ACCUMULATED into the caller's buffers, same shapes as the parameters) from the gradients
+ * w.r.t. the merged density[N,S] / rgb[N,S,3], for the samples the track owns (owner[pt] == track).  The forward
+ * is recomputed; poses are constants. */
+typedef struct {
+  float *g_W_d0, *g_b_d0, *g_W_d2, *g_b_d2, *g_W_v0, *g_b_v0, *g_W_v1, *g_b_v1, *g_W_rgb, *g_b_rgb;
+  float* g_latent;   /* or NULL */
+  float* g_table;    /* [rows, C] or NULL */
+} nlb_obj_grads_t;
+int nlb_obj_backward(const float* tdist, const float* origins, const float* directions, const float* viewdirs,
+                     const float* pose, int n_obj, int track, int N, int S, const nlb_table_t* table,
+                     const nlb_obj_mlp_t* mlp, const int32_t* owner, const float* g_density /*or NULL*/,
+                     const float* g_rgb /*or NULL*/, const nlb_obj_grads_t* grads, void* stream);
 
 /* ------------------------------------------------------------------ stage-3 ray-drop: around the U-Net
  * `R/` = NeRF_LiDAR/NeRF_Lidar_code/.  The U-Net (R/src/unet/) is not part of the library: its [2,H,W] logits are

@@ -82,6 +82,11 @@ class NlbObjMlp(C.Structure):
                [(n, C.c_int) for n in ('class_type', 'class_num')]
 
 
+class NlbObjGrads(C.Structure):
+    _fields_ = [(n, c_f) for n in ('g_W_d0', 'g_b_d0', 'g_W_d2', 'g_b_d2', 'g_W_v0', 'g_b_v0', 'g_W_v1', 'g_b_v1', 'g_W_rgb',
+                                   'g_b_rgb', 'g_latent', 'g_table')]
+
+
 class NlbRangeImage(C.Structure):
     _fields_ = [(n, c_f) for n in ('proj_range', 'proj_xyz', 'proj_semantic', 'proj_rgb', 'proj_idx', 'proj_mask')]
 
@@ -152,7 +157,9 @@ SIGNATURES = {
     'nlb_unet_workspace_bytes': (C.c_size_t, [_i, _i, _i]),
     'nlb_unet_forward': (_i, [_p, C.POINTER(NlbUnetWeights), _i, _i, _i, _i, _p, _p, _p]),
     'nlb_obj_pose': (_i, [_p, _p, _i, _i, _i, _p, _p]),
-    'nlb_obj_forward': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, C.POINTER(NlbTable), C.POINTER(NlbObjMlp), _p, _p, _p, _p, _p]),
+    'nlb_obj_forward': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, C.POINTER(NlbTable), C.POINTER(NlbObjMlp), _p, _p, _p, _p, _p, _p]),
+    'nlb_obj_backward': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, C.POINTER(NlbTable), C.POINTER(NlbObjMlp), _p, _p, _p,
+                              C.POINTER(NlbObjGrads), _p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -70,6 +70,7 @@ class Config:
     instance_obj: bool = False
     use_semantic: bool = True
     latent_size: int = 0
+    latent_reg: float = 0.001
     obj_nodecay: bool = False
     depth_loss: bool = True
     sem_detach: bool = True

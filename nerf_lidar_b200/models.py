@@ -6,7 +6,7 @@ Scope: the static-scene zipnerf path of nuscenes_single.gi
 3 sampling levels, hash-grid PropMLPs, NerfMLP with semantic + intensity heads,
 opaque background, power-transformation ray warp -- and, with Config.instance_obj, the dynamic-object
 branch (Z/internal/models.py:92-177 ctor, :306-315,401-477 forward; ObjMLP per class with split shape /
-texture latents) on csrc/obj.cu, forward (rendering) only.
+texture latents) on csrc/obj.cu (poses are constants: track refinement is outside).
 
 State-dict keys are the reference's (nerf_mlp.encoder.embeddings,
 nerf_mlp.density_layer.0.weight, prop_mlp_0.encoder.offsets, ...), so reference
@@ -329,9 +329,6 @@ class Model(nn.Module):
         bg = float(self.bg_intensity_range[0])
         obj_pose = None
         if self.instance_obj:
-            if torch.is_grad_enabled():
-                raise NotImplementedError('the dynamic-object branch is built for rendering (no_grad); its training '
-                                          'backward (ObjMLP / latent / track gradients) is not')
             track = curr_track if curr_track is not None else self.tracks
             if track is not None:     # obj_utils.get_pose: per ray, per track
                 obj_pose = ops.obj_pose(batch['timestamp'], track.to(dev))
@@ -362,7 +359,8 @@ class Model(nn.Module):
                 res = self.nerf_mlp.heads(feat, viewdirs, S)
             obj_mask = None
             if obj_pose is not None:
-                obj_mask = ops.obj_apply(self, res, tdist, rays, viewdirs, obj_pose, is_prop)
+                apply = ops.obj_apply_train if torch.is_grad_enabled() else ops.obj_apply
+                obj_mask = apply(self, res, tdist, rays, viewdirs, obj_pose, is_prop)
             sem = res['semantic'] if (not is_prop and self.config.use_semantic) else None
             inten = res['intensity'] if (not is_prop and self.config.use_intensity) else None
             comp = ops.composite(res['density'], tdist, rays.directions, far, res['rgb'], sem, inten, bg,

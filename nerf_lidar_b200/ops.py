@@ -19,7 +19,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import timed, NlbObjMlp, NlbLossesIn, NlbNerfMlpWeights, NlbNerfMlpSaved, NlbNerfMlpGradIn, NlbNerfMlpGradOut, NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
+from ._lib import timed, NlbObjGrads, NlbObjMlp, NlbLossesIn, NlbNerfMlpWeights, NlbNerfMlpSaved, NlbNerfMlpGradIn, NlbNerfMlpGradOut, NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
 
 EPS = float(torch.finfo(torch.float32).eps)
 _u_cache: Dict[Tuple, torch.Tensor] = {}
@@ -315,15 +315,30 @@ def _mlp_tensors(mlp):
     return [params.get(name) if name.startswith('intensity_layer') else params[name] for _, name in _NERF_WEIGHT_FIELDS]
 
 
+def _mlp_tensors_train(mlp):
+    """As above for the training kernels, which are compiled with the intensity head: a network built without it
+    (Config.use_intensity=False, e.g. with the dynamic-object branch) gets a frozen all-zero head -- plain
+    tensors, not parameters, not in the state dict -- whose output is discarded and whose gradients go to scratch."""
+    tensors = _mlp_tensors(mlp)
+    if all(t is not None for t in tensors):
+        return tensors
+    dummy = mlp.__dict__.get('_nlb_zero_intensity_head')
+    dev = tensors[0].device
+    if dummy is None or dummy[0].device != dev:
+        z = lambda *s: torch.zeros(*s, device=dev)
+        dummy = [z(64, mlp.bottleneck_width), z(64), z(1, 64), z(1)]
+        mlp.__dict__['_nlb_zero_intensity_head'] = dummy
+    it = iter(dummy)
+    return [t if t is not None else next(it) for t in tensors]
+
+
 @torch.no_grad()
 def nerf_mlp_pack(mlp, transposed: bool = False) -> torch.Tensor:
     """Packs the NerfMLP dense layers into the bf16 operand-block blob the fused
     kernels stream (nlb_nerf_mlp_pack / _pack_transposed).  Cached on the module and
     refreshed when any parameter has been modified in place (optimizer step,
     load_state_dict)."""
-    tensors = _mlp_tensors(mlp)
-    if transposed and any(t is None for t in tensors):
-        raise NotImplementedError('NerfMLP training kernels need the intensity head (Config.use_intensity=True)')
+    tensors = _mlp_tensors_train(mlp) if transposed else _mlp_tensors(mlp)
     version = tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
     key = '_nlb_packed_t' if transposed else '_nlb_packed'
     cache = getattr(mlp, key, None)
@@ -355,9 +370,7 @@ def _mlp_forward_raw(mlp, features, viewdirs, S, save: bool):
     new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
     density, rgb, sem, inten = new(N, S), new(N, S, 3), new(N, S, 19), new(N, S, 1)
     if getattr(mlp, 'intensity_layer', None) is None:
-        if save:
-            raise NotImplementedError('NerfMLP training kernels need the intensity head (Config.use_intensity=True)')
-        inten = None
+        inten = None            # (the packed head is all zeros; nothing is written)
     saved = None
     sv = None
     if save:
@@ -442,16 +455,17 @@ class _NerfMLP(Function):
                                  ptr(d_h0), 640, 640, 640)
         # gradient targets: the trainer's persistent buffers (views of its flat gradient, `param._nlb_grad`) are
         # added into directly; without a trainer the gradients are returned through autograd
-        params = _mlp_tensors(mlp)
-        in_place = all(getattr(p, '_nlb_grad', None) is not None for p in params)
-        if in_place:
-            targets = [p._nlb_grad for p in params]
-        else:
-            flat = torch.zeros(sum(p.numel() for p in params), device=dev, dtype=torch.float32)
-            targets, off = [], 0
-            for p in params:
-                targets.append(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
+        params = _mlp_tensors(mlp)                       # None for the intensity head of a network built without it
+        shapes = [t.shape for t in _mlp_tensors_train(mlp)]
+        in_place = all(getattr(p, '_nlb_grad', None) is not None for p in params if p is not None)
+        targets = []
+        for p, shp in zip(params, shapes):
+            if p is None:
+                targets.append(torch.zeros(shp, device=dev, dtype=torch.float32))      # scratch: discarded
+            elif in_place:
+                targets.append(p._nlb_grad)
+            else:
+                targets.append(torch.zeros(shp, device=dev, dtype=torch.float32))
         wg = NlbNerfMlpWeights(*[ptr(t) for t in targets])
         with torch.cuda.device(dev):
             with timed('nerf_mlp_bwd'):
@@ -468,7 +482,7 @@ class _NerfMLP(Function):
             with timed('nerf_mlp_wgrad_finish'):
                 check(load().nlb_nerf_mlp_wgrad_finish(ptr(rs_v0), ptr(rs_v1), ptr(viewdirs), N, ptr(cs_x), ptr(cs_g),
                                                        ptr(cs_h0), ptr(cs_hs1), ptr(cs_rgb), C.byref(wg), stream()))
-        return (g_feat, None, None, None, *([None] * len(targets) if in_place else targets))
+        return (g_feat, None, None, None, *[None if (in_place or p is None) else t for p, t in zip(params, targets)])
 
 
 def nerf_mlp_train(mlp, features: torch.Tensor, viewdirs: torch.Tensor, S: int) -> Dict[str, torch.Tensor]:
@@ -643,6 +657,118 @@ def _obj_mlp_desc(mlp, latent):
     return desc, keep
 
 
+def _obj_param_list(mlp, latent):
+    d0, d2 = mlp.density_layer[0], mlp.density_layer[2]
+    v0, v1 = mlp.lin_second_stage_0, mlp.lin_second_stage_1
+    return [d0.weight, d0.bias, d2.weight, d2.bias, v0.weight, v0.bias, v1.weight, v1.bias, mlp.rgb_layer.weight,
+            mlp.rgb_layer.bias, latent, mlp.encoder.embeddings]
+
+
+def _obj_forward_all(model, tdist, rays, viewdirs, pose, density, rgb, sem, owner):
+    """All tracks of one level, in track order, overwriting density / rgb / semantic in place; returns the byte mask."""
+    N, S = rays.N, tdist.shape[1] - 1
+    mask = torch.zeros(N, S, device=rays.device, dtype=torch.uint8)
+    n_obj = pose.shape[1]
+    lib = load()
+    with torch.cuda.device(rays.device):
+        for track_id in range(n_obj):
+            mlp, latent = model._obj_network(track_id)
+            desc, keep = _obj_mlp_desc(mlp, latent)
+            tab = _table_desc(mlp.encoder, mlp.encoder.embeddings.detach())
+            with timed('obj_forward'):
+                check(lib.nlb_obj_forward(ptr(tdist), ptr(rays.origins), ptr(rays.directions), ptr(viewdirs), ptr(pose),
+                                          n_obj, track_id, N, S, C.byref(tab), C.byref(desc), ptr(density), ptr(rgb),
+                                          ptr(sem), ptr(mask), ptr(owner), stream()))
+    return mask
+
+
+class _ObjBranch(Function):
+    """Final-level object branch in training: (density_o, rgb_o) hold the ObjMLP outputs on the samples inside a
+    box (anything elsewhere); gradients go to the ObjMLP weights, the latent codes and the object tables of the
+    owning track (csrc/obj.cu k_obj_backward: forward recomputed, nothing saved but the owner map)."""
+
+    @staticmethod
+    def forward(ctx, model, tdist, rays, viewdirs, pose, n_params, *params):
+        N, S = rays.N, tdist.shape[1] - 1
+        dev = rays.device
+        density = torch.zeros(N, S, device=dev)
+        rgb = torch.zeros(N, S, 3, device=dev)
+        sem = torch.zeros(N, S, model.nerf_mlp.class_num, device=dev)
+        owner = torch.full((N, S), -1, device=dev, dtype=torch.int32)
+        mask = _obj_forward_all(model, tdist, rays, viewdirs, pose, density, rgb, sem, owner)
+        ctx.model, ctx.rays, ctx.param_order = model, rays, params
+        ctx.save_for_backward(tdist, viewdirs, pose, owner)
+        ctx.mark_non_differentiable(sem, mask)
+        return density, rgb, sem, mask
+
+    @staticmethod
+    def backward(ctx, g_density, g_rgb, _gs, _gm):
+        tdist, viewdirs, pose, owner = ctx.saved_tensors
+        model, rays = ctx.model, ctx.rays
+        N, S = rays.N, tdist.shape[1] - 1
+        n_obj = pose.shape[1]
+        g_density = None if g_density is None else f32(g_density)
+        g_rgb = None if g_rgb is None else f32(g_rgb)
+        grads = {}          # id(param) -> (param, gradient target, returned through autograd?)
+        lib = load()
+        with torch.cuda.device(rays.device):
+            for track_id in range(n_obj):
+                mlp, latent = model._obj_network(track_id)
+                plist = _obj_param_list(mlp, latent)
+                tgt = []
+                for prm in plist:
+                    if prm is None:
+                        tgt.append(None)
+                        continue
+                    if id(prm) not in grads:
+                        buf = getattr(prm, '_nlb_grad', None)     # the trainer's persistent buffers: added into directly
+                        grads[id(prm)] = (prm, buf if buf is not None else torch.zeros_like(prm), buf is None)
+                    tgt.append(grads[id(prm)][1])
+                desc, keep = _obj_mlp_desc(mlp, latent)
+                tab = _table_desc(mlp.encoder, mlp.encoder.embeddings.detach())
+                gd = NlbObjGrads(*[ptr(t) for t in tgt])
+                with timed('obj_backward'):
+                    check(lib.nlb_obj_backward(ptr(tdist), ptr(rays.origins), ptr(rays.directions), ptr(viewdirs), ptr(pose),
+                                               n_obj, track_id, N, S, C.byref(tab), C.byref(desc), ptr(owner), ptr(g_density),
+                                               ptr(g_rgb), C.byref(gd), stream()))
+        out = []
+        for prm in ctx.param_order:
+            p_, t_, ret = grads.get(id(prm), (None, None, False))
+            out.append(t_ if ret else None)
+        return (None, None, None, None, None, None, *out)
+
+
+def obj_apply_train(model, res, tdist, rays, viewdirs, pose, is_prop: bool) -> torch.Tensor:
+    """Training-mode object branch (Z/internal/models.py:401-477).  Proposal levels: the object densities are
+    detached (`:449-451`), so the merge is a masked overwrite that only blocks the PropMLP's gradient on the object
+    samples.  Final level: `torch.where(mask, object outputs, scene outputs)` with the object outputs carrying
+    gradients to the object networks."""
+    N, S = rays.N, tdist.shape[1] - 1
+    if res.get('intensity') is not None:
+        raise NotImplementedError('object branch with an intensity head (see Model._init_objects)')
+    if is_prop:
+        with torch.no_grad():
+            d_obj = res['density'].detach().clone()
+            mask = _obj_forward_all(model, tdist, rays, viewdirs, pose, d_obj, None, None, None).bool()
+        res['density'] = torch.where(mask, d_obj, res['density'])
+        return mask
+    params, seen = [], set()
+    for track_id in range(pose.shape[1]):
+        mlp, latent = model._obj_network(track_id)
+        for prm in _obj_param_list(mlp, latent):
+            if prm is not None and id(prm) not in seen:
+                seen.add(id(prm))
+                params.append(prm)
+    d_o, rgb_o, sem_o, mask = _ObjBranch.apply(model, tdist, rays, viewdirs, pose, len(params), *params)
+    mask = mask.bool()
+    res['density'] = torch.where(mask, d_o, res['density'])
+    if res.get('rgb') is not None:
+        res['rgb'] = torch.where(mask[..., None], rgb_o, res['rgb'])
+    if res.get('semantic') is not None:
+        res['semantic'] = torch.where(mask[..., None], sem_o, res['semantic'])
+    return mask
+
+
 @torch.no_grad()
 def obj_apply(model, res: Dict[str, torch.Tensor], tdist: torch.Tensor, rays: RayBundle, viewdirs: torch.Tensor,
               pose: torch.Tensor, is_prop: bool) -> torch.Tensor:
@@ -655,16 +781,4 @@ def obj_apply(model, res: Dict[str, torch.Tensor], tdist: torch.Tensor, rays: Ra
     density = res['density']
     rgb = res['rgb'] if (not is_prop and res.get('rgb') is not None) else None
     sem = res['semantic'] if (not is_prop and res.get('semantic') is not None) else None
-    mask = torch.zeros(N, S, device=rays.device, dtype=torch.uint8)
-    n_obj = pose.shape[1]
-    lib = load()
-    with torch.cuda.device(rays.device):
-        for track_id in range(n_obj):
-            mlp, latent = model._obj_network(track_id)
-            desc, keep = _obj_mlp_desc(mlp, latent)
-            tab = _table_desc(mlp.encoder, mlp.encoder.embeddings.detach())
-            with timed('obj_forward'):
-                check(lib.nlb_obj_forward(ptr(tdist), ptr(rays.origins), ptr(rays.directions), ptr(viewdirs), ptr(pose),
-                                          n_obj, track_id, N, S, C.byref(tab), C.byref(desc), ptr(density), ptr(rgb),
-                                          ptr(sem), ptr(mask), stream()))
-    return mask.bool()
+    return _obj_forward_all(model, tdist, rays, viewdirs, pose, density, rgb, sem, None).bool()

@@ -199,6 +199,12 @@ class Trainer:
                                              sample_m=c.sample_m_train, step=step, max_step=c.max_steps,
                                              rand_inputs=rand_inputs)
         losses = compute_losses(batch, renderings, ray_history, c, step, num_patch)
+        latents = getattr(self.model, 'latent_vector_dict', None)
+        if getattr(c, 'latent_size', 0) > 0 and latents is not None:
+            # Z/train.py:394-399 with train_utils.latentReg (Z/internal/train_utils.py:456-457): the reference
+            # rebuilds the sum with torch.tensor([...]), which drops the graph -- a reported value, no gradient
+            with torch.no_grad():
+                losses['latent_reg'] = sum(c.latent_reg * torch.norm(v) for v in latents.values())
         main = sum(v for k, v in losses.items() if k not in self.PROP_LOSSES)
         prop = [v for k, v in losses.items() if k in self.PROP_LOSSES]
         prop = sum(prop) if prop else None

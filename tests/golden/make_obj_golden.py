@@ -64,6 +64,59 @@ def apply_obj_bindings(models):
     O.split_latent = True
 
 
+def loss_coefficients(N, S):
+    g = torch.Generator().manual_seed(7)
+    return torch.randn(N, S, generator=g), torch.randn(N, S, 3, generator=g)
+
+
+def branch_gradients(models, model, batch, tdist):
+    """Gradients of the final-level object branch: the per-track loop of Z/internal/models.py:401-472 executed with
+    the reference's own obj_utils.box_pts and ObjMLP modules on the golden sample distances, a fixed linear
+    functional of the merged density / rgb as the loss.  Dense parameters are stored whole, the two 70 MB table
+    gradients as their non-zero rows."""
+    ou = models.obj_utils
+    obj_pose = ou.get_pose(batch['timestamp'], model.tracks)
+    t_mids = 0.5 * (tdist[..., :-1] + tdist[..., 1:])
+    pts_w = t_mids[..., None] * batch['directions'][:, None, :] + batch['origins'][:, None, :]
+    pts_o, viewdirs_o, imap = ou.box_pts(pts=pts_w, viewdirs=batch['viewdirs'], obj_pose=obj_pose, sym=False)
+    N, S = t_mids.shape
+    dens, rgbm = torch.zeros(N, S), torch.zeros(N, S, 3)
+    model.zero_grad()
+    for track_id in range(len(model.bboxes[0].keys())):
+        idx = imap[:, :, track_id]
+        if idx.sum() == 0:
+            continue
+        pts_k = pts_o[idx][:, track_id, :]
+        stds = torch.zeros_like(pts_k)[..., 0]
+        vd_k = viewdirs_o[idx][:, track_id, :]
+        class_id = ou.query_class(model.obj_type_info[track_id])
+        obj_mlp = model.get_submodule(f'obj_mlp_{class_id}')
+        latent = model.latent_vector_dict[f'obj_latent_{track_id}'][None, ...].repeat(pts_k.shape[0], 1)
+        r = obj_mlp(False, pts_k, stds, viewdirs=vd_k, latent=latent, glo_vec=None, exposure=None)
+        for key, cur in (('density', dens), ('rgb', rgbm)):
+            tmp = torch.zeros_like(cur)
+            tmp[idx] = r[key]
+            m = idx if idx.shape == cur.shape else idx[..., None].expand(cur.shape)
+            if key == 'density':
+                dens = torch.where(m, tmp, cur)
+            else:
+                rgbm = torch.where(m, tmp, cur)
+    a, b = loss_coefficients(N, S)
+    ((dens * a).sum() + (rgbm * b).sum()).backward()
+    out = {}
+    for name, p in model.named_parameters():
+        if not (name.startswith('obj_mlp') or name.startswith('latent_vector_dict')) or p.grad is None:
+            continue
+        if name.endswith('encoder.embeddings'):
+            rows = torch.nonzero(p.grad.abs().sum(-1) > 0).reshape(-1)
+            out['grad_rows::' + name] = rows.numpy().astype(np.int64)
+            out['grad_vals::' + name] = p.grad[rows].numpy()
+        else:
+            out['grad::' + name] = p.grad.numpy().copy()
+    model.zero_grad()
+    return out
+
+
 def run_reference():
     models = ref_shims.import_reference()
     ref_shims.apply_gin_bindings(models)
@@ -100,6 +153,7 @@ def run_reference():
             if k in r:
                 out[f'rend{i}_{k}'] = r[k].numpy().astype(np.float32)
     out['pose'] = models.obj_utils.get_pose(batch['timestamp'], model.tracks).numpy().astype(np.float32)
+    out.update(branch_gradients(models, model, batch, hist[2]['tdist']))
     for k, v in osd.items():
         if not k.endswith('encoder.embeddings'):       # the tables are regenerated from the seed (30 MB each)
             out['sd::' + k] = v.numpy()
