@@ -135,23 +135,22 @@ class MLP(nn.Module):
                 'lin_second_stage_0.weight': (256, 283), 'lin_second_stage_1.weight': (256, 539),
                 'rgb_layer.weight': (3, 256)}
         have = {k: tuple(v.shape) for k, v in self.named_parameters()}
-        if not self.use_intensity and not torch.is_grad_enabled():
-            # rendering without the intensity head (the configuration of the dynamic-object branch): its rows
-            # of the fused sem | intensity layers are packed as zeros
+        if not self.use_intensity:
+            # no intensity head (the configuration of the dynamic-object branch): its rows of the fused
+            # sem | intensity layers are packed as zeros and, in training, stay a frozen all-zero head
             want = {k: v for k, v in want.items() if not k.startswith('intensity_layer')}
         bad = [f'{k}: {have.get(k)} (built for {v})' for k, v in want.items() if have.get(k) != v]
         scalars = dict(deg_view=4, net_depth_viewdirs=2, skip_layer_dir=0, density_bias=-1., rgb_premultiplier=1.,
                        rgb_bias=0., rgb_padding=0.001, class_num=19)
         bad += [f'{k}={getattr(self, k)!r} (built for {v!r})' for k, v in scalars.items() if getattr(self, k) != v]
-        if not self.use_semantic or self.no_sem_layer or (not self.use_intensity and torch.is_grad_enabled()):
-            bad.append('the semantic head (sem_layer) is required, and for training the intensity head '
-                       '(Config.use_semantic, Config.no_sem_layer=False, Config.use_intensity)')
+        if not self.use_semantic or self.no_sem_layer:
+            bad.append('the semantic head (sem_layer) is required (Config.use_semantic, Config.no_sem_layer=False)')
         if self.mlp_dtype != torch.bfloat16:
             bad.append(f'mlp_dtype={self.mlp_dtype} (the dense layers run with bf16 operands, fp32 accumulation)')
         if bad:
             raise NotImplementedError('NerfMLP: the fused tensor-core kernels are built for the nuscenes_single.gin '
                                       'architecture only; unsupported: ' + '; '.join(bad))
-        self._nlb_shapes_ok = self.use_intensity   # (without the head the check depends on the grad mode)
+        self._nlb_shapes_ok = True
 
     def heads(self, feat: torch.Tensor, viewdirs: torch.Tensor, S: int) -> Dict[str, torch.Tensor]:
         """features[N*S, 40] -> density / rgb / semantic / intensity
