@@ -326,6 +326,12 @@ class Model(nn.Module):
         anneal = (self.anneal_slope * train_frac) / ((self.anneal_slope - 1) * train_frac + 1) \
             if self.anneal_slope > 0 else 1.
         bg = float(self.bg_intensity_range[0])
+        draws = None
+        if rand and rand_inputs is None:
+            # all uniform draws of the pass from ONE generator launch (per level: jitter [N,1] | rotation noise [N,S,7])
+            counts = [N * (1 + 7 * (self.num_prop_samples[i] if i < self.num_levels - 1 else self.num_nerf_samples))
+                      for i in range(self.num_levels)]
+            draws = torch.rand(sum(counts), device=dev).split(counts)
         obj_pose = None
         if self.instance_obj:
             track = curr_track if curr_track is not None else self.tracks
@@ -342,8 +348,7 @@ class Model(nn.Module):
                 if rand_inputs is not None:
                     jitter, deg = rand_inputs[i_level]['jitter'], ops.f32(rand_inputs[i_level]['deg'])
                 else:
-                    jitter = torch.rand(N, 1, device=dev)
-                    deg = torch.rand(N, S, 7, device=dev)
+                    jitter, deg = draws[i_level][:N].view(N, 1), draws[i_level][N:].view(N, S, 7)
             sdist, tdist = ops.resample_level(sdist, weights, near, far, S, use_dilation, dilation, anneal, jitter,
                                               bool(rand), self.power_lambda, self.resample_padding)
             if is_prop:
@@ -371,7 +376,10 @@ class Model(nn.Module):
             if inten is not None:
                 rendering['intensity'] = comp['intensity']
             if res['rgb'] is None:
-                res['rgb'] = torch.zeros(1, device=dev).expand(N, S, 3)
+                zero = self.__dict__.get('_nlb_zero')
+                if zero is None or zero.device != dev:
+                    zero = self.__dict__['_nlb_zero'] = torch.zeros(1, device=dev)
+                res['rgb'] = zero.expand(N, S, 3)
             if compute_extras:
                 rendering['acc'] = comp['acc']
                 rendering['distance_mean'] = comp['distance_mean']

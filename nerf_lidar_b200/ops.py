@@ -164,6 +164,7 @@ class _PropLevel(Function):
                                               ptr(b1c), ptr(density), ptr(feats), stream()))
         ctx.save_for_backward(tdist, deg_noise, embeddings, W0c, b0c, W1c, b1c, feats, pts)
         ctx.rays, ctx.encoder, ctx.std_scale, ctx.emb_param = rays, encoder, std_scale, emb_param
+        ctx.wparams = (W0, b0, W1, b1)     # the Parameter objects (saved tensors lose their attributes)
         return density
 
     @staticmethod
@@ -171,8 +172,15 @@ class _PropLevel(Function):
         tdist, deg_noise, embeddings, W0, b0, W1, b1, feats, pts = ctx.saved_tensors
         rays, encoder = ctx.rays, ctx.encoder
         g_emb, in_place = _grad_buffer(ctx.emb_param if ctx.emb_param is not None else embeddings)
-        gW0, gb0 = torch.zeros_like(W0), torch.zeros_like(b0)
-        gW1, gb1 = torch.zeros_like(W1), torch.zeros_like(b1)
+        # the trainer's persistent gradient buffers (views of its flat gradient) are added into directly: no zero
+        # fills, no AccumulateGrad adds; without a trainer the gradients are returned through autograd
+        bufs = [getattr(prm, '_nlb_grad', None) for prm in ctx.wparams]
+        w_in_place = all(b is not None and b.is_contiguous() for b in bufs)
+        if w_in_place:
+            gW0, gb0, gW1, gb1 = bufs
+        else:
+            gW0, gb0 = torch.zeros_like(W0), torch.zeros_like(b0)
+            gW1, gb1 = torch.zeros_like(W1), torch.zeros_like(b1)
         g_density = f32(g_density)
         tab = _table_desc(encoder, embeddings)
         ws_bytes = load().nlb_prop_backward_workspace_bytes(rays.N, tdist.shape[1] - 1, C.byref(tab))
@@ -183,6 +191,8 @@ class _PropLevel(Function):
                                                C.byref(tab), ptr(W0), ptr(b0), ptr(W1),
                                                ptr(b1), ptr(feats), ptr(g_density), ptr(g_emb), ptr(gW0), ptr(gb0),
                                                ptr(gW1), ptr(gb1), ptr(ws), stream()))
+        if w_in_place:
+            return (None, None, None if in_place else g_emb, None, None, None, None, None, None, None, None)
         return (None, None, None if in_place else g_emb, gW0, gb0, gW1.reshape(1, -1), gb1, None, None, None, None)
 
 
@@ -583,11 +593,15 @@ class _RenderLosses(Function):
         ctx.save_for_backward(scales, g_rgb, g_depth, g_sem, g_int, g_dsmo, g_ssmo)
         ctx.int_shape = None if intensity is None else intensity.shape
         ctx.depth_shape = depth.shape
-        return losses
+        # six 0-dim outputs: indexing ONE output tensor costs a select node each -- a zero fill and a copy per
+        # term in the backward pass
+        return tuple(losses.unbind(0))
 
     @staticmethod
-    def backward(ctx, go):
+    def backward(ctx, *gos):
         scales, g_rgb, g_depth, g_sem, g_int, g_dsmo, g_ssmo = ctx.saved_tensors
+        zero = scales.new_zeros(()) if any(g is None for g in gos) else None
+        go = torch.stack([g if g is not None else zero for g in gos])
         w = go * scales
         o_rgb = g_rgb * w[0]
         o_depth = g_depth * w[1]

@@ -289,11 +289,14 @@ class Trainer:
         scale = 1.0 / self.world
         lib = _lib.load()
         st = _lib.stream()
+        if len(tables) == len(self.tables):
+            self._sumsq_all.zero_()          # (views of one buffer: a single fill)
         for t in tables:
             enc, ar = t['enc'], t['arena']
             decay = 0. if (c.obj_nodecay and 'obj' in t['name']) else self.decay
             t['decay'] = decay
-            t['sumsq'].zero_()
+            if len(tables) != len(self.tables):
+                t['sumsq'].zero_()
             if self.world > 1:
                 # the chunks of the other ranks hold their own partial sums: clear them for the next step's scatter
                 g = ar['grad']
