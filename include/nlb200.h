@@ -128,6 +128,22 @@ int nlb_encode_backward(const nlb_rays_t* rays, const nlb_table_t* table, const 
                         void* stream);
 size_t nlb_encode_backward_workspace_bytes(const nlb_table_t* table);
 
+/* Gradients w.r.t. the ray geometry, needed only while poses are refined (Z/train.py:200-221: origins,
+ * directions, base_x, base_y become functions of LearnPose).  Replaces, for the fused path, the reference's
+ * dy_dx output + kernel_input_backward (gridencoder.cu:201-244,343-369) and the autograd chain through the erf
+ * weights (models.py:974-977), contract_mean_std (coord.py:51-63) and cast_rays (render.py:129-168):
+ * grad_features[N*S, L*C] -> four [N,3] buffers, ACCUMULATED (pre-zero them; the three levels add into one set).
+ * tdist carries no gradient (models.py:368-369).  The sample points are regenerated from the rays
+ * (points_cache is not read). */
+typedef struct {
+  float* origins;    /* [N,3] */
+  float* directions; /* [N,3] */
+  float* base_x;     /* [N,3] */
+  float* base_y;     /* [N,3] */
+} nlb_ray_grads_t;
+int nlb_encode_input_backward(const nlb_rays_t* rays, const nlb_table_t* table, const float* grad_features,
+                              const nlb_ray_grads_t* grads, void* stream);
+
 /* Proposal level: the above + PropMLP Linear(L,64)-ReLU-Linear(64,1), softplus(x-1)
  * (models.py:887-889,996-997,1116) in one kernel.  W0[64,L] b0[64] W1[64] b1[1]
  * in nn.Linear layout.  density[N,S]. */
@@ -141,6 +157,10 @@ int nlb_prop_backward(const nlb_rays_t* rays, const nlb_table_t* table, const fl
                       float* grad_embeddings, float* gW0, float* gb0, float* gW1, float* gb1,
                       float* workspace /*nlb_prop_backward_workspace_bytes()*/, void* stream);
 size_t nlb_prop_backward_workspace_bytes(int N, int S, const nlb_table_t* table);
+/* Proposal level of the above: reads the feature gradients nlb_prop_backward left in `workspace` (call it right
+ * after, same rays / table / stream) and accumulates the ray-geometry gradients. */
+int nlb_prop_input_backward(const nlb_rays_t* rays, const nlb_table_t* table, const float* workspace,
+                            const nlb_ray_grads_t* grads, void* stream);
 
 /* ------------------------------------------------------------------ compositing
  * render.compute_alpha_weights (Z/internal/render.py:170-189) +

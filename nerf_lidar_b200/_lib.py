@@ -70,6 +70,10 @@ class NlbNerfMlpGradOut(C.Structure):
                [(n, C.c_int) for n in ('ld_v1', 'ld_v0', 'ld_g')]
 
 
+class NlbRayGrads(C.Structure):
+    _fields_ = [(n, c_f) for n in ('origins', 'directions', 'base_x', 'base_y')]
+
+
 class NlbRayOut(C.Structure):
     _fields_ = [(n, c_f) for n in ('origins', 'directions', 'viewdirs', 'radii', 'imageplane', 'base_x', 'base_y')]
 
@@ -121,6 +125,8 @@ SIGNATURES = {
     'nlb_prop_forward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p, _p, _p, _p, _p, _p]),
     'nlb_prop_backward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'nlb_prop_backward_workspace_bytes': (C.c_size_t, [_i, _i, C.POINTER(NlbTable)]),
+    'nlb_encode_input_backward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, C.POINTER(NlbRayGrads), _p]),
+    'nlb_prop_input_backward': (_i, [C.POINTER(NlbRays), C.POINTER(NlbTable), _p, C.POINTER(NlbRayGrads), _p]),
     'nlb_composite_forward': (_i, [C.POINTER(NlbCompositeIn), C.POINTER(NlbCompositeOut), _p]),
     'nlb_composite_backward': (_i, [C.POINTER(NlbCompositeIn), _p, C.POINTER(NlbCompositeGrad), _p, _p, _p, _p, _p]),
     'nlb_nerf_mlp_packed_bytes': (C.c_size_t, []),

@@ -62,8 +62,13 @@ class Config:
     sample_n_test: int = 7
     sample_m_test: int = 3
     pose_refine: bool = True
+    t_ratio: float = 0.25
+    pn_lr_init: float = 4e-5
+    pn_lr_final: float = 2e-6
     start_step: int = 10000
     end_step: int = 20000
+    learn_R: bool = True
+    learn_t: bool = True
     analytic_gradient: bool = True
     use_intensity: bool = False
     no_sem_layer: bool = True

@@ -204,9 +204,17 @@ struct SamplePoint {
   float std;      // contracted std / 2
 };
 
+// Intermediates of one sample for the gradient w.r.t. the ray geometry (k_encode_input_bwd): the
+// pre-contraction mean m = lx*base_x + ly*base_y + t*d + o, |m|^2, the contraction factor k (1 inside the
+// unit ball) and the uncontracted std.
+struct SampleGeom {
+  float t, lx, ly;
+  float mx, my, mz, m2, k, sd;
+};
+
 // j in [0,7): t = t0 + (t1-t0)*(j+.5)/7 ; deg = 2*pi*3*j/7 (+ 2*pi*noise).
 __device__ __forceinline__ SamplePoint sample_point(const RayGeom& r, float t0, float t1, int j, float noise,
-                                                    bool has_noise, float std_scale) {
+                                                    bool has_noise, float std_scale, SampleGeom* geo = nullptr) {
   const float n = 7.0f;
   float t = __fadd_rn(t0, __fdiv_rn(__fmul_rn(__fsub_rn(t1, t0), (float)j + 0.5f), n));
   // 2*pi*m is folded in double then rounded (python float -> float32 scalar)
@@ -224,9 +232,15 @@ __device__ __forceinline__ SamplePoint sample_point(const RayGeom& r, float t0, 
   float sd = __fmul_rn(__fmul_rn(std_scale, r.radius), t);
   // contract
   float m2 = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(mx, mx), __fmul_rn(my, my)), __fmul_rn(mz, mz)), kEps);
+  if (geo) {
+    geo->t = t; geo->lx = lx; geo->ly = ly;
+    geo->mx = mx; geo->my = my; geo->mz = mz;
+    geo->m2 = m2; geo->k = 1.0f; geo->sd = sd;
+  }
   if (!(m2 <= 1.0f)) {
     float m = sqrtf(m2);
     float k = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, m), 1.0f), m2);
+    if (geo) geo->k = k;
     mx *= k;
     my *= k;
     mz *= k;

@@ -399,6 +399,130 @@ __global__ void __launch_bounds__(256) k_priv_reduce(const float* __restrict__ p
   if (a != 0.f) grad_table[i] += a;
 }
 
+// ----------------------------------------------------------------------------- gradients w.r.t. the ray geometry
+// Pose-refinement window (Z/train.py:200-221): origins / directions / base_x / base_y carry gradients, which the
+// reference obtains through dy_dx + kernel_input_backward (gridencoder.cu:201-244,343-369), the erf weights, the
+// contraction (coord.py:51-63 under autograd) and cast_rays (render.py:129-168).  One thread per interval recomputes
+// its 7 samples; per sample and level it gathers the 8 corner rows once and forms both d feature / d x (the
+// trilinear derivative, dy_dx of the reference) and the feature itself (the erf weight depends on the contracted
+// std, which depends on |m|); the chain through the contraction Jacobian and the linear cast_rays map follows in
+// registers, then one warp reduction and 12 atomic adds per ray.  tdist carries no gradient (models.py:368-369).
+template <int C>
+__global__ void __launch_bounds__(kEncThreads) k_encode_input_bwd(nlb_rays_t rays, nlb_table_t tab,
+                                                                  const float* __restrict__ grad_features,
+                                                                  float* __restrict__ g_origins,
+                                                                  float* __restrict__ g_directions,
+                                                                  float* __restrict__ g_base_x,
+                                                                  float* __restrict__ g_base_y) {
+  __shared__ LevelCache lc;
+  fill_level_cache(lc, tab);
+  __syncthreads();
+  const int rows = rays.N * rays.S;
+  const int row_raw = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = row_raw < rows;
+  const int row = active ? row_raw : rows - 1;
+  const int ray = row / rays.S, s = row - ray * rays.S;
+  float acc[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+  if (active) {
+    const RayGeom rg = load_ray(rays.origins, rays.directions, rays.base_x, rays.base_y, rays.radii, ray);
+    const float t0 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s);
+    const float t1 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s + 1);
+    const bool has_noise = rays.deg_noise != nullptr;
+    const float* __restrict__ G = grad_features + (size_t)row * (tab.L * C);
+#pragma unroll 1
+    for (int j = 0; j < 7; ++j) {
+      const float noise = has_noise ? __ldg(rays.deg_noise + (size_t)row * 7 + j) : 0.f;
+      SampleGeom geo;
+      const SamplePoint p = sample_point(rg, t0, t1, j, noise, has_noise, rays.std_scale, &geo);
+      if (!in_unit_cube(p.x, p.y, p.z)) continue;  // zero features, zero gradient (gridencoder.cu:110-135)
+      const float a = staged_a(p.std);
+      float gx = 0.f, gy = 0.f, gz = 0.f, gsd = 0.f;  // dL/d(x01), dL/d(std/2)
+#pragma unroll 1
+      for (int level = 0; level < tab.L; ++level) {
+        const Level3 lv = lc.lv[level];
+        const float u = a * lc.inv_gs[level];
+        const float w = erff(u);
+        // d erf(u)/d std with u = 1/(sqrt(8) std gs): -(2/sqrt(pi)) exp(-u^2) u / std; saturated weights are flat
+        const float dw = (u < 12.f) ? -1.1283791671f * __expf(-u * u) * u / p.std : 0.f;
+        uint32_t cx, cy, cz;
+        float fx, fy, fz;
+        cell_of(p.x, lv.scale, cx, fx);
+        cell_of(p.y, lv.scale, cy, fy);
+        cell_of(p.z, lv.scale, cz, fz);
+        float rowsv[8][C];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t vx = cx + (i & 1), vy = cy + ((i >> 1) & 1), vz = cz + ((i >> 2) & 1);
+          const uint32_t idx = (C == 1) ? vertex_index3(lv, vx, vy, vz) : vertex_index3_branchy(lv, vx, vy, vz);
+          gather_row<C>(tab.embeddings + ((size_t)lv.offset + idx) * C, rowsv[i]);
+        }
+        float gf = 0.f, dfx = 0.f, dfy = 0.f, dfz = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float g = __ldg(G + level * C + c);
+          // bilinear in (y,z) of the x-pairs, then the x interpolation and its derivative
+          const float x00 = rowsv[1][c] - rowsv[0][c], x10 = rowsv[3][c] - rowsv[2][c];
+          const float x01 = rowsv[5][c] - rowsv[4][c], x11 = rowsv[7][c] - rowsv[6][c];
+          const float v00 = fmaf(fx, x00, rowsv[0][c]), v10 = fmaf(fx, x10, rowsv[2][c]);
+          const float v01 = fmaf(fx, x01, rowsv[4][c]), v11 = fmaf(fx, x11, rowsv[6][c]);
+          const float y0 = v10 - v00, y1 = v11 - v01;
+          const float e0 = fmaf(fy, y0, v00), e1 = fmaf(fy, y1, v01);
+          const float f = fmaf(fz, e1 - e0, e0);
+          const float dx0 = fmaf(fy, x10 - x00, x00), dx1 = fmaf(fy, x11 - x01, x01);
+          gf = fmaf(g, f, gf);
+          dfx = fmaf(g, fmaf(fz, dx1 - dx0, dx0), dfx);
+          dfy = fmaf(g, fmaf(fz, y1 - y0, y0), dfy);
+          dfz = fmaf(g, e1 - e0, dfz);
+        }
+        const float ws = w * lv.scale;  // pos = x * scale + 0.5
+        gx = fmaf(ws, dfx, gx);
+        gy = fmaf(ws, dfy, gy);
+        gz = fmaf(ws, dfz, gz);
+        gsd = fmaf(gf, dw, gsd);
+      }
+      // mean over the 7 samples; x01 = z/4 + 1/2, std/2
+      const float inv7 = 1.0f / 7.0f;
+      float zx = gx * (0.25f * inv7), zy = gy * (0.25f * inv7), zz = gz * (0.25f * inv7);
+      const float gsdc = gsd * (0.5f * inv7);
+      if (!(geo.m2 <= 1.0f)) {
+        // z = k(q) m with q = |m|^2, k = 2 q^-1/2 - q^-1; std' = std (k^2/q)^(1/3)
+        const float q = geo.m2, k = geo.k;
+        const float rq = 1.0f / q;
+        const float dk = rq * rq - rq * rsqrtf(q);
+        const float det = k * k * rq;
+        const float ddet = (2.0f * k * dk - det) * rq;
+        const float cb = cbrtf(det);
+        const float dsd = geo.sd * ddet / (3.0f * cb * cb);
+        const float dot = zx * geo.mx + zy * geo.my + zz * geo.mz;
+        const float coef = 2.0f * fmaf(dot, dk, gsdc * dsd);
+        zx = fmaf(coef, geo.mx, k * zx);
+        zy = fmaf(coef, geo.my, k * zy);
+        zz = fmaf(coef, geo.mz, k * zz);
+      }
+      acc[0] += zx; acc[1] += zy; acc[2] += zz;
+      acc[3] = fmaf(geo.t, zx, acc[3]); acc[4] = fmaf(geo.t, zy, acc[4]); acc[5] = fmaf(geo.t, zz, acc[5]);
+      acc[6] = fmaf(geo.lx, zx, acc[6]); acc[7] = fmaf(geo.lx, zy, acc[7]); acc[8] = fmaf(geo.lx, zz, acc[8]);
+      acc[9] = fmaf(geo.ly, zx, acc[9]); acc[10] = fmaf(geo.ly, zy, acc[10]); acc[11] = fmaf(geo.ly, zz, acc[11]);
+    }
+  }
+  // a warp's 32 intervals belong to one ray when S % 32 == 0: one reduction, 12 atomics
+  const int ray0 = __shfl_sync(NLB_FULL_MASK, ray, 0);
+  const bool uniform = __all_sync(NLB_FULL_MASK, ray == ray0);
+  if (uniform) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc[i] = warp_sum(acc[i]);
+    if ((threadIdx.x & 31) != 0) return;
+  } else if (!active) {
+    return;
+  }
+  float* dst[4] = {g_origins, g_directions, g_base_x, g_base_y};
+#pragma unroll
+  for (int i = 0; i < 12; ++i)
+    if (acc[i] != 0.f) atomicAdd(dst[i / 3] + 3 * (size_t)ray + (i % 3), acc[i]);
+}
+
 // Parity probe: the grid-space sample points (x,y,z in [0,1], contracted std/2) the
 // fused kernels generate, [N,S,7,4].
 __global__ void __launch_bounds__(128) k_sample_points(nlb_rays_t rays, float* __restrict__ points) {
@@ -1035,6 +1159,39 @@ extern "C" int nlb_encode_forward(const nlb_rays_t* rays, const nlb_table_t* tab
   }
 }
 
+static int check_ray_grads(const nlb_ray_grads_t* g, const char* who) {
+  if (!g || !g->origins || !g->directions || !g->base_x || !g->base_y) {
+    nlb_set_error("%s: the four [N,3] gradient buffers (pre-zeroed or holding earlier levels' sums) are required", who);
+    return NLB_EINVAL;
+  }
+  return NLB_OK;
+}
+
+template <int C>
+static int input_bwd_launch(const nlb_rays_t& rays, const nlb_table_t& tab, const float* gfeat,
+                            const nlb_ray_grads_t& g, cudaStream_t st, const char* who) {
+  const int rows = rays.N * rays.S;
+  k_encode_input_bwd<C><<<div_up(rows, kEncThreads), kEncThreads, 0, st>>>(rays, tab, gfeat, g.origins, g.directions,
+                                                                          g.base_x, g.base_y);
+  return nlb_check_launch(who);
+}
+
+extern "C" int nlb_encode_input_backward(const nlb_rays_t* rays, const nlb_table_t* table, const float* grad_features,
+                                         const nlb_ray_grads_t* grads, void* stream) {
+  if (int e = check_rays_table(rays, table, "encode_input_backward")) return e;
+  if (rays->N == 0) return NLB_OK;
+  if (!grad_features) { nlb_set_error("encode_input_backward: null grad_features"); return NLB_EINVAL; }
+  if (int e = check_ray_grads(grads, "encode_input_backward")) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (table->C) {
+    case 1: return input_bwd_launch<1>(*rays, *table, grad_features, *grads, st, "encode_input_backward");
+    case 2: return input_bwd_launch<2>(*rays, *table, grad_features, *grads, st, "encode_input_backward");
+    case 4: return input_bwd_launch<4>(*rays, *table, grad_features, *grads, st, "encode_input_backward");
+    case 8: return input_bwd_launch<8>(*rays, *table, grad_features, *grads, st, "encode_input_backward");
+    default: nlb_set_error("GridEncoding: C must be 1, 2, 4, or 8."); return NLB_EINVAL;
+  }
+}
+
 // Persistent launch shape of k_encode_bwd: the coarse levels that fit the shared-memory
 // budget are staged per block (see the kernel comment); the grid is the number of blocks
 // the device can keep resident (a multiple of the SM count), capped by the tile count.
@@ -1243,4 +1400,17 @@ extern "C" int nlb_prop_backward(const nlb_rays_t* rays, const nlb_table_t* tabl
   k_prop_wgrad_reduce<<<dim3(div_up(entries, 256), 64), 256, 0, st>>>(partial, 2 * blocks, entries, table->L, gW0, gb0, gW1, gb1);
   if (int e = nlb_check_launch("prop_wgrad_reduce")) return e;
   return scatter_launch<1>(*rays, *table, hl, gfeat, grad_embeddings, priv, st);
+}
+
+// The feature gradients nlb_prop_backward left in its workspace (same N, S, table) -> ray-geometry gradients.
+extern "C" int nlb_prop_input_backward(const nlb_rays_t* rays, const nlb_table_t* table, const float* workspace,
+                                       const nlb_ray_grads_t* grads, void* stream) {
+  if (int e = check_rays_table(rays, table, "prop_input_backward")) return e;
+  if (rays->N == 0) return NLB_OK;
+  if (table->C != 1) { nlb_set_error("prop_input_backward: PropMLP tables have level_dim 1"); return NLB_EINVAL; }
+  if (!workspace) { nlb_set_error("prop_input_backward: the workspace nlb_prop_backward filled is required"); return NLB_EINVAL; }
+  if (int e = check_ray_grads(grads, "prop_input_backward")) return e;
+  const int rows = rays->N * rays->S;
+  const float* gfeat = workspace + prop_ws_partial_floats(rows, table->L);
+  return input_bwd_launch<1>(*rays, *table, gfeat, *grads, (cudaStream_t)stream, "prop_input_backward");
 }

@@ -19,7 +19,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import timed, NlbObjGrads, NlbObjMlp, NlbLossesIn, NlbNerfMlpWeights, NlbNerfMlpSaved, NlbNerfMlpGradIn, NlbNerfMlpGradOut, NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
+from ._lib import timed, NlbRayGrads, NlbObjGrads, NlbObjMlp, NlbLossesIn, NlbNerfMlpWeights, NlbNerfMlpSaved, NlbNerfMlpGradIn, NlbNerfMlpGradOut, NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
 
 EPS = float(torch.finfo(torch.float32).eps)
 _u_cache: Dict[Tuple, torch.Tensor] = {}
@@ -148,9 +148,20 @@ def _grad_buffer(param: torch.Tensor) -> Tuple[torch.Tensor, bool]:
     return torch.zeros_like(param), False
 
 
+def _ray_grad_buffers(rays: RayBundle):
+    """Zeroed [4,N,3] accumulation target + its descriptor: gradients w.r.t. origins / directions / base_x /
+    base_y of one level (pose-refinement window, Z/train.py:200-221)."""
+    g = torch.zeros(4, rays.N, 3, device=rays.device, dtype=torch.float32)
+    return g, NlbRayGrads(ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(g[3]))
+
+
 class _PropLevel(Function):
     @staticmethod
-    def forward(ctx, tdist, deg_noise, embeddings, W0, b0, W1, b1, rays: RayBundle, encoder, std_scale, emb_param):
+    def forward(ctx, tdist, deg_noise, embeddings, W0, b0, W1, b1, rays: RayBundle, encoder, std_scale, emb_param,
+                origins, directions, base_x, base_y):
+        # the last four are rays.origins ... rays.base_y again, as differentiable inputs: they need gradients only
+        # while poses are refined
+        ctx.ray_grad = any(ctx.needs_input_grad[11:15])
         N, S = rays.N, tdist.shape[1] - 1
         density = torch.empty(N, S, device=rays.device, dtype=torch.float32)
         need_grad = any(ctx.needs_input_grad)
@@ -191,9 +202,17 @@ class _PropLevel(Function):
                                                C.byref(tab), ptr(W0), ptr(b0), ptr(W1),
                                                ptr(b1), ptr(feats), ptr(g_density), ptr(g_emb), ptr(gW0), ptr(gb0),
                                                ptr(gW1), ptr(gb1), ptr(ws), stream()))
+            g_rays = (None,) * 4
+            if ctx.ray_grad:
+                g, desc = _ray_grad_buffers(rays)
+                with timed(f'prop{encoder.num_levels}_input_bwd'):
+                    check(load().nlb_prop_input_backward(C.byref(rays.desc(tdist, deg_noise, ctx.std_scale)),
+                                                         C.byref(tab), ptr(ws), C.byref(desc), stream()))
+                g_rays = tuple(g.unbind(0))
         if w_in_place:
-            return (None, None, None if in_place else g_emb, None, None, None, None, None, None, None, None)
-        return (None, None, None if in_place else g_emb, gW0, gb0, gW1.reshape(1, -1), gb1, None, None, None, None)
+            return (None, None, None if in_place else g_emb, None, None, None, None, None, None, None, None, *g_rays)
+        return (None, None, None if in_place else g_emb, gW0, gb0, gW1.reshape(1, -1), gb1, None, None, None, None,
+                *g_rays)
 
 
 def prop_level(tdist, deg_noise, mlp, rays: RayBundle, std_scale: float) -> torch.Tensor:
@@ -201,12 +220,14 @@ def prop_level(tdist, deg_noise, mlp, rays: RayBundle, std_scale: float) -> torc
     enc = mlp.encoder
     l0, l2 = mlp.density_layer[0], mlp.density_layer[2]
     return _PropLevel.apply(tdist, deg_noise, enc.embeddings, l0.weight, l0.bias, l2.weight, l2.bias, rays, enc,
-                            std_scale, enc.embeddings)
+                            std_scale, enc.embeddings, rays.origins, rays.directions, rays.base_x, rays.base_y)
 
 
 class _NerfEncode(Function):
     @staticmethod
-    def forward(ctx, tdist, deg_noise, embeddings, rays: RayBundle, encoder, std_scale, emb_param):
+    def forward(ctx, tdist, deg_noise, embeddings, rays: RayBundle, encoder, std_scale, emb_param,
+                origins, directions, base_x, base_y):
+        ctx.ray_grad = any(ctx.needs_input_grad[7:11])
         N, S = rays.N, tdist.shape[1] - 1
         feats = torch.empty(N * S, encoder.output_dim, device=rays.device, dtype=torch.float32)
         pts = rays.new_points_cache(S) if any(ctx.needs_input_grad) else None
@@ -231,12 +252,20 @@ class _NerfEncode(Function):
             with timed('nerf_encode_bwd'):
                 check(load().nlb_encode_backward(C.byref(rays.desc(tdist, deg_noise, ctx.std_scale, pts, 2)),
                                                  C.byref(tab), ptr(g_feats), ptr(g_emb), ptr(ws), stream()))
-        return (None, None, None if in_place else g_emb, None, None, None, None)
+            g_rays = (None,) * 4
+            if ctx.ray_grad:
+                g, desc = _ray_grad_buffers(rays)
+                with timed('nerf_encode_input_bwd'):
+                    check(load().nlb_encode_input_backward(C.byref(rays.desc(tdist, deg_noise, ctx.std_scale)),
+                                                           C.byref(tab), ptr(g_feats), C.byref(desc), stream()))
+                g_rays = tuple(g.unbind(0))
+        return (None, None, None if in_place else g_emb, None, None, None, None, *g_rays)
 
 
 def nerf_encode(tdist, deg_noise, encoder, rays: RayBundle, std_scale: float) -> torch.Tensor:
     """features[N*S, L*C] of the NeRF level."""
-    return _NerfEncode.apply(tdist, deg_noise, encoder.embeddings, rays, encoder, std_scale, encoder.embeddings)
+    return _NerfEncode.apply(tdist, deg_noise, encoder.embeddings, rays, encoder, std_scale, encoder.embeddings,
+                             rays.origins, rays.directions, rays.base_x, rays.base_y)
 
 
 class _Composite(Function):
@@ -292,7 +321,12 @@ class _Composite(Function):
                                                     ptr(g_sem_s), ptr(g_int_s), stream()))
         if g_int_s is not None and ctx.int_shape is not None:
             g_int_s = g_int_s.reshape(ctx.int_shape)
-        return gd, g_rgb_s, g_sem_s, g_int_s, None, None, None, None, None, None
+        g_dir = None
+        if need[5]:
+            # alpha = 1 - exp(-density * delta * |d|) (render.py:170-189): the norm scales every density of the ray,
+            # so dL/d|d| = sum_s gd_s density_s / |d| and d|d|/dd = d / |d|   (pose-refinement window only)
+            g_dir = directions * ((gd * density).sum(-1) / (directions * directions).sum(-1))[:, None]
+        return gd, g_rgb_s, g_sem_s, g_int_s, None, g_dir, None, None, None, None
 
 
 def composite(density, tdist, directions, far, rgb=None, semantic=None, intensity=None, bg: float = 1.0,
@@ -492,7 +526,18 @@ class _NerfMLP(Function):
             with timed('nerf_mlp_wgrad_finish'):
                 check(load().nlb_nerf_mlp_wgrad_finish(ptr(rs_v0), ptr(rs_v1), ptr(viewdirs), N, ptr(cs_x), ptr(cs_g),
                                                        ptr(cs_h0), ptr(cs_hs1), ptr(cs_rgb), C.byref(wg), stream()))
-        return (g_feat, None, None, None, *[None if (in_place or p is None) else t for p, t in zip(params, targets)])
+        g_view = None
+        if ctx.needs_input_grad[1]:
+            # the encoded view direction enters both view layers (skip_layer_dir = 0, models.py:1010-1041): columns
+            # [256,283) of W_v0 and [512,539) of W_v1; chain through coord.pos_enc with torch on the [N,3] tensor
+            Wv0, Wv1 = f32(mlp.lin_second_stage_0.weight), f32(mlp.lin_second_stage_1.weight)
+            nd = Wv0.shape[1] - mlp.bottleneck_width
+            o1 = Wv1.shape[1] - nd
+            g_enc = rs_v0 @ Wv0[:, mlp.bottleneck_width:] + rs_v1 @ Wv1[:, o1:]
+            with torch.enable_grad():
+                v = viewdirs.detach().requires_grad_(True)
+                (g_view,) = torch.autograd.grad(mlp.dir_enc(v), v, g_enc)
+        return (g_feat, g_view, None, None, *[None if (in_place or p is None) else t for p, t in zip(params, targets)])
 
 
 def nerf_mlp_train(mlp, features: torch.Tensor, viewdirs: torch.Tensor, S: int) -> Dict[str, torch.Tensor]:

@@ -114,6 +114,13 @@ def lidar_rays(rng: np.random.Generator, n: Optional[int] = None, width: int = 1
                 patch_mask=np.zeros(dirs.shape[0]))
 
 
+def sensor_index(batch, num_cams: int = 1):
+    """`glo_idx` of the nuScenes loader (Z/internal/datasets.py:632): the index of the sensor a ray belongs to
+    in LearnPose's table -- here camera 0 for the image rays, the first LiDAR slot for the sweep rays."""
+    lidar = np.asarray(batch['lidar_mask']).reshape(-1) > 0
+    return np.where(lidar, num_cams, 0).astype(np.int32)
+
+
 def _finish(rays: Dict[str, np.ndarray], rng, lidar_mask: np.ndarray, labels: bool):
     n = rays['origins'].shape[0]
     b = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in rays.items()}

@@ -173,6 +173,7 @@ class Trainer:
         # updated rows travels under the next step's proposal levels); Model.forward and every trainer entry
         # point wait for them first
         self._pending = []
+        self.posenet = self.pn_optimizer = self.pn_lr_fn = None
         model.__dict__['_nlb_sync'] = self.sync
         model.train()
         model.training = True
@@ -226,6 +227,55 @@ class Trainer:
     def _prop_tables(self):
         return [t for t in self.tables if 'prop' in t['name']]
 
+    # ------------------------------------------------------------------------- pose refinement (Z/train.py:200-240,464-466)
+    def attach_posenet(self, net, optimizer, lr_fn):
+        """`posenet.create_posenet(...)`'s triple.  Inside the window (start_step < step < end_step) every step
+        refines the batch's rays with gradients, back-propagates into the corrections through the hot path's
+        ray-geometry gradients and steps `optimizer`; afterwards the corrections are applied without gradients."""
+        self.posenet, self.pn_optimizer, self.pn_lr_fn = net, optimizer, lr_fn
+
+    def _pose_mode(self, step: int):
+        if getattr(self, 'posenet', None) is None:
+            return None
+        from . import posenet as pn
+        return pn.pose_window(self.config, step)
+
+    def _set_pose_lr(self, step: int):
+        """Outside any capture: the learning rate is a device scalar the captured Adam reads."""
+        if self._pose_mode(step) != 'train':
+            return
+        lr = float(self.pn_lr_fn(step))
+        for group in self.pn_optimizer.param_groups:
+            if torch.is_tensor(group['lr']):
+                group['lr'].fill_(lr)
+            else:
+                group['lr'] = lr
+
+    def _refined(self, batch, mode):
+        from . import posenet as pn
+        if mode == 'train':
+            self.pn_optimizer.zero_grad(set_to_none=True)
+            return pn.refine_rays(batch, self.posenet)
+        if mode == 'apply':
+            with torch.no_grad():
+                return pn.refine_rays(batch, self.posenet)
+        return batch
+
+    def _pose_step(self, mode):
+        if mode != 'train':
+            return
+        params = [p for p in self.posenet.parameters() if p.grad is not None]
+        if self.world > 1:      # the reference wraps the posenet in DDP: mean over the ranks
+            for p in params:
+                torch.distributed.all_reduce(p.grad)
+                p.grad.div_(self.world)
+        c = self.config
+        if c.grad_max_val > 0:  # train_utils.clip_gradients (Z/internal/train_utils.py:223-232)
+            torch.nn.utils.clip_grad_value_(params, c.grad_max_val)
+        if c.grad_max_norm > 0:
+            torch.nn.utils.clip_grad_norm_(params, c.grad_max_norm)
+        self.pn_optimizer.step()
+
     def sync(self):
         """Waits (on the current stream) for the collectives a data-parallel step left in flight: afterwards the
         replicated parameters are complete on this rank."""
@@ -240,7 +290,10 @@ class Trainer:
         dev = self.flat.device
         cur = torch.cuda.current_stream(dev)
         if cur == self.stream or torch.cuda.is_current_stream_capturing():
+            if not torch.cuda.is_current_stream_capturing():
+                self._set_pose_lr(step)
             return self._train_step(batch, step, num_patch, rand_inputs)
+        self._set_pose_lr(step)
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
             out = self._train_step(batch, step, num_patch, rand_inputs)
@@ -248,20 +301,25 @@ class Trainer:
         return out
 
     def _train_step(self, batch, step, num_patch=None, rand_inputs=None):
+        pose = self._pose_mode(step)
+        batch = self._refined(batch, pose)
         losses, main, prop = self.forward_losses(batch, step, num_patch, rand_inputs)
         if self.world == 1:
             # (running the NeRF table's optimizer pass on a side stream beside the proposal backward was
             # measured: 7.30-7.35 ms per step against 7.23 ms in order -- the two contend for L2)
             (main if prop is None else main + prop).backward()
             self.optimizer_step(step)
+            self._pose_step(pose)
             return losses
-        main.backward()
+        # the refined rays feed both halves: the first backward must keep the posenet's part of the graph
+        main.backward(retain_graph=pose == 'train' and prop is not None)
         early = self.reduce_scatter_gradients(self._nerf_tables())
         if prop is not None:
             prop.backward()
         late = self.reduce_scatter_gradients(self._prop_tables(), dense=True)
         parallel.wait_all(early + late)
         self.optimizer_step(step, reduce=False)
+        self._pose_step(pose)
         return losses
 
     # ---- data parallel: reduce-scatter of the gradients -> this rank's slice of the optimizer pass -> all-gather
@@ -372,7 +430,7 @@ class Trainer:
         pose-refinement window boundaries."""
         c = self.config
         refine = c.pose_refine and c.start_step < step < int(0.6 * c.end_step)
-        return (bool(refine), step > c.end_step)
+        return (bool(refine), step > c.end_step, self._pose_mode(step))
 
     def _write_dynamic(self, step: int):
         c = self.config
@@ -399,6 +457,10 @@ class Trainer:
         loss-multiplier regime changes.  Returns the loss dictionary (static tensors,
         overwritten by the next call)."""
         dev = self.flat.device
+        if self.world > 1 and self._pose_mode(step) == 'train':
+            # the corrections' gradient all-reduce sits between the backward and their Adam step: the
+            # data-parallel window (a fifth of the run at most) is issued eagerly
+            return self.train_step(batch, step, num_patch, rand_inputs)
         key = (self._regime(step), num_patch, tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.items())),
                rand_inputs is not None)
         if self._static is None:
@@ -420,6 +482,7 @@ class Trainer:
                     dst[k].copy_(v, non_blocking=True)
             srand = st['rand']
         self._write_dynamic(step)
+        self._set_pose_lr(step)
         lib = _lib.load()
         entry = self._graphs.get(key)
         if entry is None:

@@ -161,8 +161,11 @@ def encode_features(means, stds, table, offsets, grid_sizes, C, base_resolution=
     z, sd = z / 2, sd / 2
     x01 = (z + 1) / 2
     L = offsets.shape[0] - 1
-    # autograd-capable wrapper (gradient w.r.t. the table) around grid_encode_forward
-    flat = grid_oracle._GridEncodeFn.apply(x01, table, offsets, 1.0, base_resolution, False, 0, False, 0)
+    # autograd-capable wrapper around grid_encode_forward: gradient w.r.t. the table, and w.r.t. the points through
+    # dy_dx when they carry a graph (gridencoder/grid.py:169: calc_grad_inputs = inputs.requires_grad -- the
+    # pose-refinement window)
+    flat = grid_oracle._GridEncodeFn.apply(x01, table, offsets, 1.0, base_resolution, bool(x01.requires_grad), 0,
+                                           False, 0)
     feat = flat.reshape(N, S, n, L, C)
     sd = sd.reshape(N, S, n)
     w = torch.erf(1 / torch.clamp(torch.sqrt(8 * sd[..., None] ** 2 * grid_sizes ** 2), min=1e-10))
