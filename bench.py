@@ -220,8 +220,9 @@ def run_cuda_arm(args):
 
     step_fn = trainer.train_step if args.eager else trainer.train_step_graphed
 
-    def timed_loop(n_steps, first_step, e2e, fn=None):
+    def timed_loop(n_steps, first_step, e2e, fn=None, pool=None):
         fn = fn or step_fn
+        resident_ = pool or resident
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -231,7 +232,7 @@ def run_cuda_arm(args):
             elif e2e:
                 b = host[i % n_pool]       # pinned host tensors: the graphed step copies them into its static buffers
             else:
-                b = resident[i % n_pool]
+                b = resident_[i % n_pool]
             out = fn(b, first_step + i, num_patch)
             if e2e:
                 loss_pin.copy_(out['loss'].reshape(1), non_blocking=True)
@@ -264,6 +265,30 @@ def run_cuda_arm(args):
     launches = (_lib.LAUNCHES - launches0) // n_prof * args.steps   # ABI calls per step x timed steps
     kt = _lib.TIMER.summary() if _lib.TIMER is not None else {}
     _lib.TIMER = None
+
+    # ---- secondary regime: the pose-refinement window 0 < step < 5000 -- LearnPose corrections
+    # applied to the batch with gradients, ray-geometry gradients out of the three levels, Adam on the corrections;
+    # the whole step replayed as one CUDA graph like the steady state
+    pose = None
+    if world == 1 and not args.no_pose_window:
+        from nerf_lidar_b200 import posenet
+        net, opt, lr_fn = posenet.create_posenet(1, cfg, num_lidars=1, device=dev)
+        trainer.attach_posenet(net, opt, lr_fn)
+        pool = [dict(b, glo_idx=torch.from_numpy(synthetic.sensor_index({'lidar_mask': b['lidar_mask'].cpu().numpy()})).to(dev))
+                for b in resident]
+        timed_loop(3, 1000, False, pool=pool)
+        ms_pose = timed_loop(args.steps, 1100, False, pool=pool)
+        timed_loop(2, 1300, False, trainer.train_step, pool=pool)
+        _lib.TIMER = _lib.KernelTimer()
+        ms_pose_eager = timed_loop(3, 1400, False, trainer.train_step, pool=pool)
+        kt_pose = {k: v[1] / max(v[0], 1) for k, v in _lib.TIMER.summary().items() if 'input_bwd' in k}
+        _lib.TIMER = None
+        pose = {'steps': '0 < step < Config.end_step = 5000 (gin: learn_R, not learn_t)',
+                'ms_per_step': ms_pose / args.steps, 'rays_per_s': BATCH * args.steps / (ms_pose * 1e-3),
+                'eager_ms_per_step': ms_pose_eager / 3, 'input_gradient_kernels_ms': kt_pose,
+                'correction_moved': float(net.r.detach().abs().max())}
+        trainer.attach_posenet(None, None, None)
+        del pool
 
     # ---- rendering (BASELINE configs[2] / [4]) through models.render_image: rays sharded contiguously over the
     # ranks, local chunks replayed as CUDA graphs, one packed gather at the end.  configs[4] = 4 cameras at
@@ -408,6 +433,7 @@ def run_cuda_arm(args):
                    'l2_policy': 'inputs larger than L2: 1.24 GB of table + optimizer state streamed every step, '
                                 'batches rotate over a pool of 4',
                    'render': render,
+                   'pose_refine_window': pose,
                    # bandwidth-bound kernels at 1 M rays (launch-bound at the 10 240-ray batch) and the
                    # device-resident data layer
                    'stream_kernels_1M_rays': extras})
@@ -562,6 +588,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-render', action='store_true', help='skip the rendering throughput measurement')
+    ap.add_argument('--no-pose-window', action='store_true', help='skip the pose-refinement-window step timing')
     ap.add_argument('--no-reference-kernel', action='store_true', help='skip timing the reference grid kernel (oracle/_ref)')
     ap.add_argument('--eager', action='store_true', help='issue the step eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()

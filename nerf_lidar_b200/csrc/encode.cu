@@ -406,21 +406,25 @@ __global__ void __launch_bounds__(256) k_priv_reduce(const float* __restrict__ p
 // its 7 samples; per sample and level it gathers the 8 corner rows once and forms both d feature / d x (the
 // trilinear derivative, dy_dx of the reference) and the feature itself (the erf weight depends on the contracted
 // std, which depends on |m|); the chain through the contraction Jacobian and the linear cast_rays map follows in
-// registers, then one warp reduction and 12 atomic adds per ray.  tdist carries no gradient (models.py:368-369).
+// registers, then one warp reduction and 12 atomic adds per warp.  tdist carries no gradient (models.py:368-369).
 template <int C>
 __global__ void __launch_bounds__(kEncThreads) k_encode_input_bwd(nlb_rays_t rays, nlb_table_t tab,
                                                                   const float* __restrict__ grad_features,
                                                                   float* __restrict__ g_origins,
                                                                   float* __restrict__ g_directions,
                                                                   float* __restrict__ g_base_x,
-                                                                  float* __restrict__ g_base_y) {
+                                                                  float* __restrict__ g_base_y, int level_begin,
+                                                                  int level_end) {
   __shared__ LevelCache lc;
   fill_level_cache(lc, tab);
   __syncthreads();
-  const int rows = rays.N * rays.S;
-  const int row_raw = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = row_raw < rows;
-  const int row = active ? row_raw : rows - 1;
+  // one thread per (interval, sample): 7x the threads of the forward's layout, 10 x 8 dependent gathers each
+  // (thread-per-interval with the sample loop inside was latency-bound: 0.72 ms against 0.39 ms for the forward)
+  const long items = (long)rays.N * rays.S * 7;
+  const long item_raw = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = item_raw < items;
+  const long item = active ? item_raw : items - 1;
+  const int row = (int)(item / 7), j = (int)(item - (long)row * 7);
   const int ray = row / rays.S, s = row - ray * rays.S;
   float acc[12];
 #pragma unroll
@@ -431,16 +435,15 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_input_bwd(nlb_rays_t ray
     const float t1 = __ldg(rays.tdist + (size_t)ray * (rays.S + 1) + s + 1);
     const bool has_noise = rays.deg_noise != nullptr;
     const float* __restrict__ G = grad_features + (size_t)row * (tab.L * C);
-#pragma unroll 1
-    for (int j = 0; j < 7; ++j) {
+    do {
       const float noise = has_noise ? __ldg(rays.deg_noise + (size_t)row * 7 + j) : 0.f;
       SampleGeom geo;
       const SamplePoint p = sample_point(rg, t0, t1, j, noise, has_noise, rays.std_scale, &geo);
-      if (!in_unit_cube(p.x, p.y, p.z)) continue;  // zero features, zero gradient (gridencoder.cu:110-135)
+      if (!in_unit_cube(p.x, p.y, p.z)) break;  // zero features, zero gradient (gridencoder.cu:110-135)
       const float a = staged_a(p.std);
       float gx = 0.f, gy = 0.f, gz = 0.f, gsd = 0.f;  // dL/d(x01), dL/d(std/2)
 #pragma unroll 1
-      for (int level = 0; level < tab.L; ++level) {
+      for (int level = level_begin; level < level_end; ++level) {
         const Level3 lv = lc.lv[level];
         const float u = a * lc.inv_gs[level];
         const float w = erff(u);
@@ -505,9 +508,9 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_input_bwd(nlb_rays_t ray
       acc[3] = fmaf(geo.t, zx, acc[3]); acc[4] = fmaf(geo.t, zy, acc[4]); acc[5] = fmaf(geo.t, zz, acc[5]);
       acc[6] = fmaf(geo.lx, zx, acc[6]); acc[7] = fmaf(geo.lx, zy, acc[7]); acc[8] = fmaf(geo.lx, zz, acc[8]);
       acc[9] = fmaf(geo.ly, zx, acc[9]); acc[10] = fmaf(geo.ly, zy, acc[10]); acc[11] = fmaf(geo.ly, zz, acc[11]);
-    }
+    } while (false);
   }
-  // a warp's 32 intervals belong to one ray when S % 32 == 0: one reduction, 12 atomics
+  // a warp's 32 samples belong to one ray when S % 32 == 0: one reduction, 12 atomics
   const int ray0 = __shfl_sync(NLB_FULL_MASK, ray, 0);
   const bool uniform = __all_sync(NLB_FULL_MASK, ray == ray0);
   if (uniform) {
@@ -1167,27 +1170,41 @@ static int check_ray_grads(const nlb_ray_grads_t* g, const char* who) {
   return NLB_OK;
 }
 
+// Like the forward, a table larger than L2 (the NeRF table) is walked in level groups that fit L2 together: the
+// gradients are sums over the levels, so every group simply adds its share (measured on the 10 240-ray batch:
+// 0.72 ms in one launch, DRAM-sector-bound on the four 33.5 MB hashed levels).
 template <int C>
-static int input_bwd_launch(const nlb_rays_t& rays, const nlb_table_t& tab, const float* gfeat,
+static int input_bwd_launch(const nlb_rays_t& rays, const nlb_table_t& tab, const HostLevels& hl, const float* gfeat,
                             const nlb_ray_grads_t& g, cudaStream_t st, const char* who) {
+  static const double kL2Budget = (double)env_long("NLB_GATHER_L2_MB", 70) * 1048576.0;
   const int rows = rays.N * rays.S;
-  k_encode_input_bwd<C><<<div_up(rows, kEncThreads), kEncThreads, 0, st>>>(rays, tab, gfeat, g.origins, g.directions,
-                                                                          g.base_x, g.base_y);
-  return nlb_check_launch(who);
+  int l0 = 0;
+  while (l0 < tab.L) {
+    int l1 = l0;
+    double bytes = 0.;
+    while (l1 < tab.L && (l1 == l0 || kL2Budget <= 0. || bytes + (double)hl.rows[l1] * C * 4.0 <= kL2Budget))
+      bytes += (double)hl.rows[l1++] * C * 4.0;
+    k_encode_input_bwd<C><<<div_up(rows * 7, kEncThreads), kEncThreads, 0, st>>>(rays, tab, gfeat, g.origins,
+                                                                                g.directions, g.base_x, g.base_y, l0, l1);
+    if (int e = nlb_check_launch(who)) return e;
+    l0 = l1;
+  }
+  return NLB_OK;
 }
 
 extern "C" int nlb_encode_input_backward(const nlb_rays_t* rays, const nlb_table_t* table, const float* grad_features,
                                          const nlb_ray_grads_t* grads, void* stream) {
-  if (int e = check_rays_table(rays, table, "encode_input_backward")) return e;
+  HostLevels hl;
+  if (int e = check_rays_table(rays, table, "encode_input_backward", &hl)) return e;
   if (rays->N == 0) return NLB_OK;
   if (!grad_features) { nlb_set_error("encode_input_backward: null grad_features"); return NLB_EINVAL; }
   if (int e = check_ray_grads(grads, "encode_input_backward")) return e;
   cudaStream_t st = (cudaStream_t)stream;
   switch (table->C) {
-    case 1: return input_bwd_launch<1>(*rays, *table, grad_features, *grads, st, "encode_input_backward");
-    case 2: return input_bwd_launch<2>(*rays, *table, grad_features, *grads, st, "encode_input_backward");
-    case 4: return input_bwd_launch<4>(*rays, *table, grad_features, *grads, st, "encode_input_backward");
-    case 8: return input_bwd_launch<8>(*rays, *table, grad_features, *grads, st, "encode_input_backward");
+    case 1: return input_bwd_launch<1>(*rays, *table, hl, grad_features, *grads, st, "encode_input_backward");
+    case 2: return input_bwd_launch<2>(*rays, *table, hl, grad_features, *grads, st, "encode_input_backward");
+    case 4: return input_bwd_launch<4>(*rays, *table, hl, grad_features, *grads, st, "encode_input_backward");
+    case 8: return input_bwd_launch<8>(*rays, *table, hl, grad_features, *grads, st, "encode_input_backward");
     default: nlb_set_error("GridEncoding: C must be 1, 2, 4, or 8."); return NLB_EINVAL;
   }
 }
@@ -1405,12 +1422,13 @@ extern "C" int nlb_prop_backward(const nlb_rays_t* rays, const nlb_table_t* tabl
 // The feature gradients nlb_prop_backward left in its workspace (same N, S, table) -> ray-geometry gradients.
 extern "C" int nlb_prop_input_backward(const nlb_rays_t* rays, const nlb_table_t* table, const float* workspace,
                                        const nlb_ray_grads_t* grads, void* stream) {
-  if (int e = check_rays_table(rays, table, "prop_input_backward")) return e;
+  HostLevels hl;
+  if (int e = check_rays_table(rays, table, "prop_input_backward", &hl)) return e;
   if (rays->N == 0) return NLB_OK;
   if (table->C != 1) { nlb_set_error("prop_input_backward: PropMLP tables have level_dim 1"); return NLB_EINVAL; }
   if (!workspace) { nlb_set_error("prop_input_backward: the workspace nlb_prop_backward filled is required"); return NLB_EINVAL; }
   if (int e = check_ray_grads(grads, "prop_input_backward")) return e;
   const int rows = rays->N * rays->S;
   const float* gfeat = workspace + prop_ws_partial_floats(rows, table->L);
-  return input_bwd_launch<1>(*rays, *table, gfeat, *grads, (cudaStream_t)stream, "prop_input_backward");
+  return input_bwd_launch<1>(*rays, *table, hl, gfeat, *grads, (cudaStream_t)stream, "prop_input_backward");
 }
