@@ -22,13 +22,18 @@ constexpr int kConvThreads = 256;   // 32 pixel threads (4 px each) x 8 channel 
 __global__ void __launch_bounds__(kConvThreads) k_conv3x3(const float* __restrict__ inA, int CA, const float* __restrict__ inB,
                                                           int CB, const float* __restrict__ W, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, int OC, int H, int Wd, int relu,
-                                                          float* __restrict__ out) {
+                                                          float* __restrict__ out, int ksplit, float* __restrict__ partial) {
   __shared__ float s_in[kIcChunk][kRows + 2][kCols + 2];
-  __shared__ __align__(16) float s_w[kIcChunk][9][kOcTile];
+  // row stride 68: the staging stores walk (c, k) fastest (the weights' memory order) and would otherwise hit one bank
+  __shared__ __align__(16) float s_w[kIcChunk][9][kOcTile + 4];
   const int C = CA + CB;
   const int tiles_x = (Wd + kCols - 1) / kCols;
   const int tile = blockIdx.x, tx0 = (tile % tiles_x) * kCols, ty0 = (tile / tiles_x) * kRows;
-  const int oc0 = blockIdx.y * kOcTile, n = blockIdx.z;
+  const int oc0 = blockIdx.y * kOcTile, n = blockIdx.z / ksplit, ks = blockIdx.z - n * ksplit;
+  // split over the input channels (ksplit > 1): this block sums the chunks [ic_begin, ic_end) into its own slice of
+  // `partial`; k_conv_finish adds the slices in order and applies the epilogue
+  const int chunks = (C + kIcChunk - 1) / kIcChunk, per = (chunks + ksplit - 1) / ksplit;
+  const int ic_begin = ks * per * kIcChunk, ic_end = min(C, (ks + 1) * per * kIcChunk);
   const int pt = threadIdx.x & 31, ct = threadIdx.x >> 5;      // pixel thread, channel thread
   const int py = pt >> 3, px = (pt & 7) * 4;                    // this thread's 4 pixels: row py, columns px..px+3
   float acc[8][4];
@@ -37,22 +42,26 @@ __global__ void __launch_bounds__(kConvThreads) k_conv3x3(const float* __restric
 #pragma unroll
     for (int p = 0; p < 4; ++p) acc[o][p] = 0.f;
   const size_t plane = (size_t)H * Wd;
-  for (int ic0 = 0; ic0 < C; ic0 += kIcChunk) {
+  for (int ic0 = ic_begin; ic0 < ic_end; ic0 += kIcChunk) {
     __syncthreads();
     for (int e = threadIdx.x; e < kIcChunk * (kRows + 2) * (kCols + 2); e += kConvThreads) {
       const int c = e / ((kRows + 2) * (kCols + 2)), r = (e / (kCols + 2)) % (kRows + 2), q = e % (kCols + 2);
       const int ic = ic0 + c, y = ty0 + r - 1, x = tx0 + q - 1;
       float v = 0.f;
-      if (ic < C && y >= 0 && y < H && x >= 0 && x < Wd) {
+      if (ic < ic_end && y >= 0 && y < H && x >= 0 && x < Wd) {
         const float* src = ic < CA ? inA + ((size_t)n * CA + ic) * plane : inB + ((size_t)n * CB + (ic - CA)) * plane;
         v = __ldg(src + (size_t)y * Wd + x);
       }
       s_in[c][r][q] = v;
     }
+    // W[oc][ic0 .. ic0+8)[3][3] is 72 contiguous floats per output channel: consecutive threads read consecutive
+    // addresses (with o fastest every thread touched its own 32-byte sector: 147 KB of L2 sectors per chunk and
+    // block, ~9 TB/s over the chip at the FMA rate -- the kernel was L2-bound on its own weights)
     for (int e = threadIdx.x; e < kIcChunk * 9 * kOcTile; e += kConvThreads) {
-      const int o = e % kOcTile, k = (e / kOcTile) % 9, c = e / (kOcTile * 9);
+      const int o = e / (kIcChunk * 9), r = e - o * (kIcChunk * 9);
+      const int c = r / 9, k = r - c * 9;
       const int ic = ic0 + c, oc = oc0 + o;
-      s_w[c][k][o] = (ic < C && oc < OC) ? __ldg(W + ((size_t)oc * C + ic) * 9 + k) : 0.f;
+      s_w[c][k][o] = (ic < ic_end && oc < OC) ? __ldg(W + ((size_t)oc * C + ic0) * 9 + r) : 0.f;
     }
     __syncthreads();
 #pragma unroll 2
@@ -77,6 +86,23 @@ __global__ void __launch_bounds__(kConvThreads) k_conv3x3(const float* __restric
   }
   const int y = ty0 + py;
   if (y >= H) return;
+  if (ksplit > 1) {
+    float* base = partial + (size_t)ks * (gridDim.z / ksplit) * OC * plane;   // slice ks of [ksplit][N, OC, H, W]
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const int oc = oc0 + ct * 8 + o;
+      if (oc >= OC) continue;
+      float* dst = base + (((size_t)n * OC + oc) * H + y) * Wd + tx0 + px;
+      if (tx0 + px + 3 < Wd && (Wd & 3) == 0) {
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[o][0], acc[o][1], acc[o][2], acc[o][3]);
+      } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          if (tx0 + px + p < Wd) dst[p] = acc[o][p];
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int o = 0; o < 8; ++o) {
     const int oc = oc0 + ct * 8 + o;
@@ -91,6 +117,19 @@ __global__ void __launch_bounds__(kConvThreads) k_conv3x3(const float* __restric
       }
     }
   }
+}
+
+// Sum of the ksplit partial slices (in slice order: deterministic) + folded BatchNorm + ReLU.
+__global__ void k_conv_finish(const float* __restrict__ partial, int ksplit, size_t slice /*N*OC*plane*/, size_t plane, int OC,
+                              const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                              float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= slice) return;
+  float acc = __ldg(partial + i);
+  for (int k = 1; k < ksplit; ++k) acc += __ldg(partial + (size_t)k * slice + i);
+  const int oc = (int)((i / plane) % OC);
+  const float r = fmaf(acc, scale ? __ldg(scale + oc) : 1.f, shift ? __ldg(shift + oc) : 0.f);
+  out[i] = relu ? fmaxf(r, 0.f) : r;
 }
 
 __global__ void k_maxpool2(const float* __restrict__ in, int planes, int H, int Wd, float* __restrict__ out) {
@@ -149,13 +188,38 @@ __global__ void k_conv1x1(const float* __restrict__ in, const float* __restrict_
   }
 }
 
+// Split of the input-channel loop: the layers below full resolution have 8-128 tiles for 148 SMs (measured before
+// the split: 64 -> 64 at 32 x 1024, 256 blocks, 123 us; 512 -> 512 at 2 x 64, 16 blocks, 561 us for HALF the flops).
+// Enough slices for ~4 blocks per SM, at most `max_split` (the partial buffer holds 128 floats per full-resolution
+// pixel: a level-k tensor is 64 / 2^k of them, so up to 2^(k+1) slices fit).
+static int pick_ksplit(int blocks, int C, size_t slice_floats, size_t partial_floats) {
+  static const int want = 4 * nlb_sm_count();
+  int ks = (want + blocks - 1) / blocks;
+  const int chunks = (C + kIcChunk - 1) / kIcChunk;
+  if (ks > chunks) ks = chunks;
+  if ((size_t)ks * slice_floats > partial_floats) ks = (int)(partial_floats / slice_floats);
+  if (ks < 1) ks = 1;
+  // no empty slices: ceil(chunks / ks) chunks per slice must leave the last slice non-empty
+  while (ks > 1 && (ks - 1) * ((chunks + ks - 1) / ks) >= chunks) --ks;
+  return ks;
+}
+
 static int conv3x3(const float* inA, int CA, const float* inB, int CB, const nlb_unet_conv_t& L, int OC, int N, int H, int Wd,
-                   float* out, cudaStream_t st) {
+                   float* out, float* partial, size_t partial_floats, cudaStream_t st) {
   if (!inA || !L.weight || !L.scale || !L.shift || !out || (CB > 0 && !inB)) { nlb_set_error("unet: null pointer in a 3x3 layer"); return NLB_EINVAL; }
   const int tiles = ((Wd + kCols - 1) / kCols) * ((H + kRows - 1) / kRows);
-  dim3 grid(tiles, (OC + kOcTile - 1) / kOcTile, N);
-  k_conv3x3<<<grid, kConvThreads, 0, st>>>(inA, CA, inB, CB, L.weight, L.scale, L.shift, OC, H, Wd, 1, out);
-  return nlb_check_launch("unet conv3x3");
+  const int oc_tiles = (OC + kOcTile - 1) / kOcTile;
+  const size_t plane = (size_t)H * Wd, slice = (size_t)N * OC * plane;
+  static const bool kNoSplit = getenv("NLB_UNET_NO_SPLIT") != nullptr;   // A/B timing
+  const int ksplit = (partial && !kNoSplit) ? pick_ksplit(tiles * oc_tiles * N, CA + CB, slice, partial_floats) : 1;
+  dim3 grid(tiles, oc_tiles, N * ksplit);
+  k_conv3x3<<<grid, kConvThreads, 0, st>>>(inA, CA, inB, CB, L.weight, L.scale, L.shift, OC, H, Wd, 1, out, ksplit, partial);
+  if (int e = nlb_check_launch("unet conv3x3")) return e;
+  if (ksplit > 1) {
+    k_conv_finish<<<(unsigned)((slice + 255) / 256), 256, 0, st>>>(partial, ksplit, slice, plane, OC, L.scale, L.shift, 1, out);
+    return nlb_check_launch("unet conv finish");
+  }
+  return NLB_OK;
 }
 
 }  // namespace unet
@@ -169,7 +233,8 @@ extern "C" size_t nlb_unet_workspace_bytes(int N, int H, int W) {
   const size_t px = (size_t)N * H * W;
   // x1 64, x2 128/4, x3 256/16, x4 512/64, x5 1024/256 pixel-equivalents of floats + four scratch tensors (pooled /
   // upsampled input, mid tensor, two ping-pong decoder outputs) of at most 64 channels at full resolution (96 reserved)
-  return (64 + 32 + 16 + 8 + 4 + 4 * 96) * px * sizeof(float) + 1024;
+  // + the partial sums of the input-channel split (128)
+  return (64 + 32 + 16 + 8 + 4 + 4 * 96 + 128) * px * sizeof(float) + 1024;
 }
 
 extern "C" int nlb_unet_forward(const float* image, const nlb_unet_weights_t* w, int N, int Cin, int H, int W, float* logits,
@@ -194,10 +259,12 @@ extern "C" int nlb_unet_forward(const float* image, const nlb_unet_weights_t* w,
   float* s1 = s0 + 96 * px;              // scratch: mid tensor of a DoubleConv
   float* s2 = s1 + 96 * px;              // scratch: decoder level outputs (ping-pong)
   float* s3 = s2 + 96 * px;
+  float* part = s3 + 96 * px;            // partial sums of the input-channel split
+  const size_t part_floats = 128 * px;
   auto double_conv = [&](const float* inA, int CA, const float* inB, int CB, const nlb_unet_conv_t* L, int mid, int oc, int h,
                          int wd, float* out) -> int {
-    if (int e = unet::conv3x3(inA, CA, inB, CB, L[0], mid, N, h, wd, s1, st)) return e;
-    return unet::conv3x3(s1, mid, nullptr, 0, L[1], oc, N, h, wd, out, st);
+    if (int e = unet::conv3x3(inA, CA, inB, CB, L[0], mid, N, h, wd, s1, part, part_floats, st)) return e;
+    return unet::conv3x3(s1, mid, nullptr, 0, L[1], oc, N, h, wd, out, part, part_floats, st);
   };
   auto pool = [&](const float* in, int C, int h, int wd) {
     const size_t total = (size_t)N * C * (h / 2) * (wd / 2);
