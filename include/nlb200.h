@@ -505,19 +505,30 @@ int nlb_raydrop_select(const float* logits /*[2,H,W]*/, float mask_thre, const f
 /* The ray-drop U-Net itself, inference (R/src/unet/unet_model.py:6-47, unet_parts.py:8-77; n_classes logits per
  * pixel, `regression` head not built).  BatchNorm is passed folded (eval mode): scale = gamma / sqrt(var + eps),
  * shift = beta - mean * scale.  Weights in torch layout: Conv2d [OC, C, 3, 3], ConvTranspose2d [C, C/2, 2, 2]. */
-typedef struct { const float* weight; const float* scale; const float* shift; } nlb_unet_conv_t;
+typedef struct {
+  const float* weight; const float* scale; const float* shift;
+  const float* packed;   /* nlb_unet_pack_conv() copy of `weight`, or NULL: with it the layer runs on the tensor cores
+                            in TF32 -- what torch's default (torch.backends.cudnn.allow_tf32 = True) makes of the
+                            reference's Conv2d on a GPU; without it in strict fp32 */
+} nlb_unet_conv_t;
 typedef struct {
   nlb_unet_conv_t inc[2];          /* DoubleConv(n_channels, 64) */
   nlb_unet_conv_t down[4][2];      /* Down(64,128) ... Down(512, 1024 / factor) */
   nlb_unet_conv_t up[4][2];        /* Up(1024, 512 / factor) ... Up(128, 64): DoubleConv after the concatenation */
   const float* up_weight[4];       /* ConvTranspose2d weights / biases (bilinear == 0), else NULL */
   const float* up_bias[4];
+  const float* up_packed[4];       /* nlb_unet_pack_convtranspose() copies of up_weight (TF32 tensor-core path) or NULL */
   const float* outc_weight;        /* [n_classes, 64] */
   const float* outc_bias;          /* [n_classes] */
   int bilinear;                    /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) instead, factor = 2 */
   int n_classes;
 } nlb_unet_weights_t;
 size_t nlb_unet_workspace_bytes(int N, int H, int W);
+/* weight[OC,C,3,3] -> packed[OC*C*9] (pre-swizzled [oc tile][32-channel chunk][tap] operand blocks); OC % 64 == 0 and
+ * C % 32 == 0, else NLB_EUNSUPPORTED (such a layer keeps packed = NULL). */
+int nlb_unet_pack_conv(const float* weight, int OC, int C, float* packed, void* stream);
+/* ConvTranspose2d weight[C,OC,2,2] -> packed[C*OC*4], same conditions. */
+int nlb_unet_pack_convtranspose(const float* weight, int C, int OC, float* packed, void* stream);
 /* image[N,Cin,H,W] -> logits[N,n_classes,H,W]; H, W multiples of 16. */
 int nlb_unet_forward(const float* image, const nlb_unet_weights_t* w, int N, int Cin, int H, int W, float* logits,
                      float* workspace, void* stream);

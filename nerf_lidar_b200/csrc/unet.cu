@@ -9,6 +9,7 @@
 // concatenation of an Up block is never materialised (the kernel reads its input channels from two tensors); the
 // folded BatchNorm scale / shift and the ReLU are the epilogue.
 #include "common.cuh"
+#include "umma.cuh"
 #include "../../include/nlb200.h"
 
 namespace nlb {
@@ -119,6 +120,241 @@ __global__ void __launch_bounds__(kConvThreads) k_conv3x3(const float* __restric
   }
 }
 
+// ----------------------------------------------------------------------------- 3x3 convolution on tcgen05 (TF32)
+// torch's default for convolutions is TF32 (torch.backends.cudnn.allow_tf32 = True), so what the reference's U-Net
+// computes on a GPU is this arithmetic: fp32 storage, operands read with a 10-bit mantissa, fp32 accumulation.
+// Implicit GEMM per CTA: M = 128 pixels (1 x 128 or 2 x 64 of the image), N = NT output channels, K = 32 input
+// channels x 9 taps per chunk.  One pipeline stage = one (chunk, tap): A[128 px][32 ch] built by the 128 staging
+// threads from a raw halo tile ([32][R+2][CW+2] floats, fetched one chunk ahead with 4-byte cp.async, zero fill at the
+// borders), B[NT][32] = a pre-packed, pre-swizzled block of the weights fetched with one bulk copy; both are
+// SWIZZLE_128B K-major operand blocks (32 fp32 = one 128-byte row); 4 tcgen05.mma (K = 8) per stage, accumulator in
+// TMEM.  Warps 0-3: staging + epilogue (folded BatchNorm + ReLU, or a raw partial slice when the input channels are
+// split over CTAs), warp 4: MMA issue, warps 5-7: weight copies, one warp per ring slot (a bulk copy keeps its
+// issuing thread busy for ~800 cycles whatever its size -- tools/bulk_probe.cu -- against 256 cycles of MMA per
+// stage: with ONE copy thread the ring ran at the copy-issue rate, 3.7 us per chunk).
+constexpr int kTcM = 128, kTcKc = 32, kTcStages = 3;
+constexpr int kTcThreads = 128 + 32 + 32 * kTcStages;
+constexpr int kTcABytes = kTcM * kTcKc * 4;   // 16 KB
+
+template <int NT, int CW>
+struct TcShape {
+  static constexpr int R = kTcM / CW;
+  static constexpr int kPlane = (R + 2) * (CW + 2);      // floats per channel of the raw tile
+  static constexpr int kRawFloats = kTcKc * kPlane;
+  static constexpr int kBBytes = NT * kTcKc * 4;
+  static constexpr int kStageBytes = kTcABytes + kBBytes;
+  static constexpr size_t kSmem = 1024 + (size_t)kTcStages * kStageBytes + 2 * (size_t)kRawFloats * 4 + 256;
+  static constexpr int kRawPer = (kPlane + 127) / 128;   // raw-tile elements per staging thread and channel
+};
+
+__host__ __device__ inline int packed_offset_floats(int o, int c) {   // (row, channel) inside a [NT][32] fp32 block
+  return (o >> 3) * 256 + (o & 7) * 32 + (((c >> 2) ^ (o & 7)) << 2) + (c & 3);
+}
+
+// W[OC][C][3][3] -> blocks [oc tile][chunk][tap][NT x 32] in operand layout
+__global__ void k_pack_conv_weights(const float* __restrict__ W, int OC, int C, int NT, float* __restrict__ packed) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)OC * C * 9;
+  if (i >= total) return;
+  const int k = (int)(i % 9), ic = (int)((i / 9) % C), oc = (int)(i / ((size_t)9 * C));
+  const int chunks = C / kTcKc;
+  const size_t block = ((size_t)(oc / NT) * chunks + ic / kTcKc) * 9 + k;
+  packed[block * ((size_t)NT * kTcKc) + packed_offset_floats(oc % NT, ic % kTcKc)] = W[i];
+}
+
+// W[C][OC][2][2] (ConvTranspose2d) -> blocks [virtual-channel tile][chunk][NT x 32], v = (dy * 2 + dx) * OC + oc
+__global__ void k_pack_convT_weights(const float* __restrict__ W, int C, int OC, int NT, float* __restrict__ packed) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)C * OC * 4;
+  if (i >= total) return;
+  const int t4 = (int)(i % 4), oc = (int)((i / 4) % OC), ic = (int)(i / ((size_t)4 * OC));
+  const int v = t4 * OC + oc, chunks = C / kTcKc;
+  const size_t block = (size_t)(v / NT) * chunks + ic / kTcKc;
+  packed[block * ((size_t)NT * kTcKc) + packed_offset_floats(v % NT, ic % kTcKc)] = W[i];
+}
+
+// kTransposed: ConvTranspose2d(kernel 2, stride 2) as the same implicit GEMM with ONE tap (the centre) and 4 x oc_real
+// virtual output channels v = (dy * 2 + dx) * oc_real + oc, scattered to out[oc, 2y + dy, 2x + dx] + bias (`shift`).
+template <int NT, int CW, bool kTransposed>
+__global__ void __launch_bounds__(kTcThreads, 1) k_conv3x3_tf32(const float* __restrict__ inA, int CA,
+                                                                const float* __restrict__ inB, int CB,
+                                                                const float* __restrict__ packed,
+                                                                const float* __restrict__ scale,
+                                                                const float* __restrict__ shift, int OC, int H, int Wd,
+                                                                float* __restrict__ out, int ksplit,
+                                                                float* __restrict__ partial, int oc_real) {
+  using namespace umma;
+  using Sh = TcShape<NT, CW>;
+  constexpr int kTaps = kTransposed ? 1 : 9;
+  extern __shared__ uint8_t smem_raw_[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw_ + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = base;
+  float* raw = reinterpret_cast<float*>(base + kTcStages * Sh::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw + 2 * Sh::kRawFloats);
+  uint64_t* full = bars;                 // [kTcStages]: 128 staging arrivals + the weight copy's bytes
+  uint64_t* empty = bars + kTcStages;    // [kTcStages]: the stage's MMAs have completed
+  uint64_t* acc_bar = bars + 2 * kTcStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 1);
+
+  const int C = CA + CB;
+  const int warp = threadIdx.x >> 5;
+  const int tiles_x = Wd / CW;
+  const int tx0 = (blockIdx.x % tiles_x) * CW, ty0 = (blockIdx.x / tiles_x) * Sh::R;
+  const int oc_tile = blockIdx.y, oc0 = oc_tile * NT;
+  const int n = blockIdx.z / ksplit, ks = blockIdx.z - n * ksplit;
+  const int chunks_all = C / kTcKc, per = (chunks_all + ksplit - 1) / ksplit;
+  const int chunk_begin = ks * per, chunk_end = min(chunks_all, chunk_begin + per);
+  const int n_chunks = max(chunk_end - chunk_begin, 0);
+  const int n_stages = n_chunks * kTaps;
+  const size_t plane = (size_t)H * Wd;
+
+  if (threadIdx.x == 0) {
+    for (int s_ = 0; s_ < kTcStages; ++s_) {
+      mbar_init(&full[s_], 128 + 1);
+      mbar_init(&empty[s_], 1);
+    }
+    mbar_init(acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, NT);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    // ---------------------------------------------------------------- staging threads: pixel m of the tile
+    const int m = threadIdx.x;
+    const int pr = m / CW, pxl = m - pr * CW;
+    // this thread's share of one raw channel plane: (smem offset, global offset, in range), the same for every channel
+    int so[Sh::kRawPer], go[Sh::kRawPer];
+    bool ok[Sh::kRawPer];
+#pragma unroll
+    for (int k = 0; k < Sh::kRawPer; ++k) {
+      const int e = m + 128 * k;
+      const int rr = e / (CW + 2), q = e - rr * (CW + 2);
+      const int y = ty0 + rr - 1, x = tx0 + q - 1;
+      so[k] = e < Sh::kPlane ? e : -1;
+      ok[k] = e < Sh::kPlane && y >= 0 && y < H && x >= 0 && x < Wd;
+      go[k] = ok[k] ? y * Wd + x : 0;
+    }
+    auto fetch = [&](int chunk, int buf) {
+      const int ic0 = chunk * kTcKc;
+      const float* src = ic0 < CA ? inA + ((size_t)n * CA + ic0) * plane : inB + ((size_t)n * CB + (ic0 - CA)) * plane;
+      float* dst = raw + buf * Sh::kRawFloats;
+#pragma unroll 4
+      for (int c = 0; c < kTcKc; ++c) {
+#pragma unroll
+        for (int k = 0; k < Sh::kRawPer; ++k)
+          if (so[k] >= 0) cp_async4_zfill(dst + c * Sh::kPlane + so[k], src + (size_t)c * plane + go[k], ok[k]);
+      }
+      cp_async_commit();
+    };
+    if (n_chunks > 0) fetch(chunk_begin, 0);
+    int stage = 0;
+    for (int ci = 0; ci < n_chunks; ++ci) {
+      if (ci + 1 < n_chunks) {
+        fetch(chunk_begin + ci + 1, (ci + 1) & 1);
+        cp_async_wait_group<1>();
+      } else {
+        cp_async_wait_group<0>();
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // chunk ci of the raw tile is complete for all staging threads
+      const float* rt = raw + (ci & 1) * Sh::kRawFloats;
+#pragma unroll 1
+      for (int tap = 0; tap < kTaps; ++tap, ++stage) {
+        const int slot = stage % kTcStages;
+        mbar_wait_warp(&empty[slot], ((stage / kTcStages) & 1) ^ 1);
+        const int ky = kTransposed ? 1 : tap / 3, kx = kTransposed ? 1 : tap - ky * 3;
+        const float* srcp = rt + (pr + ky) * (CW + 2) + pxl + kx;
+        uint8_t* arow = ring + slot * Sh::kStageBytes + (m >> 3) * 1024 + (m & 7) * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 v;
+          v.x = srcp[(4 * j + 0) * Sh::kPlane];
+          v.y = srcp[(4 * j + 1) * Sh::kPlane];
+          v.z = srcp[(4 * j + 2) * Sh::kPlane];
+          v.w = srcp[(4 * j + 3) * Sh::kPlane];
+          *reinterpret_cast<float4*>(arow + ((j ^ (m & 7)) << 4)) = v;
+        }
+        fence_proxy_async();
+        mbar_arrive(&full[slot]);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // everyone is done with this raw buffer before it is refilled
+    }
+    // ---------------------------------------------------------------- epilogue: TMEM lane m = pixel m
+    const int y = ty0 + pr, x = tx0 + pxl;
+    if (n_stages > 0) {
+      mbar_wait_warp(acc_bar, 0);
+      tcgen05_fence_after();
+    }
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    float* dst = ksplit > 1 ? partial + (size_t)ks * (gridDim.z / ksplit) * OC * plane : out;
+#pragma unroll 1
+    for (int c0 = 0; c0 < NT; c0 += 32) {
+      float v[32];
+      if (n_stages > 0) {
+        tmem_ld32(tl + c0, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (y < H) {
+        if constexpr (kTransposed) {
+          const int t4 = (oc0 + c0) / oc_real, ocb = oc0 + c0 - t4 * oc_real;   // a 32-column group has one tap
+          float* o = out + (((size_t)n * oc_real + ocb) * (2 * H) + 2 * y + (t4 >> 1)) * (2 * Wd) + 2 * x + (t4 & 1);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[(size_t)j * (4 * plane)] = v[j] + __ldg(shift + ocb + j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int oc = oc0 + c0 + j;
+            float r = v[j];
+            if (ksplit == 1) r = fmaxf(fmaf(r, __ldg(scale + oc), __ldg(shift + oc)), 0.f);
+            dst[(((size_t)n * OC + oc) * H + y) * Wd + x] = r;
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  } else if (warp == 4) {
+    // ---------------------------------------------------------------- MMA issue
+    const uint32_t idesc = make_idesc_tf32(kTcM, NT);
+    for (int stage = 0; stage < n_stages; ++stage) {
+      const int slot = stage % kTcStages;
+      mbar_wait_warp(&full[slot], (stage / kTcStages) & 1);
+      tcgen05_fence_after();
+      if (elect_one_sync()) {
+        const uint64_t da = make_desc_sw128(ring + slot * Sh::kStageBytes);
+        const uint64_t db = make_desc_sw128(ring + slot * Sh::kStageBytes + kTcABytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) mma_tf32_ss(tmem, da + kk * 2, db + kk * 2, idesc, stage > 0 || kk > 0);
+        mma_commit(&empty[slot]);
+        if (stage == n_stages - 1) mma_commit(acc_bar);
+      }
+      __syncwarp();
+    }
+    tcgen05_fence_before();
+  } else {
+    // ---------------------------------------------------------------- weight copies: warp 5 + s serves ring slot s
+    if ((threadIdx.x & 31) == 0) {
+      for (int stage = warp - 5; stage < n_stages; stage += kTcStages) {
+        const int slot = stage % kTcStages;
+        mbar_wait_relaxed(&empty[slot], ((stage / kTcStages) & 1) ^ 1);
+        const int chunk = chunk_begin + stage / kTaps, tap = stage % kTaps;
+        const float* src = packed + (((size_t)oc_tile * chunks_all + chunk) * kTaps + tap) * ((size_t)NT * kTcKc);
+        mbar_expect_tx(&full[slot], Sh::kBBytes);
+        bulk_g2s(ring + slot * Sh::kStageBytes + kTcABytes, src, Sh::kBBytes, &full[slot]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem, NT);
+  }
+}
+
 // Sum of the ksplit partial slices (in slice order: deterministic) + folded BatchNorm + ReLU.
 __global__ void k_conv_finish(const float* __restrict__ partial, int ksplit, size_t slice /*N*OC*plane*/, size_t plane, int OC,
                               const float* __restrict__ scale, const float* __restrict__ shift, int relu,
@@ -204,6 +440,71 @@ static int pick_ksplit(int blocks, int C, size_t slice_floats, size_t partial_fl
   return ks;
 }
 
+// The tensor-core path needs whole 32-channel chunks on both inputs, whole output-channel tiles and an image the
+// 128-pixel tile divides (1 x 128 or 2 x 64); everything else (the first layer: 6 input channels) stays on k_conv3x3.
+static bool tc_eligible(int CA, int CB, int OC, int H, int Wd) {
+  return CA % kTcKc == 0 && CB % kTcKc == 0 && OC % 64 == 0 && (Wd % 128 == 0 || Wd == 64) && H >= 1;
+}
+static int tc_oc_tile(int OC) { return OC % 128 == 0 ? 128 : 64; }
+
+template <int NT, int CW>
+static int launch_tf32(const float* inA, int CA, const float* inB, int CB, const nlb_unet_conv_t& L, int OC, int N, int H,
+                       int Wd, float* out, float* partial, size_t partial_floats, cudaStream_t st, int oc_real = 0) {
+  using Sh = TcShape<NT, CW>;
+  static bool attr[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr[dev]) {
+    if (cudaFuncSetAttribute(k_conv3x3_tf32<NT, CW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sh::kSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_conv3x3_tf32<NT, CW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sh::kSmem) != cudaSuccess) {
+      nlb_set_error("unet: cannot reserve %zu bytes of shared memory", Sh::kSmem);
+      return NLB_ECUDA;
+    }
+    attr[dev] = true;
+  }
+  const int tiles = (Wd / CW) * ((H + Sh::R - 1) / Sh::R), oc_tiles = OC / NT;
+  const size_t slice = (size_t)N * OC * H * Wd;
+  // one CTA per SM (200 KB of shared memory): slices of the input channels until every SM has a CTA (a layer with
+  // that many tiles already is not split: no partial slices, no finishing kernel)
+  const int blocks = tiles * oc_tiles * N, chunks = (CA + CB) / kTcKc;
+  int ksplit = (nlb_sm_count() * 5 / 4 + blocks - 1) / blocks;
+  if (ksplit > chunks) ksplit = chunks;
+  if ((size_t)ksplit * slice > partial_floats) ksplit = (int)(partial_floats / slice);
+  if (ksplit < 1) ksplit = 1;
+  while (ksplit > 1 && (ksplit - 1) * ((chunks + ksplit - 1) / ksplit) >= chunks) --ksplit;
+  if (oc_real > 0) {   // transposed convolution: OC = 4 * oc_real virtual channels, never split
+    k_conv3x3_tf32<NT, CW, true><<<dim3(tiles, oc_tiles, N), kTcThreads, Sh::kSmem, st>>>(
+        inA, CA, inB, CB, L.packed, nullptr, L.shift, OC, H, Wd, out, 1, nullptr, oc_real);
+    return nlb_check_launch("unet convtranspose tf32");
+  }
+  k_conv3x3_tf32<NT, CW, false><<<dim3(tiles, oc_tiles, N * ksplit), kTcThreads, Sh::kSmem, st>>>(
+      inA, CA, inB, CB, L.packed, L.scale, L.shift, OC, H, Wd, out, ksplit, partial, 0);
+  if (int e = nlb_check_launch("unet conv3x3 tf32")) return e;
+  if (ksplit > 1) {
+    k_conv_finish<<<(unsigned)((slice + 255) / 256), 256, 0, st>>>(partial, ksplit, slice, (size_t)H * Wd, OC, L.scale, L.shift, 1, out);
+    return nlb_check_launch("unet conv finish");
+  }
+  return NLB_OK;
+}
+
+static int conv3x3_tf32(const float* inA, int CA, const float* inB, int CB, const nlb_unet_conv_t& L, int OC, int N, int H,
+                        int Wd, float* out, float* partial, size_t partial_floats, cudaStream_t st, int oc_real = 0) {
+  const bool wide = Wd % 128 == 0;
+  const int nt = tc_oc_tile(oc_real > 0 ? oc_real : OC);
+  if (nt == 128)
+    return wide ? launch_tf32<128, 128>(inA, CA, inB, CB, L, OC, N, H, Wd, out, partial, partial_floats, st, oc_real)
+                : launch_tf32<128, 64>(inA, CA, inB, CB, L, OC, N, H, Wd, out, partial, partial_floats, st, oc_real);
+  return wide ? launch_tf32<64, 128>(inA, CA, inB, CB, L, OC, N, H, Wd, out, partial, partial_floats, st, oc_real)
+              : launch_tf32<64, 64>(inA, CA, inB, CB, L, OC, N, H, Wd, out, partial, partial_floats, st, oc_real);
+}
+
+// ConvTranspose2d(C, OC, 2, 2) on the same kernel: in[N,C,H,W] -> out[N,OC,2H,2W]
+static int convtranspose_tf32(const float* in, int C, const float* packed, const float* bias, int OC, int N, int H, int Wd,
+                              float* out, cudaStream_t st) {
+  nlb_unet_conv_t L{nullptr, nullptr, bias, packed};
+  return conv3x3_tf32(in, C, nullptr, 0, L, 4 * OC, N, H, Wd, out, nullptr, 0, st, OC);
+}
+
 static int conv3x3(const float* inA, int CA, const float* inB, int CB, const nlb_unet_conv_t& L, int OC, int N, int H, int Wd,
                    float* out, float* partial, size_t partial_floats, cudaStream_t st) {
   if (!inA || !L.weight || !L.scale || !L.shift || !out || (CB > 0 && !inB)) { nlb_set_error("unet: null pointer in a 3x3 layer"); return NLB_EINVAL; }
@@ -211,6 +512,8 @@ static int conv3x3(const float* inA, int CA, const float* inB, int CB, const nlb
   const int oc_tiles = (OC + kOcTile - 1) / kOcTile;
   const size_t plane = (size_t)H * Wd, slice = (size_t)N * OC * plane;
   static const bool kNoSplit = getenv("NLB_UNET_NO_SPLIT") != nullptr;   // A/B timing
+  if (L.packed && tc_eligible(CA, CB, OC, H, Wd) && partial)
+    return conv3x3_tf32(inA, CA, inB, CB, L, OC, N, H, Wd, out, partial, partial_floats, st);
   const int ksplit = (partial && !kNoSplit) ? pick_ksplit(tiles * oc_tiles * N, CA + CB, slice, partial_floats) : 1;
   dim3 grid(tiles, oc_tiles, N * ksplit);
   k_conv3x3<<<grid, kConvThreads, 0, st>>>(inA, CA, inB, CB, L.weight, L.scale, L.shift, OC, H, Wd, 1, out, ksplit, partial);
@@ -297,9 +600,13 @@ extern "C" int nlb_unet_forward(const float* image, const nlb_unet_weights_t* w,
     } else {
       c_up = c_low / 2;
       if (!w->up_weight[u]) { nlb_set_error("unet_forward: transposed-convolution weights of up%d are required", u + 1); return NLB_EINVAL; }
-      const size_t total = (size_t)c_up * (2 * h) * (2 * wd);
-      unet::k_convtranspose2<<<dim3((unsigned)((total + 255) / 256), N), 256, 0, st>>>(low, w->up_weight[u], w->up_bias[u], c_low,
-                                                                                      c_up, h, wd, s0);
+      if (w->up_packed[u] && w->up_bias[u] && unet::tc_eligible(c_low, 0, c_up, h, wd)) {
+        if (int e = unet::convtranspose_tf32(low, c_low, w->up_packed[u], w->up_bias[u], c_up, N, h, wd, s0, st)) return e;
+      } else {
+        const size_t total = (size_t)c_up * (2 * h) * (2 * wd);
+        unet::k_convtranspose2<<<dim3((unsigned)((total + 255) / 256), N), 256, 0, st>>>(low, w->up_weight[u], w->up_bias[u],
+                                                                                        c_low, c_up, h, wd, s0);
+      }
     }
     h *= 2; wd *= 2;
     const int cin = c_skip[u] + c_up;
@@ -312,4 +619,30 @@ extern "C" int nlb_unet_forward(const float* image, const nlb_unet_weights_t* w,
   unet::k_conv1x1<<<dim3((unsigned)(((size_t)H * W + 255) / 256), N), 256, 0, st>>>(low, w->outc_weight, w->outc_bias, 64,
                                                                                     w->n_classes, (size_t)H * W, logits);
   return nlb_check_launch("unet_forward");
+}
+
+// Operand-layout copy of a 3x3 layer's weights for the TF32 tensor-core path (nlb_unet_conv_t.packed): same number
+// of floats as the weights.  Layers the path does not serve (C not a multiple of 32, OC not a multiple of 64) need
+// none: returns NLB_EUNSUPPORTED and the caller leaves `packed` NULL.
+extern "C" int nlb_unet_pack_conv(const float* weight, int OC, int C, float* packed, void* stream) {
+  if (!weight || !packed) { nlb_set_error("unet_pack_conv: null pointer"); return NLB_EINVAL; }
+  if (OC < 64 || OC % 64 || C < unet::kTcKc || C % unet::kTcKc) {
+    nlb_set_error("unet_pack_conv: the TF32 path needs OC %% 64 == 0 and C %% 32 == 0 (got %d, %d)", OC, C);
+    return NLB_EUNSUPPORTED;
+  }
+  const size_t total = (size_t)OC * C * 9;
+  unet::k_pack_conv_weights<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(weight, OC, C, unet::tc_oc_tile(OC), packed);
+  return nlb_check_launch("unet_pack_conv");
+}
+
+// The same for a ConvTranspose2d(C, OC, kernel 2, stride 2) weight [C, OC, 2, 2] (nlb_unet_weights_t.up_packed).
+extern "C" int nlb_unet_pack_convtranspose(const float* weight, int C, int OC, float* packed, void* stream) {
+  if (!weight || !packed) { nlb_set_error("unet_pack_convtranspose: null pointer"); return NLB_EINVAL; }
+  if (OC < 64 || OC % 64 || C < unet::kTcKc || C % unet::kTcKc) {
+    nlb_set_error("unet_pack_convtranspose: the TF32 path needs OC %% 64 == 0 and C %% 32 == 0 (got %d, %d)", OC, C);
+    return NLB_EUNSUPPORTED;
+  }
+  const size_t total = (size_t)C * OC * 4;
+  unet::k_pack_convT_weights<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(weight, C, OC, unet::tc_oc_tile(OC), packed);
+  return nlb_check_launch("unet_pack_convtranspose");
 }

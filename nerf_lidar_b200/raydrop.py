@@ -144,6 +144,7 @@ class UNet(nn.Module):
         if regression:
             raise NotImplementedError('UNet(regression=True): the range-regression head is not built')
         self.n_channels, self.n_classes, self.bilinear, self.regression = n_channels, n_classes, bilinear, regression
+        self.tf32 = None      # None: follow torch.backends.cudnn.allow_tf32; True / False: force
         self.inc = DoubleConv(n_channels, 64)
         self.down1 = Down(64, 128)
         self.down2 = Down(128, 256)
@@ -157,16 +158,24 @@ class UNet(nn.Module):
         self.outc = OutConv(64, n_classes)
 
     @staticmethod
-    def _fold(dc: DoubleConv, keep):
-        """(conv weight, BatchNorm folded to scale / shift) of both halves of a DoubleConv."""
+    def _fold(dc: DoubleConv, keep, tf32: bool):
+        """(conv weight, BatchNorm folded to scale / shift, operand-layout copy of the weight for the TF32 tensor-core
+        path) of both halves of a DoubleConv."""
         out = []
         for ci, bi in ((0, 1), (3, 4)):
             conv, bn = dc.double_conv[ci], dc.double_conv[bi]
             scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
             shift = bn.bias.detach() - bn.running_mean * scale
             t = [f32(conv.weight.detach()), f32(scale), f32(shift)]
+            packed = None
+            oc, c = t[0].shape[:2]
+            if tf32 and oc % 64 == 0 and c % 32 == 0:
+                packed = torch.empty_like(t[0])
+                with torch.cuda.device(packed.device):
+                    check(load().nlb_unet_pack_conv(ptr(t[0]), oc, c, ptr(packed), stream()))
+                t.append(packed)
             keep += t
-            out.append(NlbUnetConv(*[ptr(x) for x in t]))
+            out.append(NlbUnetConv(ptr(t[0]), ptr(t[1]), ptr(t[2]), ptr(packed)))
         return out
 
     @torch.no_grad()
@@ -179,20 +188,30 @@ class UNet(nn.Module):
             raise RuntimeError(f'UNet: expected {self.n_channels} input channels, got {cin}')
         # folded BatchNorm terms / weight pointers, rebuilt only when a parameter or buffer changed (18 layers x a
         # handful of tiny launches would otherwise cost more than the convolutions)
-        version = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        # precision: the reference's Conv2d layers follow torch.backends.cudnn.allow_tf32 (True by default: TF32
+        # tensor-core convolutions), and so does this module unless `self.tf32` says otherwise
+        tf32 = torch.backends.cudnn.allow_tf32 if self.tf32 is None else bool(self.tf32)
+        version = (tf32,) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
         cached = self.__dict__.get('_nlb_folded')
         if cached is None or cached[0] != version:
             keep = []
             w = NlbUnetWeights()
-            w.inc[0], w.inc[1] = self._fold(self.inc, keep)
+            w.inc[0], w.inc[1] = self._fold(self.inc, keep, tf32)
             for i, d in enumerate((self.down1, self.down2, self.down3, self.down4)):
-                w.down[i][0], w.down[i][1] = self._fold(d.maxpool_conv[1], keep)
+                w.down[i][0], w.down[i][1] = self._fold(d.maxpool_conv[1], keep, tf32)
             for i, u in enumerate((self.up1, self.up2, self.up3, self.up4)):
-                w.up[i][0], w.up[i][1] = self._fold(u.conv, keep)
+                w.up[i][0], w.up[i][1] = self._fold(u.conv, keep, tf32)
                 if not self.bilinear:
                     t = [f32(u.up.weight.detach()), f32(u.up.bias.detach())]
                     keep += t
                     w.up_weight[i], w.up_bias[i] = ptr(t[0]), ptr(t[1])
+                    cin_t, cout_t = t[0].shape[:2]
+                    if tf32 and cout_t % 64 == 0 and cin_t % 32 == 0:
+                        packed = torch.empty_like(t[0])
+                        with torch.cuda.device(packed.device):
+                            check(load().nlb_unet_pack_convtranspose(ptr(t[0]), cin_t, cout_t, ptr(packed), stream()))
+                        keep.append(packed)
+                        w.up_packed[i] = ptr(packed)
             t = [f32(self.outc.conv.weight.detach().reshape(self.n_classes, 64)), f32(self.outc.conv.bias.detach())]
             keep += t
             w.outc_weight, w.outc_bias = ptr(t[0]), ptr(t[1])
