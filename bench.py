@@ -416,6 +416,7 @@ def run_cuda_arm(args):
     if world == 1 and not args.no_reference_kernel:
         ref_kernel = reference_kernel_leg(model, resident[0], per_kernel)
     extras = stream_kernel_leg(dev, hbm_peak) if world == 1 else None
+    stage3 = stage3_leg(dev) if world == 1 and not args.no_render else None
     value = BATCH * world * args.steps / (ms * 1e-3)
     e2e = BATCH * world * args.steps / (ms_e2e * 1e-3)
     if roofline is not None:
@@ -434,6 +435,7 @@ def run_cuda_arm(args):
                                 'batches rotate over a pool of 4',
                    'render': render,
                    'pose_refine_window': pose,
+                   'stage3_raydrop': stage3,
                    # bandwidth-bound kernels at 1 M rays (launch-bound at the 10 240-ray batch) and the
                    # device-resident data layer
                    'stream_kernels_1M_rays': extras})
@@ -497,6 +499,82 @@ def stream_kernel_leg(dev, hbm_peak, n=1 << 20):
         c2w = torch.eye(3, 4, dtype=torch.float64, device=dev).repeat(64, 1, 1)
         ms = timeit(lambda: raygen.pixels_to_rays(px, py, p2c, c2w, cam_idx=cam))
         out['camera_rays'] = {'ms': round(ms, 4), 'rays_per_s': round(n / ms * 1e3), 'alg_gbs': round(88 * n / ms / 1e6, 1)}
+    torch.cuda.empty_cache()
+    return out
+
+
+def stage3_leg(dev):
+    """Stage 3 on one synthetic 32 x 1024 sweep: depth filter -> range projection -> ray-drop U-Net ->
+    drop selection, all on the device; the U-Net alone in both precisions, and the SAME layers evaluated by torch
+    (cuDNN) the way the reference's `UNet.forward` (R/src/unet/unet_model.py:34-47) runs on a GPU."""
+    import torch
+    import torch.nn.functional as F
+    from nerf_lidar_b200 import raydrop
+    H, W = 32, 1024
+    g = torch.Generator(device=dev).manual_seed(0)
+    az = torch.linspace(-3.14159, 3.14159, W, device=dev).repeat(H)
+    el = torch.linspace(0.186, -0.535, H, device=dev).repeat_interleave(W)
+    depth = 3 + 60 * torch.rand(H * W, device=dev, generator=g)
+    pts = torch.stack([torch.cos(el) * torch.cos(az), torch.cos(el) * torch.sin(az), torch.sin(el)], -1) * depth[:, None]
+    sem = torch.randint(0, 19, (H * W,), device=dev, generator=g).float()
+    rgb = torch.rand(H * W, 3, device=dev, generator=g)
+    torch.manual_seed(0)
+    net = raydrop.UNet(6, 2, bilinear=True).to(dev).eval()
+
+    def features():
+        fm = raydrop.depth_filter(pts, sem, return_mask=True, width=1, threshold=1)
+        scan = raydrop.LaserScan(H=H, W=W, fov_up=10.67, fov_down=-30.67)
+        scan.set_points(pts, semantic=sem, rgb=rgb)
+        scan.do_range_projection()
+        x = torch.cat([scan.proj_range[None], scan.proj_semantic[None], scan.proj_mask[None], scan.proj_rgb.permute(2, 0, 1)], 0)
+        return fm, scan, x[None].contiguous()
+
+    def whole():
+        fm, scan, x = features()
+        return raydrop.drop_rays(net(x)[0], scan, pts, sem, fm, mask_thre=0.5)
+
+    def torch_forward(x):
+        dc = lambda m, t: m.double_conv(t)
+        xs = [dc(net.inc, x)]
+        for d in (net.down1, net.down2, net.down3, net.down4):
+            xs.append(dc(d.maxpool_conv[1], d.maxpool_conv[0](xs[-1])))
+        y = xs[-1]
+        for u, skip in zip((net.up1, net.up2, net.up3, net.up4), xs[-2::-1]):
+            y = dc(u.conv, torch.cat([skip, u.up(y)], 1))
+        return net.outc.conv(y)
+
+    def timeit(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    with torch.no_grad():
+        _, _, x = features()
+        out = {'sweep': f'{H} x {W} points, 6-channel features, UNet(6, 2, bilinear=True)',
+               'whole_stage_ms': round(timeit(whole), 4)}
+        net.tf32 = True
+        out['unet_tf32_ms'] = round(timeit(lambda: net(x)), 4)
+        a = net(x)
+        net.tf32 = False
+        out['unet_fp32_ms'] = round(timeit(lambda: net(x)), 4)
+        out['tf32_vs_fp32_max_abs_logit'] = float((a - net(x)).abs().max())
+        net.tf32 = None
+        old = torch.backends.cudnn.allow_tf32
+        try:
+            torch.backends.cudnn.allow_tf32 = True
+            out['torch_cudnn_tf32_ms'] = round(timeit(lambda: torch_forward(x)), 4)
+            torch.backends.cudnn.allow_tf32 = False
+            out['torch_cudnn_fp32_ms'] = round(timeit(lambda: torch_forward(x)), 4)
+        finally:
+            torch.backends.cudnn.allow_tf32 = old
+        out['points_per_s'] = round(H * W / out['whole_stage_ms'] * 1e3)
     torch.cuda.empty_cache()
     return out
 
