@@ -106,6 +106,26 @@ def main():
             lst = [torch.empty_like(chk) for _ in range(world)]
             dist.all_gather(lst, chk)
             assert all(torch.equal(lst[0], x) for x in lst), (i, rank, 'ranks disagree after the all-gather')
+    # pose-refinement window under data parallelism (Z/train.py:97,200-221,464-466: the posenet is DDP-wrapped):
+    # every rank refines its own rays, the corrections' gradients are averaged over the ranks before their Adam
+    # step, so the corrections stay identical everywhere
+    if os.environ.get('DPW_POSE', '1') == '1':
+        from nerf_lidar_b200 import posenet
+        for h in halves:
+            h['glo_idx'] = torch.from_numpy(synthetic.sensor_index({'lidar_mask': h['lidar_mask'].cpu().numpy()})).to(dev)
+        net, opt, lr_fn = posenet.create_posenet(1, cfg, num_lidars=1, device=dev)
+        dp.attach_posenet(net, opt, lr_fn)
+        for i in range(2):
+            step = 1000 + i
+            out = dp.train_step_graphed(halves[rank], step, 0, rins[rank])   # falls back to the eager window step
+            dp.sync()
+            assert torch.isfinite(out['loss']).all()
+        lst = [torch.empty_like(net.r.data) for _ in range(world)]
+        dist.all_gather(lst, net.r.data.contiguous())
+        assert all(torch.equal(lst[0], x) for x in lst), 'pose corrections differ between the ranks'
+        assert float(net.r.detach().abs().max()) > 0 and float(net.t.detach().abs().max()) == 0.0
+        print(f'rank {rank} pose corrections after 2 window steps: max |r| {float(net.r.detach().abs().max()):.2e}', flush=True)
+        dp.attach_posenet(None, None, None)
     dist.barrier()
     if rank == 0:
         print('dp ok')
