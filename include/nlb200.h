@@ -520,6 +520,8 @@ typedef struct {
   const float* up_packed[4];       /* nlb_unet_pack_convtranspose() copies of up_weight (TF32 tensor-core path) or NULL */
   const float* outc_weight;        /* [n_classes, 64] */
   const float* outc_bias;          /* [n_classes] */
+  const float* outr_weight;        /* [1, 64] range-regression head (UNet(regression=True)) or NULL */
+  const float* outr_bias;          /* [1] */
   int bilinear;                    /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) instead, factor = 2 */
   int n_classes;
 } nlb_unet_weights_t;
@@ -529,9 +531,10 @@ size_t nlb_unet_workspace_bytes(int N, int H, int W);
 int nlb_unet_pack_conv(const float* weight, int OC, int C, float* packed, void* stream);
 /* ConvTranspose2d weight[C,OC,2,2] -> packed[C*OC*4], same conditions. */
 int nlb_unet_pack_convtranspose(const float* weight, int C, int OC, float* packed, void* stream);
-/* image[N,Cin,H,W] -> logits[N,n_classes,H,W]; H, W multiples of 16. */
+/* image[N,Cin,H,W] -> logits[N,n_classes,H,W] (+ regression[N,1,H,W] = sigmoid(outr(x)), or NULL); H, W multiples
+ * of 16. */
 int nlb_unet_forward(const float* image, const nlb_unet_weights_t* w, int N, int Cin, int H, int W, float* logits,
-                     float* workspace, void* stream);
+                     float* regression, float* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -101,7 +101,7 @@ class NlbUnetConv(C.Structure):
 
 class NlbUnetWeights(C.Structure):
     _fields_ = [('inc', NlbUnetConv * 2), ('down', (NlbUnetConv * 2) * 4), ('up', (NlbUnetConv * 2) * 4),
-                ('up_weight', c_f * 4), ('up_bias', c_f * 4), ('up_packed', c_f * 4), ('outc_weight', c_f), ('outc_bias', c_f),
+                ('up_weight', c_f * 4), ('up_bias', c_f * 4), ('up_packed', c_f * 4), ('outc_weight', c_f), ('outc_bias', c_f), ('outr_weight', c_f), ('outr_bias', c_f),
                 ('bilinear', C.c_int), ('n_classes', C.c_int)]
 
 
@@ -163,7 +163,7 @@ SIGNATURES = {
     'nlb_unet_workspace_bytes': (C.c_size_t, [_i, _i, _i]),
     'nlb_unet_pack_conv': (_i, [_p, _i, _i, _p, _p]),
     'nlb_unet_pack_convtranspose': (_i, [_p, _i, _i, _p, _p]),
-    'nlb_unet_forward': (_i, [_p, C.POINTER(NlbUnetWeights), _i, _i, _i, _i, _p, _p, _p]),
+    'nlb_unet_forward': (_i, [_p, C.POINTER(NlbUnetWeights), _i, _i, _i, _i, _p, _p, _p, _p]),
     'nlb_obj_pose': (_i, [_p, _p, _i, _i, _i, _p, _p]),
     'nlb_obj_forward': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, C.POINTER(NlbTable), C.POINTER(NlbObjMlp), _p, _p, _p, _p, _p, _p]),
     'nlb_obj_backward': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, C.POINTER(NlbTable), C.POINTER(NlbObjMlp), _p, _p, _p,

@@ -413,14 +413,14 @@ __global__ void k_convtranspose2(const float* __restrict__ in, const float* __re
 
 // OutConv: 1x1 convolution with bias
 __global__ void k_conv1x1(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias, int C,
-                          int OC, size_t plane, float* __restrict__ out) {
+                          int OC, size_t plane, float* __restrict__ out, int sigmoid) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
   if (i >= plane) return;
   for (int oc = 0; oc < OC; ++oc) {
     float acc = bias ? __ldg(bias + oc) : 0.f;
     for (int ic = 0; ic < C; ++ic) acc = fmaf(__ldg(in + ((size_t)n * C + ic) * plane + i), __ldg(W + (size_t)oc * C + ic), acc);
-    out[((size_t)n * OC + oc) * plane + i] = acc;
+    out[((size_t)n * OC + oc) * plane + i] = sigmoid ? 1.0f / (1.0f + expf(-acc)) : acc;
   }
 }
 
@@ -541,7 +541,7 @@ extern "C" size_t nlb_unet_workspace_bytes(int N, int H, int W) {
 }
 
 extern "C" int nlb_unet_forward(const float* image, const nlb_unet_weights_t* w, int N, int Cin, int H, int W, float* logits,
-                                float* workspace, void* stream) {
+                                float* regression, float* workspace, void* stream) {
   if (N == 0) return NLB_OK;
   if (N < 0 || Cin < 1 || !image || !w || !logits || !workspace) { nlb_set_error("unet_forward: bad argument"); return NLB_EINVAL; }
   if (H < 16 || W < 16 || H % 16 || W % 16) {
@@ -617,7 +617,12 @@ extern "C" int nlb_unet_forward(const float* image, const nlb_unet_weights_t* w,
     c_low = c_out[u];
   }
   unet::k_conv1x1<<<dim3((unsigned)(((size_t)H * W + 255) / 256), N), 256, 0, st>>>(low, w->outc_weight, w->outc_bias, 64,
-                                                                                    w->n_classes, (size_t)H * W, logits);
+                                                                                    w->n_classes, (size_t)H * W, logits, 0);
+  if (regression) {   // UNet(regression=True): reg = sigmoid(outr(x)) (unet_model.py:45-46)
+    if (!w->outr_weight) { nlb_set_error("unet_forward: a regression output needs the outr layer"); return NLB_EINVAL; }
+    unet::k_conv1x1<<<dim3((unsigned)(((size_t)H * W + 255) / 256), N), 256, 0, st>>>(low, w->outr_weight, w->outr_bias, 64, 1,
+                                                                                      (size_t)H * W, regression, 1);
+  }
   return nlb_check_launch("unet_forward");
 }
 

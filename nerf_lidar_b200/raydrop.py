@@ -137,12 +137,11 @@ class OutConv(nn.Module):
 
 class UNet(nn.Module):
     """R/src/unet/unet_model.py:6-47: same constructor, sub-module names and state-dict keys (reference checkpoints
-    load as they are); `forward` is inference only (BatchNorm running statistics), on csrc/unet.cu."""
+    load as they are).  Inference (`.eval()`) runs on csrc/unet.cu; training mode evaluates the same layers with
+    torch (see `_forward_torch`)."""
 
     def __init__(self, n_channels, n_classes, bilinear=False, regression=False):
         super().__init__()
-        if regression:
-            raise NotImplementedError('UNet(regression=True): the range-regression head is not built')
         self.n_channels, self.n_classes, self.bilinear, self.regression = n_channels, n_classes, bilinear, regression
         self.tf32 = None      # None: follow torch.backends.cudnn.allow_tf32; True / False: force
         self.inc = DoubleConv(n_channels, 64)
@@ -156,6 +155,27 @@ class UNet(nn.Module):
         self.up3 = Up(256, 128 // factor, bilinear)
         self.up4 = Up(128, 64, bilinear)
         self.outc = OutConv(64, n_classes)
+        if regression:
+            self.outr = OutConv(64, 1)
+
+    def _forward_torch(self, x):
+        """Training mode (R/src/model/ray_drop_train.py:73-125 trains this network with torch.optim.Adam): the layers
+        as torch evaluates them -- batch statistics in the BatchNorms, autograd, cuDNN -- exactly the reference's
+        `UNet.forward` (unet_model.py:31-47, unet_parts.py:59-69).  Outside the hot path; inference runs on
+        csrc/unet.cu."""
+        import torch.nn.functional as F
+        dc = lambda m, t: m.double_conv(t)
+        xs = [dc(self.inc, x)]
+        for d in (self.down1, self.down2, self.down3, self.down4):
+            xs.append(dc(d.maxpool_conv[1], d.maxpool_conv[0](xs[-1])))
+        y = xs[-1]
+        for u, skip in zip((self.up1, self.up2, self.up3, self.up4), xs[-2::-1]):
+            y = u.up(y)
+            dy, dx = skip.shape[2] - y.shape[2], skip.shape[3] - y.shape[3]
+            y = F.pad(y, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+            y = dc(u.conv, torch.cat([skip, y], dim=1))
+        logits = self.outc.conv(y)
+        return (logits, torch.sigmoid(self.outr.conv(y))) if self.regression else logits
 
     @staticmethod
     def _fold(dc: DoubleConv, keep, tf32: bool):
@@ -178,10 +198,14 @@ class UNet(nn.Module):
             out.append(NlbUnetConv(ptr(t[0]), ptr(t[1]), ptr(t[2]), ptr(packed)))
         return out
 
-    @torch.no_grad()
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor):
+        """logits [N, n_classes, H, W], or (logits, reg [N, 1, H, W]) with regression=True."""
         if self.training:
-            raise NotImplementedError('UNet: inference only (call .eval(); training the ray-drop network is not built)')
+            return self._forward_torch(x)
+        with torch.no_grad():
+            return self._forward_kernels(x)
+
+    def _forward_kernels(self, x: torch.Tensor):
         x = f32(x)
         N, cin, H, W = x.shape
         if cin != self.n_channels:
@@ -215,12 +239,17 @@ class UNet(nn.Module):
             t = [f32(self.outc.conv.weight.detach().reshape(self.n_classes, 64)), f32(self.outc.conv.bias.detach())]
             keep += t
             w.outc_weight, w.outc_bias = ptr(t[0]), ptr(t[1])
+            if self.regression:
+                t = [f32(self.outr.conv.weight.detach().reshape(1, 64)), f32(self.outr.conv.bias.detach())]
+                keep += t
+                w.outr_weight, w.outr_bias = ptr(t[0]), ptr(t[1])
             w.bilinear, w.n_classes = int(bool(self.bilinear)), int(self.n_classes)
             self.__dict__['_nlb_folded'] = cached = (version, w, keep)
         w = cached[1]
         lib = load()
         ws = torch.empty(lib.nlb_unet_workspace_bytes(N, H, W) // 4, device=x.device)
         out = torch.empty(N, self.n_classes, H, W, device=x.device)
+        reg = torch.empty(N, 1, H, W, device=x.device) if self.regression else None
         with torch.cuda.device(x.device):
-            check(lib.nlb_unet_forward(ptr(x), C.byref(w), N, cin, H, W, ptr(out), ptr(ws), stream()))
-        return out
+            check(lib.nlb_unet_forward(ptr(x), C.byref(w), N, cin, H, W, ptr(out), ptr(reg), ptr(ws), stream()))
+        return (out, reg) if self.regression else out

@@ -25,8 +25,7 @@ def test_unet_mirror_has_the_reference_parameters():
         keys = list(net.state_dict())
         assert 'inc.double_conv.0.weight' in keys and 'down4.maxpool_conv.1.double_conv.4.running_var' in keys
         assert ('up1.up.weight' in keys) == (not bil) and 'outc.conv.bias' in keys
-    with pytest.raises(NotImplementedError):
-        raydrop.UNet(6, 2, regression=True)
+    assert 'outr.conv.weight' in raydrop.UNet(6, 2, regression=True).state_dict()
 
 
 @pytest.mark.gpu
@@ -99,8 +98,43 @@ def test_unet_batches_shapes_and_errors():
         net(torch.zeros(1, 6, 24, 64, device='cuda'))                       # not a multiple of 16
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 5, 32, 64, device='cuda'))
-    with pytest.raises(NotImplementedError):
-        net.train()(x)
+
+
+@pytest.mark.gpu
+def test_unet_training_mode_and_regression_head():
+    """Training mode evaluates the same layers with torch (autograd, batch statistics), as the reference trains this
+    network (R/src/model/ray_drop_train.py:73-125); in eval mode the kernels agree with that torch evaluation, incl.
+    the range-regression head sigmoid(outr(x)) of UNet(regression=True)."""
+    import make_unet_golden as mg
+    torch.manual_seed(0)
+    net = raydrop.UNet(6, 2, bilinear=True, regression=True).cuda()
+    x = mg.image().cuda()
+    gt = (torch.rand(1, 32, 1024, device='cuda') > 0.5).long()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    net.train()
+    losses = []
+    for _ in range(3):
+        logits, reg = net(x)
+        loss = torch.nn.functional.cross_entropy(logits, gt) + (reg[:, 0] - 0.5).abs().mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert losses[-1] < losses[0]
+    net.eval()
+    net.tf32 = False
+    logits, reg = net(x)                                    # csrc/unet.cu on the updated weights and statistics
+    old = torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        with torch.no_grad():
+            want_l, want_r = net._forward_torch(x)          # torch, eval-mode BatchNorm
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert reg.shape == (1, 1, 32, 1024) and float(reg.min()) >= 0 and float(reg.max()) <= 1
+    scale = float(want_l.abs().max())
+    assert float((logits - want_l).abs().max()) <= 1e-4 * max(scale, 1.0), (float((logits - want_l).abs().max()), scale)
+    assert float((reg - want_r).abs().max()) <= 1e-5
 
 
 @pytest.mark.gpu
