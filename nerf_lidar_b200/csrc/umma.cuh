@@ -40,9 +40,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // warp barrier.  128 epilogue threads spinning on try_wait flood the SM's memory-I/O queue
 // that tcgen05.mma issue also goes through: measured 133-140 cycles per MMA issue with
 // per-thread spinning against 64.5 (the tensor pipe's own rate) without.
+#ifndef NLB_POLL_NS
+#define NLB_POLL_NS 40
+#endif
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
   if ((threadIdx.x & 31) == 0) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+    while (!mbar_try_wait(bar, parity)) {
+      if (NLB_POLL_NS > 0) __nanosleep(NLB_POLL_NS);
+    }
   }
   __syncwarp();
 }
