@@ -466,6 +466,8 @@ typedef struct {
   float *g_W_d0, *g_b_d0, *g_W_d2, *g_b_d2, *g_W_v0, *g_b_v0, *g_W_v1, *g_b_v1, *g_W_rgb, *g_b_rgb;
   float* g_latent;   /* or NULL */
   float* g_table;    /* [rows, C] or NULL */
+  float* g_pose;     /* [N, n_obj, 9] or NULL: gradient w.r.t. the interpolated pose (centre, yaw, wlh) of THIS track's
+                        column, accumulated -- track refinement, Z/train.py:244-257 */
 } nlb_obj_grads_t;
 int nlb_obj_backward(const float* tdist, const float* origins, const float* directions, const float* viewdirs,
                      const float* pose, int n_obj, int track, int N, int S, const nlb_table_t* table,

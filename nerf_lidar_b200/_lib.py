@@ -88,7 +88,7 @@ class NlbObjMlp(C.Structure):
 
 class NlbObjGrads(C.Structure):
     _fields_ = [(n, c_f) for n in ('g_W_d0', 'g_b_d0', 'g_W_d2', 'g_b_d2', 'g_W_v0', 'g_b_v0', 'g_W_v1', 'g_b_v1', 'g_W_rgb',
-                                   'g_b_rgb', 'g_latent', 'g_table')]
+                                   'g_b_rgb', 'g_latent', 'g_table', 'g_pose')]
 
 
 class NlbRangeImage(C.Structure):

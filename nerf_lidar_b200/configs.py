@@ -69,6 +69,10 @@ class Config:
     end_step: int = 20000
     learn_R: bool = True
     learn_t: bool = True
+    track_refine: bool = False
+    track_start_opt: int = 5000
+    tn_lr_init: float = 1e-4
+    tn_lr_final: float = 1e-5
     analytic_gradient: bool = True
     use_intensity: bool = False
     no_sem_layer: bool = True

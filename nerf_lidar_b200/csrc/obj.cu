@@ -89,6 +89,52 @@ __device__ __forceinline__ bool box_point(const float* __restrict__ tdist, const
   return fabsf(px) < 1.f && fabsf(py) < 1.f && fabsf(pz) < 1.f;
 }
 
+// Backward of box_point w.r.t. the interpolated pose (track refinement, Z/train.py:244-257: the track's centre and
+// yaw are functions of Track_opt's corrections): gq = dL/d(box coordinates), gu = dL/d(unit view direction in the
+// box frame) -> gp[0..6] = dL/d(centre xyz, yaw, wlh).  rotate_yaw_z with its quirk is x' = c x - s y,
+// y' = s x' + c y, linear in (x, y): rot(p) + rot(-t) = rot(p - t).
+__device__ __forceinline__ void box_point_grad(const float* __restrict__ tdist, const float* __restrict__ origins,
+                                               const float* __restrict__ directions, const float* __restrict__ viewdirs,
+                                               const float* __restrict__ pose, int n_obj, int track, int S, int pt,
+                                               const float (&gq)[3], const float (&gu)[3], float (&gp)[7]) {
+  const int ray = pt / S, s = pt - ray * S;
+  const float* td = tdist + (size_t)ray * (S + 1) + s;
+  const float tm = 0.5f * (__ldg(td) + __ldg(td + 1));
+  const float* ps = pose + ((size_t)ray * n_obj + track) * kInfo;
+  const float ax = tm * __ldg(directions + 3 * ray) + __ldg(origins + 3 * ray) - __ldg(ps);
+  const float ay = tm * __ldg(directions + 3 * ray + 1) + __ldg(origins + 3 * ray + 1) - __ldg(ps + 1);
+  const float az = tm * __ldg(directions + 3 * ray + 2) + __ldg(origins + 3 * ray + 2) - __ldg(ps + 2);
+  const float theta = __ldg(ps + 3);
+  const float c = cosf(theta), sn = sinf(theta);
+  float sc[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) sc[k] = 1.f / (__ldg(ps + 4 + k) * 0.5f + 1e-9f);
+  // position
+  const float x1 = c * ax - sn * ay, y1 = sn * x1 + c * ay;
+  const float gx1 = gq[0] * sc[0], gy1 = gq[1] * sc[1], gz1 = gq[2] * sc[2];
+  const float dx1 = -sn * ax - c * ay, dy1 = c * x1 + sn * dx1 - sn * ay;
+  gp[0] = -(gx1 * c + gy1 * sn * c);
+  gp[1] = -(-gx1 * sn + gy1 * (c - sn * sn));
+  gp[2] = -gz1;
+  gp[3] = gx1 * dx1 + gy1 * dy1;
+  gp[4] = -0.5f * gq[0] * x1 * sc[0] * sc[0];
+  gp[5] = -0.5f * gq[1] * y1 * sc[1] * sc[1];
+  gp[6] = -0.5f * gq[2] * az * sc[2] * sc[2];
+  // view direction: u = w / |w|, w = rot(v) * scale
+  const float v0 = __ldg(viewdirs + 3 * ray), v1 = __ldg(viewdirs + 3 * ray + 1), v2 = __ldg(viewdirs + 3 * ray + 2);
+  const float vx1 = c * v0 - sn * v1, vy1 = sn * vx1 + c * v1;
+  const float w[3] = {vx1 * sc[0], vy1 * sc[1], v2 * sc[2]};
+  const float nrm = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  const float u[3] = {w[0] / nrm, w[1] / nrm, w[2] / nrm};
+  const float ug = u[0] * gu[0] + u[1] * gu[1] + u[2] * gu[2];
+  const float gw[3] = {(gu[0] - u[0] * ug) / nrm, (gu[1] - u[1] * ug) / nrm, (gu[2] - u[2] * ug) / nrm};
+  const float dvx1 = -sn * v0 - c * v1, dvy1 = c * vx1 + sn * dvx1 - sn * v1;
+  gp[3] += gw[0] * sc[0] * dvx1 + gw[1] * sc[1] * dvy1;
+  gp[4] += -0.5f * gw[0] * vx1 * sc[0] * sc[0];
+  gp[5] += -0.5f * gw[1] * vy1 * sc[1] * sc[1];
+  gp[6] += -0.5f * gw[2] * v2 * sc[2] * sc[2];
+}
+
 struct Dims {
   int F, K0, hidden, bott, dir_dim, Kv, vw;  // K0 = F + latent_shape, Kv = bott + dir_dim + latent_tex
   int o_wd0, o_bd0, o_wd2, o_bd2, o_wv0, o_bv0, o_wv1, o_bv1, o_wrgb, o_brgb, total;  // float offsets in shared memory
@@ -444,6 +490,17 @@ __global__ void __launch_bounds__(32) k_obj_backward(const float* __restrict__ t
         dinv[k] = acc;
       }
       __syncwarp();
+      // ---- unit view direction (track refinement): through coord.pos_enc, d sin(a + pi/2) = -sin(a)
+      float gu_l = 0.f;
+      if (g.g_pose && lane < 3) {
+        const float v = lane == 0 ? ux : (lane == 1 ? uy : uz);
+        const float* ge = dinv + d.bott;
+        gu_l = ge[lane];
+        for (int s = 0; s < m.deg_view; ++s) {
+          const float sc2 = (float)(1 << s), a = v * sc2;
+          gu_l += sc2 * (cosf(a) * ge[3 + 3 * s + lane] - sinf(a) * ge[3 + 3 * m.deg_view + 3 * s + lane]);
+        }
+      }
       // ---- bottleneck: dx = d_inv[:bott] (+ the density path on unit 0), texture latent
       for (int k = lane; k < d.bott; k += 32) dx[k] = dinv[k];
       for (int k = lane; k < m.latent_tex; k += 32) G[d.o_lat + m.latent_shape + k] += dinv[d.bott + d.dir_dim + k];
@@ -461,23 +518,61 @@ __global__ void __launch_bounds__(32) k_obj_backward(const float* __restrict__ t
       dense_bwd(W + d.o_wd0, G + d.o_wd0, G + d.o_bd0, in0, dz, d.K0, d.hidden, d.hidden + 1, din, lane);
       __syncwarp();
       for (int k = lane; k < m.latent_shape; k += 32) G[d.o_lat + k] += din[d.F + k];
-      // ---- grid: scatter the feature gradient to the 8 corners of every level (one level per lane)
-      if (lane < tab.L && g.g_table) {
+      // ---- grid: scatter the feature gradient to the 8 corners of every level (one level per lane); with track
+      // refinement also the trilinear slope of the level (the reference's dy_dx) for dL/d(grid coordinates)
+      float sl[3] = {0.f, 0.f, 0.f};
+      if (lane < tab.L && (g.g_table || g.g_pose)) {
         const Level3 lv = level3(tab.offsets, lane, tab.S, tab.H);
         uint32_t cx, cy, cz;
         float fx, fy, fz;
         cell_of(gx, lv.scale, cx, fx);
         cell_of(gy, lv.scale, cy, fy);
         cell_of(gz, lv.scale, cz, fz);
+        uint32_t idx[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float w = 1.f;
-          w *= (i & 1) ? fx : 1.f - fx;
-          w *= (i & 2) ? fy : 1.f - fy;
-          w *= (i & 4) ? fz : 1.f - fz;
-          const uint32_t idx = vertex_index3_branchy(lv, cx + (i & 1), cy + ((i >> 1) & 1), cz + ((i >> 2) & 1));
+        for (int i = 0; i < 8; ++i) idx[i] = vertex_index3_branchy(lv, cx + (i & 1), cy + ((i >> 1) & 1), cz + ((i >> 2) & 1));
+        if (g.g_table) {
 #pragma unroll
-          for (int c = 0; c < C; ++c) atomicAdd(g.g_table + ((size_t)lv.offset + idx) * C + c, w * din[lane * C + c]);
+          for (int i = 0; i < 8; ++i) {
+            float w = 1.f;
+            w *= (i & 1) ? fx : 1.f - fx;
+            w *= (i & 2) ? fy : 1.f - fy;
+            w *= (i & 4) ? fz : 1.f - fz;
+#pragma unroll
+            for (int c = 0; c < C; ++c) atomicAdd(g.g_table + ((size_t)lv.offset + idx[i]) * C + c, w * din[lane * C + c]);
+          }
+        }
+        if (g.g_pose) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            float r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = __ldg(tab.embeddings + ((size_t)lv.offset + idx[i]) * C + c);
+            const float x00 = r[1] - r[0], x10 = r[3] - r[2], x01 = r[5] - r[4], x11 = r[7] - r[6];
+            const float v00 = fmaf(fx, x00, r[0]), v10 = fmaf(fx, x10, r[2]), v01 = fmaf(fx, x01, r[4]), v11 = fmaf(fx, x11, r[6]);
+            const float y0 = v10 - v00, y1 = v11 - v01;
+            const float e0 = fmaf(fy, y0, v00), e1 = fmaf(fy, y1, v01);
+            const float dx0 = fmaf(fy, x10 - x00, x00), dx1 = fmaf(fy, x11 - x01, x01);
+            const float gf = din[lane * C + c] * lv.scale;
+            sl[0] = fmaf(gf, fmaf(fz, dx1 - dx0, dx0), sl[0]);
+            sl[1] = fmaf(gf, fmaf(fz, y1 - y0, y0), sl[1]);
+            sl[2] = fmaf(gf, e1 - e0, sl[2]);
+          }
+        }
+      }
+      if (g.g_pose) {
+        float gq[3], gu[3], gp[7];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          gq[k] = 0.5f * warp_sum(sl[k]);                    // grid coordinate = (box coordinate + 1) / 2
+          gu[k] = __shfl_sync(NLB_FULL_MASK, gu_l, k);
+        }
+        box_point_grad(tdist, origins, directions, viewdirs, pose, n_obj, track, S, q, gq, gu, gp);
+        if (lane < 7) {
+          float v = gp[0];
+#pragma unroll
+          for (int k = 1; k < 7; ++k) v = lane == k ? gp[k] : v;
+          atomicAdd(g.g_pose + ((size_t)(q / S) * n_obj + track) * kInfo + lane, v);
         }
       }
       __syncwarp();

@@ -336,7 +336,12 @@ class Model(nn.Module):
         if self.instance_obj:
             track = curr_track if curr_track is not None else self.tracks
             if track is not None:     # obj_utils.get_pose: per ray, per track
-                obj_pose = ops.obj_pose(batch['timestamp'], track.to(dev))
+                if torch.is_grad_enabled() and track.requires_grad:
+                    # track refinement (Z/train.py:244-257): the blend stays in torch so the gradient of the poses
+                    # (csrc/obj.cu k_obj_backward) reaches the track corrections
+                    obj_pose = ops.obj_pose_torch(ops.f32(batch['timestamp']), track.to(dev))
+                else:
+                    obj_pose = ops.obj_pose(batch['timestamp'], track.to(dev))
         for i_level in range(self.num_levels):
             is_prop = i_level < (self.num_levels - 1)
             S = self.num_prop_samples[i_level] if is_prop else self.num_nerf_samples

@@ -770,6 +770,8 @@ class _ObjBranch(Function):
         g_rgb = None if g_rgb is None else f32(g_rgb)
         grads = {}          # id(param) -> (param, gradient target, returned through autograd?)
         lib = load()
+        # track refinement (Z/train.py:244-257): the interpolated poses carry a graph back to Track_opt
+        g_pose = torch.zeros_like(pose) if ctx.needs_input_grad[4] else None
         with torch.cuda.device(rays.device):
             for track_id in range(n_obj):
                 mlp, latent = model._obj_network(track_id)
@@ -785,7 +787,7 @@ class _ObjBranch(Function):
                     tgt.append(grads[id(prm)][1])
                 desc, keep = _obj_mlp_desc(mlp, latent)
                 tab = _table_desc(mlp.encoder, mlp.encoder.embeddings.detach())
-                gd = NlbObjGrads(*[ptr(t) for t in tgt])
+                gd = NlbObjGrads(*[ptr(t) for t in tgt], ptr(g_pose))
                 with timed('obj_backward'):
                     check(lib.nlb_obj_backward(ptr(tdist), ptr(rays.origins), ptr(rays.directions), ptr(viewdirs), ptr(pose),
                                                n_obj, track_id, N, S, C.byref(tab), C.byref(desc), ptr(owner), ptr(g_density),
@@ -794,7 +796,23 @@ class _ObjBranch(Function):
         for prm in ctx.param_order:
             p_, t_, ret = grads.get(id(prm), (None, None, False))
             out.append(t_ if ret else None)
-        return (None, None, None, None, None, None, *out)
+        return (None, None, None, None, g_pose, None, *out)
+
+
+def obj_pose_torch(time: torch.Tensor, tracks: torch.Tensor) -> torch.Tensor:
+    """obj_utils.get_pose (Z/internal/obj_utils.py:431-475) in torch, for a track table that carries a graph (track
+    refinement): the two entries closest in time (stable order on ties, like the kernel), blended by
+    clamp(|t - t2| / (|t1 - t2| + 1e-9), 0, 1).  time [N,1], tracks [n_obj, T, 9] -> [N, n_obj, 9]."""
+    ts = tracks[:, :, -2]                                                  # [n_obj, T]
+    diff = (time.reshape(-1, 1, 1) - ts[None]).abs()                        # [N, n_obj, T]
+    idx = torch.sort(diff.detach(), dim=-1, stable=True).indices[..., :2]
+    n_obj, T, D = tracks.shape
+    flat = tracks.reshape(n_obj * T, D)
+    base = torch.arange(n_obj, device=tracks.device)[None, :, None] * T
+    info = flat.index_select(0, (idx + base).reshape(-1)).reshape(*idx.shape, D)   # [N, n_obj, 2, 9]
+    t1, t2 = info[..., 0, -2], info[..., 1, -2]
+    w1 = ((time.reshape(-1, 1) - t2).abs() / ((t1 - t2).abs() + 1e-9)).clamp(0, 1)[..., None]
+    return w1 * info[..., 0, :] + (1 - w1) * info[..., 1, :]
 
 
 def obj_apply_train(model, res, tdist, rays, viewdirs, pose, is_prop: bool) -> torch.Tensor:

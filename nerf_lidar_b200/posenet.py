@@ -57,6 +57,58 @@ class LearnPose(nn.Module):
         return c2w
 
 
+class Track_opt(nn.Module):
+    """Per object and track entry a yaw and a centre correction (posenet_v2.py:65-76; same parameter names)."""
+
+    def __init__(self, bboxes: torch.Tensor, learn_R: bool = True, learn_t: bool = True):
+        super().__init__()
+        n_obj, n_ts, _ = bboxes.shape
+        self.init_bboxes = bboxes
+        self.opt_r = nn.Parameter(torch.zeros(n_obj, n_ts, 1), requires_grad=learn_R)
+        self.opt_t = nn.Parameter(torch.zeros(n_obj, n_ts, 3), requires_grad=learn_t)
+        self.tracks = bboxes
+
+    def forward(self):
+        return self.opt_r, self.opt_t
+
+
+def refined_track(tracknet: Track_opt, device=None) -> torch.Tensor:
+    """Z/train.py:251-256: track[:, :, :3] += opt_t, track[:, :, 3:4] += opt_r (a new tensor carrying the graph)."""
+    raw = tracknet.tracks.to(device if device is not None else tracknet.opt_r.device)
+    return torch.cat([raw[:, :, :3] + tracknet.opt_t, raw[:, :, 3:4] + tracknet.opt_r, raw[:, :, 4:]], -1)
+
+
+def track_window(config: Config, step: int) -> Optional[str]:
+    """'train' inside track_start_opt < step < track_start_opt + 5000, 'apply' after it, None before / when off."""
+    if not config.track_refine:
+        return None
+    if config.track_start_opt < step < config.track_start_opt + 5000:
+        return 'train'
+    if step > config.track_start_opt + 5000:
+        return 'apply'
+    return None
+
+
+def create_tracknet(config: Config, tracks: torch.Tensor, device=None):
+    """(tracknet, optimizer, lr_fn) of Z/internal/train_utils.py:303-326."""
+    from .train import learning_rate_decay
+    net = Track_opt(tracks.to(device) if device is not None else tracks)
+    if device is not None:
+        net = net.to(device)
+    start = config.track_start_opt
+
+    def lr_fn(step):
+        return learning_rate_decay(step - start, config.tn_lr_init, config.tn_lr_final, config.max_steps - start,
+                                   config.lr_delay_steps, config.lr_delay_mult)
+
+    params = list(net.parameters())
+    on_gpu = params[0].is_cuda
+    lr = torch.tensor(config.tn_lr_init, device=params[0].device) if on_gpu else config.tn_lr_init
+    opt = torch.optim.Adam(params, lr=lr, betas=(config.adam_beta1, config.adam_beta2), eps=config.adam_eps,
+                           capturable=on_gpu)
+    return net, opt, lr_fn
+
+
 def refine_rays(batch: Dict[str, torch.Tensor], posenet: LearnPose) -> Dict[str, torch.Tensor]:
     """Z/train.py:208-221: origins += t, every direction-like field rotated by R (row-wise R v).  Returns a
     new dictionary; run under torch.no_grad() after the window."""

@@ -174,6 +174,7 @@ class Trainer:
         # point wait for them first
         self._pending = []
         self.posenet = self.pn_optimizer = self.pn_lr_fn = None
+        self.tracknet = self.tn_optimizer = self.tn_lr_fn = None
         model.__dict__['_nlb_sync'] = self.sync
         model.train()
         model.training = True
@@ -190,7 +191,7 @@ class Trainer:
     # issued between the two and travels while the proposal half is still computing.
     PROP_LOSSES = ('interlevel',)
 
-    def forward_losses(self, batch, step: int, num_patch: Optional[int] = None, rand_inputs=None):
+    def forward_losses(self, batch, step: int, num_patch: Optional[int] = None, rand_inputs=None, curr_track=None):
         """Forward pass and loss dictionary; returns (losses, loss_main, loss_prop)."""
         c = self.config
         train_frac = float(np.clip((step - 1) / (c.max_steps - 1), 0, 1))
@@ -198,7 +199,7 @@ class Trainer:
             num_patch = (c.batch_size_per_rank // 4) // (c.patch_size ** 2) if hasattr(c, 'batch_size_per_rank') else 0
         renderings, ray_history = self.model(True, batch, train_frac, True, zero_glo=False, sample_n=c.sample_n_train,
                                              sample_m=c.sample_m_train, step=step, max_step=c.max_steps,
-                                             rand_inputs=rand_inputs)
+                                             curr_track=curr_track, rand_inputs=rand_inputs)
         losses = compute_losses(batch, renderings, ray_history, c, step, num_patch)
         latents = getattr(self.model, 'latent_vector_dict', None)
         if getattr(c, 'latent_size', 0) > 0 and latents is not None:
@@ -234,6 +235,43 @@ class Trainer:
         ray-geometry gradients and steps `optimizer`; afterwards the corrections are applied without gradients."""
         self.posenet, self.pn_optimizer, self.pn_lr_fn = net, optimizer, lr_fn
 
+    def attach_tracknet(self, net, optimizer, lr_fn):
+        """`posenet.create_tracknet(...)`'s triple (Z/train.py:99-103,244-266,467-471): inside
+        track_start_opt < step < track_start_opt + 5000 the object tracks are refined -- `Model.forward` gets
+        `curr_track` with a graph, the object branch returns the gradient of the interpolated poses -- afterwards the
+        refined tracks are applied without gradients."""
+        self.tracknet, self.tn_optimizer, self.tn_lr_fn = net, optimizer, lr_fn
+
+    def _track_mode(self, step: int):
+        if getattr(self, 'tracknet', None) is None:
+            return None
+        from . import posenet as pn
+        return pn.track_window(self.config, step)
+
+    def _current_track(self, mode):
+        from . import posenet as pn
+        if mode == 'train':
+            self.tn_optimizer.zero_grad(set_to_none=True)
+            return pn.refined_track(self.tracknet, self.flat.device)
+        if mode == 'apply':
+            with torch.no_grad():
+                return pn.refined_track(self.tracknet, self.flat.device)
+        return None
+
+    def _side_step(self, net, optimizer):
+        """Gradient mean over the ranks (the reference wraps the side networks in DDP), clipping, Adam."""
+        params = [p for p in net.parameters() if p.grad is not None]
+        if self.world > 1:
+            for p in params:
+                torch.distributed.all_reduce(p.grad)
+                p.grad.div_(self.world)
+        c = self.config
+        if c.grad_max_val > 0:  # train_utils.clip_gradients (Z/internal/train_utils.py:223-232)
+            torch.nn.utils.clip_grad_value_(params, c.grad_max_val)
+        if c.grad_max_norm > 0:
+            torch.nn.utils.clip_grad_norm_(params, c.grad_max_norm)
+        optimizer.step()
+
     def _pose_mode(self, step: int):
         if getattr(self, 'posenet', None) is None:
             return None
@@ -242,14 +280,16 @@ class Trainer:
 
     def _set_pose_lr(self, step: int):
         """Outside any capture: the learning rate is a device scalar the captured Adam reads."""
-        if self._pose_mode(step) != 'train':
-            return
-        lr = float(self.pn_lr_fn(step))
-        for group in self.pn_optimizer.param_groups:
-            if torch.is_tensor(group['lr']):
-                group['lr'].fill_(lr)
-            else:
-                group['lr'] = lr
+        for mode, opt, fn in ((self._pose_mode(step), self.pn_optimizer, self.pn_lr_fn),
+                              (self._track_mode(step), self.tn_optimizer, self.tn_lr_fn)):
+            if mode != 'train':
+                continue
+            lr = float(fn(step))
+            for group in opt.param_groups:
+                if torch.is_tensor(group['lr']):
+                    group['lr'].fill_(lr)
+                else:
+                    group['lr'] = lr
 
     def _refined(self, batch, mode):
         from . import posenet as pn
@@ -261,20 +301,11 @@ class Trainer:
                 return pn.refine_rays(batch, self.posenet)
         return batch
 
-    def _pose_step(self, mode):
-        if mode != 'train':
-            return
-        params = [p for p in self.posenet.parameters() if p.grad is not None]
-        if self.world > 1:      # the reference wraps the posenet in DDP: mean over the ranks
-            for p in params:
-                torch.distributed.all_reduce(p.grad)
-                p.grad.div_(self.world)
-        c = self.config
-        if c.grad_max_val > 0:  # train_utils.clip_gradients (Z/internal/train_utils.py:223-232)
-            torch.nn.utils.clip_grad_value_(params, c.grad_max_val)
-        if c.grad_max_norm > 0:
-            torch.nn.utils.clip_grad_norm_(params, c.grad_max_norm)
-        self.pn_optimizer.step()
+    def _pose_step(self, mode, track_mode=None):
+        if mode == 'train':
+            self._side_step(self.posenet, self.pn_optimizer)
+        if track_mode == 'train':
+            self._side_step(self.tracknet, self.tn_optimizer)
 
     def sync(self):
         """Waits (on the current stream) for the collectives a data-parallel step left in flight: afterwards the
@@ -301,15 +332,15 @@ class Trainer:
         return out
 
     def _train_step(self, batch, step, num_patch=None, rand_inputs=None):
-        pose = self._pose_mode(step)
+        pose, tmode = self._pose_mode(step), self._track_mode(step)
         batch = self._refined(batch, pose)
-        losses, main, prop = self.forward_losses(batch, step, num_patch, rand_inputs)
+        losses, main, prop = self.forward_losses(batch, step, num_patch, rand_inputs, self._current_track(tmode))
         if self.world == 1:
             # (running the NeRF table's optimizer pass on a side stream beside the proposal backward was
             # measured: 7.30-7.35 ms per step against 7.23 ms in order -- the two contend for L2)
             (main if prop is None else main + prop).backward()
             self.optimizer_step(step)
-            self._pose_step(pose)
+            self._pose_step(pose, tmode)
             return losses
         # the refined rays feed both halves: the first backward must keep the posenet's part of the graph
         main.backward(retain_graph=pose == 'train' and prop is not None)
@@ -319,7 +350,7 @@ class Trainer:
         late = self.reduce_scatter_gradients(self._prop_tables(), dense=True)
         parallel.wait_all(early + late)
         self.optimizer_step(step, reduce=False)
-        self._pose_step(pose)
+        self._pose_step(pose, tmode)
         return losses
 
     # ---- data parallel: reduce-scatter of the gradients -> this rank's slice of the optimizer pass -> all-gather
@@ -430,7 +461,7 @@ class Trainer:
         pose-refinement window boundaries."""
         c = self.config
         refine = c.pose_refine and c.start_step < step < int(0.6 * c.end_step)
-        return (bool(refine), step > c.end_step, self._pose_mode(step))
+        return (bool(refine), step > c.end_step, self._pose_mode(step), self._track_mode(step))
 
     def _write_dynamic(self, step: int):
         c = self.config
@@ -457,7 +488,7 @@ class Trainer:
         loss-multiplier regime changes.  Returns the loss dictionary (static tensors,
         overwritten by the next call)."""
         dev = self.flat.device
-        if self.world > 1 and self._pose_mode(step) == 'train':
+        if self.world > 1 and 'train' in (self._pose_mode(step), self._track_mode(step)):
             # the corrections' gradient all-reduce sits between the backward and their Adam step: the
             # data-parallel window (a fifth of the run at most) is issued eagerly
             return self.train_step(batch, step, num_patch, rand_inputs)

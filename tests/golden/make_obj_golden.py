@@ -75,7 +75,12 @@ def branch_gradients(models, model, batch, tdist):
     functional of the merged density / rgb as the loss.  Dense parameters are stored whole, the two 70 MB table
     gradients as their non-zero rows."""
     ou = models.obj_utils
-    obj_pose = ou.get_pose(batch['timestamp'], model.tracks)
+    # track refinement (Z/train.py:244-257): the refined track is a function of Track_opt's corrections, so the
+    # gradient reaches get_pose's blend and box_pts' translation / yaw -- kept here w.r.t. the interpolated pose
+    # and w.r.t. the track table itself
+    tracks_leaf = model.tracks.detach().clone().requires_grad_(True)
+    obj_pose = ou.get_pose(batch['timestamp'], tracks_leaf)
+    obj_pose.retain_grad()
     t_mids = 0.5 * (tdist[..., :-1] + tdist[..., 1:])
     pts_w = t_mids[..., None] * batch['directions'][:, None, :] + batch['origins'][:, None, :]
     pts_o, viewdirs_o, imap = ou.box_pts(pts=pts_w, viewdirs=batch['viewdirs'], obj_pose=obj_pose, sym=False)
@@ -103,7 +108,7 @@ def branch_gradients(models, model, batch, tdist):
                 rgbm = torch.where(m, tmp, cur)
     a, b = loss_coefficients(N, S)
     ((dens * a).sum() + (rgbm * b).sum()).backward()
-    out = {}
+    out = {'grad_pose': obj_pose.grad.numpy().copy(), 'grad_tracks': tracks_leaf.grad.numpy().copy()}
     for name, p in model.named_parameters():
         if not (name.startswith('obj_mlp') or name.startswith('latent_vector_dict')) or p.grad is None:
             continue
