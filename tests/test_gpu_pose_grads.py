@@ -87,6 +87,59 @@ def test_encode_ray_gradients_vs_oracle(which, full_state_dict_visible):
         assert err < 2e-2, (which, k, err)
 
 
+@pytest.mark.parametrize('C,L,log2,rand', [(2, 7, 15, True), (8, 4, 14, False), (1, 5, 12, True)])
+def test_encode_ray_gradients_other_tables_and_ragged_rows(C, L, log2, rand):
+    """Other table shapes (the ObjMLP's L7 x C2 grid, level_dim 8, an odd level count), a sample count that is not
+    a multiple of 32 (a warp's samples then span several rays: the per-lane atomics path), a ragged last block,
+    rand=False (no rotation noise), and the empty batch; low resolutions so every level is in the fp32-exact
+    regime of the test above."""
+    from nerf_lidar_b200 import ops
+    from nerf_lidar_b200._lib import NlbRayGrads, check, load, ptr, stream
+    from nerf_lidar_b200.gridencoder import GridEncoder
+    from tests.test_gpu_encode import _slice_batch
+    import ctypes as Ct
+    n_rays, S = 53, 9
+    batch, _, _ = _setup(17, S, True)
+    batch = _slice_batch(batch, n_rays)
+    g0 = torch.Generator().manual_seed(100 * C + L)
+    s_ = torch.sort(torch.rand(n_rays, S + 1, generator=g0), -1).values
+    t = zo.s_to_t(s_, batch['near'], batch['far'])
+    deg = torch.rand(n_rays, S, 7, generator=g0) if rand else None
+    enc = GridEncoder(input_dim=3, num_levels=L, level_dim=C, base_resolution=16, desired_resolution=256,
+                      log2_hashmap_size=log2).cuda()
+    with torch.no_grad():
+        enc.embeddings.copy_(torch.rand(enc.embeddings.shape, generator=g0) * 2 - 1)
+    emb, offs, gs = enc.embeddings.detach().cpu(), enc.offsets.cpu(), enc.grid_sizes.cpu()
+    leaf = {k: batch[k].clone().requires_grad_(True) for k in GEOM}
+    means, stds = zo.cast_rays(t, leaf['origins'], leaf['directions'], batch['radii'], leaf['base_x'], leaf['base_y'], deg)
+    # the oracle's encode assumes base resolution 16 and per-level scale from the grid sizes it is given
+    from oracle import grid_oracle as go
+    z, sd_ = zo.contract_mean_std(means.reshape(-1, 3), stds.reshape(-1))
+    x01 = (z / 2 + 1) / 2
+    flat = go._GridEncodeFn.apply(x01, emb, offs, float(np.log2(enc.per_level_scale)), 16, True, 0, False, 0)
+    w = torch.erf(1 / torch.clamp(torch.sqrt(8 * (sd_ / 2).reshape(n_rays, S, 7)[..., None] ** 2 * gs ** 2), min=1e-10))
+    feat = (flat.reshape(n_rays, S, 7, L, C) * w[..., None]).mean(-3).flatten(-2, -1)
+    g = torch.randn(n_rays * S, L * C, generator=g0)
+    feat.backward(g.reshape(n_rays, S, -1))
+    cu, rays = _cuda_rays(ops, batch)
+    degc = None if deg is None else deg.cuda()
+    ops.nerf_encode(t.cuda(), degc, enc, rays, 0.35).backward(g.cuda())
+    for k in GEOM:
+        err = _rel_l2(cu[k].grad.cpu(), leaf[k].grad)
+        assert err < 2e-4, (C, L, k, err)
+    # empty batch: nothing launched, no error even with null buffers
+    empty = ops.RayBundle({k: v[:0].cuda() for k, v in batch.items()})
+    t0 = torch.zeros(0, S + 1, device='cuda')
+    from nerf_lidar_b200.ops import _table_desc
+    z4 = NlbRayGrads(None, None, None, None)
+    check(load().nlb_encode_input_backward(Ct.byref(empty.desc(t0, None, 0.35)), Ct.byref(_table_desc(enc, enc.embeddings.detach())),
+                                           None, Ct.byref(z4), stream()))
+    # a missing gradient buffer is an argument error, not a crash
+    bad = load().nlb_encode_input_backward(Ct.byref(rays.desc(t.cuda(), degc, 0.35)),
+                                           Ct.byref(_table_desc(enc, enc.embeddings.detach())), ptr(g.cuda()), Ct.byref(z4), stream())
+    assert bad != 0
+
+
 @pytest.mark.parametrize('heads', ['torch32', 'fused'])
 def test_model_ray_gradients_vs_oracle(heads):
     """The whole step: all losses differentiated w.r.t. origins, directions, viewdirs, base_x, base_y against fp32
