@@ -101,6 +101,26 @@ def test_unet_batches_shapes_and_errors():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('shape,bilinear', [((2, 6, 32, 1024), True), ((1, 6, 64, 2048), False), ((3, 6, 16, 128), True),
+                                            ((1, 6, 48, 64), False)])
+def test_unet_tf32_other_shapes(shape, bilinear):
+    """The tensor-core path at other image shapes and batch sizes (batched sweeps, a 64-beam 2048-column image, the
+    smallest image whose deepest level is still one 2 x 64 tile wide enough -- 16 x 128 is not: its levels below
+    W = 64 run on the fp32 kernels -- and a height the 2-row tile does not divide) against the fp32 kernels."""
+    import make_unet_golden as mg
+    net = mg.seeded(raydrop.UNet, bilinear).cuda()
+    x = torch.randn(*shape, device='cuda', generator=torch.Generator(device='cuda').manual_seed(shape[2] + shape[3]))
+    net.tf32 = True
+    a = net(x)
+    net.tf32 = False
+    b = net(x)
+    assert a.shape == (shape[0], 2, shape[2], shape[3]) and torch.isfinite(a).all()
+    scale = float(b.abs().max())
+    assert float((a - b).abs().max()) <= 2e-3 * max(scale, 0.1), (float((a - b).abs().max()), scale)
+    assert not torch.equal(a, b)
+
+
+@pytest.mark.gpu
 def test_unet_training_mode_and_regression_head():
     """Training mode evaluates the same layers with torch (autograd, batch statistics), as the reference trains this
     network (R/src/model/ray_drop_train.py:73-125); in eval mode the kernels agree with that torch evaluation, incl.
