@@ -388,6 +388,8 @@ def run_cuda_arm(args):
     rows_mlp = rays_model * SAMPLES[-1]
     if 'nerf_mlp_wgrad' in per_kernel:   # HBM-bound: 5.6 KB of bf16 operands per row (csrc/nerf_wgrad.cu)
         per_kernel['nerf_mlp_wgrad']['alg_gbs'] = 5600.0 * rows_mlp / (per_kernel['nerf_mlp_wgrad']['avg_ms'] * 1e-3) / 1e9
+    if 'mlp_grad_sums' in per_kernel:    # one pass over the 1008 bf16 columns of pre-activation gradients (csrc/reduce.cu)
+        per_kernel['mlp_grad_sums']['alg_gbs'] = 2016.0 * rows_mlp / (per_kernel['mlp_grad_sums']['avg_ms'] * 1e-3) / 1e9
     for name, macs in (('nerf_mlp_fwd', 264192), ('nerf_mlp_bwd', 257024), ('nerf_mlp_wgrad', 253184)):
         if name in per_kernel:
             t = 2.0 * macs * rows_mlp / (per_kernel[name]['avg_ms'] * 1e-3) / 1e12

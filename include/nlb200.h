@@ -302,6 +302,18 @@ int nlb_nerf_mlp_wgrad_finish(const float* rs_v0, const float* rs_v1, const floa
 int nlb_colsum_bf16(const void* x, int64_t M, int cols, int ld, float* out, void* stream);
 int nlb_group_sum_bf16(const void* x, int64_t groups, int S, int cols, int ld, float* out, void* stream);
 
+/* The same reductions as jobs of ONE launch (what a NerfMLP backward issues: five bias gradients and two per-ray
+ * sums, 661 MB at the bench size): x bf16 [rows, ld] read with 16-byte loads (x and out 16-byte aligned, ld a
+ * multiple of 8, cols a power of two in [8, 256]).  group = 0: out[cols] = column sums (overwritten); group = S > 0:
+ * out[rows / S, cols] = sums over S consecutive rows.  At most 8 jobs. */
+typedef struct {
+  const void* x;
+  int64_t rows;
+  int cols, ld, group;
+  float* out;
+} nlb_bf16_sum_job_t;
+int nlb_bf16_sums(const nlb_bf16_sum_job_t* jobs, int njobs, void* stream);
+
 /* Dev probe: clock64() stamps of block 0's MMA thread / epilogue thread for the first two
  * tiles of nlb_nerf_mlp_forward are written to buf[128] (int64); NULL switches it off. */
 int nlb_debug_set_timeline(void* buf);
@@ -320,6 +332,33 @@ int nlb_distortion_loss(const float* sdist, const float* weights, int N, int S, 
                         void* stream);
 int nlb_interlevel_loss(const float* c, const float* w, int Sc, const float* cp, const float* wp, int Sp,
                         float pulse_width, int N, float* loss_ray, float* grad_wp, void* stream);
+
+/* Loss assembly: the reference sums its loss dictionary and back-propagates the sum (Z/train.py:283-462); as torch
+ * scalar arithmetic that is ~45 tiny launches per step.
+ * weighted_sums (one block): for every term in order, out[out_index] += coef * sum_i x[i] * (w ? w[i] : 1), i < n;
+ *   a term with x == NULL adds coef * (the value this call has formed so far for output index n).  Outputs that
+ *   no term names keep their contents, named ones are overwritten.  At most 24 terms, 16 outputs.
+ * scale_tensors (one launch): dst[i] = src[i] * (coef * g * s) + (src2 ? src2[i] * (coef2 * g * s2) : 0), with
+ *   g / s / s2 device scalars (NULL = 1): every gradient a backward pass seeds.  At most 8 jobs. */
+typedef struct {
+  const float* x;
+  const float* w;
+  int64_t n;
+  float coef;
+  int out_index;
+} nlb_sum_term_t;
+int nlb_weighted_sums(const nlb_sum_term_t* terms, int nterms, float* out, int nout, void* stream);
+typedef struct {
+  const float* src;
+  const float* src2;
+  float* dst;
+  int64_t n;
+  const float* g;
+  const float* s;
+  const float* s2;
+  float coef, coef2;
+} nlb_scale_job_t;
+int nlb_scale_tensors(const nlb_scale_job_t* jobs, int njobs, void* stream);
 
 /* ------------------------------------------------------------------ supervision losses
  * Value and gradient of the losses of Z/train.py:283-455 on the final rendering:

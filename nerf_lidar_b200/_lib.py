@@ -70,6 +70,20 @@ class NlbNerfMlpGradOut(C.Structure):
                [(n, C.c_int) for n in ('ld_v1', 'ld_v0', 'ld_g')]
 
 
+class NlbBf16SumJob(C.Structure):
+    _fields_ = [('x', C.c_void_p), ('rows', C.c_int64), ('cols', C.c_int), ('ld', C.c_int), ('group', C.c_int),
+                ('out', C.c_void_p)]
+
+
+class NlbSumTerm(C.Structure):
+    _fields_ = [('x', C.c_void_p), ('w', C.c_void_p), ('n', C.c_int64), ('coef', C.c_float), ('out_index', C.c_int)]
+
+
+class NlbScaleJob(C.Structure):
+    _fields_ = [('src', C.c_void_p), ('src2', C.c_void_p), ('dst', C.c_void_p), ('n', C.c_int64), ('g', C.c_void_p),
+                ('s', C.c_void_p), ('s2', C.c_void_p), ('coef', C.c_float), ('coef2', C.c_float)]
+
+
 class NlbRayGrads(C.Structure):
     _fields_ = [(n, c_f) for n in ('origins', 'directions', 'base_x', 'base_y')]
 
@@ -141,6 +155,9 @@ SIGNATURES = {
     'nlb_nerf_mlp_wgrad_finish': (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, C.POINTER(NlbNerfMlpWeights), _p]),
     'nlb_colsum_bf16': (_i, [_p, C.c_int64, _i, _i, _p, _p]),
     'nlb_group_sum_bf16': (_i, [_p, C.c_int64, _i, _i, _i, _p, _p]),
+    'nlb_bf16_sums': (_i, [C.POINTER(NlbBf16SumJob), _i, _p]),
+    'nlb_weighted_sums': (_i, [C.POINTER(NlbSumTerm), _i, _p, _i, _p]),
+    'nlb_scale_tensors': (_i, [C.POINTER(NlbScaleJob), _i, _p]),
     'nlb_debug_set_timeline': (_i, [_p]),
     'nlb_distortion_loss': (_i, [_p, _p, _i, _i, _p, _p, _p]),
     'nlb_interlevel_loss': (_i, [_p, _p, _i, _p, _p, _i, _f, _i, _p, _p, _p]),

@@ -6,6 +6,7 @@
 // The reference spends ~4.4 GB/step of HBM traffic in five separate passes
 // (zero_grad, p^2 segment mean, its backward, nan_to_num, Adam); this is one pass
 // of 16 B read + 16 B written per parameter.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/nlb200.h"
 
@@ -106,6 +107,29 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ param, float* 
 
 using namespace nlb;
 
+// Grid of the streaming pass: every block owns one contiguous range, so the grid is exactly the number of blocks
+// the device keeps resident (one wave; 148 x 8 blocks of equal work ran as 1.6 waves at 5 resident blocks per SM).
+// NLB_ADAM_BLOCKS_PER_SM overrides the occupancy query (A/B timing).
+static int adam_blocks(int64_t n, bool decay) {
+  static int per_sm[2][64] = {{0}};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int& occ = per_sm[decay ? 1 : 0][dev];
+  if (occ == 0) {
+    const char* e = getenv("NLB_ADAM_BLOCKS_PER_SM");
+    if (e && *e) occ = atoi(e);
+    if (occ <= 0) {
+      if (decay) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_adam<true>, 256, 0);
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_adam<false>, 256, 0);
+    }
+    if (occ <= 0) occ = 4;
+  }
+  const int64_t want = (n / 4 + 255) / 256;
+  const int64_t cap = (int64_t)nlb_sm_count() * occ;
+  return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
 static void bias_terms(float lr, float beta1, float beta2, int step, float& lr_c, float& rsqrt_bc2) {
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
@@ -148,8 +172,7 @@ extern "C" int nlb_adam_table_step_range(float* param, float* grad, float* exp_a
   float* g = grad + first;
   float lr_c, rs;
   bias_terms(lr, beta1, beta2, step, lr_c, rs);
-  int64_t want = (count / 4 + 255) / 256;
-  const int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+  const int blocks = adam_blocks(count, decay_mult != 0.f);
   if (decay_mult != 0.f)
     k_adam<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, exp_avg, exp_avg_sq, count, dt, lr_c, rs, beta1, beta2, eps, grad_scale, level_sumsq, nlb_dynamic_scalars(), first);
   else
@@ -170,8 +193,7 @@ extern "C" int nlb_adam_step(float* param, float* grad, float* exp_avg, float* e
   dt.L = 0;
   float lr_c, rs;
   bias_terms(lr, beta1, beta2, step, lr_c, rs);
-  int64_t want = (n / 4 + 255) / 256;
-  const int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+  const int blocks = adam_blocks(n, false);
   k_adam<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, dt, lr_c, rs, beta1, beta2, eps, grad_scale, nullptr, nlb_dynamic_scalars(), 0);
   return nlb_check_launch("adam_step");
 }

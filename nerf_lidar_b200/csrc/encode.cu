@@ -1265,15 +1265,21 @@ static int scatter_launch(const nlb_rays_t& rays, const nlb_table_t& tab, const 
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_bwd<C>, kEncThreads, smem);
   if (per_sm < 1) per_sm = 1;
+  // development switches (A/B timing): fewer resident blocks per SM than the occupancy limit
+  static const int kBlocksPerSm = (int)env_long("NLB_SCATTER_BLOCKS_PER_SM", 0);
+  static const int kPairBlocksPerSm = (int)env_long("NLB_SCATTER_PAIR_BLOCKS_PER_SM", 0);
+  if (kBlocksPerSm > 0 && kBlocksPerSm < per_sm) per_sm = kBlocksPerSm;
   int blocks_staged = sm_count() * per_sm;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_bwd<C>, kEncThreads, 0);
   if (per_sm < 1) per_sm = 1;
+  if (kBlocksPerSm > 0 && kBlocksPerSm < per_sm) per_sm = kBlocksPerSm;
   int blocks_plain = sm_count() * per_sm;
   if (blocks_staged > tiles) blocks_staged = tiles;
   if (blocks_plain > tiles) blocks_plain = tiles;
   static const bool kLegacyHashed = getenv("NLB_SCATTER_HASHED_LEGACY") != nullptr;  // A/B timing
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_bwd_hashed_pair<C>, kEncThreads, 0);
   if (per_sm < 1) per_sm = 1;
+  if (kPairBlocksPerSm > 0 && kPairBlocksPerSm < per_sm) per_sm = kPairBlocksPerSm;
   const int blocks_pair = sm_count() * per_sm;
   // level groups: consecutive levels whose gradient rows fit the L2 budget together, so a
   // fine level stays L2-resident while every tile updates it (level-major order)

@@ -159,6 +159,74 @@ __global__ void __launch_bounds__(kLossWarps * 32) k_interlevel(const float* __r
   if (lane == 0) loss_ray[ray] = part;
 }
 
+
+// ----------------------------------------------------------------------------- loss assembly
+// Z/train.py:283-462 sums its loss dictionary and back-propagates the sum; issued as torch scalar arithmetic that
+// is ~45 tiny launches per step (means, multiplier products, the python sum, their backward nodes).  Two generic
+// launches instead: k_weighted_sums forms every scalar of the dictionary in one block, k_scale_tensors seeds all
+// gradients of a backward pass.
+constexpr int kMaxSumTerms = 24, kMaxSumOut = 16, kMaxScaleJobs = 8;
+struct SumTerms {
+  nlb_sum_term_t t[kMaxSumTerms];
+  int n;
+};
+
+__global__ void __launch_bounds__(1024) k_weighted_sums(const __grid_constant__ SumTerms T, float* __restrict__ out,
+                                                        int nout) {
+  __shared__ float s_warp[32];
+  __shared__ float s_out[kMaxSumOut];
+  __shared__ int s_named[kMaxSumOut];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < kMaxSumOut) { s_out[tid] = 0.f; s_named[tid] = 0; }
+  __syncthreads();
+  for (int k = 0; k < T.n; ++k) {
+    const nlb_sum_term_t& q = T.t[k];
+    if (q.coef == 0.f) {   // names the output (it will be written) without reading x: 0 * NaN must stay 0
+      if (tid == 0) s_named[q.out_index] = 1;
+      __syncthreads();
+      continue;
+    }
+    if (q.x == nullptr) {  // coef * (an earlier result of this call)
+      if (tid == 0) { s_out[q.out_index] += q.coef * s_out[(int)q.n]; s_named[q.out_index] = 1; }
+      __syncthreads();
+      continue;
+    }
+    float a = 0.f;
+    if (q.w) {
+      for (int64_t i = tid; i < q.n; i += 1024) a = fmaf(__ldg(q.x + i), __ldg(q.w + i), a);
+    } else {
+      for (int64_t i = tid; i < q.n; i += 1024) a += __ldg(q.x + i);
+    }
+    a = warp_sum(a);
+    if (lane == 0) s_warp[warp] = a;
+    __syncthreads();
+    if (warp == 0) {
+      a = warp_sum(s_warp[lane]);
+      if (lane == 0) { s_out[q.out_index] += q.coef * a; s_named[q.out_index] = 1; }
+    }
+    __syncthreads();
+  }
+  if (tid < nout && s_named[tid]) out[tid] = s_out[tid];
+}
+
+struct ScaleJobs {
+  nlb_scale_job_t j[kMaxScaleJobs];
+};
+
+__global__ void __launch_bounds__(256) k_scale_tensors(const __grid_constant__ ScaleJobs J) {
+  const nlb_scale_job_t& q = J.j[blockIdx.y];
+  const float g = q.g ? __ldg(q.g) : 1.0f;
+  const float a = q.coef * g * (q.s ? __ldg(q.s) : 1.0f);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (q.src2) {
+    const float b = q.coef2 * g * (q.s2 ? __ldg(q.s2) : 1.0f);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q.n; i += stride)
+      q.dst[i] = fmaf(__ldg(q.src2 + i), b, __ldg(q.src + i) * a);
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q.n; i += stride) q.dst[i] = __ldg(q.src + i) * a;
+  }
+}
+
 }  // namespace nlb
 
 using namespace nlb;
@@ -185,4 +253,40 @@ extern "C" int nlb_interlevel_loss(const float* c, const float* w, int Sc, const
   k_interlevel<<<div_up(N, kLossWarps), kLossWarps * 32, smem, (cudaStream_t)stream>>>(c, w, Sc, cp, wp, Sp, pulse_width, N,
                                                                                      loss_ray, grad_wp);
   return nlb_check_launch("interlevel_loss");
+}
+
+extern "C" int nlb_weighted_sums(const nlb_sum_term_t* terms, int nterms, float* out, int nout, void* stream) {
+  if (!terms || !out || nterms < 1 || nterms > kMaxSumTerms || nout < 1 || nout > kMaxSumOut) {
+    nlb_set_error("weighted_sums: 1..%d terms, 1..%d outputs", kMaxSumTerms, kMaxSumOut);
+    return NLB_EINVAL;
+  }
+  SumTerms T;
+  T.n = nterms;
+  for (int k = 0; k < nterms; ++k) {
+    const nlb_sum_term_t& q = terms[k];
+    if (q.out_index < 0 || q.out_index >= nout || q.n < 0 || (!q.x && q.n >= nout)) {
+      nlb_set_error("weighted_sums: term %d names an output outside [0,%d)", k, nout);
+      return NLB_EINVAL;
+    }
+    T.t[k] = q;
+  }
+  k_weighted_sums<<<1, 1024, 0, (cudaStream_t)stream>>>(T, out, nout);
+  return nlb_check_launch("weighted_sums");
+}
+
+extern "C" int nlb_scale_tensors(const nlb_scale_job_t* jobs, int njobs, void* stream) {
+  if (!jobs || njobs < 1 || njobs > kMaxScaleJobs) { nlb_set_error("scale_tensors: 1..%d jobs", kMaxScaleJobs); return NLB_EINVAL; }
+  ScaleJobs J;
+  int64_t longest = 0;
+  for (int k = 0; k < njobs; ++k) {
+    const nlb_scale_job_t& q = jobs[k];
+    if (q.n < 0 || (q.n > 0 && (!q.src || !q.dst))) { nlb_set_error("scale_tensors: bad arguments in job %d", k); return NLB_EINVAL; }
+    J.j[k] = q;
+    if (q.n > longest) longest = q.n;
+  }
+  if (longest == 0) return NLB_OK;
+  int64_t bx = (longest + 1023) / 1024;   // four elements per thread
+  if (bx > 148 * 8) bx = 148 * 8;
+  k_scale_tensors<<<dim3((unsigned)bx, njobs), 256, 0, (cudaStream_t)stream>>>(J);
+  return nlb_check_launch("scale_tensors");
 }

@@ -19,7 +19,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import timed, NlbRayGrads, NlbObjGrads, NlbObjMlp, NlbLossesIn, NlbNerfMlpWeights, NlbNerfMlpSaved, NlbNerfMlpGradIn, NlbNerfMlpGradOut, NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
+from ._lib import timed, NlbBf16SumJob, NlbSumTerm, NlbScaleJob, NlbRayGrads, NlbObjGrads, NlbObjMlp, NlbLossesIn, NlbNerfMlpWeights, NlbNerfMlpSaved, NlbNerfMlpGradIn, NlbNerfMlpGradOut, NlbCompositeGrad, NlbCompositeIn, NlbCompositeOut, NlbRays, NlbTable, check, f32, load, ptr, stream
 
 EPS = float(torch.finfo(torch.float32).eps)
 _u_cache: Dict[Tuple, torch.Tensor] = {}
@@ -465,6 +465,19 @@ def group_sum_bf16(x: torch.Tensor, S: int) -> torch.Tensor:
     return out
 
 
+@torch.no_grad()
+def bf16_sums(jobs) -> None:
+    """[(x bf16 [M, cols] with dense rows, group, out fp32)]: group = 0 -> out[cols] = column sums, group = S ->
+    out[M / S, cols] = sums over S consecutive rows; all jobs in ONE launch (nlb_bf16_sums)."""
+    arr = (NlbBf16SumJob * len(jobs))()
+    for q, (x, group, out) in zip(arr, jobs):
+        M, cols = x.shape
+        q.x, q.rows, q.cols, q.ld, q.group, q.out = _bf16_rows_ptr(x).value, M, cols, x.stride(0), int(group), ptr(out)
+    with torch.cuda.device(jobs[0][0].device):
+        with timed('mlp_grad_sums'):
+            check(load().nlb_bf16_sums(arr, len(jobs), stream()))
+
+
 class _NerfMLP(Function):
     """Training path of the NerfMLP, all on tcgen05: fused forward that saves bf16 activations, fused
     data-gradient chain, and the weight gradients dW = dZ^T A as MN-major UMMA products (csrc/nerf_wgrad.cu)
@@ -517,11 +530,12 @@ class _NerfMLP(Function):
                                                    C.byref(gout), stream()))
             with timed('nerf_mlp_wgrad'):
                 check(load().nlb_nerf_mlp_wgrad(C.byref(sv), C.byref(gout), M, C.byref(wg), stream()))
-        # bias gradients and per-ray sums (the view-direction encoding is a per-ray constant): one
-        # bandwidth-bound pass each (csrc/reduce.cu), folded into the gradient buffers by one small kernel
-        cs_x, cs_g, cs_h0 = colsum_bf16(d_x), colsum_bf16(d_g), colsum_bf16(d_h0)
-        cs_hs1, cs_rgb = colsum_bf16(d_hs1), colsum_bf16(d_rgb)
-        rs_v0, rs_v1 = group_sum_bf16(d_v0, S), group_sum_bf16(d_v1, S)
+        # bias gradients and per-ray sums (the view-direction encoding is a per-ray constant): ONE bandwidth-bound
+        # launch over the seven matrices (csrc/reduce.cu), folded into the gradient buffers by one small kernel
+        cs_x, cs_g, cs_h0, cs_hs1, cs_rgb = torch.empty(496, device=dev, dtype=torch.float32).split([256, 128, 64, 32, 16])
+        rs_v0, rs_v1 = torch.empty(2, M // S, 256, device=dev, dtype=torch.float32).unbind(0)
+        bf16_sums([(d_x, 0, cs_x), (d_g, 0, cs_g), (d_h0, 0, cs_h0), (d_hs1, 0, cs_hs1), (d_rgb, 0, cs_rgb),
+                   (d_v0, S, rs_v0), (d_v1, S, rs_v1)])
         with torch.cuda.device(dev):
             with timed('nerf_mlp_wgrad_finish'):
                 check(load().nlb_nerf_mlp_wgrad_finish(ptr(rs_v0), ptr(rs_v1), ptr(viewdirs), N, ptr(cs_x), ptr(cs_g),
@@ -598,43 +612,54 @@ def interlevel_per_ray(c, w, cp, wp, pulse_width: float) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- supervision losses
+def _render_losses_launch(rgb, depth, semantic, intensity, batch, cfg):
+    """One call of csrc/render_losses.cu: (losses[6], scales[6], g_rgb, g_depth, g_sem, g_int, g_dsmo, g_ssmo) -- the six
+    loss values [data, depth, sem, int, d_smo, s_smo] and their gradients up to the per-loss scale factors."""
+    rgb, depth = f32(rgb), f32(depth).reshape(-1)
+    N = depth.shape[0]
+    dev = depth.device
+    sem = f32(semantic) if semantic is not None else None
+    inten = f32(intensity).reshape(-1) if intensity is not None else None
+    K = sem.shape[-1] if sem is not None else 0
+    t = {k: f32(batch[k]).reshape(-1) if k != 'rgb' else f32(batch[k][..., :3])
+         for k in ('rgb', 'depth', 'semantic', 'intensity', 'patch_mask', 'lidar_mask') if k in batch}
+    # Z/train.py:286-289,307: the loss applies where the dataset mask is non-zero; instance_obj clears it
+    valid = None
+    if not cfg.get('instance_obj', False) and batch.get('mask') is not None:
+        valid = f32(batch['mask']).reshape(-1)
+    new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    losses, scales = new(6), new(6)
+    g_rgb, g_depth = new(N, 3), new(N)
+    g_sem = new(N, K) if sem is not None else None
+    g_int = new(N) if inten is not None else None
+    num_patch = int(cfg['num_patch'])
+    g_dsmo = g_ssmo = None
+    if num_patch > 0:   # accumulated with atomics: one zero fill for both
+        smo = torch.zeros(N * (1 + K), device=dev)
+        g_dsmo = smo[:N]
+        g_ssmo = smo[N:].view(N, K) if sem is not None else None
+    ws = new(load().nlb_render_losses_workspace_bytes() // 4)
+    lin = NlbLossesIn(ptr(rgb), ptr(depth), ptr(sem), ptr(inten), ptr(t['rgb']), ptr(t['depth']),
+                      ptr(t.get('semantic')), ptr(t.get('intensity')), ptr(t['patch_mask']), ptr(t['lidar_mask']),
+                      ptr(valid), N, K, num_patch, int(cfg['patch_size']), int(cfg['lidar_supervision']),
+                      int(cfg['only_lidar_supervision']), int(cfg['charb']), float(cfg['charb_padding']),
+                      float(cfg['depth_mult']), float(cfg['sem_mult']), float(cfg['int_mult']),
+                      float(cfg['smooth_mult']), 0., 0.)
+    with torch.cuda.device(dev):
+        with timed('render_losses'):
+            check(load().nlb_render_losses(C.byref(lin), ptr(losses), ptr(scales), ptr(g_rgb), ptr(g_depth),
+                                           ptr(g_sem), ptr(g_int), ptr(g_dsmo), ptr(g_ssmo), ptr(ws), stream()))
+    return losses, scales, g_rgb, g_depth, g_sem, g_int, g_dsmo, g_ssmo
+
+
 class _RenderLosses(Function):
     """data / depth / sem / int / d_smo / s_smo of Z/train.py:283-455 in four launches
     (csrc/render_losses.cu); returns the six loss values as one tensor."""
 
     @staticmethod
     def forward(ctx, rgb, depth, semantic, intensity, batch, cfg):
-        rgb, depth = f32(rgb), f32(depth).reshape(-1)
-        N = depth.shape[0]
-        dev = depth.device
-        sem = f32(semantic) if semantic is not None else None
-        inten = f32(intensity).reshape(-1) if intensity is not None else None
-        K = sem.shape[-1] if sem is not None else 0
-        t = {k: f32(batch[k]).reshape(-1) if k != 'rgb' else f32(batch[k][..., :3])
-             for k in ('rgb', 'depth', 'semantic', 'intensity', 'patch_mask', 'lidar_mask') if k in batch}
-        # Z/train.py:286-289,307: the loss applies where the dataset mask is non-zero; instance_obj clears it
-        valid = None
-        if not cfg.get('instance_obj', False) and batch.get('mask') is not None:
-            valid = f32(batch['mask']).reshape(-1)
-        new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
-        losses, scales = new(6), new(6)
-        g_rgb, g_depth = new(N, 3), new(N)
-        g_sem = new(N, K) if sem is not None else None
-        g_int = new(N) if inten is not None else None
-        num_patch = int(cfg['num_patch'])
-        g_dsmo = torch.zeros(N, device=dev) if num_patch > 0 else None
-        g_ssmo = torch.zeros(N, K, device=dev) if (num_patch > 0 and sem is not None) else None
-        ws = new(load().nlb_render_losses_workspace_bytes() // 4)
-        lin = NlbLossesIn(ptr(rgb), ptr(depth), ptr(sem), ptr(inten), ptr(t['rgb']), ptr(t['depth']),
-                          ptr(t.get('semantic')), ptr(t.get('intensity')), ptr(t['patch_mask']), ptr(t['lidar_mask']),
-                          ptr(valid), N, K, num_patch, int(cfg['patch_size']), int(cfg['lidar_supervision']),
-                          int(cfg['only_lidar_supervision']), int(cfg['charb']), float(cfg['charb_padding']),
-                          float(cfg['depth_mult']), float(cfg['sem_mult']), float(cfg['int_mult']),
-                          float(cfg['smooth_mult']), 0., 0.)
-        with torch.cuda.device(dev):
-            with timed('render_losses'):
-                check(load().nlb_render_losses(C.byref(lin), ptr(losses), ptr(scales), ptr(g_rgb), ptr(g_depth),
-                                               ptr(g_sem), ptr(g_int), ptr(g_dsmo), ptr(g_ssmo), ptr(ws), stream()))
+        losses, scales, g_rgb, g_depth, g_sem, g_int, g_dsmo, g_ssmo = _render_losses_launch(
+            rgb, depth, semantic, intensity, batch, cfg)
         ctx.save_for_backward(scales, g_rgb, g_depth, g_sem, g_int, g_dsmo, g_ssmo)
         ctx.int_shape = None if intensity is None else intensity.shape
         ctx.depth_shape = depth.shape
@@ -658,13 +683,164 @@ class _RenderLosses(Function):
             if g_ssmo is not None:
                 o_sem = torch.addcmul(o_sem, g_ssmo, w[5])
         o_int = (g_int * w[3]).reshape(ctx.int_shape) if g_int is not None else None
-        return o_rgb, o_depth, o_sem, o_int, None, None
+        return o_rgb, o_depth.reshape(ctx.depth_shape), o_sem, o_int, None, None
 
 
 def render_losses(rendering: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], cfg: Dict) -> torch.Tensor:
     """[data, depth, sem, int, d_smo, s_smo] for the final rendering (see _RenderLosses)."""
     return _RenderLosses.apply(rendering['rgb'], rendering['depth'], rendering.get('semantic'),
                                rendering.get('intensity'), batch, cfg)
+
+
+# ----------------------------------------------------------------------------- loss assembly in two launches
+def weighted_sums(terms, out: torch.Tensor) -> None:
+    """nlb_weighted_sums: terms = [(x, w, coef, out_index)] with x a float32 CUDA tensor (every element is summed),
+    w an optional weight tensor of the same size; x = an int names an output this call has already formed."""
+    arr = (NlbSumTerm * len(terms))()
+    for q, (x, w, coef, oi) in zip(arr, terms):
+        if isinstance(x, int):
+            q.x, q.w, q.n = None, None, x
+        else:
+            q.x, q.w, q.n = ptr(x), ptr(w), x.numel()
+        q.coef, q.out_index = float(coef), int(oi)
+    with torch.cuda.device(out.device):
+        with timed('loss_sums'):
+            check(load().nlb_weighted_sums(arr, len(terms), ptr(out), out.numel(), stream()))
+
+
+def scale_tensors(jobs) -> None:
+    """nlb_scale_tensors: jobs = [(src, src2, dst, g, s, s2, coef, coef2)]: dst = src * (coef g s) + src2 * (coef2 g s2);
+    g / s / s2 one-element CUDA tensors or None (= 1)."""
+    arr = (NlbScaleJob * len(jobs))()
+    for q, (src, src2, dst, g, s1, s2, coef, coef2) in zip(arr, jobs):
+        q.src, q.src2, q.dst, q.n = ptr(src), ptr(src2), ptr(dst), src.numel()
+        q.g, q.s, q.s2 = ptr(g), ptr(s1), ptr(s2)
+        q.coef, q.coef2 = float(coef), float(coef2)
+    with torch.cuda.device(jobs[0][0].device):
+        with timed('loss_seed'):
+            check(load().nlb_scale_tensors(arr, len(jobs), stream()))
+
+
+class _InterlevelTotal(Function):
+    """mult * sum over the proposal levels of mean(anti-interlevel loss) (train_utils.py:134-172) as ONE scalar:
+    a k_interlevel launch per level, one k_weighted_sums; the backward seeds every level's weights in one launch."""
+
+    @staticmethod
+    def forward(ctx, c, w, mult, pulse_widths, cps, *wps):
+        c, w = f32(c), f32(w)
+        N, Sc = w.shape
+        dev = w.device
+        out = torch.empty(1, device=dev, dtype=torch.float32)
+        grads, terms, coefs = [], [], []
+        for cp, wp, pw in zip(cps, wps, pulse_widths):
+            cp, wp = f32(cp), f32(wp)
+            Sp = wp.shape[1]
+            loss = torch.empty(N, device=dev, dtype=torch.float32)
+            grad = torch.empty_like(wp)
+            with torch.cuda.device(dev):
+                with timed('interlevel'):
+                    check(load().nlb_interlevel_loss(ptr(c), ptr(w), Sc, ptr(cp), ptr(wp), Sp, float(pw), N,
+                                                     ptr(loss), ptr(grad), stream()))
+            coef = float(mult) / (N * Sp)
+            grads.append(grad)
+            coefs.append(coef)
+            terms.append((loss, None, coef, 0))
+        weighted_sums(terms, out)
+        ctx.save_for_backward(*grads)
+        ctx.coefs = coefs
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        g = f32(g)
+        outs = [torch.empty_like(t) for t in ctx.saved_tensors]
+        scale_tensors([(src, None, dst, g, None, None, coef, 0.) for src, dst, coef in zip(ctx.saved_tensors, outs, ctx.coefs)])
+        return (None, None, None, None, None, *outs)
+
+
+def interlevel_total(c, w, cps, wps, pulse_widths, mult: float) -> torch.Tensor:
+    """config.anti_interlevel_loss_mult * sum_l mean(interlevel_l); (c, w) the detached final-level histogram."""
+    return _InterlevelTotal.apply(c.detach(), w.detach(), float(mult), tuple(float(p) for p in pulse_widths),
+                                  tuple(t.detach() for t in cps), *wps)
+
+
+class _MainLoss(Function):
+    """Every loss term that reaches the NeRF level -- the six supervision losses of csrc/render_losses.cu and the
+    distortion loss -- with their sum, and the step's total, formed by ONE k_weighted_sums launch; the backward
+    seeds rgb / depth / semantic / intensity / final-level weights in ONE k_scale_tensors launch.
+    Returns (main, values[6] = [data, depth, sem, int, d_smo, s_smo], extras[3] = [distortion, total, hash_decay
+    copy]); only `main` carries a gradient."""
+
+    @staticmethod
+    def forward(ctx, rgb, depth, semantic, intensity, weights, sdist, batch, cfg, used, dist_mult, prop_value,
+                hash_decay, extra_values):
+        losses, scales, g_rgb, g_depth, g_sem, g_int, g_dsmo, g_ssmo = _render_losses_launch(
+            rgb, depth, semantic, intensity, batch, cfg)
+        dev = losses.device
+        out = torch.empty(4, device=dev, dtype=torch.float32)
+        # (zero-weight terms name every output, so all four are written whatever the configuration)
+        terms = [(losses[:1], None, 0.0, k) for k in range(4)] + [(losses[k:k + 1], None, 1.0, 0) for k in range(6) if used[k]]
+        g_dist = None
+        ctx.dist_coef = 0.
+        if dist_mult > 0:   # stepfun.lossfun_distortion on the final level, mean over the rays
+            sdist, weights_c = f32(sdist), f32(weights)
+            N, S = weights_c.shape
+            dl = torch.empty(N, device=dev, dtype=torch.float32)
+            g_dist = torch.empty_like(weights_c)
+            with torch.cuda.device(dev):
+                with timed('distortion'):
+                    check(load().nlb_distortion_loss(ptr(sdist), ptr(weights_c), N, S, ptr(dl), ptr(g_dist), stream()))
+            ctx.dist_coef = float(dist_mult) / N
+            terms += [(dl, None, ctx.dist_coef, 1), (1, None, 1.0, 0)]
+        for v in extra_values:          # reported values without a gradient (latent_reg)
+            terms.append((f32(v).reshape(1), None, 1.0, 0))
+        terms.append((0, None, 1.0, 2))            # total = main (+ proposal losses + hash decay)
+        if prop_value is not None:
+            terms.append((f32(prop_value).reshape(1), None, 1.0, 2))
+        if hash_decay is not None:
+            hd = f32(hash_decay).reshape(1)
+            terms += [(hd, None, 1.0, 3), (3, None, 1.0, 2)]
+        weighted_sums(terms, out)
+        ctx.save_for_backward(scales, g_rgb, g_depth, g_sem, g_int, g_dsmo, g_ssmo, g_dist)
+        ctx.used = tuple(1.0 if u else 0.0 for u in used)
+        ctx.shapes = (rgb.shape, depth.shape, None if semantic is None else semantic.shape,
+                      None if intensity is None else intensity.shape)
+        main, extras = out.split([1, 3])
+        ctx.mark_non_differentiable(losses, extras)
+        return main.view(()), losses, extras
+
+    @staticmethod
+    def backward(ctx, g, _gl, _go):
+        scales, g_rgb, g_depth, g_sem, g_int, g_dsmo, g_ssmo, g_dist = ctx.saved_tensors
+        g = f32(g)
+        u = ctx.used
+        sc = lambda k: scales[k:k + 1]
+        o_rgb, o_depth = torch.empty_like(g_rgb), torch.empty_like(g_depth)
+        jobs = [(g_rgb, None, o_rgb, g, sc(0), None, u[0], 0.),
+                (g_depth, g_dsmo, o_depth, g, sc(1), sc(4), u[1], u[4])]
+        o_sem = o_int = o_w = None
+        if g_sem is not None:
+            o_sem = torch.empty_like(g_sem)
+            jobs.append((g_sem, g_ssmo, o_sem, g, sc(2), sc(5), u[2], u[5]))
+        if g_int is not None:
+            o_int = torch.empty_like(g_int)
+            jobs.append((g_int, None, o_int, g, sc(3), None, u[3], 0.))
+        if g_dist is not None:
+            o_w = torch.empty_like(g_dist)
+            jobs.append((g_dist, None, o_w, g, None, None, ctx.dist_coef, 0.))
+        scale_tensors(jobs)
+        shp = ctx.shapes
+        return (o_rgb.view(shp[0]), o_depth.view(shp[1]), None if o_sem is None else o_sem.view(shp[2]),
+                None if o_int is None else o_int.view(shp[3]), o_w, None, None, None, None, None, None, None, None)
+
+
+def main_loss(rendering, weights, sdist, batch, cfg, used, dist_mult: float, prop_value=None, hash_decay=None,
+              extra_values=()):
+    """See _MainLoss."""
+    return _MainLoss.apply(rendering['rgb'], rendering['depth'], rendering.get('semantic'), rendering.get('intensity'),
+                           weights, sdist.detach(), batch, cfg, tuple(bool(x) for x in used), float(dist_mult),
+                           None if prop_value is None else prop_value.detach(),
+                           None if hash_decay is None else hash_decay.detach(), tuple(extra_values))
 
 
 # ----------------------------------------------------------------------------- dynamic objects (csrc/obj.cu)

@@ -22,6 +22,9 @@ import numpy as np
 import torch
 
 from . import _lib, parallel
+
+# development switch (A/B timing): the loss dictionary summed and differentiated by torch scalar kernels
+_FUSED_LOSSES = os.environ.get('NLB_LOSS_UNFUSED', '') in ('', '0')
 from .configs import Config
 from .models import Model
 
@@ -62,12 +65,9 @@ def distortion_loss(ray_history, config: Config):
     return config.distortion_loss_mult * ops.distortion_per_ray(t, w).mean()
 
 
-def compute_losses(batch: Dict[str, torch.Tensor], renderings, ray_history, config: Config, step: int,
-                   num_patch: int) -> Dict[str, torch.Tensor]:
-    """The loss dictionary of Z/train.py:283-455 for the nuScenes camera+LiDAR run on the fused
-    kernels: supervision terms in csrc/render_losses.cu (incl. the dataset mask `batch['mask']`,
-    Z/train.py:286-327), regularisers in csrc/losses.cu."""
-    from . import ops
+def _supervision_setup(renderings, config: Config, step: int, num_patch: int):
+    """(rendering inputs, kernel configuration, loss name -> index into [data, depth, sem, int, d_smo, s_smo]) of
+    the supervision terms of Z/train.py:283-455; the step-dependent multipliers follow Z/train.py:330-371."""
     final = renderings[-1]
     refine = config.pose_refine and config.start_step < step < int(0.6 * config.end_step)
     dep_lam = 0. if refine else (0.4 if step > config.end_step else 0.1)
@@ -81,23 +81,68 @@ def compute_losses(batch: Dict[str, torch.Tensor], renderings, ray_history, conf
                charb_padding=config.charb_padding, depth_mult=dep_lam if config.depth_loss else 0.,
                sem_mult=sem_lam, int_mult=0.1, smooth_mult=0.01,
                instance_obj=bool(getattr(config, 'instance_obj', False)))
-    vals = ops.render_losses(rend, batch, cfg)
-    losses = {'data': vals[0]}
+    index = {'data': 0}
     if config.depth_loss:
-        losses['depth'] = vals[1]
+        index['depth'] = 1
     if num_patch > 0:
-        losses['d_smo'] = vals[4]
+        index['d_smo'] = 4
         if use_sem:
-            losses['s_smo'] = vals[5]
+            index['s_smo'] = 5
     if use_sem:
-        losses['sem'] = vals[2]
+        index['sem'] = 2
     if use_int:
-        losses['int'] = vals[3]
+        index['int'] = 3
+    return rend, cfg, index
+
+
+def compute_losses(batch: Dict[str, torch.Tensor], renderings, ray_history, config: Config, step: int,
+                   num_patch: int) -> Dict[str, torch.Tensor]:
+    """The loss dictionary of Z/train.py:283-455 for the nuScenes camera+LiDAR run on the fused
+    kernels: supervision terms in csrc/render_losses.cu (incl. the dataset mask `batch['mask']`,
+    Z/train.py:286-327), regularisers in csrc/losses.cu.  Every entry carries its own autograd graph (the
+    trainer uses `compute_losses_fused`, which forms the sums and seeds the backward pass in three launches)."""
+    from . import ops
+    rend, cfg, index = _supervision_setup(renderings, config, step, num_patch)
+    vals = ops.render_losses(rend, batch, cfg)
+    losses = {k: vals[i] for k, i in index.items()}
     if config.anti_interlevel_loss_mult > 0:
         losses['interlevel'] = anti_interlevel_loss(ray_history, config)
     if config.distortion_loss_mult > 0:
         losses['distortion'] = distortion_loss(ray_history, config)
     return losses
+
+
+def compute_losses_fused(batch: Dict[str, torch.Tensor], renderings, ray_history, config: Config, step: int,
+                         num_patch: int, extra_values: Optional[Dict[str, torch.Tensor]] = None):
+    """The same dictionary as `compute_losses` with its sums formed on the device in two launches
+    (ops.interlevel_total, ops.main_loss): returns (values, main, prop) -- `values` the detached entries plus
+    'hash_decay' (when the forward reported it) and 'loss' = the step's total, `main` / `prop` the two scalars to
+    back-propagate (prop is None without an anti-interlevel loss).  `extra_values`: reported entries without a
+    gradient that count into the total (latent_reg)."""
+    from . import ops
+    rend, cfg, index = _supervision_setup(renderings, config, step, num_patch)
+    last = ray_history[-1]
+    prop = None
+    if config.anti_interlevel_loss_mult > 0 and len(ray_history) > 1:
+        prop = ops.interlevel_total(last['sdist'], last['weights'], [rr['sdist'] for rr in ray_history[:-1]],
+                                    [rr['weights'] for rr in ray_history[:-1]], config.pulse_width,
+                                    config.anti_interlevel_loss_mult)
+    extra_values = extra_values or {}
+    used = [i in index.values() for i in range(6)]
+    main, vals, extras = ops.main_loss(rend, last['weights'], last['sdist'], batch, cfg, used,
+                                       max(float(config.distortion_loss_mult), 0.), prop,
+                                       renderings[-1].get('hash_decay'), list(extra_values.values()))
+    values = {k: vals[i] for k, i in index.items()}
+    if prop is not None:
+        values['interlevel'] = prop.detach()
+    if config.distortion_loss_mult > 0:
+        values['distortion'] = extras[0]
+    for k, v in extra_values.items():
+        values[k] = v
+    if 'hash_decay' in renderings[-1]:
+        values['hash_decay'] = extras[2]
+    values['loss'] = extras[1]
+    return values, main, prop
 
 
 # ----------------------------------------------------------------------------- trainer
@@ -155,6 +200,8 @@ class Trainer:
         self.dense = dense
         self.decay = config.hash_decay_mults if config.hash_decay_mults > 0 else 0.
         self.hash_decay_value = torch.zeros((), device=dev)  # persistent: written in place (CUDA-graph safe)
+        self._one = torch.ones((), device=dev)
+        self._hd_coef = None
         # per-level sums of squares of all tables in one buffer: ONE small all-reduce per step in data-parallel runs
         self._sumsq_all = torch.zeros(sum(t['enc'].num_levels for t in self.tables), device=dev)
         o = 0
@@ -200,13 +247,23 @@ class Trainer:
         renderings, ray_history = self.model(True, batch, train_frac, True, zero_glo=False, sample_n=c.sample_n_train,
                                              sample_m=c.sample_m_train, step=step, max_step=c.max_steps,
                                              curr_track=curr_track, rand_inputs=rand_inputs)
-        losses = compute_losses(batch, renderings, ray_history, c, step, num_patch)
         latents = getattr(self.model, 'latent_vector_dict', None)
+        extra = {}
         if getattr(c, 'latent_size', 0) > 0 and latents is not None:
             # Z/train.py:394-399 with train_utils.latentReg (Z/internal/train_utils.py:456-457): the reference
             # rebuilds the sum with torch.tensor([...]), which drops the graph -- a reported value, no gradient
             with torch.no_grad():
-                losses['latent_reg'] = sum(c.latent_reg * torch.norm(v) for v in latents.values())
+                extra['latent_reg'] = sum(c.latent_reg * torch.norm(v) for v in latents.values())
+        if not _FUSED_LOSSES:
+            return self._forward_losses_unfused(batch, renderings, ray_history, step, num_patch, extra)
+        # the sums of the dictionary, the step's total and (in the backward pass) every gradient seed come from
+        # three launches; the returned values are detached views of their outputs
+        return compute_losses_fused(batch, renderings, ray_history, c, step, num_patch, extra)
+
+    def _forward_losses_unfused(self, batch, renderings, ray_history, step, num_patch, extra):
+        """The same step with the dictionary summed by torch (A/B timing: NLB_LOSS_UNFUSED=1)."""
+        losses = compute_losses(batch, renderings, ray_history, self.config, step, num_patch)
+        losses.update(extra)
         main = sum(v for k, v in losses.items() if k not in self.PROP_LOSSES)
         prop = [v for k, v in losses.items() if k in self.PROP_LOSSES]
         prop = sum(prop) if prop else None
@@ -331,6 +388,12 @@ class Trainer:
         cur.wait_stream(self.stream)
         return out
 
+    def _backward(self, *losses, retain_graph: bool = False):
+        """Back-propagates the given scalars (None entries are skipped) from a cached unit seed: `loss.backward()`
+        fills a fresh ones tensor per root and `main + prop` is one more launch."""
+        roots = [l for l in losses if l is not None]
+        torch.autograd.backward(roots, [self._one] * len(roots), retain_graph=retain_graph)
+
     def _train_step(self, batch, step, num_patch=None, rand_inputs=None):
         pose, tmode = self._pose_mode(step), self._track_mode(step)
         batch = self._refined(batch, pose)
@@ -338,15 +401,15 @@ class Trainer:
         if self.world == 1:
             # (running the NeRF table's optimizer pass on a side stream beside the proposal backward was
             # measured: 7.30-7.35 ms per step against 7.23 ms in order -- the two contend for L2)
-            (main if prop is None else main + prop).backward()
+            self._backward(main, prop)
             self.optimizer_step(step)
             self._pose_step(pose, tmode)
             return losses
         # the refined rays feed both halves: the first backward must keep the posenet's part of the graph
-        main.backward(retain_graph=pose == 'train' and prop is not None)
+        self._backward(main, retain_graph=pose == 'train' and prop is not None)
         early = self.reduce_scatter_gradients(self._nerf_tables())
         if prop is not None:
-            prop.backward()
+            self._backward(prop)
         late = self.reduce_scatter_gradients(self._prop_tables(), dense=True)
         parallel.wait_all(early + late)
         self.optimizer_step(step, reduce=False)
@@ -432,11 +495,20 @@ class Trainer:
 
     def _update_hash_decay_value(self):
         # Model.hash_decay_loss of the UPDATED tables (mean over levels of the per-level mean square): the next
-        # forward reports it as renderings[-1]['hash_decay'] without re-reading 310 MB of tables
-        vals = [(t['sumsq'] / t['counts']).mean() for t in self.tables if t.get('decay', 0) > 0]
-        if vals:
-            self.hash_decay_value.copy_(self.decay * sum(vals))
-            self.model._hash_decay_value = self.hash_decay_value
+        # forward reports it as renderings[-1]['hash_decay'] without re-reading 310 MB of tables.  One launch: the
+        # per-level sums of squares (all tables, one buffer) against decay / (levels x values per level)
+        if self.decay <= 0 or not any(t.get('decay', 0) > 0 for t in self.tables):
+            return
+        if self._hd_coef is None:
+            coef = []
+            for t in self.tables:
+                L = t['enc'].num_levels
+                on = 1.0 if t.get('decay', 0) > 0 else 0.0
+                coef.append(on * self.decay / (L * t['counts']))
+            self._hd_coef = torch.cat(coef).contiguous()
+        from . import ops
+        ops.weighted_sums([(self._sumsq_all, self._hd_coef, 1.0, 0)], self.hash_decay_value)
+        self.model._hash_decay_value = self.hash_decay_value
 
     def _mark_packed_stale(self):
         """The dense parameters changed through raw pointers (torch's version counters do not see it): the
@@ -546,7 +618,7 @@ class Trainer:
                     ctx[0].__enter__()
                     try:
                         captured, main, prop = self.forward_losses(st['batch'], step, num_patch, srand)
-                        main.backward()
+                        self._backward(main)
                     finally:
                         self.model.__dict__.pop('_nlb_before_nerf_table', None)
                         ctx.pop().__exit__(None, None, None)
@@ -555,7 +627,7 @@ class Trainer:
                     if prop is not None:
                         g_prop = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g_prop, pool=g.pool(), stream=self.stream):
-                            prop.backward()
+                            self._backward(prop)
                     g_opt = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g_opt, pool=g.pool(), stream=self.stream):
                         self.optimizer_step(step, reduce=False, publish=False)

@@ -109,3 +109,84 @@ def test_patch_layout_violation_is_loud():
     batch['patch_mask'] = batch['patch_mask'].roll(7)
     bad = train.compute_losses(batch, rend, hist, cfg, 6000, 1)
     assert np.isnan(float(bad['d_smo'])) and np.isnan(float(bad['s_smo']))
+
+
+@pytest.mark.parametrize('step,num_patch_on,hash_decay', [(6000, True, True), (3000, True, False), (6000, False, True)])
+def test_fused_loss_assembly_vs_summed_dictionary(step, num_patch_on, hash_decay):
+    """train.compute_losses_fused (ops.interlevel_total + ops.main_loss: the dictionary's sums from k_weighted_sums,
+    every gradient seed from k_scale_tensors) against `compute_losses` summed and differentiated by torch: every
+    entry, main / prop / total, and the gradients w.r.t. the rendered rgb / depth / semantic / intensity, the
+    final-level weights (distortion) and both proposal levels' weights (anti-interlevel); also with a non-unit
+    seed, which the reference never uses but autograd allows."""
+    from nerf_lidar_b200 import configs, synthetic, train
+    cfg = configs.nuscenes_single()
+    B = 4096
+    num_patch = (B // 4) // 1024 if num_patch_on else 0
+    cpu = synthetic.to_torch(synthetic.make_train_batch(B, seed=11))
+    batch = {k: v.cuda() for k, v in cpu.items()}
+    N = cpu['origins'].shape[0]
+    g = torch.Generator().manual_seed(2)
+    rgb = torch.rand(N, 3, generator=g)
+    depth = (cpu['depth'] + torch.randn(N, generator=g) * 0.3).abs().add(0.05)
+    sem = torch.softmax(torch.randn(N, 19, generator=g) * 2, dim=-1)
+    inten = torch.rand(N, generator=g)
+    s2, w2 = _hist(N, 32, 3)
+    s0, w0 = _hist(N, 64, 4)
+    s1, w1 = _hist(N, 64, 5)
+    hd = torch.tensor(0.0123, device='cuda')
+    reg = torch.tensor(0.5, device='cuda')
+
+    def leaves():
+        return [t.clone().cuda().requires_grad_(True) for t in (rgb, depth, sem, inten, w0, w1, w2)]
+
+    def setup(l):
+        rend = [dict(), dict(), dict(rgb=l[0], depth=l[1], semantic=l[2], intensity=l[3])]
+        if hash_decay:
+            rend[-1]['hash_decay'] = hd
+        hist = [dict(sdist=s0.cuda(), weights=l[4]), dict(sdist=s1.cuda(), weights=l[5]), dict(sdist=s2.cuda(), weights=l[6])]
+        return rend, hist
+
+    for seed in (1.0, 0.37):
+        a, b = leaves(), leaves()
+        rend, hist = setup(a)
+        want = train.compute_losses(batch, rend, hist, cfg, step, num_patch)
+        want['latent_reg'] = reg
+        w_main = sum(v for k, v in want.items() if k != 'interlevel')
+        w_prop = want['interlevel']
+        w_total = w_main.detach() + w_prop.detach() + (hd if hash_decay else 0.)
+        torch.autograd.backward([w_main, w_prop], [torch.tensor(seed, device='cuda')] * 2)
+        rend, hist = setup(b)
+        vals, main, prop = train.compute_losses_fused(batch, rend, hist, cfg, step, num_patch, {'latent_reg': reg})
+        torch.autograd.backward([main, prop], [torch.tensor(seed, device='cuda')] * 2)
+        assert set(vals) == set(want) | {'loss'} | ({'hash_decay'} if hash_decay else set())
+        rel = lambda x, y: abs(float(x) - float(y)) / max(abs(float(y)), 1e-12)
+        for k in want:
+            assert rel(vals[k], want[k]) < 2e-6, (k, float(vals[k]), float(want[k]))
+        assert rel(main, w_main) < 2e-6 and rel(prop, w_prop) < 2e-6 and rel(vals['loss'], w_total) < 2e-6
+        if hash_decay:
+            assert float(vals['hash_decay']) == float(hd)
+        assert not any(v.requires_grad for v in vals.values())
+        for name, ta, tb in zip(('rgb', 'depth', 'semantic', 'intensity', 'w_prop0', 'w_prop1', 'w_final'), a, b):
+            assert tb.grad is not None and tb.grad.shape == ta.grad.shape, name
+            assert_close(tb.grad, ta.grad, 2e-6, 'grad ' + name)
+
+
+def test_weighted_sums_and_scale_tensors():
+    """The two generic launches of the loss assembly against torch: weighted sums with and without per-element
+    weights, a term that re-uses an earlier output, outputs no term names staying untouched, zero coefficients not
+    reading their (NaN) input; scaled copies with one and two sources and device scalars."""
+    from nerf_lidar_b200 import ops
+    torch.manual_seed(0)
+    x, y, w = torch.randn(10007, device='cuda'), torch.randn(5, 77, device='cuda'), torch.rand(10007, device='cuda')
+    nan = torch.full((3,), float('nan'), device='cuda')
+    out = torch.full((5,), -1.0, device='cuda')
+    ops.weighted_sums([(x, None, 0.5, 0), (y, None, 2.0, 1), (x, w, 1.0, 2), (0, None, 3.0, 1), (nan, None, 0.0, 3)], out)
+    want = torch.stack([0.5 * x.sum(), 2.0 * y.sum() + 1.5 * x.sum(), (x * w).sum(), x.new_zeros(()), x.new_tensor(-1.0)])
+    assert_close(out, want, 1e-5, 'weighted sums', atol=1e-4)
+    g, s1, s2 = torch.tensor(0.3, device='cuda'), torch.tensor([2.0], device='cuda'), torch.tensor([-4.0], device='cuda')
+    d1, d2 = torch.empty_like(x), torch.empty_like(y)
+    ops.scale_tensors([(x, w, d1, g, s1, s2, 1.0, 0.5), (y, None, d2, None, s1, None, 3.0, 0.)])
+    assert_close(d1, x * 0.6 + w * (0.5 * 0.3 * -4.0), 1e-6, 'two sources')
+    assert_close(d2, y * 6.0, 1e-6, 'one source')
+    with pytest.raises(RuntimeError):
+        ops.weighted_sums([(x, None, 1.0, 7)], out)

@@ -133,3 +133,37 @@ def test_bf16_reductions_vs_torch(cols):
                  'group_sum of a slice')
     with pytest.raises(RuntimeError):  # a transposed view has no dense rows
         ops.colsum_bf16(x.t())
+
+
+@pytest.mark.gpu
+def test_bf16_sums_one_launch_vs_torch():
+    """nlb_bf16_sums: the seven reductions of a NerfMLP backward as jobs of one launch (column sums of matrices of
+    different widths incl. column slices of a wider buffer, per-ray sums) against torch in fp32; ragged row counts,
+    argument errors."""
+    from nerf_lidar_b200 import ops
+    torch.manual_seed(5)
+    S, N = 32, 613
+    M = N * S
+    mk = lambda cols: (torch.randn(M, cols, device='cuda') * 0.5).to(torch.bfloat16)
+    d_x, d_h0, d_hs1, d_rgb, dcat = mk(256), mk(64), mk(32), mk(16), mk(640)
+    d_g, d_v0, d_v1 = dcat[:, :128], dcat[:, 128:384], dcat[:, 384:]
+    cs = torch.full((496,), 7.0, device='cuda')          # overwritten, not accumulated
+    cs_x, cs_g, cs_h0, cs_hs1, cs_rgb = cs.split([256, 128, 64, 32, 16])
+    rs_v0, rs_v1 = torch.full((2, N, 256), 7.0, device='cuda').unbind(0)
+    ops.bf16_sums([(d_x, 0, cs_x), (d_g, 0, cs_g), (d_h0, 0, cs_h0), (d_hs1, 0, cs_hs1), (d_rgb, 0, cs_rgb),
+                   (d_v0, S, rs_v0), (d_v1, S, rs_v1)])
+    for name, got, src in (('x', cs_x, d_x), ('g', cs_g, d_g), ('h0', cs_h0, d_h0), ('hs1', cs_hs1, d_hs1),
+                           ('rgb', cs_rgb, d_rgb)):
+        assert_close(got, src.float().sum(0), 1e-4, 'colsum ' + name)
+    assert_close(rs_v0, d_v0.float().view(N, S, 256).sum(1), 1e-5, 'group sum v0')
+    assert_close(rs_v1, d_v1.float().view(N, S, 256).sum(1), 1e-5, 'group sum v1')
+    # a single small job, fewer rows than row lanes; separate (non-adjacent) outputs
+    few = mk(16)[:5]
+    o1, o2 = torch.empty(16, device='cuda'), torch.empty(32, device='cuda')
+    ops.bf16_sums([(few, 0, o1), (d_hs1, 0, o2)])
+    assert_close(o1, few.float().sum(0), 1e-5, 'five rows')
+    assert_close(o2, d_hs1.float().sum(0), 1e-4, 'second output')
+    with pytest.raises(RuntimeError):       # rows not a multiple of the group size
+        ops.bf16_sums([(d_v0[:S + 1], S, rs_v0)])
+    with pytest.raises((RuntimeError, NotImplementedError)):   # 4 columns: below the 16-byte vector width
+        ops.bf16_sums([(mk(4), 0, torch.empty(4, device='cuda'))])
