@@ -80,7 +80,15 @@ struct LevelCache {
 // point-level: 30 of ~180 instructions of a lookup), so the argument is a * (1 / gs); std = 0 gives inf -> 1
 // like the reference's clamp.  Agreement with the reference expression: ~2 ulp of the argument.
 __device__ __forceinline__ float staged_a(float sd) { return rsqrtf(8.0f * sd * sd); }
-__device__ __forceinline__ float erf_weight_a(float a, float inv_gs) { return erff(a * inv_gs); }
+// For x >= 4, erf(x) = 1 - 1.5e-8 or closer: 1.0f is the correctly rounded value (and what torch.erf returns), so the
+// ~40-instruction erff is branched around.  On the driving-scene rays (pixel footprint 4.6e-4 x t) every sample of
+// the levels up to resolution 512 and 87 % of those at 1024 saturate (whole warps take the short path): the erf
+// loop was 160 of ~560 warp instructions per level of the forward kernels, 280 per level of the one-lane scatter.
+__device__ __forceinline__ float erf_weight_a(float a, float inv_gs) {
+  const float x = a * inv_gs;
+  if (x >= 4.0f) return 1.0f;
+  return erff(x);
+}
 
 __device__ __forceinline__ void fill_level_cache(LevelCache& lc, const nlb_table_t& tab) {
   if (threadIdx.x < tab.L) {
@@ -664,10 +672,79 @@ __device__ __forceinline__ void pair_partial(const float* __restrict__ emb, RowO
   }
 }
 
+// One level of one pair lane with CONSECUTIVE SAME-CELL SAMPLES MERGED: the lane's four corner weights (erf weight x
+// trilinear weight) are summed over the samples of a cell -- exactly what the scatter kernels do -- and the cell's
+// four rows are gathered once.  On the bench's rays an interval's 7 multisamples fall into 1.1 / 1.3 / 1.5 / 2.0 /
+// 2.9 / 4.4 / 5.3 / 6.3 cells at resolutions 16 .. 2048 (tests/analysis_cell_sharing.py), so the 8-level proposal
+// table needs 25 instead of 56 gather groups per interval; lanes that merge drop out of the gather instructions,
+// whose cost is one L1 wavefront per distinct line.  Same value up to fp32 rounding: sum_k (sum_j e_j w_kj) r_k
+// instead of sum_j e_j (sum_k w_kj r_k).
+template <int C, bool kDense>
+__device__ __forceinline__ void pair_level_merged(const float* __restrict__ emb, const Level3& lv, int h, int iv,
+                                                  const float4 (*s_pts)[kPairIv], const float (*s_w)[kPairIv],
+                                                  float (&acc)[C]) {
+  uint32_t cx = 0, cy = 0, cz = 0;
+  float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+  bool live = false;
+  const uint32_t off = lv.offset;
+#pragma unroll 1
+  for (int j = 0; j <= 7; ++j) {  // the sentinel iteration flushes the last cell
+    float4 p = make_float4(0.f, 0.f, 0.f, -1.f);
+    if (j < 7) p = s_pts[j][iv];
+    const bool valid = p.w >= 0.f;
+    uint32_t nx = 0, ny = 0, nz = 0;
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    if (valid) {
+      cell_of(p.x, lv.scale, nx, fx);
+      cell_of(p.y, lv.scale, ny, fy);
+      cell_of(p.z, lv.scale, nz, fz);
+    }
+    if (live && (j == 7 || (valid && (nx != cx || ny != cy || nz != cz)))) {
+      float r[4][C];
+      if constexpr (kDense) {
+        const uint32_t i00 = off + cx + h + cy * lv.s1 + cz * lv.s2;
+        gather_row<C>(emb + i00 * (uint32_t)C, r[0]);
+        gather_row<C>(emb + (i00 + lv.s1) * (uint32_t)C, r[1]);
+        gather_row<C>(emb + (i00 + lv.s2) * (uint32_t)C, r[2]);
+        gather_row<C>(emb + (i00 + lv.s1 + lv.s2) * (uint32_t)C, r[3]);
+      } else {
+        const uint32_t vx = cx + h;
+        const uint32_t hy0 = cy * 2654435761u, hy1 = hy0 + 2654435761u;
+        const uint32_t hz0 = cz * 805459861u, hz1 = hz0 + 805459861u;
+        gather_row<C>(emb + (off + ((vx ^ hy0 ^ hz0) & lv.mask)) * (uint32_t)C, r[0]);
+        gather_row<C>(emb + (off + ((vx ^ hy1 ^ hz0) & lv.mask)) * (uint32_t)C, r[1]);
+        gather_row<C>(emb + (off + ((vx ^ hy0 ^ hz1) & lv.mask)) * (uint32_t)C, r[2]);
+        gather_row<C>(emb + (off + ((vx ^ hy1 ^ hz1) & lv.mask)) * (uint32_t)C, r[3]);
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float f = w0 * r[0][c];
+        f = fmaf(w1, r[1][c], f);
+        f = fmaf(w2, r[2][c], f);
+        f = fmaf(w3, r[3][c], f);
+        acc[c] += f;
+      }
+      w0 = w1 = w2 = w3 = 0.f;
+      live = false;
+    }
+    if (valid) {
+      cx = nx; cy = ny; cz = nz;
+      live = true;
+      const float coef = s_w[j][iv];
+      const float wx = h ? fx : 1.f - fx;
+      const float wy0 = wx * (1.f - fy), wy1 = wx * fy;
+      w0 = fmaf(coef, wy0 * (1.f - fz), w0);
+      w1 = fmaf(coef, wy1 * (1.f - fz), w1);
+      w2 = fmaf(coef, wy0 * fz, w2);
+      w3 = fmaf(coef, wy1 * fz, w3);
+    }
+  }
+}
+
 // Fused encode forward (any level_dim) with two lanes per interval -- see k_prop_fwd_pair below for the why.
 // At C = 4 the x / x+1 rows of an even-x cell are one 32-byte sector, so the pair's loads also halve the
 // L2 -> L1 sector traffic of those cells.
-template <int C>
+template <int C, bool kMerge>
 __global__ void __launch_bounds__(kEncThreads) k_encode_fwd_pair(nlb_rays_t rays, nlb_table_t tab,
                                                                  float* __restrict__ features, int level_begin,
                                                                  int level_end) {
@@ -696,7 +773,10 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_fwd_pair(nlb_rays_t rays
     float acc[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0.f;
-    if (ok) {
+    if (ok && kMerge) {
+      if (lv.dense) pair_level_merged<C, true>(emb, lv, h, iv, s_pts, s_w, acc);  // uniform per level
+      else pair_level_merged<C, false>(emb, lv, h, iv, s_pts, s_w, acc);
+    } else if (ok) {
       const uint32_t off = lv.offset;
       if (lv.dense) {  // uniform per level
 #pragma unroll 1
@@ -835,7 +915,7 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_bwd_hashed_pair(nlb_rays
   }
 }
 
-template <int L>
+template <int L, bool kMerge>
 __global__ void __launch_bounds__(kEncThreads) k_prop_fwd_pair(nlb_rays_t rays, nlb_table_t tab,
                                                                const float* __restrict__ W0, const float* __restrict__ b0,
                                                                const float* __restrict__ W1, const float* __restrict__ b1,
@@ -867,7 +947,12 @@ __global__ void __launch_bounds__(kEncThreads) k_prop_fwd_pair(nlb_rays_t rays, 
     const float* __restrict__ emb = tab.embeddings;  // row = offset + idx in 32 bits (offsets are int32)
     const uint32_t off = lv.offset;
     float acc = 0.f;
-    if (ok) {
+    if (ok && kMerge) {
+      float a1[1] = {0.f};
+      if (lv.dense) pair_level_merged<1, true>(emb, lv, h, iv, s_pts, s_w, a1);  // uniform per level
+      else pair_level_merged<1, false>(emb, lv, h, iv, s_pts, s_w, a1);
+      acc = a1[0];
+    } else if (ok) {
       if (lv.dense) {  // uniform per level
 #pragma unroll 1
         for (int j = 0; j < 7; ++j) {
@@ -1120,10 +1205,12 @@ static int encode_forward_launch(const nlb_rays_t& rays_in, const nlb_table_t& t
   static const double kL2Budget = (double)env_long("NLB_GATHER_L2_MB", 70) * 1048576.0;
   const int rows = rays_in.N * rays_in.S;
   static const bool kLegacy = getenv("NLB_ENC_FWD_LEGACY") != nullptr;  // one lane per interval (A/B timing)
+  static const bool kMerge = env_long("NLB_FWD_MERGE", 0) != 0;          // same-cell samples share one gather (measured slower)
   dim3 grid(div_up(rows, kLegacy ? kEncThreads : kPairIv));
   auto launch = [&](const nlb_rays_t& r, int l0, int l1) {
     if (kLegacy) k_encode_fwd<C><<<grid, kEncThreads, 0, st>>>(r, tab, features, l0, l1);
-    else k_encode_fwd_pair<C><<<grid, kEncThreads, 0, st>>>(r, tab, features, l0, l1);
+    else if (kMerge) k_encode_fwd_pair<C, true><<<grid, kEncThreads, 0, st>>>(r, tab, features, l0, l1);
+    else k_encode_fwd_pair<C, false><<<grid, kEncThreads, 0, st>>>(r, tab, features, l0, l1);
   };
   double total = 0.;
   for (int l = 0; l < tab.L; ++l) total += (double)hl.rows[l] * C * 4.0;
@@ -1371,7 +1458,12 @@ extern "C" int nlb_prop_forward(const nlb_rays_t* rays, const nlb_table_t* table
   if (kLegacy) {
     NLB_PROP_DISPATCH(table->L, (k_prop_fwd<L_><<<div_up(rows, kEncThreads), kEncThreads, 0, st>>>(*rays, *table, W0, b0, W1, b1, density, features)));
   } else {
-    NLB_PROP_DISPATCH(table->L, (k_prop_fwd_pair<L_><<<div_up(rows, kPairIv), kEncThreads, 0, st>>>(*rays, *table, W0, b0, W1, b1, density, features)));
+    static const bool kMerge = env_long("NLB_FWD_MERGE", 0) != 0;  // same-cell samples share one gather (measured slower)
+    if (kMerge) {
+      NLB_PROP_DISPATCH(table->L, (k_prop_fwd_pair<L_, true><<<div_up(rows, kPairIv), kEncThreads, 0, st>>>(*rays, *table, W0, b0, W1, b1, density, features)));
+    } else {
+      NLB_PROP_DISPATCH(table->L, (k_prop_fwd_pair<L_, false><<<div_up(rows, kPairIv), kEncThreads, 0, st>>>(*rays, *table, W0, b0, W1, b1, density, features)));
+    }
   }
   return nlb_check_launch("prop_forward");
 }

@@ -1,6 +1,6 @@
 #!/bin/bash
-# Dev tool (GPU box): A/B timing of the development switches in one gpurun call.
-#   tools/ab_sweep.sh > gpurun_out/ab_sweep.txt
+# Dev tool (GPU box): A/B timing of development switches in one gpurun call.
+#   tools/ab_sweep.sh "name ENV=1 ..." "name2 ENV2=..." > gpurun_out/ab_sweep.txt      (no arguments: the default build twice)
 cd "$(dirname "$0")/.."
 B="python bench.py --no-cpu-baseline --no-render --no-pose-window --no-reference-kernel --steps 20 --warmup 5"
 line() { python - "$1" <<'P'
@@ -10,18 +10,10 @@ for l in open(sys.argv[1]):
     if l.startswith('{') and '"metric"' in l:
         d = json.loads(l)
         k = d['roofline']['kernels']
-        pick = {n: k[n]['avg_ms'] for n in ('adam_table', 'mlp_grad_sums', 'mlp_bias_grad', 'mlp_ray_sum', 'nerf_encode_bwd', 'prop8_bwd', 'prop6_bwd', 'nerf_encode_fwd', 'loss_sums', 'loss_seed') if n in k}
+        pick = {n: k[n]['avg_ms'] for n in ('adam_table', 'mlp_grad_sums', 'nerf_encode_bwd', 'prop8_bwd', 'prop6_bwd', 'nerf_encode_fwd', 'prop8_fwd', 'prop6_fwd', 'nerf_mlp_fwd', 'nerf_mlp_bwd', 'nerf_mlp_wgrad') if n in k}
         print('   ms_per_step %.4f  e2e %.4f  eager %.3f  launches %d  %s' % (d['ms_per_step'], d['e2e']['ms_per_step'], d['config']['eager_ms_per_step'], d['gpu_launches'], pick))
 P
 }
 run() { echo "== $1"; shift; env "$@" $B > /tmp/ab.log 2>&1 || tail -5 /tmp/ab.log; line /tmp/ab.log; }
-run default X=1
-run default-again X=1
-run loss-unfused NLB_LOSS_UNFUSED=1
-run adam-8-per-sm NLB_ADAM_BLOCKS_PER_SM=8
-run adam-4-per-sm NLB_ADAM_BLOCKS_PER_SM=4
-run scatter-4-per-sm NLB_SCATTER_BLOCKS_PER_SM=4
-run scatter-3-per-sm NLB_SCATTER_BLOCKS_PER_SM=3
-run pair-8-per-sm NLB_SCATTER_PAIR_BLOCKS_PER_SM=8
-run scatter-l2-40 NLB_SCATTER_L2_MB=40
-run gather-l2-100 NLB_GATHER_L2_MB=100
+if [ $# -eq 0 ]; then set -- "default X=1" "default-again X=1"; fi
+for spec in "$@"; do run $spec; done
