@@ -290,12 +290,6 @@ typedef struct {
 } nlb_nerf_mlp_wgrads_t;
 int nlb_nerf_mlp_wgrad(const nlb_nerf_mlp_saved_t* saved, const nlb_nerf_mlp_grad_out_t* dz, int M,
                        const nlb_nerf_mlp_wgrads_t* grads, void* stream);
-/* The same launch with the reductions nlb_nerf_mlp_wgrad_finish needs formed on the way (S = 32 samples per ray
- * only: a 32-row pipeline stage is one ray): the producer warps sum the slabs they copied.  `sums` (16-byte
- * aligned, overwritten) = [cs_x 256 | cs_g 128 | cs_h0 64 | cs_hs1 32 | cs_rgb 16 | rs_v0 (M/32) x 256 | rs_v1 (M/32) x 256]
- * floats -- no second pass over the 661 MB of pre-activation gradients (nlb_bf16_sums). */
-int nlb_nerf_mlp_wgrad_sums(const nlb_nerf_mlp_saved_t* saved, const nlb_nerf_mlp_grad_out_t* dz, int M, int S,
-                            const nlb_nerf_mlp_wgrads_t* grads, float* sums, void* stream);
 int nlb_nerf_mlp_wgrad_finish(const float* rs_v0, const float* rs_v1, const float* viewdirs, int N,
                               const float* cs_x, const float* cs_g, const float* cs_h0, const float* cs_hs1,
                               const float* cs_rgb, const nlb_nerf_mlp_wgrads_t* grads, void* stream);

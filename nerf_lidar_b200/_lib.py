@@ -152,7 +152,6 @@ SIGNATURES = {
                                    C.POINTER(NlbNerfMlpGradOut), _p]),
     'nlb_nerf_mlp_wgrad': (_i, [C.POINTER(NlbNerfMlpSaved), C.POINTER(NlbNerfMlpGradOut), _i,
                                 C.POINTER(NlbNerfMlpWeights), _p]),
-    'nlb_nerf_mlp_wgrad_sums': (_i, [C.POINTER(NlbNerfMlpSaved), C.POINTER(NlbNerfMlpGradOut), _i, _i, C.POINTER(NlbNerfMlpWeights), _p, _p]),
     'nlb_nerf_mlp_wgrad_finish': (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, C.POINTER(NlbNerfMlpWeights), _p]),
     'nlb_colsum_bf16': (_i, [_p, C.c_int64, _i, _i, _p, _p]),
     'nlb_group_sum_bf16': (_i, [_p, C.c_int64, _i, _i, _i, _p, _p]),

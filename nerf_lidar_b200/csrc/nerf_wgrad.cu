@@ -56,9 +56,6 @@ struct Stream {                 // one operand matrix of a role: rows [r0, r0+64
   int ld;                       // elements
   int log2_cpr;                 // log2(16-byte chunks per row)
   int smem_off;
-  // optional sums of a pre-activation gradient stream, formed by the producers from the slabs they copied:
-  float* colsum;                // [cols]          += column sums over all rows (bias gradient)
-  float* raysum;                // [M / 32, cols]  += sums over the 32 rows of a stage (= one ray when S = 32)
 };
 struct Op {                     // D[128, n] (+)= A^T B on the stage's slabs, accumulated in TMEM columns [tmem_col, +n)
   int a_off, b_off, n, tmem_col;
@@ -117,62 +114,6 @@ __device__ __forceinline__ void copy_stream(uint8_t* slab0, const __nv_bfloat16*
   }
 }
 
-// The sums of one stage of a stream, from the chunks THIS thread copied (same index arithmetic as copy_stream, so
-// the thread reads back its own cp.async destinations once its wait_group has returned: no barrier, no swizzle
-// reasoning): the thread owns 8 columns and kRows / ROWS_PER_ITER rows of the stage.  `acc` collects the column
-// sums over all stages; the stage's own partial is added into raysum[stage] with two vector reductions (the 32
-// rows of a stage are the 32 samples of one ray: the view-direction columns need per-ray sums).
-template <int LOG2CPR>
-__device__ __forceinline__ void sum_stream(const uint8_t* slab0, int tid, float (&acc)[8], float* raysum, int stage) {
-  constexpr int CPR = 1 << LOG2CPR;
-  constexpr int TOTAL = kRows * CPR;
-  constexpr int ITERS = (TOTAL + kProdThreads - 1) / kProdThreads;
-  constexpr int ROWS_PER_ITER = kProdThreads / CPR;
-  if (TOTAL < kProdThreads && tid >= TOTAL) return;
-  const int r = tid >> LOG2CPR, ch = tid & (CPR - 1);
-  const uint8_t* src = slab0 + (ch >> 3) * kBlk + (r >> 3) * 1024 + (r & 7) * 128 + (((ch & 7) ^ (r & 7)) * 16);
-  float p[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) p[k] = 0.f;
-#pragma unroll
-  for (int k = 0; k < ITERS; ++k) {
-    const uint4 v = *reinterpret_cast<const uint4*>(src + k * (ROWS_PER_ITER / 8) * 1024);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float2 f = __bfloat1622float2(h[q]);
-      p[2 * q] += f.x;
-      p[2 * q + 1] += f.y;
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] += p[k];
-  if (raysum) {
-    float* dst = raysum + (size_t)stage * (8 * CPR) + ch * 8;
-    atomicAdd(reinterpret_cast<float4*>(dst), make_float4(p[0], p[1], p[2], p[3]));
-    atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(p[4], p[5], p[6], p[7]));
-  }
-}
-
-__device__ __forceinline__ void sum_stream_any(const Stream& s, const uint8_t* st, int tid, float (&acc)[8], int stage) {
-  switch (s.log2_cpr) {
-    case 5: sum_stream<5>(st + s.smem_off, tid, acc, s.raysum, stage); break;
-    case 4: sum_stream<4>(st + s.smem_off, tid, acc, s.raysum, stage); break;
-    case 3: sum_stream<3>(st + s.smem_off, tid, acc, s.raysum, stage); break;
-    case 2: sum_stream<2>(st + s.smem_off, tid, acc, s.raysum, stage); break;
-    default: sum_stream<1>(st + s.smem_off, tid, acc, s.raysum, stage); break;
-  }
-}
-
-// adds a thread's column sums into colsum[cols] (threads beyond the stream's chunk pattern hold nothing)
-__device__ __forceinline__ void flush_colsum(const Stream& s, int tid, const float (&acc)[8]) {
-  const int cpr = 1 << s.log2_cpr;
-  if (kRows * cpr < kProdThreads && tid >= kRows * cpr) return;
-  float* dst = s.colsum + (tid & (cpr - 1)) * 8;
-  atomicAdd(reinterpret_cast<float4*>(dst), make_float4(acc[0], acc[1], acc[2], acc[3]));
-  atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(acc[4], acc[5], acc[6], acc[7]));
-}
-
 struct Bars {
   uint64_t full[kStages], empty[kStages], done;
   uint32_t tmem_base;
@@ -211,12 +152,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_wgrad(const __grid_con
     // ===== producers: 16-byte async copies, rows beyond M are zero-filled; a stage is handed over when every
     // producer thread's copies of it have landed (wait_group) and are visible to the tensor pipe (proxy fence)
     const int tid = threadIdx.x;
-    // the pre-activation gradient streams are s[1] and s[3] of a role (see the host side)
-    const bool sum1 = role.ns > 1 && (role.s[1].colsum || role.s[1].raysum);
-    const bool sum3 = role.ns > 3 && (role.s[3].colsum || role.s[3].raysum);
-    float acc1[8], acc3[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc1[k] = acc3[k] = 0.f;
     for (int it = 0; it < n_it + kInFlight - 1; ++it) {
       if (it < n_it) {
         const int slot = it % kStages;
@@ -237,18 +172,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_nerf_mlp_wgrad(const __grid_con
       cp_async_commit();
       if (it >= kInFlight - 1) {
         cp_async_wait_group<kInFlight - 1>();
-        const int ps = it - (kInFlight - 1);          // the stage whose copies (of this thread) have landed
-        if (sum1 | sum3) {
-          const uint8_t* st = base + (ps % kStages) * kStageBytes;
-          if (sum1) sum_stream_any(role.s[1], st, tid, acc1, t0 + ps);
-          if (sum3) sum_stream_any(role.s[3], st, tid, acc3, t0 + ps);
-        }
         fence_proxy_async();
-        mbar_arrive(&bars.full[ps % kStages]);
+        mbar_arrive(&bars.full[(it - (kInFlight - 1)) % kStages]);
       }
     }
-    if (sum1 && role.s[1].colsum) flush_colsum(role.s[1], tid, acc1);
-    if (sum3 && role.s[3].colsum) flush_colsum(role.s[3], tid, acc3);
   } else if (elect_one_sync()) {
     // ===== MMA issuer
     for (int it = 0; it < n_it; ++it) {
@@ -421,9 +348,8 @@ using namespace nlb::wgrad;
 
 static int log2i(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
-// `sums` (optional): [cs_x 256 | cs_g 128 | cs_h0 64 | cs_hs1 32 | cs_rgb 16 | rs_v0 (M/32) x 256 | rs_v1 (M/32) x 256]
-static int wgrad_launch(const nlb_nerf_mlp_saved_t* sv, const nlb_nerf_mlp_grad_out_t* go, int M,
-                        const nlb_nerf_mlp_wgrads_t* g, float* sums, void* stream) {
+extern "C" int nlb_nerf_mlp_wgrad(const nlb_nerf_mlp_saved_t* sv, const nlb_nerf_mlp_grad_out_t* go, int M,
+                                  const nlb_nerf_mlp_wgrads_t* g, void* stream) {
   if (M == 0) return NLB_OK;
   if (!sv || !go || !g) { nlb_set_error("nerf_mlp_wgrad: null pointer"); return NLB_EINVAL; }
   if (!sv->f0 || !sv->h0 || !sv->x || !sv->g || !sv->h1 || !sv->h2) {
@@ -450,7 +376,7 @@ static int wgrad_launch(const nlb_nerf_mlp_saved_t* sv, const nlb_nerf_mlp_grad_
   cudaFuncSetAttribute(k_nerf_mlp_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
 
   auto bf = [](const void* p) { return reinterpret_cast<const __nv_bfloat16*>(p); };
-  auto stream_of = [&](const void* p, int ld, int cols, int off) { return Stream{bf(p), ld, log2i(cols / 8), off, nullptr, nullptr}; };
+  auto stream_of = [&](const void* p, int ld, int cols, int off) { return Stream{bf(p), ld, log2i(cols / 8), off}; };
   auto plain = [](int a_off, int b_off, int n, int col, float* base, int stride, int cols_valid, int rows_valid) {
     Op o{};
     o.a_off = a_off; o.b_off = b_off; o.n = n; o.tmem_col = col;
@@ -529,20 +455,6 @@ static int wgrad_launch(const nlb_nerf_mlp_saved_t* sv, const nlb_nerf_mlp_grad_
       R.op[1 + mt] = q;
     }
   }
-  if (sums) {
-    // every pre-activation gradient is summed by ONE role that streams it anyway (d_v1 by role 1, not again by role 2)
-    const size_t rays = (size_t)M / kRows;
-    if (cudaMemsetAsync(sums, 0, sizeof(float) * (496 + 2 * rays * 256), (cudaStream_t)stream) != cudaSuccess)
-      return nlb_check_launch("nerf_mlp_wgrad memset");
-    float* rs = sums + 496;
-    P.role[0].s[1].raysum = rs;                    // d_v0
-    P.role[1].s[1].raysum = rs + rays * 256;       // d_v1
-    P.role[3].s[1].colsum = sums + 256;            // d_g
-    P.role[4].s[1].colsum = sums;                  // d_x
-    P.role[4].s[3].colsum = sums + 384;            // d_h0
-    P.role[5].s[1].colsum = sums + 448;            // d_hs1
-    P.role[5].s[3].colsum = sums + 480;            // d_rgb
-  }
   // CTAs per role in proportion to the bytes it streams, at most one per stage
   const int total_stages = (M + kRows - 1) / kRows;
   int sum_b = 0;
@@ -570,22 +482,6 @@ static int wgrad_launch(const nlb_nerf_mlp_saved_t* sv, const nlb_nerf_mlp_grad_
   }
   k_nerf_mlp_wgrad<<<cta, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
   return nlb_check_launch("nerf_mlp_wgrad");
-}
-
-extern "C" int nlb_nerf_mlp_wgrad(const nlb_nerf_mlp_saved_t* sv, const nlb_nerf_mlp_grad_out_t* go, int M,
-                                  const nlb_nerf_mlp_wgrads_t* g, void* stream) {
-  return wgrad_launch(sv, go, M, g, nullptr, stream);
-}
-
-extern "C" int nlb_nerf_mlp_wgrad_sums(const nlb_nerf_mlp_saved_t* sv, const nlb_nerf_mlp_grad_out_t* go, int M, int S,
-                                       const nlb_nerf_mlp_wgrads_t* g, float* sums, void* stream) {
-  if (!sums) { nlb_set_error("nerf_mlp_wgrad_sums: null sums buffer"); return NLB_EINVAL; }
-  if (S != kRows || M % kRows != 0) {
-    nlb_set_error("nerf_mlp_wgrad_sums: built for S = %d samples per ray (a pipeline stage is one ray); use nlb_bf16_sums", kRows);
-    return NLB_EUNSUPPORTED;
-  }
-  if (reinterpret_cast<uintptr_t>(sums) & 15) { nlb_set_error("nerf_mlp_wgrad_sums: the sums buffer must be 16-byte aligned"); return NLB_EINVAL; }
-  return wgrad_launch(sv, go, M, g, sums, stream);
 }
 
 extern "C" int nlb_nerf_mlp_wgrad_finish(const float* rs_v0, const float* rs_v1, const float* viewdirs, int N,

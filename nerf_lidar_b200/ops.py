@@ -12,7 +12,6 @@ There is no CPU path: every function requires CUDA tensors."""
 from __future__ import annotations
 
 import ctypes as C
-import os
 import math
 from typing import Dict, Optional, Tuple
 
@@ -479,10 +478,6 @@ def bf16_sums(jobs) -> None:
             check(load().nlb_bf16_sums(arr, len(jobs), stream()))
 
 
-# development switch (A/B timing): the reductions of the backward pass as their own launch (nlb_bf16_sums)
-_WGRAD_SUMS = os.environ.get('NLB_WGRAD_SUMS', '1') != '0'
-
-
 class _NerfMLP(Function):
     """Training path of the NerfMLP, all on tcgen05: fused forward that saves bf16 activations, fused
     data-gradient chain, and the weight gradients dW = dZ^T A as MN-major UMMA products (csrc/nerf_wgrad.cu)
@@ -533,24 +528,14 @@ class _NerfMLP(Function):
             with timed('nerf_mlp_bwd'):
                 check(load().nlb_nerf_mlp_backward(C.byref(gin), C.byref(sv), M, ptr(blob_t), ptr(g_feat),
                                                    C.byref(gout), stream()))
-            # weight gradients; at S = 32 the same launch also forms the bias-gradient column sums and the per-ray
-            # sums (the view-direction encoding is a per-ray constant) from the slabs its producers copy
-            fused_sums = S == 32 and M % 32 == 0 and _WGRAD_SUMS
             with timed('nerf_mlp_wgrad'):
-                if fused_sums:
-                    sums = torch.empty(496 + 2 * (M // S) * 256, device=dev, dtype=torch.float32)
-                    check(load().nlb_nerf_mlp_wgrad_sums(C.byref(sv), C.byref(gout), M, S, C.byref(wg), ptr(sums), stream()))
-                else:
-                    check(load().nlb_nerf_mlp_wgrad(C.byref(sv), C.byref(gout), M, C.byref(wg), stream()))
-        if fused_sums:
-            cs_x, cs_g, cs_h0, cs_hs1, cs_rgb = sums[:496].split([256, 128, 64, 32, 16])
-            rs_v0, rs_v1 = sums[496:].view(2, M // S, 256).unbind(0)
-        else:
-            # ONE bandwidth-bound launch over the seven matrices (csrc/reduce.cu)
-            cs_x, cs_g, cs_h0, cs_hs1, cs_rgb = torch.empty(496, device=dev, dtype=torch.float32).split([256, 128, 64, 32, 16])
-            rs_v0, rs_v1 = torch.empty(2, M // S, 256, device=dev, dtype=torch.float32).unbind(0)
-            bf16_sums([(d_x, 0, cs_x), (d_g, 0, cs_g), (d_h0, 0, cs_h0), (d_hs1, 0, cs_hs1), (d_rgb, 0, cs_rgb),
-                       (d_v0, S, rs_v0), (d_v1, S, rs_v1)])
+                check(load().nlb_nerf_mlp_wgrad(C.byref(sv), C.byref(gout), M, C.byref(wg), stream()))
+        # bias gradients and per-ray sums (the view-direction encoding is a per-ray constant): ONE bandwidth-bound
+        # launch over the seven matrices (csrc/reduce.cu), folded into the gradient buffers by one small kernel
+        cs_x, cs_g, cs_h0, cs_hs1, cs_rgb = torch.empty(496, device=dev, dtype=torch.float32).split([256, 128, 64, 32, 16])
+        rs_v0, rs_v1 = torch.empty(2, M // S, 256, device=dev, dtype=torch.float32).unbind(0)
+        bf16_sums([(d_x, 0, cs_x), (d_g, 0, cs_g), (d_h0, 0, cs_h0), (d_hs1, 0, cs_hs1), (d_rgb, 0, cs_rgb),
+                   (d_v0, S, rs_v0), (d_v1, S, rs_v1)])
         with torch.cuda.device(dev):
             with timed('nerf_mlp_wgrad_finish'):
                 check(load().nlb_nerf_mlp_wgrad_finish(ptr(rs_v0), ptr(rs_v1), ptr(viewdirs), N, ptr(cs_x), ptr(cs_g),

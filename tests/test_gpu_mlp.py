@@ -167,47 +167,3 @@ def test_bf16_sums_one_launch_vs_torch():
         ops.bf16_sums([(d_v0[:S + 1], S, rs_v0)])
     with pytest.raises((RuntimeError, NotImplementedError)):   # 4 columns: below the 16-byte vector width
         ops.bf16_sums([(mk(4), 0, torch.empty(4, device='cuda'))])
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize('n_rays', [1, 37, 1000])
-def test_wgrad_with_fused_sums_vs_separate(n_rays):
-    """nlb_nerf_mlp_wgrad_sums (the producers of the weight-gradient kernel sum the slabs they copy) on random bf16
-    operands: the sums buffer against torch in fp32 -- column sums of d_x / d_g / d_h0 / d_hs1 / d_rgb, per-ray sums
-    of d_v0 / d_v1 -- and every weight gradient against nlb_nerf_mlp_wgrad of the same operands (fp32 atomics:
-    equal up to summation order).  Ray counts below and above one stage per CTA; S != 32 is refused."""
-    import ctypes as C
-    from nerf_lidar_b200._lib import NlbNerfMlpSaved, NlbNerfMlpGradOut, NlbNerfMlpWeights, load, check, ptr, stream
-    torch.manual_seed(n_rays)
-    S = 32
-    M = n_rays * S
-    mk = lambda cols: (torch.randn(M, cols, device='cuda') * 0.25).to(torch.bfloat16)
-    sv_t = dict(h0=mk(64), x=mk(256), g=mk(128), h1=mk(256), h2=mk(256), f0=mk(64))
-    dcat = mk(640)
-    d_g, d_v0, d_v1 = dcat[:, :128], dcat[:, 128:384], dcat[:, 384:]
-    d_rgb, d_hs1, d_x, d_h0 = mk(16), mk(32), mk(256), mk(64)
-    sv = NlbNerfMlpSaved(*[ptr(sv_t[k]) for k in ('h0', 'x', 'g', 'h1', 'h2', 'f0')])
-    gout = NlbNerfMlpGradOut(ptr(d_rgb), d_v1.data_ptr(), d_v0.data_ptr(), ptr(d_hs1), d_g.data_ptr(), ptr(d_x), ptr(d_h0),
-                             640, 640, 640)
-    shapes = [(64, 40), (64,), (256, 64), (256,), (64, 256), (64,), (19, 64), (19,), (64, 256), (64,), (1, 64), (1,),
-              (256, 283), (256,), (256, 539), (256,), (3, 256), (3,)]
-
-    def targets():
-        return [torch.zeros(s, device='cuda') for s in shapes]
-
-    ta, tb = targets(), targets()
-    check(load().nlb_nerf_mlp_wgrad(C.byref(sv), C.byref(gout), M, C.byref(NlbNerfMlpWeights(*[ptr(t) for t in ta])), stream()))
-    sums = torch.full((496 + 2 * n_rays * 256,), 9.0, device='cuda')     # overwritten, not accumulated
-    check(load().nlb_nerf_mlp_wgrad_sums(C.byref(sv), C.byref(gout), M, S, C.byref(NlbNerfMlpWeights(*[ptr(t) for t in tb])),
-                                         ptr(sums), stream()))
-    for i, (a, b) in enumerate(zip(ta, tb)):
-        assert_close(b, a, 1e-5, f'weight gradient {i}', atol=1e-6)
-    cs_x, cs_g, cs_h0, cs_hs1, cs_rgb = sums[:496].split([256, 128, 64, 32, 16])
-    for name, got, src in (('x', cs_x, d_x), ('g', cs_g, d_g), ('h0', cs_h0, d_h0), ('hs1', cs_hs1, d_hs1), ('rgb', cs_rgb, d_rgb)):
-        assert_close(got, src.float().sum(0), 1e-4, 'colsum ' + name, atol=1e-4)
-    rs = sums[496:].view(2, n_rays, 256)
-    assert_close(rs[0], d_v0.float().view(n_rays, S, 256).sum(1), 1e-5, 'per-ray sums v0', atol=1e-5)
-    assert_close(rs[1], d_v1.float().view(n_rays, S, 256).sum(1), 1e-5, 'per-ray sums v1', atol=1e-5)
-    with pytest.raises(NotImplementedError):
-        check(load().nlb_nerf_mlp_wgrad_sums(C.byref(sv), C.byref(gout), M, 16, C.byref(NlbNerfMlpWeights(*[ptr(t) for t in tb])),
-                                             ptr(sums), stream()))
