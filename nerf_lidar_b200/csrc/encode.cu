@@ -362,20 +362,21 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_bwd(nlb_rays_t rays, nlb
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int row = tile * kEncThreads + threadIdx.x;
     const bool row_ok = row < rows_total;
-    if (row_ok) stage_points(rays, row, s_pts);  // column threadIdx.x is private to this thread: no barrier
     const float* gin = grad_features + (size_t)row * LC;
+    // the next level's gradient row is fetched while this level is scattered (the first one under the staging):
+    // the load was the one exposed global round trip per (tile, level) of a kernel that runs at 20 warps per SM
+    float g_next[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) g_next[c] = 0.f;
+    if (row_ok) gather_row<C>(gin + level_begin * C, g_next);
+    if (row_ok) stage_points(rays, row, s_pts);  // column threadIdx.x is private to this thread: no barrier
 #pragma unroll 1
     for (int level = level_begin; level < level_end; ++level) {
       float g[C];
       bool any = false;
-      if (row_ok) {
-        gather_row<C>(gin + level * C, g);
 #pragma unroll
-        for (int c = 0; c < C; ++c) { g[c] = g[c] / 7.0f; any |= (g[c] != 0.f); }
-      } else {
-#pragma unroll
-        for (int c = 0; c < C; ++c) g[c] = 0.f;
-      }
+      for (int c = 0; c < C; ++c) { g[c] = g_next[c] / 7.0f; any |= (g[c] != 0.f); }
+      if (row_ok && level + 1 < level_end) gather_row<C>(gin + (level + 1) * C, g_next);
       const Level3 lv = lc.lv[level];
       if (lv.dense) {  // uniform per level: the whole warp takes the same branch
         if ((int)(lv.offset + lv.hashmap_size) <= staged_rows)
@@ -848,18 +849,22 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_bwd_hashed_pair(nlb_rays
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int row = tile * kPairIv + iv;
     const bool row_ok = row < rows_total;
+    const float* gin = grad_features + (size_t)row * LC;
+    float g_next[C];   // prefetched one level ahead (see k_encode_bwd); the first one travels under the staging
+#pragma unroll
+    for (int c = 0; c < C; ++c) g_next[c] = 0.f;
+    if (row_ok) gather_row<C>(gin + level_begin * C, g_next);
     __syncwarp(pair_mask);  // the pair is done with the previous tile's points
     if (row_ok) stage_points_pair(rays, row, h, iv, s_pts);
     __syncwarp(pair_mask);
     if (!row_ok) continue;
-    const float* gin = grad_features + (size_t)row * LC;
 #pragma unroll 1
     for (int level = level_begin; level < level_end; ++level) {
       float g[C];
       bool any = false;
-      gather_row<C>(gin + level * C, g);
 #pragma unroll
-      for (int c = 0; c < C; ++c) { g[c] = g[c] / 7.0f; any |= (g[c] != 0.f); }
+      for (int c = 0; c < C; ++c) { g[c] = g_next[c] / 7.0f; any |= (g[c] != 0.f); }
+      if (level + 1 < level_end) gather_row<C>(gin + (level + 1) * C, g_next);
       if (!any) continue;
       const Level3 lv = lc.lv[level];
       const float inv_gs = lc.inv_gs[level];
