@@ -774,6 +774,7 @@ class _MainLoss(Function):
     @staticmethod
     def forward(ctx, rgb, depth, semantic, intensity, weights, sdist, batch, cfg, used, dist_mult, prop_value,
                 hash_decay, extra_values):
+        ctx.set_materialize_grads(False)   # the two value-only outputs would each get a zero fill in the backward pass
         losses, scales, g_rgb, g_depth, g_sem, g_int, g_dsmo, g_ssmo = _render_losses_launch(
             rgb, depth, semantic, intensity, batch, cfg)
         dev = losses.device
@@ -812,6 +813,8 @@ class _MainLoss(Function):
     @staticmethod
     def backward(ctx, g, _gl, _go):
         scales, g_rgb, g_depth, g_sem, g_int, g_dsmo, g_ssmo, g_dist = ctx.saved_tensors
+        if g is None:
+            return (None,) * 13
         g = f32(g)
         u = ctx.used
         sc = lambda k: scales[k:k + 1]
