@@ -1307,14 +1307,24 @@ extern "C" int nlb_encode_input_backward(const nlb_rays_t* rays, const nlb_table
 static int sm_count() { return nlb_sm_count(); }
 
 
-constexpr int kPrivCopies = 16;
-constexpr size_t kPrivBudgetBytes = 1 << 20;  // per copy
+static int priv_copies() {
+  static const int v = (int)env_long("NLB_SCATTER_PRIV_COPIES", 16);
+  return v < 1 ? 1 : v;
+}
+#define kPrivCopies priv_copies()
+// Budget per copy: the resolution-64 level of a C = 1 table (1.26 MB with the two coarser ones) is privatised too --
+// measured 0.497 -> 0.478 / 0.721 -> 0.692 ms for the two proposal scatters; the same level of the C = 4 table
+// (5 MB per copy) measured slower (0.712 -> 0.734 ms) and stays on warp aggregation.  NLB_SCATTER_PRIV_KB overrides.
+static size_t priv_budget_bytes() {
+  static const size_t v = (size_t)env_long("NLB_SCATTER_PRIV_KB", 1400) * 1024;
+  return v;
+}
 
 // rows of the leading dense levels that get privatised global copies (beyond the staged ones)
 static int priv_rows_for(const nlb_table_t& tab, const HostLevels& hl) {
   int rows = 0;
   for (int l = 0; l < tab.L && hl.dense[l]; ++l) {
-    if ((size_t)(rows + hl.rows[l]) * tab.C * sizeof(float) > kPrivBudgetBytes) break;
+    if ((size_t)(rows + hl.rows[l]) * tab.C * sizeof(float) > priv_budget_bytes()) break;
     rows += hl.rows[l];
   }
   return rows;
