@@ -381,7 +381,13 @@ def run_cuda_arm(args):
                     if dom in ALG_BYTES else None,
                     'note': 'achieved = SURVEY 8(d) algorithmic bytes / measured launch time; it can exceed the HBM '
                             'peak because merged same-cell corners and L2-resident level groups never reach DRAM '
-                            '(traffic = DRAM bytes per launch from the committed ncu --set full capture)'}
+                            '(traffic = DRAM bytes per launch from the committed ncu --set full capture).  NOT an HBM '
+                            'efficiency: the scatter kernels are bound by the L2 reduction (RED) request rate -- the '
+                            'hashed levels issue the 0.72 lane-reductions per clock per SM the probe measured '
+                            '(profiles/r1_s15_gather_probe.txt, DESIGN.md section 8)'}
+        if roofline['traffic']:
+            roofline['dram_gbs'] = roofline['traffic'] / (per_kernel[dom]['avg_ms'] * 1e-3) / 1e9
+            roofline['dram_frac_of_peak'] = roofline['dram_gbs'] / hbm_peak
     # the only dense contraction on the path: fused NerfMLP kernels against the measured sustained bf16 rate
     roofline_mlp = None
     tf_peak = float(peaks.get('bf16_tflops_sustained', 1356.8))
