@@ -174,23 +174,21 @@ struct SumTerms {
 __global__ void __launch_bounds__(1024) k_weighted_sums(const __grid_constant__ SumTerms T, float* __restrict__ out,
                                                         int nout) {
   __shared__ float s_warp[32];
+  __shared__ float s_val[kMaxSumTerms];   // sum_i x[i] w[i] of every term that reads memory
   __shared__ float s_out[kMaxSumOut];
   __shared__ int s_named[kMaxSumOut];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < kMaxSumOut) { s_out[tid] = 0.f; s_named[tid] = 0; }
-  __syncthreads();
+  // scalar terms (most of a loss dictionary): one thread each, all loads in flight together -- walking them one
+  // after the other paid a global round trip per term.  A zero coefficient reads nothing (0 * NaN must stay 0).
+  if (tid < T.n) {
+    const nlb_sum_term_t& q = T.t[tid];
+    if (q.x != nullptr && q.n == 1 && q.coef != 0.f) s_val[tid] = __ldg(q.x) * (q.w ? __ldg(q.w) : 1.0f);
+  }
+  // array terms: the whole block, one term after the other
   for (int k = 0; k < T.n; ++k) {
     const nlb_sum_term_t& q = T.t[k];
-    if (q.coef == 0.f) {   // names the output (it will be written) without reading x: 0 * NaN must stay 0
-      if (tid == 0) s_named[q.out_index] = 1;
-      __syncthreads();
-      continue;
-    }
-    if (q.x == nullptr) {  // coef * (an earlier result of this call)
-      if (tid == 0) { s_out[q.out_index] += q.coef * s_out[(int)q.n]; s_named[q.out_index] = 1; }
-      __syncthreads();
-      continue;
-    }
+    if (q.x == nullptr || q.n <= 1 || q.coef == 0.f) continue;   // (uniform over the block)
     float a = 0.f;
     if (q.w) {
       for (int64_t i = tid; i < q.n; i += 1024) a = fmaf(__ldg(q.x + i), __ldg(q.w + i), a);
@@ -198,14 +196,25 @@ __global__ void __launch_bounds__(1024) k_weighted_sums(const __grid_constant__ 
       for (int64_t i = tid; i < q.n; i += 1024) a += __ldg(q.x + i);
     }
     a = warp_sum(a);
+    __syncthreads();               // s_warp of the previous term has been read
     if (lane == 0) s_warp[warp] = a;
     __syncthreads();
     if (warp == 0) {
       a = warp_sum(s_warp[lane]);
-      if (lane == 0) { s_out[q.out_index] += q.coef * a; s_named[q.out_index] = 1; }
+      if (lane == 0) s_val[k] = a;
     }
-    __syncthreads();
   }
+  __syncthreads();
+  if (tid == 0) {                  // the terms in order: a term without x adds an output formed so far
+    for (int k = 0; k < T.n; ++k) {
+      const nlb_sum_term_t& q = T.t[k];
+      s_named[q.out_index] = 1;
+      if (q.coef == 0.f) continue;
+      const float v = q.x == nullptr ? s_out[(int)q.n] : (q.n == 0 ? 0.f : s_val[k]);
+      s_out[q.out_index] += q.coef * v;
+    }
+  }
+  __syncthreads();
   if (tid < nout && s_named[tid]) out[tid] = s_out[tid];
 }
 
