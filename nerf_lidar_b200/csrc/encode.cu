@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_input_bwd(nlb_rays_t ray
       for (int level = level_begin; level < level_end; ++level) {
         const Level3 lv = lc.lv[level];
         const float u = a * lc.inv_gs[level];
-        const float w = erff(u);
+        const float w = u >= 4.0f ? 1.0f : erff(u);   // (see erf_weight_a: exact, and most levels saturate)
         // d erf(u)/d std with u = 1/(sqrt(8) std gs): -(2/sqrt(pi)) exp(-u^2) u / std; saturated weights are flat
         const float dw = (u < 12.f) ? -1.1283791671f * __expf(-u * u) * u / p.std : 0.f;
         uint32_t cx, cy, cz;
