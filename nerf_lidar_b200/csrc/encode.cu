@@ -1307,11 +1307,11 @@ extern "C" int nlb_encode_input_backward(const nlb_rays_t* rays, const nlb_table
 static int sm_count() { return nlb_sm_count(); }
 
 
+// privatised copies of the coarse rows (a block adds into copy blockIdx % copies); 4 .. 32 measured alike
 static int priv_copies() {
   static const int v = (int)env_long("NLB_SCATTER_PRIV_COPIES", 16);
   return v < 1 ? 1 : v;
 }
-#define kPrivCopies priv_copies()
 // Budget per copy: the resolution-64 level of a C = 1 table (1.26 MB with the two coarser ones) is privatised too --
 // measured 0.497 -> 0.478 / 0.721 -> 0.692 ms for the two proposal scatters; the same level of the C = 4 table
 // (5 MB per copy) measured slower (0.712 -> 0.734 ms) and stays on warp aggregation.  NLB_SCATTER_PRIV_KB overrides.
@@ -1331,7 +1331,7 @@ static int priv_rows_for(const nlb_table_t& tab, const HostLevels& hl) {
 }
 
 static size_t scatter_workspace_floats(const nlb_table_t& tab, const HostLevels& hl) {
-  return (size_t)kPrivCopies * priv_rows_for(tab, hl) * tab.C;
+  return (size_t)priv_copies() * priv_rows_for(tab, hl) * tab.C;
 }
 
 template <int C>
@@ -1352,7 +1352,7 @@ static int scatter_launch(const nlb_rays_t& rays, const nlb_table_t& tab, const 
   int priv_rows = workspace ? priv_rows_for(tab, hl) : 0;
   if (priv_rows <= staged_rows) priv_rows = 0;
   if (priv_rows > 0 &&
-      cudaMemsetAsync(workspace, 0, (size_t)kPrivCopies * priv_rows * C * sizeof(float), st) != cudaSuccess)
+      cudaMemsetAsync(workspace, 0, (size_t)priv_copies() * priv_rows * C * sizeof(float), st) != cudaSuccess)
     return nlb_check_launch("encode_backward memset");
   const int tiles = (int)div_up(rays.N * rays.S, kEncThreads);
   // per device (function attributes are device state): a process may drive several GPUs
@@ -1408,14 +1408,14 @@ static int scatter_launch(const nlb_rays_t& rays, const nlb_table_t& tab, const 
     } else {
       k_encode_bwd<C><<<first ? blocks_staged : blocks_plain, kEncThreads, first ? smem : 0, st>>>(
           rays, tab, grad_features, grad_embeddings, first ? staged_rows : 0, tiles, l0, l1, workspace, priv_rows,
-          kPrivCopies);
+          priv_copies());
     }
     if (int e = nlb_check_launch("encode_backward")) return e;
     l0 = l1;
   }
   if (priv_rows > 0) {
     const int n = priv_rows * C;
-    k_priv_reduce<<<div_up(n, 256), 256, 0, st>>>(workspace, kPrivCopies, n, grad_embeddings);
+    k_priv_reduce<<<div_up(n, 256), 256, 0, st>>>(workspace, priv_copies(), n, grad_embeddings);
     if (int e = nlb_check_launch("encode_backward reduce")) return e;
   }
   return NLB_OK;
