@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(256) k_priv_reduce(const float* __restrict__ p
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float a = 0.f;
+#pragma unroll 8   // (the loads of the copies in flight together; same summation order)
   for (int c = 0; c < copies; ++c) a += __ldg(priv + (size_t)c * n + i);
   if (a != 0.f) grad_table[i] += a;
 }
@@ -1133,6 +1134,7 @@ __global__ void __launch_bounds__(256) k_prop_wgrad_reduce(const float* __restri
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= entries) return;
   float a = 0.f;
+#pragma unroll 8   // (18 dependent-free loads per thread were issued one round trip at a time)
   for (int b = blockIdx.y; b < blocks; b += gridDim.y) a += __ldg(partial + (size_t)b * entries + e);
   const int n0 = kPropHidden * L;
   float* dst = e < n0 ? gW0 + e : e < n0 + kPropHidden ? gb0 + (e - n0)
