@@ -71,3 +71,48 @@ def test_ctypes_mirrors_match_the_header(tmp_path):
         assert len(py_fields) == len(c_fields), (name, py_fields, c_fields)
         for pf, cf in zip(py_fields, c_fields):      # same order; offsets must agree field by field
             assert getattr(cls, pf).offset == int(got[f'{name}.{cf}']), (name, pf, cf)
+
+
+def _header_prototypes():
+    """{function: (return kind, [argument kinds])} with kinds 'ptr' / 'int' / 'u32' / 'i64' / 'size' / 'f32' / 'f64'."""
+    src = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
+    src = re.sub(r'//[^\n]*', '', src)
+    src = re.sub(r'typedef\s+struct\s*\{.*?\}\s*nlb_\w+_t\s*;', '', src, flags=re.S)
+
+    def kind(t):
+        t = t.strip()
+        if '*' in t or '[' in t:
+            return 'ptr'
+        base = re.sub(r'\b(const|unsigned)\b', lambda m: m.group(0), t)
+        words = base.replace('const', '').split()
+        ty = ' '.join(words[:-1]) if len(words) > 1 else words[0]
+        return {'int': 'int', 'int32_t': 'int', 'uint32_t': 'u32', 'unsigned int': 'u32', 'int64_t': 'i64', 'size_t': 'size',
+                'float': 'f32', 'double': 'f64', 'void': 'void', 'char': 'char'}[ty]
+
+    out = {}
+    for ret, name, args in re.findall(r'([\w\s\*]+?)\s*\b(nlb_\w+)\s*\(([^;{]*?)\)\s*;', src, flags=re.S):
+        args = ' '.join(args.split())
+        arg_kinds = [] if args in ('', 'void') else [kind(a) for a in args.split(',')]
+        out[name] = ('ptr' if '*' in ret else kind(ret + ' x'), arg_kinds)
+    return out
+
+
+def test_ctypes_signatures_match_the_header():
+    """Argument count and kind (pointer / int / uint32 / int64 / float) of every entry of _lib.SIGNATURES against the
+    prototypes of include/nlb200.h."""
+    protos = _header_prototypes()
+    assert set(_lib.SIGNATURES) <= set(protos), sorted(set(_lib.SIGNATURES) - set(protos))
+
+    def ckind(t):
+        if t is None:
+            return 'void'
+        if t in (C.c_void_p, C.c_char_p) or hasattr(t, 'contents') or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return 'ptr'
+        return {C.c_int: 'int', C.c_int32: 'int', C.c_uint32: 'u32', C.c_int64: 'i64', C.c_size_t: 'size', C.c_float: 'f32',
+                C.c_double: 'f64'}[t]
+
+    for name, (res, args) in _lib.SIGNATURES.items():
+        want_res, want_args = protos[name]
+        got_args = [ckind(a) for a in args]
+        assert got_args == want_args, (name, got_args, want_args)
+        assert ckind(res) == want_res or (want_res == 'size' and ckind(res) in ('size', 'i64')), (name, ckind(res), want_res)
